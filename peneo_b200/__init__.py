@@ -1,0 +1,19 @@
+"""peneo_b200 — B200-native (sm_100a) implementation of PEneo's decoder hot path.
+
+Public surface mirrors the reference (ZeningLin/PEneo):
+  PEneoDecoderB200 / PEneoOutput      <- model/peneo_decoder.py  PEneoDecoder / PEneoOutput
+  HandshakingTaggingScheme            <- model/peneo_decoder.py  HandshakingTaggingScheme
+  decode_peneo / sample_decode_peneo / parse_matrix_spots  <- pipeline/decode.py
+"""
+from .decode import decode_peneo, parse_matrix_spots, sample_decode_peneo  # noqa: F401
+from .decoder import PEneoDecoderB200, PEneoOutput  # noqa: F401
+from .tagging import HandshakingTaggingScheme  # noqa: F401
+
+__all__ = [
+    "PEneoDecoderB200",
+    "PEneoOutput",
+    "HandshakingTaggingScheme",
+    "decode_peneo",
+    "sample_decode_peneo",
+    "parse_matrix_spots",
+]

@@ -1,0 +1,119 @@
+// Shared helpers for the peneo_b200 kernels: error plumbing, pair-index arithmetic, packed
+// weight layout.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+
+#include "../../include/peneo_b200.h"
+
+namespace peneo {
+
+constexpr int kNumHeads = PENEO_NUM_HEADS;
+__host__ __device__ constexpr int head_classes(int h) { return h == 0 ? 2 : 3; }
+
+// ---- error plumbing (thread-local message, negative status codes) ---------------------------
+void set_error(const char* fmt, ...);
+const char* get_error();
+
+#define PENEO_CUDA_TRY(expr)                                                              \
+  do {                                                                                    \
+    cudaError_t _e = (expr);                                                              \
+    if (_e != cudaSuccess) {                                                              \
+      peneo::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return PENEO_E_CUDA;                                                                \
+    }                                                                                     \
+  } while (0)
+
+#define PENEO_REQUIRE(cond, ...)     \
+  do {                               \
+    if (!(cond)) {                   \
+      peneo::set_error(__VA_ARGS__); \
+      return PENEO_E_INVALID;        \
+    }                                \
+  } while (0)
+
+// ---- pair index arithmetic --------------------------------------------------------------------
+// Flat upper-triangular index p(i, j) = i*n - i(i-1)/2 + (j - i), i <= j < n
+// (row-major order of torch.nonzero(row <= col), model/peneo_decoder.py:143-147, 171-173).
+__host__ __device__ __forceinline__ int64_t pair_count(int64_t n) { return n * (n + 1) / 2; }
+__host__ __device__ __forceinline__ int32_t row_start(int32_t i, int32_t n) { return i * n - (i * (i - 1)) / 2; }
+
+__device__ __forceinline__ void pair_from_flat(int32_t p, int32_t n, int32_t& i, int32_t& j) {
+  // i = largest row with row_start(i) <= p.  Float estimate, then exact integer fix-up.
+  const float t = 2.0f * n + 1.0f;
+  float disc = t * t - 8.0f * static_cast<float>(p);
+  int32_t r = static_cast<int32_t>((t - sqrtf(fmaxf(disc, 0.0f))) * 0.5f);
+  r = max(0, min(r, n - 1));
+  while (r > 0 && row_start(r, n) > p) --r;
+  while (r + 1 < n && row_start(r + 1, n) <= p) ++r;
+  i = r;
+  j = r + (p - row_start(r, n));
+}
+
+__device__ __forceinline__ float silu_exact(float x) { return x / (1.0f + expf(-x)); }
+
+// ---- packed weights ---------------------------------------------------------------------------
+// One device buffer written by peneo_pack_weights; offsets in bytes from its start.
+constexpr int kMaxMidLayers = 7;  // num_layers <= 8
+
+struct PackLayout {
+  // PENEO_PREC_FP32: fp32 copies in the reference's own [out, in] layouts.
+  size_t f_w1, f_b1, f_w2, f_b2, f_wc, f_bc;
+  size_t f_mid_w[kNumHeads][kMaxMidLayers], f_mid_b[kNumHeads][kMaxMidLayers];
+  size_t f_out_w[kNumHeads], f_out_b[kNumHeads];
+  // PENEO_PREC_BF16 (d == 384, num_layers == 2): converted / concatenated / pre-scaled matrices.
+  size_t w1_bf16;    // [hid, hin]
+  size_t b1;         // [hid] fp32
+  size_t w2_bf16;    // [d, hid]
+  size_t b2;         // [d] fp32
+  size_t wc_bf16;    // [2d, d]   rows [0,d) = 0.5*W_c[:, :d], rows [d,2d) = 0.5*W_c[:, d:]
+  size_t bc_half;    // [2d] fp32: zeros then 0.5*b_c
+  size_t wmid_bf16;  // [5d, d]   0.5 * W_mid, heads stacked
+  size_t bmid_half;  // [5d] fp32 0.5 * b_mid
+  size_t wout_bf16;  // [15*16, 128] bf16: chunk c = (head c/3, features 128*(c%3)..), rows >= C zero
+  size_t bout;       // [5*4] fp32
+  size_t total;
+};
+
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+inline PackLayout pack_layout(const peneo_dims& dm, int prec) {
+  PackLayout L{};
+  size_t off = 0;
+  const size_t d = dm.d, hid = dm.hid, hin = dm.hin;
+  auto take = [&](size_t bytes) {
+    size_t at = off;
+    off = align_up(off + bytes, 1024);
+    return at;
+  };
+  if (prec == PENEO_PREC_FP32) {
+    if (dm.shrink) {
+      L.f_w1 = take(hid * hin * 4), L.f_b1 = take(hid * 4);
+      L.f_w2 = take(d * hid * 4), L.f_b2 = take(d * 4);
+    }
+    L.f_wc = take(d * 2 * d * 4), L.f_bc = take(d * 4);
+    for (int h = 0; h < kNumHeads; ++h) {
+      for (int l = 0; l + 1 < dm.num_layers; ++l) L.f_mid_w[h][l] = take(d * d * 4), L.f_mid_b[h][l] = take(d * 4);
+      L.f_out_w[h] = take(head_classes(h) * d * 4), L.f_out_b[h] = take(16);
+    }
+  } else {
+    L.w1_bf16 = take(hid * hin * 2), L.b1 = take(hid * 4);
+    L.w2_bf16 = take(d * hid * 2), L.b2 = take(d * 4);
+    L.wc_bf16 = take(2 * d * d * 2), L.bc_half = take(2 * d * 4);
+    L.wmid_bf16 = take(5 * d * d * 2), L.bmid_half = take(5 * d * 4);
+    L.wout_bf16 = take(15 * 16 * 128 * 2), L.bout = take(5 * 4 * 4);
+  }
+  L.total = off;
+  return L;
+}
+
+inline bool bf16_supported(const peneo_dims& dm) {
+  return dm.shrink == 1 && dm.d == 384 && dm.hid == 768 && dm.num_layers == 2 && dm.hin % 64 == 0;
+}
+
+}  // namespace peneo

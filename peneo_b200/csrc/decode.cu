@@ -1,0 +1,461 @@
+// Decode kernels.
+//   K3 decode_spots   : per pair softmax -> argmax -> max-prob, ordered compaction of pred != 0
+//                       (HandshakingTaggingScheme.get_spots_from_shaking_tag, model/peneo_decoder.py:98-114)
+//   K4 decode_resolve : 1-1 map resolution (parse_matrix_spots, pipeline/decode.py:9-69) and the
+//                       key/value chain walk of sample_decode_peneo (pipeline/decode.py:216-368)
+// Both are HBM/latency-bound integer work: K3 reads every logit exactly once.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace peneo {
+
+constexpr int kSpotChunk = 4096;     // pairs per CTA
+constexpr int kSpotWarpPairs = 512;  // pairs per warp (8 warps)
+
+// ------------------------------------------------------------------------------------------------
+// K3
+// ------------------------------------------------------------------------------------------------
+template <int DT>
+__device__ __forceinline__ float load_as_float(const void* base, int64_t idx) {
+  if constexpr (DT == PENEO_DT_F32) return static_cast<const float*>(base)[idx];
+  else if constexpr (DT == PENEO_DT_BF16) return __bfloat162float(static_cast<const __nv_bfloat16*>(base)[idx]);
+  else if constexpr (DT == PENEO_DT_F16) return __half2float(static_cast<const __half*>(base)[idx]);
+  else return 0.f;
+}
+template <int DT>
+__device__ __forceinline__ float round_like(float v) {
+  if constexpr (DT == PENEO_DT_BF16) return __bfloat162float(__float2bfloat16_rn(v));
+  else if constexpr (DT == PENEO_DT_F16) return __half2float(__float2half_rn(v));
+  else return v;
+}
+
+// softmax over C classes the way ATen does it (exp(x - max) / sum in fp32, result rounded to the
+// tensor dtype), then argmax of the *probabilities* (first maximum) and its value.
+template <int DT, int C>
+__device__ __forceinline__ void classify(const void* base, int64_t row, int& pred, float& score) {
+  float x[C];
+#pragma unroll
+  for (int c = 0; c < C; ++c) x[c] = load_as_float<DT>(base, row * C + c);
+  float m = x[0];
+#pragma unroll
+  for (int c = 1; c < C; ++c) m = fmaxf(m, x[c]);
+  float e[C], sum = 0.f;
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    e[c] = expf(x[c] - m);
+    sum += e[c];
+  }
+  pred = 0;
+  score = round_like<DT>(e[0] / sum);
+#pragma unroll
+  for (int c = 1; c < C; ++c) {
+    const float pc = round_like<DT>(e[c] / sum);
+    if (pc > score) score = pc, pred = c;
+  }
+}
+
+struct SpotArgs {
+  const void* in[kNumHeads];
+  int32_t batch, n, pairs, cap, chunks;
+  int32_t* spot_p;
+  int32_t* spot_tag;
+  float* spot_score;
+  int32_t* counts;
+  int32_t* ticket;  // [batch*5]
+  int32_t* status;  // [batch*5*chunks] : inclusive prefix + 1, 0 = not ready
+};
+
+template <int DT>
+__global__ void __launch_bounds__(256) decode_spots_kernel(const SpotArgs a) {
+  __shared__ int32_t buf_p[8][kSpotWarpPairs];
+  __shared__ float buf_s[8][kSpotWarpPairs];
+  __shared__ uint8_t buf_t[8][kSpotWarpPairs];
+  __shared__ int32_t wcount[8];
+  __shared__ int32_t s_chunk, s_base;
+  const int h = blockIdx.y, b = blockIdx.z, list = b * kNumHeads + h;
+  const int lane = threadIdx.x % 32, warp = threadIdx.x / 32;
+  // chunks are claimed in start order so the chained prefix below can never wait on a CTA that
+  // has not been scheduled
+  if (threadIdx.x == 0) s_chunk = atomicAdd(&a.ticket[list], 1);
+  __syncthreads();
+  const int chunk = s_chunk;
+  const int C = head_classes(h);
+  const char* base = static_cast<const char*>(a.in[h]);
+  const int64_t doc_row0 = (int64_t)b * a.pairs;
+  int cnt = 0;
+  const int p0 = chunk * kSpotChunk + warp * kSpotWarpPairs;
+#pragma unroll 4
+  for (int it = 0; it < kSpotWarpPairs / 32; ++it) {
+    const int p = p0 + it * 32 + lane;
+    int pred = 0;
+    float score = 1.f;
+    if (p < a.pairs) {
+      if constexpr (DT == PENEO_DT_I64) {
+        pred = static_cast<int>(reinterpret_cast<const int64_t*>(base)[doc_row0 + p]);
+      } else if (C == 2) {
+        classify<DT, 2>(base, doc_row0 + p, pred, score);
+      } else {
+        classify<DT, 3>(base, doc_row0 + p, pred, score);
+      }
+    }
+    const bool hit = pred != 0;
+    const unsigned mask = __ballot_sync(0xffffffffu, hit);
+    if (hit) {
+      const int pos = cnt + __popc(mask & ((1u << lane) - 1));
+      buf_p[warp][pos] = p, buf_s[warp][pos] = score, buf_t[warp][pos] = static_cast<uint8_t>(pred);
+    }
+    cnt += __popc(mask);
+  }
+  if (lane == 0) wcount[warp] = cnt;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int total = 0;
+    for (int w = 0; w < 8; ++w) total += wcount[w];
+    int prefix = 0;
+    if (chunk > 0) {
+      volatile int32_t* st = a.status + (int64_t)list * a.chunks + chunk - 1;
+      int v;
+      while ((v = *st) == 0) {
+      }
+      prefix = v - 1;
+    }
+    __threadfence();
+    atomicExch(&a.status[(int64_t)list * a.chunks + chunk], prefix + total + 1);
+    if (chunk == a.chunks - 1) a.counts[list] = prefix + total;
+    s_base = prefix;
+  }
+  __syncthreads();
+  int off = s_base;
+  for (int w = 0; w < warp; ++w) off += wcount[w];
+  const int64_t out0 = (int64_t)list * a.cap;
+  for (int r = lane; r < cnt; r += 32) {
+    const int dst = off + r;
+    if (dst < a.cap) {
+      a.spot_p[out0 + dst] = buf_p[warp][r];
+      a.spot_tag[out0 + dst] = buf_t[warp][r];
+      a.spot_score[out0 + dst] = buf_s[warp][r];
+    }
+  }
+}
+
+size_t decode_spots_workspace_bytes(int batch, int n) {
+  const int64_t pairs = pair_count(n);
+  const int64_t chunks = (pairs + kSpotChunk - 1) / kSpotChunk;
+  return static_cast<size_t>((int64_t)batch * kNumHeads * (1 + chunks) * sizeof(int32_t));
+}
+
+int launch_decode_spots(int batch, int n, const void* const in[kNumHeads], int in_dtype, int cap, int32_t* spot_p,
+                        int32_t* spot_tag, float* spot_score, int32_t* counts, void* ws, cudaStream_t st) {
+  PENEO_REQUIRE(batch >= 0 && n >= 1 && cap >= 1, "decode_spots: bad sizes batch=%d n=%d cap=%d", batch, n, cap);
+  PENEO_REQUIRE(n <= 46340, "decode_spots: n too large");
+  if (batch == 0) return PENEO_OK;
+  SpotArgs a{};
+  for (int h = 0; h < kNumHeads; ++h) a.in[h] = in[h];
+  a.batch = batch, a.n = n, a.pairs = static_cast<int32_t>(pair_count(n)), a.cap = cap;
+  a.chunks = (a.pairs + kSpotChunk - 1) / kSpotChunk;
+  a.spot_p = spot_p, a.spot_tag = spot_tag, a.spot_score = spot_score, a.counts = counts;
+  a.ticket = static_cast<int32_t*>(ws);
+  a.status = a.ticket + (int64_t)batch * kNumHeads;
+  PENEO_CUDA_TRY(cudaMemsetAsync(ws, 0, decode_spots_workspace_bytes(batch, n), st));
+  PENEO_REQUIRE(batch <= 65535, "decode_spots: batch too large for one launch");
+  dim3 grid(a.chunks, kNumHeads, batch);
+  switch (in_dtype) {
+    case PENEO_DT_F32: decode_spots_kernel<PENEO_DT_F32><<<grid, 256, 0, st>>>(a); break;
+    case PENEO_DT_BF16: decode_spots_kernel<PENEO_DT_BF16><<<grid, 256, 0, st>>>(a); break;
+    case PENEO_DT_F16: decode_spots_kernel<PENEO_DT_F16><<<grid, 256, 0, st>>>(a); break;
+    case PENEO_DT_I64: decode_spots_kernel<PENEO_DT_I64><<<grid, 256, 0, st>>>(a); break;
+    default: set_error("decode_spots: unsupported dtype %d", in_dtype); return PENEO_E_INVALID;
+  }
+  PENEO_CUDA_TRY(cudaGetLastError());
+  return PENEO_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4 : one CTA per document
+// ------------------------------------------------------------------------------------------------
+struct ResolveArgs {
+  int32_t batch, n, cap, npow2, decode_gt;
+  float thresh;
+  const int32_t* spot_p;
+  const int32_t* spot_tag;
+  const float* spot_score;
+  const int32_t* counts;
+  int32_t* out;
+  int64_t doc_ints;
+  uint32_t* bitmap;  // [batch][ceil(n*n/32)]
+  int64_t bitmap_words;
+};
+
+struct SpotList {
+  const int32_t* p;
+  const int32_t* tag;
+  const float* score;
+  int32_t cnt;
+};
+
+// filtered, swapped (head, tail) of spot s; returns false when the spot is dropped
+__device__ __forceinline__ bool spot_edge(const SpotList& L, int s, int n, bool triu, float thresh, int& hd, int& tl,
+                                          float& sc) {
+  const int tag = L.tag[s];
+  sc = L.score[s];
+  if (tag == 0 || sc < thresh) return false;
+  int i, j;
+  pair_from_flat(L.p[s], n, i, j);
+  if (triu && tag == 2) {
+    hd = j, tl = i;
+  } else {
+    hd = i, tl = j;
+  }
+  return true;
+}
+
+__device__ void bitonic_sort_u64(unsigned long long* key, int npow2) {
+  for (int k = 2; k <= npow2; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int t = threadIdx.x; t < npow2; t += blockDim.x) {
+        const int ixj = t ^ j;
+        if (ixj > t) {
+          const unsigned long long a = key[t], b = key[ixj];
+          const bool up = (t & k) == 0;
+          if ((a > b) == up) key[t] = b, key[ixj] = a;
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// Builds one 1-1 map.  out_pairs receives (head, tail) in the reference's dict order, map[head] = tail.
+__device__ int resolve_map(const SpotList& L, int n, int npow2, bool triu, bool top, float thresh,
+                           unsigned long long* best1, unsigned long long* best2, uint32_t* first, uint32_t* ord2,
+                           unsigned long long* sortbuf, int32_t* map, int32_t* out_pairs, int32_t* s_count) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  for (int t = tid; t < n; t += nt) best1[t] = 0ull, best2[t] = 0ull, first[t] = 0xFFFFFFFFu, ord2[t] = 0xFFFFFFFFu, map[t] = -1;
+  for (int t = tid; t < npow2; t += nt) sortbuf[t] = ~0ull;
+  if (tid == 0) *s_count = 0;
+  __syncthreads();
+  for (int s = tid; s < L.cnt; s += nt) {
+    int hd, tl;
+    float sc;
+    if (!spot_edge(L, s, n, triu, thresh, hd, tl, sc)) continue;
+    const unsigned long long key = (static_cast<unsigned long long>(__float_as_uint(sc)) << 32) | (0xFFFFFFFFu - s);
+    atomicMax(&best1[hd], key);
+    atomicMin(&first[hd], static_cast<uint32_t>(s));
+  }
+  __syncthreads();
+  if (top) {
+    // stage 2: per tail keep the best head; heads are visited in order of first arrival
+    for (int hd = tid; hd < n; hd += nt) {
+      if (best1[hd] == 0ull) continue;
+      const int s = static_cast<int>(0xFFFFFFFFu - static_cast<uint32_t>(best1[hd]));
+      int h2, tl;
+      float sc;
+      spot_edge(L, s, n, triu, thresh, h2, tl, sc);
+      const unsigned long long key = (best1[hd] & 0xFFFFFFFF00000000ull) | (0xFFFFFFFFu - first[hd]);
+      atomicMax(&best2[tl], key);
+      atomicMin(&ord2[tl], first[hd]);
+    }
+    __syncthreads();
+    for (int tl = tid; tl < n; tl += nt) {
+      if (best2[tl] == 0ull) continue;
+      const int slot = atomicAdd(s_count, 1);
+      sortbuf[slot] = (static_cast<unsigned long long>(ord2[tl]) << 32) | static_cast<uint32_t>(tl);
+    }
+  } else {
+    // GT mode: {head: [tails...]} then first element -> tail of the first-arriving spot per head
+    for (int hd = tid; hd < n; hd += nt) {
+      if (first[hd] == 0xFFFFFFFFu) continue;
+      const int slot = atomicAdd(s_count, 1);
+      sortbuf[slot] = (static_cast<unsigned long long>(first[hd]) << 32) | static_cast<uint32_t>(hd);
+    }
+  }
+  __syncthreads();
+  const int cnt = *s_count;
+  bitonic_sort_u64(sortbuf, npow2);
+  for (int r = tid; r < cnt; r += nt) {
+    const unsigned long long e = sortbuf[r];
+    int hd, tl;
+    float sc;
+    if (top) {
+      tl = static_cast<int>(static_cast<uint32_t>(e));
+      const int s = static_cast<int>(0xFFFFFFFFu - static_cast<uint32_t>(best2[tl]));  // first[] of the winning head
+      int t2;
+      spot_edge(L, s, n, triu, thresh, hd, t2, sc);
+    } else {
+      hd = static_cast<int>(static_cast<uint32_t>(e));
+      int h2;
+      spot_edge(L, static_cast<int>(e >> 32), n, triu, thresh, h2, tl, sc);
+    }
+    out_pairs[2 * r] = hd, out_pairs[2 * r + 1] = tl;
+    map[hd] = tl;
+  }
+  __syncthreads();
+  return cnt;
+}
+
+// ordered compaction of the filtered (head, tail) edges of a spot list; optionally sets the bitmap
+__device__ int emit_edges(const SpotList& L, int n, float thresh, int32_t* out_pairs, uint32_t* bitmap, int32_t* s_warp,
+                          int32_t* s_run) {
+  const int tid = threadIdx.x, lane = tid % 32, warp = tid / 32, nw = blockDim.x / 32;
+  if (tid == 0) *s_run = 0;
+  __syncthreads();
+  for (int s0 = 0; s0 < L.cnt; s0 += blockDim.x) {
+    const int s = s0 + tid;
+    int hd = 0, tl = 0;
+    float sc;
+    const bool keep = s < L.cnt && spot_edge(L, s, n, true, thresh, hd, tl, sc);
+    const unsigned mask = __ballot_sync(0xffffffffu, keep);
+    if (lane == 0) s_warp[warp] = __popc(mask);
+    __syncthreads();
+    int off = *s_run;
+    for (int w = 0; w < warp; ++w) off += s_warp[w];
+    if (keep) {
+      const int pos = off + __popc(mask & ((1u << lane) - 1));
+      out_pairs[2 * pos] = hd, out_pairs[2 * pos + 1] = tl;
+      if (bitmap) {
+        const int64_t bit = (int64_t)hd * n + tl;
+        atomicOr(&bitmap[bit >> 5], 1u << (bit & 31));
+      }
+    }
+    __syncthreads();
+    if (tid == 0) {
+      int tot = 0;
+      for (int w = 0; w < nw; ++w) tot += s_warp[w];
+      *s_run += tot;
+    }
+    __syncthreads();
+  }
+  return *s_run;
+}
+
+__device__ __forceinline__ void chain_walk(int hd, int tl, const int32_t* le, const int32_t* lgh, const int32_t* lgt,
+                                           int& nseg, int& last_tail) {
+  // pipeline/decode.py:257-296: follow line-grouping heads while LE and LG-t2t agree; 1000-step cap
+  nseg = 1;
+  int cur_h = hd, cur_t = tl, nxt = lgh[cur_h], ops = 0;
+  while (nxt >= 0) {
+    if (++ops > 1000) break;
+    if (nxt == cur_h) break;
+    const int nt = le[nxt];
+    if (nt < 0) break;
+    if (lgt[cur_t] != nt) break;
+    ++nseg;
+    cur_h = nxt, cur_t = nt;
+    nxt = lgh[cur_h];
+  }
+  last_tail = cur_t;
+}
+
+__global__ void __launch_bounds__(256) decode_resolve_kernel(const ResolveArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int n = a.n, np2 = a.npow2, b = blockIdx.x;
+  unsigned long long* best1 = reinterpret_cast<unsigned long long*>(smem_raw);
+  unsigned long long* best2 = best1 + n;
+  unsigned long long* sortbuf = best2 + n;
+  uint32_t* first = reinterpret_cast<uint32_t*>(sortbuf + np2);
+  uint32_t* ord2 = first + n;
+  int32_t* le = reinterpret_cast<int32_t*>(ord2 + n);
+  int32_t* lgh = le + n;
+  int32_t* lgt = lgh + n;
+  __shared__ int32_t s_count, s_run, s_warp[8];
+
+  int32_t* out = a.out + (int64_t)b * a.doc_ints;
+  int32_t* o_le = out + 16;
+  int32_t* o_lgh = o_le + 2 * n;
+  int32_t* o_lgt = o_lgh + 2 * n;
+  int32_t* o_elh = o_lgt + 2 * n;
+  int32_t* o_elt = o_elh + 2 * a.cap;
+  int32_t* o_kv = o_elt + 2 * a.cap;
+
+  auto list = [&](int h) {
+    SpotList L;
+    const int64_t off = ((int64_t)b * kNumHeads + h) * a.cap;
+    L.p = a.spot_p + off, L.tag = a.spot_tag + off, L.score = a.spot_score + off;
+    L.cnt = min(a.counts[b * kNumHeads + h], a.cap);
+    return L;
+  };
+  const bool top = a.decode_gt == 0;
+  const int n_le = resolve_map(list(0), n, np2, false, top, a.thresh, best1, best2, first, ord2, sortbuf, le, o_le, &s_count);
+  const int n_lgt = resolve_map(list(4), n, np2, true, top, a.thresh, best1, best2, first, ord2, sortbuf, lgt, o_lgt, &s_count);
+  const int n_lgh = resolve_map(list(3), n, np2, true, top, a.thresh, best1, best2, first, ord2, sortbuf, lgh, o_lgh, &s_count);
+
+  uint32_t* bitmap = a.bitmap + (int64_t)b * a.bitmap_words;
+  const int n_elt = emit_edges(list(2), n, a.thresh, o_elt, bitmap, s_warp, &s_run);
+  __syncthreads();
+  const int n_elh = emit_edges(list(1), n, a.thresh, o_elh, nullptr, s_warp, &s_run);
+  __threadfence_block();
+  __syncthreads();
+
+  // key/value pairs: one thread per entity-linking h2h edge, ordered compaction of the valid ones
+  const int tid = threadIdx.x, lane = tid % 32, warp = tid / 32;
+  if (tid == 0) s_run = 0;
+  __syncthreads();
+  for (int e0 = 0; e0 < n_elh; e0 += blockDim.x) {
+    const int e = e0 + tid;
+    bool ok = false;
+    int kh = 0, vh = 0, nk = 0, nv = 0;
+    if (e < n_elh) {
+      kh = o_elh[2 * e], vh = o_elh[2 * e + 1];
+      const int kt = le[kh], vt = le[vh];
+      if (kt >= 0 && vt >= 0) {
+        int klast, vlast;
+        chain_walk(kh, kt, le, lgh, lgt, nk, klast);
+        chain_walk(vh, vt, le, lgh, lgt, nv, vlast);
+        const int64_t bit = (int64_t)klast * n + vlast;
+        ok = (bitmap[bit >> 5] >> (bit & 31)) & 1u;
+      }
+    }
+    const unsigned mask = __ballot_sync(0xffffffffu, ok);
+    if (lane == 0) s_warp[warp] = __popc(mask);
+    __syncthreads();
+    int off = s_run;
+    for (int w = 0; w < warp; ++w) off += s_warp[w];
+    if (ok) {
+      const int pos = off + __popc(mask & ((1u << lane) - 1));
+      o_kv[4 * pos] = kh, o_kv[4 * pos + 1] = vh, o_kv[4 * pos + 2] = nk, o_kv[4 * pos + 3] = nv;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      int tot = 0;
+      for (int w = 0; w < 8; ++w) tot += s_warp[w];
+      s_run += tot;
+    }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    out[0] = n_le, out[1] = n_lgh, out[2] = n_lgt, out[3] = n_elh, out[4] = n_elt, out[5] = s_run;
+    for (int q = 6; q < 16; ++q) out[q] = 0;
+  }
+}
+
+size_t decode_resolve_doc_ints(int n, int cap) { return 16 + 6 * (size_t)n + 8 * (size_t)cap; }
+size_t decode_resolve_workspace_bytes(int batch, int n) {
+  const int64_t words = ((int64_t)n * n + 31) / 32;
+  return static_cast<size_t>(batch * words * 4);
+}
+
+int launch_decode_resolve(int batch, int n, int cap, const int32_t* spot_p, const int32_t* spot_tag,
+                          const float* spot_score, const int32_t* counts, int decode_gt, float score_thresh,
+                          int32_t* out, void* ws, cudaStream_t st) {
+  PENEO_REQUIRE(n >= 1 && n <= 4096, "decode_resolve: n=%d outside [1, 4096]", n);
+  PENEO_REQUIRE(cap >= 1, "decode_resolve: cap must be positive");
+  if (batch == 0) return PENEO_OK;
+  ResolveArgs a{};
+  a.batch = batch, a.n = n, a.cap = cap, a.decode_gt = decode_gt, a.thresh = score_thresh;
+  int np2 = 1;
+  while (np2 < n) np2 <<= 1;
+  a.npow2 = np2;
+  a.spot_p = spot_p, a.spot_tag = spot_tag, a.spot_score = spot_score, a.counts = counts, a.out = out;
+  a.doc_ints = static_cast<int64_t>(decode_resolve_doc_ints(n, cap));
+  a.bitmap = static_cast<uint32_t*>(ws);
+  a.bitmap_words = ((int64_t)n * n + 31) / 32;
+  PENEO_CUDA_TRY(cudaMemsetAsync(ws, 0, decode_resolve_workspace_bytes(batch, n), st));
+  const size_t smem = (size_t)(2 * n + np2) * 8 + (size_t)5 * n * 4;
+  PENEO_CUDA_TRY(cudaFuncSetAttribute(decode_resolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      static_cast<int>(smem)));
+  decode_resolve_kernel<<<batch, 256, smem, st>>>(a);
+  PENEO_CUDA_TRY(cudaGetLastError());
+  return PENEO_OK;
+}
+
+}  // namespace peneo

@@ -1,0 +1,52 @@
+// Internal launcher declarations shared between the .cu files (not part of the C ABI).
+#pragma once
+#include "common.cuh"
+
+namespace peneo {
+
+// simt_kernels.cu
+int launch_sgemm_nt(const float* A, int64_t lda, const float* W, int64_t ldw, const float* bias, float* C, int64_t ldc,
+                    int M, int N, int K, int act, float out_scale, cudaStream_t st);
+int launch_cast_rows(const void* src, int src_dtype, int64_t src_stride, void* dst, int dst_dtype, int64_t rows,
+                     int cols, cudaStream_t st);
+int pack_weights_impl(const peneo_dims& dm, int prec, const peneo_params& P, void* pack, cudaStream_t st);
+int launch_pair_heads_simt(const peneo_dims& dm, const void* pack, const float* ab, int batch, int n,
+                           float* const logits[kNumHeads], cudaStream_t st);
+
+// gemm_tc.cu : C[M, N] = act(A[M, K] W[N, K]^T + bias) ; A, W bf16 K-contiguous; C bf16
+int launch_gemm_tc(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* W, int64_t ldw, const float* bias,
+                   __nv_bfloat16* C, int64_t ldc, int64_t M, int N, int K, int act, cudaStream_t st);
+
+// pair_heads_tc.cu
+int launch_pair_heads_tc(const void* pack, const PackLayout& L, const __nv_bfloat16* ab, int batch, int n,
+                         float* const logits[kNumHeads], cudaStream_t st);
+
+// loss.cu
+size_t pair_loss_workspace_bytes(int batch, int n);
+int launch_pair_loss_fwd(int batch, int n, const float* const logits[kNumHeads], const int64_t* const tags[kNumHeads],
+                         const float* class_w, const float* ratio, float* out6, void* ws, cudaStream_t st);
+int launch_pair_loss_bwd(int batch, int n, const float* const logits[kNumHeads], const int64_t* const tags[kNumHeads],
+                         const float* class_w, const float* ratio, const float* grad_out, const void* ws,
+                         float* const dlogits[kNumHeads], cudaStream_t st);
+int launch_scatter_tags(const int32_t* spots, int64_t num_spots, int batch, int n, int64_t* tags, cudaStream_t st);
+
+// decode.cu
+size_t decode_spots_workspace_bytes(int batch, int n);
+int launch_decode_spots(int batch, int n, const void* const in[kNumHeads], int in_dtype, int cap, int32_t* spot_p,
+                        int32_t* spot_tag, float* spot_score, int32_t* counts, void* ws, cudaStream_t st);
+size_t decode_resolve_doc_ints(int n, int cap);
+size_t decode_resolve_workspace_bytes(int batch, int n);
+int launch_decode_resolve(int batch, int n, int cap, const int32_t* spot_p, const int32_t* spot_tag,
+                          const float* spot_score, const int32_t* counts, int decode_gt, float score_thresh,
+                          int32_t* out, void* ws, cudaStream_t st);
+
+// selftest.cu
+int run_selftest(uint32_t* failed_mask, char* report, size_t report_bytes);
+int run_probe_rates(double* out, int n_out);
+
+// tensor-map helper (gemm_tc.cu)
+struct TensorMap2D;
+int make_tensor_map_bf16(void* tmap_out, const void* gptr, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes,
+                         uint32_t box_inner, uint32_t box_outer);
+
+}  // namespace peneo

@@ -1,0 +1,290 @@
+"""Drop-in replacements for pipeline/decode.py of ZeningLin/PEneo.
+
+``parse_matrix_spots``, ``sample_decode_peneo`` and ``decode_peneo`` keep the reference's
+signatures and return objects (pipeline/decode.py:9-14, 72-85, 381-396).  Spot extraction
+(softmax / argmax / max-prob / compaction) and link resolution (1-1 maps, key-value chain walk)
+run as CUDA kernels through the C ABI; the only host work left is what needs Python objects:
+joining token strings, merging boxes and building the ordered dicts.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from .ops import _TORCH_DT, _require_cuda, _stream, seq_len_from_pairs, shaking_len
+
+NUM_HEADS = 5
+
+
+def merge_bbox(bbox_list):
+    """Union box of a list of boxes (data/data_utils.py:62-76)."""
+    x0, y0, x1, y1 = list(zip(*bbox_list))
+    return [min(x0), min(y0), max(x1), max(y1)]
+
+
+def _thresh_f32(score_thresh: float) -> float:
+    """Smallest float32 >= score_thresh, so that the device's fp32 `score < t` equals the
+    reference's `float(score) < score_thresh` for every fp32 score."""
+    t = np.float32(score_thresh)
+    if float(t) < float(score_thresh):
+        t = np.nextafter(t, np.float32(np.inf), dtype=np.float32)
+    return float(t)
+
+
+class DeviceDecode:
+    """Result of the two decode kernels for a batch, copied to the host once."""
+
+    def __init__(self, n: int, cap: int, batch: int, records: np.ndarray, counts: np.ndarray,
+                 spots: Optional[Tuple[np.ndarray, np.ndarray, np.ndarray]]):
+        self.n, self.cap, self.batch = n, cap, batch
+        self.records, self.counts, self.spots = records, counts, spots
+
+    def doc(self, b: int):
+        n, cap = self.n, self.cap
+        rec = self.records[b]
+        hdr = rec[:16]
+        off = 16
+        le = rec[off : off + 2 * n].reshape(-1, 2)[: hdr[0]]
+        off += 2 * n
+        lgh = rec[off : off + 2 * n].reshape(-1, 2)[: hdr[1]]
+        off += 2 * n
+        lgt = rec[off : off + 2 * n].reshape(-1, 2)[: hdr[2]]
+        off += 2 * n
+        elh = rec[off : off + 2 * cap].reshape(-1, 2)[: hdr[3]]
+        off += 2 * cap
+        elt = rec[off : off + 2 * cap].reshape(-1, 2)[: hdr[4]]
+        off += 2 * cap
+        kv = rec[off : off + 4 * cap].reshape(-1, 4)[: hdr[5]]
+        return le, lgh, lgt, elh, elt, kv
+
+
+def _as_batched_inputs(shakings: Sequence[torch.Tensor]):
+    """Normalise five [B, P, C] logits (or [B, P] / [B, P, 1] tags) to contiguous CUDA tensors
+    of one dtype.  Mode follows model/peneo_decoder.py:98-104."""
+    first = shakings[0]
+    tag_mode = not (first.dim() > 2 and first.shape[-1] > 1)
+    outs = []
+    for k, t in enumerate(shakings):
+        _require_cuda(t, "shaking tensor")
+        if tag_mode:
+            t = t.reshape(t.shape[0], -1)
+            t = t if t.dtype == torch.int64 else t.long()
+        else:
+            if t.dtype not in (torch.float32, torch.bfloat16, torch.float16):
+                t = t.float()
+            if t.dtype != first.dtype:
+                t = t.to(first.dtype if first.dtype in (torch.float32, torch.bfloat16, torch.float16) else torch.float32)
+        outs.append(t.contiguous())
+    return outs, tag_mode
+
+
+def device_decode(shakings: Sequence[torch.Tensor], n: int, decode_gt: bool = False, score_thresh: float = 0,
+                  cap: Optional[int] = None, want_spots: bool = False) -> DeviceDecode:
+    """Run K3 (spots) + K4 (resolve) for a batch and bring the compact result to the host."""
+    lib = _lib.load()
+    ins, tag_mode = _as_batched_inputs(shakings)
+    b = ins[0].shape[0]
+    p = shaking_len(n)
+    for k, t in enumerate(ins):
+        if t.shape[1] != p:
+            raise ValueError(f"shaking tensor {k} has {t.shape[1]} rows, expected {p} for seq_len {n}")
+    dev = ins[0].device
+    dt = _TORCH_DT[ins[0].dtype]
+    if cap is None:
+        cap = min(p, max(8 * n, 1024))
+    while True:
+        spot_p = torch.empty(b * NUM_HEADS * cap, dtype=torch.int32, device=dev)
+        spot_tag = torch.empty_like(spot_p)
+        spot_score = torch.empty(b * NUM_HEADS * cap, dtype=torch.float32, device=dev)
+        counts = torch.empty(b * NUM_HEADS, dtype=torch.int32, device=dev)
+        ws = torch.empty(max(16, lib.peneo_decode_spots_workspace_bytes(b, n)), dtype=torch.uint8, device=dev)
+        _lib.check(
+            lib.peneo_decode_spots(b, n, _lib.ptrs5(ins), dt, cap, spot_p.data_ptr(), spot_tag.data_ptr(),
+                                   spot_score.data_ptr(), counts.data_ptr(), ws.data_ptr(), _stream(dev)),
+            "peneo_decode_spots",
+        )
+        doc_ints = lib.peneo_decode_resolve_doc_ints(n, cap)
+        rec = torch.empty(b, doc_ints, dtype=torch.int32, device=dev)
+        ws2 = torch.empty(max(16, lib.peneo_decode_resolve_workspace_bytes(b, n)), dtype=torch.uint8, device=dev)
+        _lib.check(
+            lib.peneo_decode_resolve(b, n, cap, spot_p.data_ptr(), spot_tag.data_ptr(), spot_score.data_ptr(),
+                                     counts.data_ptr(), int(decode_gt), _thresh_f32(score_thresh), rec.data_ptr(),
+                                     ws2.data_ptr(), _stream(dev)),
+            "peneo_decode_resolve",
+        )
+        counts_h = counts.cpu().numpy()
+        if counts_h.max(initial=0) <= cap:
+            break
+        cap = p  # a list overflowed: redo with the worst-case capacity
+    records = rec.cpu().numpy()
+    spots = None
+    if want_spots:
+        spots = (spot_p.cpu().numpy().reshape(b, NUM_HEADS, cap), spot_tag.cpu().numpy().reshape(b, NUM_HEADS, cap),
+                 spot_score.cpu().numpy().reshape(b, NUM_HEADS, cap))
+    return DeviceDecode(n, cap, b, records, counts_h.reshape(b, NUM_HEADS), spots)
+
+
+def _unflatten(p: np.ndarray, n: int):
+    p = p.astype(np.int64)
+    t = 2 * n + 1
+    i = np.floor((t - np.sqrt((t * t - 8 * p).astype(np.float64))) / 2).astype(np.int64)
+    i = np.clip(i, 0, n - 1)
+    i = np.where(i * n - i * (i - 1) // 2 > p, i - 1, i)
+    i = np.where((i + 1) * n - (i + 1) * i // 2 <= p, i + 1, i)
+    return i, i + (p - (i * n - i * (i - 1) // 2))
+
+
+def spots_from_device(dd: DeviceDecode, b: int, head: int) -> List[Tuple[int, int, int, float]]:
+    """The reference's spot list [(i, j, tag, score)] for one document / head."""
+    cnt = int(dd.counts[b, head])
+    sp, st, ss = dd.spots
+    ii, jj = _unflatten(sp[b, head, :cnt], dd.n)
+    return [(int(i), int(j), int(t), s.item()) for i, j, t, s in zip(ii, jj, st[b, head, :cnt], ss[b, head, :cnt])]
+
+
+def _assemble(dd: DeviceDecode, b: int, text: List[str], bbox):
+    """Host glue: ordered dicts, line strings / boxes and key-value strings from the kernels' records."""
+    le_a, lgh_a, lgt_a, elh_a, elt_a, kv_a = dd.doc(b)
+    le = {int(h): int(t) for h, t in le_a}
+    lg_head = {int(h): int(t) for h, t in lgh_a}
+    lg_tail = {int(h): int(t) for h, t in lgt_a}
+    el_head: Dict[int, List[int]] = {}
+    for h, t in elh_a:
+        el_head.setdefault(int(h), []).append(int(t))
+    el_tail: Dict[int, List[int]] = {}
+    for h, t in elt_a:
+        el_tail.setdefault(int(h), []).append(int(t))
+    if bbox is not None and hasattr(bbox, "tolist"):
+        bbox = bbox.tolist()
+
+    lines = []
+    for h, t in le.items():
+        s = "".join(text[h : t + 1])
+        lines.append((s, merge_bbox(bbox[h : t + 1])) if bbox is not None else s)
+
+    def chain(head: int, nseg: int):
+        segs = [(head, le[head])]
+        cur = head
+        for _ in range(nseg - 1):
+            cur = lg_head[cur]
+            segs.append((cur, le[cur]))
+        return segs
+
+    pairs = []
+    for kh, vh, nk, nv in kv_a:
+        ks, vs = chain(int(kh), int(nk)), chain(int(vh), int(nv))
+        ktxt = "".join("".join(text[h : t + 1]) for h, t in ks).strip()
+        vtxt = "".join("".join(text[h : t + 1]) for h, t in vs).strip()
+        if bbox is not None:
+            kbox = merge_bbox([merge_bbox(bbox[h : t + 1]) for h, t in ks])
+            vbox = merge_bbox([merge_bbox(bbox[h : t + 1]) for h, t in vs])
+            pairs.append((ktxt, vtxt, kbox, vbox))
+        else:
+            pairs.append((ktxt, vtxt))
+    return pairs, lines, le, el_head, el_tail, lg_head, lg_tail
+
+
+def parse_matrix_spots(matrix_spots, top_score_only: bool = False, triu_mode: bool = False, score_thresh: float = 0):
+    """pipeline/decode.py:9-69 for callers that hold a Python spot list (tiny, host-side by nature:
+    its input and output are Python objects).  The batched decode path does this step on the GPU."""
+    spot_map: dict = {}
+    for head_idx, tail_idx, tag, score in matrix_spots:
+        if tag == 0 or score < score_thresh:
+            continue
+        if triu_mode and tag == 2:
+            head_idx, tail_idx = tail_idx, head_idx
+        if not top_score_only:
+            spot_map.setdefault(head_idx, []).append(tail_idx)
+        elif head_idx not in spot_map or score > spot_map[head_idx][1]:
+            spot_map[head_idx] = (tail_idx, score)
+    if not top_score_only:
+        return spot_map
+    reverse: dict = {}
+    for k, (v, s) in spot_map.items():
+        if v not in reverse or s > reverse[v][1]:
+            reverse[v] = (k, s)
+    return {k: v for v, (k, _s) in reverse.items()}
+
+
+def _infer_seq_len(seq_len, shaking_ind2matrix_ind, shaking: torch.Tensor) -> int:
+    if shaking_ind2matrix_ind is not None:
+        return seq_len_from_pairs(len(shaking_ind2matrix_ind))
+    if seq_len is not None:
+        return int(seq_len)
+    raise AssertionError("seq_len or shaking_ind2matrix_ind must be given")  # pipeline/decode.py:145-147
+
+
+def _to_device(t, device):
+    if not torch.is_tensor(t):
+        t = torch.as_tensor(t)
+    return t if t.is_cuda else t.to(device)
+
+
+def sample_decode_peneo(
+    handshaking_tagger,
+    text: List[str],
+    line_extraction_shaking: torch.Tensor,
+    ent_linking_h2h_shaking: torch.Tensor,
+    ent_linking_t2t_shaking: torch.Tensor,
+    line_grouping_h2h_shaking: torch.Tensor,
+    line_grouping_t2t_shaking: torch.Tensor,
+    bbox: torch.Tensor = None,
+    seq_len: int = None,
+    shaking_ind2matrix_ind: List[Tuple[int]] = None,
+    decode_gt: bool = False,
+    score_thresh: float = 0,
+) -> Tuple:
+    """Decode one sample (pipeline/decode.py:72-378).  Returns the reference's 7-tuple
+    (kv_pairs, lines, LE dict, EL-head dict, EL-tail dict, LG-head dict, LG-tail dict)."""
+    sh = [line_extraction_shaking, ent_linking_h2h_shaking, ent_linking_t2t_shaking, line_grouping_h2h_shaking,
+          line_grouping_t2t_shaking]
+    n = _infer_seq_len(seq_len, shaking_ind2matrix_ind, sh[0])
+    device = next((t.device for t in sh if torch.is_tensor(t) and t.is_cuda), torch.device("cuda"))
+    sh = [_to_device(t, device).unsqueeze(0) for t in sh]
+    dd = device_decode(sh, n, decode_gt=decode_gt, score_thresh=score_thresh)
+    return _assemble(dd, 0, text, bbox)
+
+
+def decode_peneo(
+    handshaking_tagger,
+    texts: List[List[str]],
+    line_extraction_shaking_outputs,
+    ent_linking_h2h_shaking_outputs,
+    ent_linking_t2t_shaking_outputs,
+    line_grouping_h2h_shaking_outputs,
+    line_grouping_t2t_shaking_outputs,
+    line_extraction_shaking_tags,
+    ent_linking_h2h_shaking_tags,
+    ent_linking_t2t_shaking_tags,
+    line_grouping_h2h_shaking_tags,
+    line_grouping_t2t_shaking_tags,
+    orig_bboxes,
+    file_ids: List[str],
+):
+    """Decode predictions and ground truth of a list of samples (pipeline/decode.py:381-511).
+    Samples of equal length are decoded together in one pair of kernel launches."""
+    outs = [line_extraction_shaking_outputs, ent_linking_h2h_shaking_outputs, ent_linking_t2t_shaking_outputs,
+            line_grouping_h2h_shaking_outputs, line_grouping_t2t_shaking_outputs]
+    tags = [line_extraction_shaking_tags, ent_linking_h2h_shaking_tags, ent_linking_t2t_shaking_tags,
+            line_grouping_h2h_shaking_tags, line_grouping_t2t_shaking_tags]
+    count = min(len(file_ids), len(texts), len(orig_bboxes), *[len(o) for o in outs], *[len(t) for t in tags])
+    all_pred, all_gt, all_ids = [None] * count, [None] * count, []
+    if len(texts) == 0:  # sic: the reference tests len(texts) (pipeline/decode.py:471)
+        return [], [], []
+    by_len: Dict[int, List[int]] = {}
+    for s in range(count):
+        by_len.setdefault(len(orig_bboxes[s]), []).append(s)
+    device = next((o[0].device for o in outs if len(o) and torch.is_tensor(o[0]) and o[0].is_cuda), torch.device("cuda"))
+    for n, idxs in by_len.items():
+        pred_in = [torch.stack([_to_device(o[s], device) for s in idxs]) for o in outs]
+        gt_in = [torch.stack([_to_device(t[s], device) for s in idxs]) for t in tags]
+        dp = device_decode(pred_in, n, decode_gt=False)
+        dg = device_decode(gt_in, n, decode_gt=True)
+        for r, s in enumerate(idxs):
+            all_pred[s] = _assemble(dp, r, texts[s], None)
+            all_gt[s] = _assemble(dg, r, texts[s], None)
+    all_ids = [file_ids[s] for s in range(count)]
+    return all_pred, all_gt, all_ids

@@ -1,0 +1,260 @@
+"""GPU parity tests: the CUDA path (through the C ABI, via peneo_b200) against the CPU oracle and
+the reference-generated golden fixtures.  Run on the B200 box: pytest -m gpu."""
+import numpy as np
+import pytest
+import torch
+
+import peneo_oracle as orc
+from peneo_b200 import (HandshakingTaggingScheme, PEneoDecoderB200, decode_peneo, ops, sample_decode_peneo, synth)
+
+pytestmark = pytest.mark.gpu
+
+FP32_TOL = 1e-3  # north_star: pairwise logits within 1e-3 (fp32) / 2e-2 (bf16) of the reference,
+BF16_TOL = 2e-2  # measured as max|delta| <= tol * max|ref| per output tensor
+
+
+class Cfg:
+    def __init__(self, hidden, shrink=True, num_layers=2, inference_mode=True, precision=None, ratios=(1.0,) * 5,
+                 weights=(1.0, 10.0, 10.0), ohem=(-1, -1)):
+        self.backbone_config = {"hidden_size": hidden, "hidden_dropout_prob": 0.1}
+        self.peneo_decoder_shrink = shrink
+        self.peneo_classifier_num_layers = num_layers
+        self.peneo_loss_ratio = list(ratios)
+        self.peneo_category_weights = list(weights)
+        self.peneo_ohem_num_positive, self.peneo_ohem_num_negative = ohem
+        self.inference_mode = inference_mode
+        if precision is not None:
+            self.peneo_b200_precision = precision
+
+
+def rel_err(got, ref):
+    return (got.double().cpu() - ref.double()).abs().max().item() / max(ref.abs().max().item(), 1e-30)
+
+
+def build(case_or_sd, hin, hidden, shrink, L, precision, **kw):
+    dec = PEneoDecoderB200(Cfg(hidden, shrink, L, precision=precision, **kw), hin)
+    dec.load_state_dict(case_or_sd)
+    return dec.cuda().eval()
+
+
+def _state(case):
+    if case["state_dict"] is not None:
+        return case["state_dict"]
+    return synth.init_decoder_state(case["hin"], case["hidden"], case["shrink"], case["num_layers"], seed=case["seed"],
+                                    trained_like=(case["init"] == "trained"))
+
+
+def test_tcgen05_selftest():
+    mask, report = ops.selftest()
+    print("\n" + report)
+    assert mask == 0, report
+
+
+def test_probe_rates_report():
+    r = ops.probe_rates()
+    print({k: f"{v:.3e}" for k, v in r.items()})
+    assert all(v > 0 for v in r.values())
+
+
+def test_heads_fp32_match_reference_golden(golden):
+    for case in golden("heads.pt"):
+        dec = build(_state(case), case["hin"], case["hidden"], case["shrink"], case["num_layers"], "fp32")
+        x = synth.hidden_states(case["batch"], case["seq_len"], case["hin"], doc_id0=case["x_doc_id0"]).cuda()
+        with torch.no_grad():
+            out = dec(x)
+        for k in range(5):
+            assert out[k].shape == case["logits"][k].shape
+            e = rel_err(out[k], case["logits"][k])
+            assert e <= FP32_TOL, (case["name"], k, e)
+            assert e <= 2e-5, (case["name"], k, e)  # the fp32 kernels are in fact exact to rounding
+
+
+def test_heads_bf16_match_reference_golden(golden):
+    for case in golden("heads.pt"):
+        if not (case["shrink"] and case["hidden"] == 768 and case["num_layers"] == 2):
+            continue
+        dec = build(_state(case), case["hin"], case["hidden"], True, 2, "bf16")
+        x = synth.hidden_states(case["batch"], case["seq_len"], case["hin"], doc_id0=case["x_doc_id0"]).cuda()
+        with torch.no_grad():
+            out = dec(x)
+        for k in range(5):
+            e = rel_err(out[k], case["logits"][k])
+            print(case["name"], k, f"bf16 rel err {e:.3e}")
+            assert e <= BF16_TOL, (case["name"], k, e)
+
+
+@pytest.mark.parametrize("n,batch,trained", [(64, 3, True), (127, 2, True), (255, 1, False)])
+def test_heads_vs_oracle_medium(n, batch, trained):
+    sd = synth.init_decoder_state(seed=2, trained_like=trained)
+    x = synth.hidden_states(batch, n, 768, doc_id0=5)
+    ref = orc.heads_chunked(orc.split_params(sd, torch.float64), x.double())
+    for prec, tol in (("fp32", FP32_TOL), ("bf16", BF16_TOL)):
+        dec = build(sd, 768, 768, True, 2, prec)
+        with torch.no_grad():
+            out = dec(x.cuda())
+        for k in range(5):
+            e = rel_err(out[k], ref[k])
+            print(n, prec, k, f"{e:.3e}")
+            assert e <= tol, (n, prec, k, e)
+
+
+def test_bf16_and_fp32_paths_agree_at_full_size():
+    """N = 511 (seq 512 minus CLS), batch 2: no CPU oracle at this size in reasonable time for every
+    pair, so (a) the two independent CUDA paths must agree within the bf16 tolerance and (b) a
+    sample of rows is checked against the fp64 oracle."""
+    n, b = 511, 2
+    sd = synth.init_decoder_state(seed=0, trained_like=True)
+    x = synth.hidden_states(b, n, 768)
+    outs = {}
+    for prec in ("fp32", "bf16"):
+        dec = build(sd, 768, 768, True, 2, prec)
+        with torch.no_grad():
+            outs[prec] = [o.cpu() for o in dec(x.cuda())]
+    for k in range(5):
+        assert rel_err(outs["bf16"][k], outs["fp32"][k]) <= BF16_TOL
+    # oracle on rows i in {0, 200, 510} of doc 1
+    p = orc.split_params(sd, torch.float64)
+    a, bm = orc.token_projections(p, x[1:2].double())
+    for i in (0, 200, 510):
+        s = orc.silu(a[:, i : i + 1, :] + bm[:, i:, :])
+        p0 = orc.shaking_index(i, i, n)
+        for k, layers in enumerate(p["heads"]):
+            ref = orc.classifier(layers, s)[0]
+            got = outs["fp32"][k][1, p0 : p0 + (n - i)]
+            assert rel_err(got, ref) <= FP32_TOL
+            assert (outs["bf16"][k][1, p0 : p0 + (n - i)].double() - ref).abs().max().item() <= BF16_TOL * max(
+                outs["fp32"][k].abs().max().item(), 1e-30)
+
+
+def test_loss_forward_and_dlogits_match_oracle(golden):
+    for case in golden("train.pt"):
+        logits = [l.cuda().requires_grad_(True) for l in case["logits"]]
+        docs = [synth.make_document(case["seq_len"], doc_id=case["doc_id0"] + b) for b in range(case["batch"])]
+        tags = [torch.stack([d.tags()[k] for d in docs]).cuda() for k in range(5)]
+        from peneo_b200.autograd import pair_loss_op
+
+        total, subs = pair_loss_op(logits, tags, [1.0, 10.0, 10.0], list(case["ratios"]))
+        assert abs(total.item() - case["loss"].item()) <= 1e-5 * max(1.0, abs(case["loss"].item()))
+        for k in range(5):
+            assert abs(subs[k].item() - case["sub_losses"][k].item()) <= 1e-5 * max(1.0, abs(case["sub_losses"][k].item()))
+        total.backward()
+        ref_logits = [l.double().requires_grad_(True) for l in case["logits"]]
+        ref_total, _ = orc.decoder_loss(ref_logits, [t.cpu() for t in tags], [1.0, 10.0, 10.0], case["ratios"])
+        ref_total.backward()
+        for k in range(5):
+            assert rel_err(logits[k].grad, ref_logits[k].grad) <= 1e-4
+
+
+def _regen(case):
+    r = case["regen"]
+    doc = synth.make_document(r["n"], doc_id=r["doc_id"], style=r["style"])
+    if r["kind"] == "planted_gt":
+        return doc.tags()
+    dt = torch.bfloat16 if r.get("dtype") == "bf16" else torch.float32
+    return synth.planted_logits(doc, seed=r["doc_id"], dtype=dt)
+
+
+def _same_result(got, ref):
+    assert got[0] == ref[0], "kv pairs differ"
+    assert got[1] == ref[1], "lines differ"
+    for a, b in zip(got[2:], ref[2:]):
+        assert list(a.items()) == list(b.items()), "dict (incl. insertion order) differs"
+
+
+def test_decode_matches_reference_golden_objects(golden):
+    tagger = HandshakingTaggingScheme()
+    g = golden("decode.pt")
+    for case in g["samples"]:
+        sh = case["shakings"] if case["shakings"] is not None else _regen(case)
+        sh = [s.cuda() for s in sh]
+        got = sample_decode_peneo(tagger, case["text"], *sh, bbox=case["bbox"], seq_len=case["seq_len"],
+                                  decode_gt=case["decode_gt"], score_thresh=case["score_thresh"])
+        try:
+            _same_result(got, case["result"])
+        except AssertionError as e:
+            raise AssertionError(f"{case['name']}: {e}")
+
+
+def test_spot_extraction_matches_reference_golden(golden):
+    tagger = HandshakingTaggingScheme()
+    for case in golden("decode.pt")["samples"]:
+        sh = case["shakings"] if case["shakings"] is not None else _regen(case)
+        for k in (0, 1, 4):
+            got = tagger.get_spots_from_shaking_tag(sh[k].cuda(), seq_len=case["seq_len"])
+            ref = case["spots"][k]
+            assert [s[:3] for s in got] == [s[:3] for s in ref], (case["name"], k)
+            for a, b in zip(got, ref):
+                # scores: same formula, libm vs CUDA expf may differ in the last bits
+                assert abs(a[3] - b[3]) <= 4 * np.finfo(np.float32).eps * max(abs(b[3]), 1e-30) or sh[k].dtype != torch.float32 and abs(a[3] - b[3]) <= 1e-2, (case["name"], k, a, b)
+
+
+def test_decode_batch_matches_reference_golden(golden):
+    b = golden("decode.pt")["batch"]
+    docs = [synth.make_document(b["n"], doc_id=d) for d in b["doc_ids"]]
+    outs = [[synth.planted_logits(d, seed=did)[k].cuda() for d, did in zip(docs, b["doc_ids"])] for k in range(5)]
+    tg = [[d.tags()[k].cuda() for d in docs] for k in range(5)]
+    got = decode_peneo(HandshakingTaggingScheme(), [d.text for d in docs], *outs, *tg, [d.bbox for d in docs],
+                       ["f0", "f1", "f2"])
+    assert got[2] == b["result"][2]
+    for side in (0, 1):
+        for s_got, s_ref in zip(got[side], b["result"][side]):
+            _same_result(s_got, s_ref)
+
+
+def test_tag_scatter_matches_reference_golden(golden):
+    for case in golden("tags.pt"):
+        got = HandshakingTaggingScheme.spots2shaking_tag4batch(case["batch_spots"], seq_len=case["n"])
+        assert torch.equal(got, case["tags"])
+    # later spot wins at a duplicate cell
+    got = HandshakingTaggingScheme.spots2shaking_tag4batch([[(1, 2, 1), (0, 3, 2), (1, 2, 2)]], seq_len=5)
+    assert got[0, orc.shaking_index(1, 2, 5)] == 2 and got[0, orc.shaking_index(0, 3, 5)] == 2
+
+
+@pytest.mark.parametrize("n", [511, 1023, 2047])
+def test_decode_round_trip_at_full_size(n):
+    """Size-independent property at BASELINE sizes: decoding planted logits reproduces the GT decode
+    of the planted tags, and matches the CPU oracle's decode of the same logits."""
+    tagger = HandshakingTaggingScheme()
+    doc = synth.make_document(n, doc_id=n)
+    logits = synth.planted_logits(doc, seed=n)
+    pred = sample_decode_peneo(tagger, doc.text, *[l.cuda() for l in logits], seq_len=n)
+    gt = sample_decode_peneo(tagger, doc.text, *[t.cuda() for t in doc.tags()], seq_len=n, decode_gt=True)
+    assert pred[0] == gt[0] and pred[1] == gt[1] and pred[2] == gt[2]
+    assert len(pred[0]) > 0 and len(pred[1]) > 10
+    ref = orc.sample_decode(doc.text, logits, n)
+    _same_result(pred, ref)
+
+
+def test_decode_dense_garbage_overflow_path():
+    """Random logits make ~2/3 of all pairs positive: exercises capacity overflow + re-run and the
+    arrival-order tie-breaks on long lists; compared with the CPU oracle."""
+    n = 96
+    g = torch.Generator().manual_seed(3)
+    sh = [torch.randn(n * (n + 1) // 2, c, generator=g) for c in (2, 3, 3, 3, 3)]
+    text = [f"t{i} " for i in range(n)]
+    got = sample_decode_peneo(HandshakingTaggingScheme(), text, *[s.cuda() for s in sh], seq_len=n)
+    ref = orc.sample_decode(text, sh, n)
+    _same_result(got, ref)
+
+
+def test_module_interface_matches_reference_contract():
+    sd = synth.init_decoder_state(seed=4, trained_like=True)
+    dec = PEneoDecoderB200(Cfg(768, inference_mode=False), 768)
+    missing = dec.load_state_dict(sd)
+    assert not missing.missing_keys and not missing.unexpected_keys
+    assert set(dec.state_dict().keys()) == set(sd.keys())
+    dec = dec.cuda().eval()
+    n, b = 23, 2
+    x = synth.hidden_states(b, n, 768).cuda()
+    docs = [synth.make_document(n, doc_id=70 + i) for i in range(b)]
+    tags = [torch.stack([d.tags()[k] for d in docs]).cuda() for k in range(5)]
+    bbox = torch.zeros(b, n, 4)
+    with torch.no_grad():
+        out = dec(x, bbox, *tags, attention_mask=torch.ones(b, n), input_ids=None, fname=["a", "b"])
+    assert out.orig_bbox is bbox
+    ref_logits = orc.heads_chunked(orc.split_params(sd, torch.float64), x.cpu().double())
+    ref_total, ref_subs = orc.decoder_loss([l.float() for l in ref_logits], [t.cpu() for t in tags], [1.0, 10.0, 10.0])
+    assert abs(out.loss.item() - ref_total.item()) <= 2e-2 * abs(ref_total.item())
+    assert out.line_extraction_shaking_outputs.shape == (b, n * (n + 1) // 2, 2)
+    with pytest.raises(RuntimeError):
+        dec(x.cpu())
