@@ -14,7 +14,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .ops import _TORCH_DT, _require_cuda, _stream, seq_len_from_pairs, shaking_len
+from .ops import COUNTERS, _TORCH_DT, _require_cuda, _stream, seq_len_from_pairs, shaking_len
 
 NUM_HEADS = 5
 
@@ -115,6 +115,7 @@ def device_decode(shakings: Sequence[torch.Tensor], n: int, decode_gt: bool = Fa
                                      ws2.data_ptr(), _stream(dev)),
             "peneo_decode_resolve",
         )
+        COUNTERS["kernels"] += 2
         counts_h = counts.cpu().numpy()
         if counts_h.max(initial=0) <= cap:
             break

@@ -14,6 +14,9 @@ from ._lib import DT_BF16, DT_F16, DT_F32, DT_I64, HEAD_CLASSES, NUM_HEADS, PREC
 
 HEAD_NAMES = ("line_extraction", "ent_linking_h2h", "ent_linking_t2t", "line_grouping_h2h", "line_grouping_t2t")
 
+# our own kernel launches since import (bench.py reports the per-step delta as gpu_launches)
+COUNTERS = {"kernels": 0}
+
 _TORCH_DT = {torch.float32: DT_F32, torch.bfloat16: DT_BF16, torch.float16: DT_F16, torch.int64: DT_I64}
 
 
@@ -115,6 +118,8 @@ def token_projections(pack: WeightPack, x: torch.Tensor) -> torch.Tensor:
     tokens = x2.shape[0]
     out_dt = torch.float32 if pack.prec == PREC_FP32 else torch.bfloat16
     ab = torch.empty(tokens, 2 * dm.d, dtype=out_dt, device=x.device)
+    direct = (x2.dtype == out_dt and x2.stride(0) % (8 if pack.prec == PREC_BF16 else 4) == 0 and x2.data_ptr() % 16 == 0)
+    COUNTERS["kernels"] += (0 if direct else 1) + (4 if pack.prec == PREC_FP32 and dm.shrink else 3 if dm.shrink else 2)
     ws = torch.empty(lib.peneo_token_proj_workspace_bytes(dm.c(), pack.prec, tokens), dtype=torch.uint8, device=x.device)
     _lib.check(
         lib.peneo_token_proj_fwd(dm.c(), pack.prec, pack.buf.data_ptr(), x2.data_ptr(), _TORCH_DT[x2.dtype],
@@ -130,6 +135,7 @@ def pair_heads(pack: WeightPack, ab: torch.Tensor, batch: int, n: int) -> List[t
     lib = _lib.load()
     p = shaking_len(n)
     logits = [torch.empty(batch, p, c, dtype=torch.float32, device=ab.device) for c in HEAD_CLASSES]
+    COUNTERS["kernels"] += 1
     _lib.check(
         lib.peneo_pair_heads_fwd(pack.dims.c(), pack.prec, pack.buf.data_ptr(), ab.data_ptr(), batch, n,
                                  _lib.ptrs5(logits), _stream(ab.device)),

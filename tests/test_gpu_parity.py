@@ -109,7 +109,7 @@ def test_bf16_and_fp32_paths_agree_at_full_size():
     for prec in ("fp32", "bf16"):
         dec = build(sd, 768, 768, True, 2, prec)
         with torch.no_grad():
-            outs[prec] = [o.cpu() for o in dec(x.cuda())]
+            outs[prec] = [o.cpu() for o in dec(x.cuda())[:5]]
     for k in range(5):
         assert rel_err(outs["bf16"][k], outs["fp32"][k]) <= BF16_TOL
     # oracle on rows i in {0, 200, 510} of doc 1
