@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(192, 1)
   const uint32_t tmem = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (ptx::elect_one()) {
       for (int kb = 0; kb < num_k; ++kb) {
         const int s = kb % kGemmStages;
         const uint32_t ph = (kb / kGemmStages) & 1;
@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(192, 1)
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (ptx::elect_one()) {
       constexpr uint32_t idesc = ptx::umma_idesc_bf16(128, 128);
       for (int kb = 0; kb < num_k; ++kb) {
         const int s = kb % kGemmStages;
