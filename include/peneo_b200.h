@@ -5,13 +5,16 @@
  * boundary a maintainer would bind (ctypes) to replace, one for one:
  *
  *   peneo_pack_weights ............ parameter reads of PEneoDecoder        model/peneo_decoder.py:204-313
- *   peneo_token_proj_fwd/bwd ...... shrink_projection + the per-token half
+ *   peneo_token_proj_fwd .......... shrink_projection + the per-token half
  *                                   of HandshakingKernel.combine_fc         model/peneo_decoder.py:215-222, 126, 349-350
  *   peneo_pair_heads_fwd .......... HandshakingKernel.forward (pair part)
  *                                   + the five classifier heads             model/peneo_decoder.py:149-177, 355-363
  *   peneo_pair_loss_fwd ........... calculate_peneo_loss / CrossEntropyLossOHEM
  *                                   (OHEM off) + the ratio-weighted sum     model/peneo_decoder.py:315-336, 375-428; model/custom_loss.py:189-202
- *   peneo_pair_heads_bwd .......... autograd backward of the above          (implicit in the reference)
+ *   peneo_pair_loss_ohem .......... CrossEntropyLossOHEM with hard-example
+ *                                   selection (forward value + d loss/d logits) model/custom_loss.py:204-288
+ *   peneo_heads_bwd ............... autograd backward of token_proj + pair_heads (implicit in the reference:
+ *                                   loss.backward() through model/peneo_decoder.py:349-363)
  *   peneo_scatter_tags ............ HandshakingTaggingScheme.spots2shaking_tag4batch   model/peneo_decoder.py:34-73
  *   peneo_decode_spots ............ HandshakingTaggingScheme.get_spots_from_shaking_tag model/peneo_decoder.py:75-115
  *   peneo_decode_resolve .......... parse_matrix_spots + the key/value chain walk of
@@ -117,6 +120,31 @@ int peneo_pair_loss_bwd(int32_t batch, int32_t n, const float* const logits[PENE
                         const int64_t* const tags[PENEO_NUM_HEADS], const float* class_w_host,
                         const float* ratio_host, const float* grad_out, const void* workspace,
                         float* const dlogits[PENEO_NUM_HEADS], void* stream);
+
+/* ------------------------------------------------------------------ heads, backward */
+/* Gradient outputs, fp32, same layouts as peneo_params (all OVERWRITTEN by peneo_heads_bwd). */
+typedef struct peneo_grads {
+  float* shrink_w1;
+  float* shrink_b1;
+  float* shrink_w2;
+  float* shrink_b2;
+  float* combine_w;
+  float* combine_b;
+  float* mid_w[PENEO_NUM_HEADS * 8];
+  float* mid_b[PENEO_NUM_HEADS * 8];
+  float* out_w[PENEO_NUM_HEADS];
+  float* out_b[PENEO_NUM_HEADS];
+} peneo_grads;
+
+/* Backward of peneo_token_proj_fwd + peneo_pair_heads_fwd for `batch` documents of `n` tokens:
+ * given dlogits[h] = d loss / d logits[h] (fp32 [batch, P, C_h]) computes every parameter gradient
+ * and, when dx != NULL, d loss / d x (fp32 [batch*n, hin], contiguous).  The pair activations are
+ * recomputed from x chunk by chunk (nothing of size [P, d] is kept from the forward pass).
+ * `pack` must be a PENEO_PREC_FP32 pack when prec == PENEO_PREC_FP32. */
+size_t peneo_heads_bwd_workspace_bytes(const peneo_dims* dims, int prec, int32_t batch, int32_t n);
+int peneo_heads_bwd(const peneo_dims* dims, int prec, const void* pack, const void* x, int x_dtype,
+                    int64_t x_row_stride, int32_t batch, int32_t n, const float* const dlogits[PENEO_NUM_HEADS],
+                    const peneo_grads* grads, float* dx, void* workspace, void* stream);
 
 /* ------------------------------------------------------------------ tags */
 /* Dense tags from sparse spots: tags[b, p(i,j)] = tag for every (b, i, j, tag) quadruple

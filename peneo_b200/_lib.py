@@ -27,6 +27,8 @@ SYMBOLS = (
     "peneo_token_proj_workspace_bytes",
     "peneo_token_proj_fwd",
     "peneo_pair_heads_fwd",
+    "peneo_heads_bwd_workspace_bytes",
+    "peneo_heads_bwd",
     "peneo_pair_loss_workspace_bytes",
     "peneo_pair_loss_fwd",
     "peneo_pair_loss_bwd",
@@ -53,6 +55,10 @@ class Params(C.Structure):
         ("mid_w", C.c_void_p * (NUM_HEADS * 8)), ("mid_b", C.c_void_p * (NUM_HEADS * 8)),
         ("out_w", C.c_void_p * NUM_HEADS), ("out_b", C.c_void_p * NUM_HEADS),
     ]
+
+
+class Grads(C.Structure):
+    _fields_ = Params._fields_
 
 
 PtrArray5 = C.c_void_p * NUM_HEADS
@@ -82,6 +88,10 @@ def load() -> C.CDLL:
     lib.peneo_token_proj_workspace_bytes.argtypes = [C.POINTER(Dims), C.c_int, i64]
     lib.peneo_token_proj_fwd.argtypes = [C.POINTER(Dims), C.c_int, vp, vp, C.c_int, i64, i64, vp, vp, vp]
     lib.peneo_pair_heads_fwd.argtypes = [C.POINTER(Dims), C.c_int, vp, vp, i32, i32, PtrArray5, vp]
+    lib.peneo_heads_bwd_workspace_bytes.restype = sz
+    lib.peneo_heads_bwd_workspace_bytes.argtypes = [C.POINTER(Dims), C.c_int, i32, i32]
+    lib.peneo_heads_bwd.argtypes = [C.POINTER(Dims), C.c_int, vp, vp, C.c_int, i64, i32, i32, PtrArray5,
+                                    C.POINTER(Grads), vp, vp, vp]
     lib.peneo_pair_loss_workspace_bytes.restype = sz
     lib.peneo_pair_loss_workspace_bytes.argtypes = [i32, i32]
     lib.peneo_pair_loss_fwd.argtypes = [i32, i32, PtrArray5, PtrArray5, C.POINTER(C.c_float), C.POINTER(C.c_float), vp,

@@ -30,6 +30,12 @@ int launch_pair_loss_bwd(int batch, int n, const float* const logits[kNumHeads],
                          float* const dlogits[kNumHeads], cudaStream_t st);
 int launch_scatter_tags(const int32_t* spots, int64_t num_spots, int batch, int n, int64_t* tags, cudaStream_t st);
 
+// train.cu
+size_t heads_bwd_workspace_bytes(const peneo_dims& dm, int batch, int n);
+int launch_heads_bwd_fp32(const peneo_dims& dm, const void* pack, const void* x, int x_dtype, int64_t x_row_stride,
+                          int batch, int n, const float* const dlogits[kNumHeads], const peneo_grads& gr, float* dx,
+                          void* workspace, cudaStream_t st);
+
 // decode.cu
 size_t decode_spots_workspace_bytes(int batch, int n);
 int launch_decode_spots(int batch, int n, const void* const in[kNumHeads], int in_dtype, int cap, int32_t* spot_p,

@@ -1,0 +1,532 @@
+// Backward of the decoder heads, PENEO_PREC_FP32 (CUDA-core fp32, every configuration the reference
+// accepts).  What autograd does for model/peneo_decoder.py:349-363 in the reference, restated as
+// explicit kernels:
+//
+//   g_z   = dlogits                                  (from peneo_pair_loss_bwd / peneo_pair_loss_ohem)
+//   dW_out += g_z^T m ,  db_out += sum g_z           m = SiLU(u_last)
+//   g_u   = (g_z W_out) * SiLU'(u)                   ... back through every hidden layer ...
+//   dW_mid += g_u^T h_in , db_mid += sum g_u
+//   g_s   = sum_heads g_u0 W_mid0 ;  g_v = g_s * SiLU'(a_i + b_j)
+//   dA[i] = sum_{j >= i} g_v(i, j) ;  dBm[j] = sum_{i <= j} g_v(i, j)
+//   then the per-token chain (combine_fc halves, shrink MLP) down to d sequence_output.
+//
+// Nothing of size [P, D] is kept from the forward pass: the pair activations are recomputed one
+// chunk of whole pair-rows at a time (a chunk = rows i0..i1 of one document = a contiguous range
+// of flat pair indices), so the workspace is O(chunk * D * num_layers), not O(P * D).
+#include <cstdlib>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace peneo {
+
+namespace {
+
+__device__ __forceinline__ float sigmoid_exact(float x) { return 1.0f / (1.0f + expf(-x)); }
+__device__ __forceinline__ float dsilu_exact(float x) {
+  const float s = sigmoid_exact(x);
+  return s * (1.0f + x * (1.0f - s));
+}
+
+// ------------------------------------------------------------------------------------------------
+// C[M, N] = op(A) op(B) (+ bias[N]),  written (mode 0), added (mode 1) or atomically added (mode 2,
+// split-K over gridDim.z).  TA: A is stored [K, M]; else [M, K].  TB: B is stored [N, K]; else [K, N].
+// Optional second output C2 = SiLU(C) (modes 0 only).  64x64 tile, BK = 16, 256 threads, 4x4/thread.
+// Vector loads run along the contiguous dimension, which must be a multiple of 4 (checked by the
+// launcher); the other dimension is guarded per element.
+// ------------------------------------------------------------------------------------------------
+template <bool TA, bool TB>
+__global__ void __launch_bounds__(256) sgemm_kernel(const float* __restrict__ A, int64_t lda, const float* __restrict__ B,
+                                                    int64_t ldb, float* __restrict__ C, int64_t ldc, int M, int N, int K,
+                                                    int kslice, int mode, const float* __restrict__ bias,
+                                                    float* __restrict__ C2, int64_t ldc2) {
+  __shared__ __align__(16) float As[16][64 + 4];
+  __shared__ __align__(16) float Bs[16][64 + 4];
+  const int tid = threadIdx.x, tx = tid % 16, ty = tid / 16;
+  const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+  const int kbeg = blockIdx.z * kslice, kend = min(K, kbeg + kslice);
+  float acc[4][4] = {};
+  for (int k0 = kbeg; k0 < kend; k0 += 16) {
+    if (TA) {  // A[k, m]: vector along m
+      const int k = tid / 16, m4 = (tid % 16) * 4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (k0 + k < kend && m0 + m4 < M) v = *reinterpret_cast<const float4*>(A + (int64_t)(k0 + k) * lda + m0 + m4);
+      *reinterpret_cast<float4*>(&As[k][m4]) = v;
+    } else {  // A[m, k]: vector along k
+      const int m = tid / 4, k4 = (tid % 4) * 4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (m0 + m < M && k0 + k4 < kend) v = *reinterpret_cast<const float4*>(A + (int64_t)(m0 + m) * lda + k0 + k4);
+      As[k4 + 0][m] = v.x, As[k4 + 1][m] = v.y, As[k4 + 2][m] = v.z, As[k4 + 3][m] = v.w;
+    }
+    if (TB) {  // B[n, k]: vector along k
+      const int n = tid / 4, k4 = (tid % 4) * 4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (n0 + n < N && k0 + k4 < kend) v = *reinterpret_cast<const float4*>(B + (int64_t)(n0 + n) * ldb + k0 + k4);
+      Bs[k4 + 0][n] = v.x, Bs[k4 + 1][n] = v.y, Bs[k4 + 2][n] = v.z, Bs[k4 + 3][n] = v.w;
+    } else {  // B[k, n]: vector along n
+      const int k = tid / 16, n4 = (tid % 16) * 4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (k0 + k < kend && n0 + n4 < N) v = *reinterpret_cast<const float4*>(B + (int64_t)(k0 + k) * ldb + n0 + n4);
+      *reinterpret_cast<float4*>(&Bs[k][n4]) = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) {
+      const float4 a = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+      const float4 b = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+      const float ar[4] = {a.x, a.y, a.z, a.w}, br[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[r][c] = fmaf(ar[r], br[c], acc[r][c]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int m = m0 + ty * 4 + r;
+    if (m >= M) continue;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int n = n0 + tx * 4 + c;
+      if (n >= N) continue;
+      float v = acc[r][c];
+      float* dst = C + (int64_t)m * ldc + n;
+      if (mode == 2) {
+        atomicAdd(dst, v);
+      } else {
+        if (bias) v += bias[n];
+        if (mode == 1) v += *dst;
+        *dst = v;
+        if (C2) C2[(int64_t)m * ldc2 + n] = v * sigmoid_exact(v);
+      }
+    }
+  }
+}
+
+struct Gemm {
+  bool ta = false, tb = false;
+  const float* A = nullptr;
+  int64_t lda = 0;
+  const float* B = nullptr;
+  int64_t ldb = 0;
+  float* C = nullptr;
+  int64_t ldc = 0;
+  int M = 0, N = 0, K = 0;
+  int mode = 0;  // 0 store, 1 add, 2 split-K atomic add
+  const float* bias = nullptr;
+  float* C2 = nullptr;
+  int64_t ldc2 = 0;
+};
+
+int run_gemm(const Gemm& g, cudaStream_t st) {
+  if (g.M == 0 || g.N == 0) return PENEO_OK;
+  const bool ok = (g.ta ? (g.M % 4 == 0) : (g.K % 4 == 0)) && (g.tb ? (g.K % 4 == 0) : (g.N % 4 == 0)) &&
+                  g.lda % 4 == 0 && g.ldb % 4 == 0 && (reinterpret_cast<uintptr_t>(g.A) & 15) == 0 &&
+                  (reinterpret_cast<uintptr_t>(g.B) & 15) == 0;
+  PENEO_REQUIRE(ok, "sgemm: operand not 4-element aligned (M=%d N=%d K=%d lda=%lld ldb=%lld ta=%d tb=%d)", g.M, g.N, g.K,
+                (long long)g.lda, (long long)g.ldb, (int)g.ta, (int)g.tb);
+  int splits = 1, kslice = (g.K + 15) / 16 * 16;
+  const int tiles = ((g.N + 63) / 64) * ((g.M + 63) / 64);
+  if (g.mode == 2) {
+    splits = std::max(1, std::min((g.K + 255) / 256, (148 * 4 + tiles - 1) / tiles));
+    kslice = ((g.K + splits - 1) / splits + 15) / 16 * 16;
+    splits = (g.K + kslice - 1) / kslice;
+  }
+  if (kslice == 0) kslice = 16;
+  dim3 grid((g.N + 63) / 64, (g.M + 63) / 64, splits);
+#define GO(TA, TB)                                                                                                   \
+  sgemm_kernel<TA, TB><<<grid, 256, 0, st>>>(g.A, g.lda, g.B, g.ldb, g.C, g.ldc, g.M, g.N, g.K, kslice, g.mode, g.bias, \
+                                             g.C2, g.ldc2)
+  if (g.ta && g.tb) GO(true, true);
+  else if (g.ta) GO(true, false);
+  else if (g.tb) GO(false, true);
+  else GO(false, false);
+#undef GO
+  PENEO_CUDA_TRY(cudaGetLastError());
+  return PENEO_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// pair-chunk kernels.  A chunk is the flat pair range [p0, p0 + rows) of document b.
+// ------------------------------------------------------------------------------------------------
+// S[r, :] = SiLU(a_i + b_j)
+__global__ void build_s_kernel(const float* __restrict__ ab, int b, int n, int d, int p0, float* __restrict__ S) {
+  const int r = blockIdx.x;
+  int i, j;
+  pair_from_flat(p0 + r, n, i, j);
+  const float* ai = ab + ((int64_t)b * n + i) * 2 * d;
+  const float* bj = ab + ((int64_t)b * n + j) * 2 * d + d;
+  for (int f = threadIdx.x; f < d; f += blockDim.x) S[(int64_t)r * d + f] = silu_exact(ai[f] + bj[f]);
+}
+
+// Last hidden layer + output layer of one head, 128 rows per CTA:
+//   m = SiLU(U) ; G = (dz W_out) * SiLU'(U) ; dW_out += dz^T m ; db_out += sum dz ; db_mid += sum G
+template <int C>
+__global__ void __launch_bounds__(128) head_out_bwd_kernel(const float* __restrict__ U, const float* __restrict__ dz,
+                                                           const float* __restrict__ Wout, int rows, int d,
+                                                           float* __restrict__ G, float* __restrict__ dWout,
+                                                           float* __restrict__ dbout, float* __restrict__ dbmid) {
+  __shared__ float sdz[128][C];
+  const int r0 = blockIdx.x * 128, nr = min(128, rows - r0);
+  for (int e = threadIdx.x; e < nr * C; e += 128) sdz[e / C][e % C] = dz[(int64_t)r0 * C + e];
+  __syncthreads();
+  if (threadIdx.x < C) {
+    float s = 0.f;
+    for (int r = 0; r < nr; ++r) s += sdz[r][threadIdx.x];
+    atomicAdd(&dbout[threadIdx.x], s);
+  }
+  for (int f = threadIdx.x; f < d; f += 128) {
+    float w[C], aw[C], ab_ = 0.f;
+#pragma unroll
+    for (int c = 0; c < C; ++c) w[c] = Wout[c * d + f], aw[c] = 0.f;
+    for (int r = 0; r < nr; ++r) {
+      const float u = U[(int64_t)(r0 + r) * d + f];
+      const float s = sigmoid_exact(u);
+      const float m = u * s, ds = s * (1.0f + u * (1.0f - s));
+      float gm = 0.f;
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        gm = fmaf(sdz[r][c], w[c], gm);
+        aw[c] = fmaf(sdz[r][c], m, aw[c]);
+      }
+      const float g = gm * ds;
+      G[(int64_t)(r0 + r) * d + f] = g;
+      ab_ += g;
+    }
+#pragma unroll
+    for (int c = 0; c < C; ++c) atomicAdd(&dWout[c * d + f], aw[c]);
+    atomicAdd(&dbmid[f], ab_);
+  }
+}
+
+// num_layers == 1: z = S W_out^T + b_out.  dS (+)= dz W_out ; dW_out += dz^T S ; db_out += sum dz
+template <int C>
+__global__ void __launch_bounds__(128) out_only_bwd_kernel(const float* __restrict__ S, const float* __restrict__ dz,
+                                                           const float* __restrict__ Wout, int rows, int d,
+                                                           float* __restrict__ dS, int accumulate,
+                                                           float* __restrict__ dWout, float* __restrict__ dbout) {
+  __shared__ float sdz[128][C];
+  const int r0 = blockIdx.x * 128, nr = min(128, rows - r0);
+  for (int e = threadIdx.x; e < nr * C; e += 128) sdz[e / C][e % C] = dz[(int64_t)r0 * C + e];
+  __syncthreads();
+  if (threadIdx.x < C) {
+    float s = 0.f;
+    for (int r = 0; r < nr; ++r) s += sdz[r][threadIdx.x];
+    atomicAdd(&dbout[threadIdx.x], s);
+  }
+  for (int f = threadIdx.x; f < d; f += 128) {
+    float w[C], aw[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) w[c] = Wout[c * d + f], aw[c] = 0.f;
+    for (int r = 0; r < nr; ++r) {
+      const int64_t at = (int64_t)(r0 + r) * d + f;
+      const float s = S[at];
+      float g = 0.f;
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        g = fmaf(sdz[r][c], w[c], g);
+        aw[c] = fmaf(sdz[r][c], s, aw[c]);
+      }
+      dS[at] = accumulate ? dS[at] + g : g;
+    }
+#pragma unroll
+    for (int c = 0; c < C; ++c) atomicAdd(&dWout[c * d + f], aw[c]);
+  }
+}
+
+// G = dH * SiLU'(U) (in place over dH) ; db += column sums.  128 rows per CTA.
+__global__ void __launch_bounds__(128) act_bwd_kernel(float* __restrict__ dH, const float* __restrict__ U, int rows,
+                                                      int d, int64_t ld_dh, int64_t ld_u, float* __restrict__ db) {
+  const int r0 = blockIdx.x * 128, nr = min(128, rows - r0);
+  for (int f = threadIdx.x; f < d; f += 128) {
+    float acc = 0.f;
+    for (int r = 0; r < nr; ++r) {
+      const float g = dH[(int64_t)(r0 + r) * ld_dh + f] * dsilu_exact(U[(int64_t)(r0 + r) * ld_u + f]);
+      dH[(int64_t)(r0 + r) * ld_dh + f] = g;
+      acc += g;
+    }
+    if (db) atomicAdd(&db[f], acc);
+  }
+}
+
+// column sums of X[rows, d] (ld) into out[d] (atomic)
+__global__ void __launch_bounds__(128) colsum_kernel(const float* __restrict__ X, int rows, int d, int64_t ld,
+                                                     float* __restrict__ out) {
+  const int r0 = blockIdx.x * 128, nr = min(128, rows - r0);
+  for (int f = threadIdx.x; f < d; f += 128) {
+    float acc = 0.f;
+    for (int r = 0; r < nr; ++r) acc += X[(int64_t)(r0 + r) * ld + f];
+    atomicAdd(&out[f], acc);
+  }
+}
+
+// g_v = dS * SiLU'(a_i + b_j), in place
+__global__ void gv_kernel(float* __restrict__ dS, const float* __restrict__ ab, int b, int n, int d, int p0) {
+  const int r = blockIdx.x;
+  int i, j;
+  pair_from_flat(p0 + r, n, i, j);
+  const float* ai = ab + ((int64_t)b * n + i) * 2 * d;
+  const float* bj = ab + ((int64_t)b * n + j) * 2 * d + d;
+  for (int f = threadIdx.x; f < d; f += blockDim.x) dS[(int64_t)r * d + f] *= dsilu_exact(ai[f] + bj[f]);
+}
+
+// dA[t] = sum_{j >= t} g_v(t, j) for pair-rows t in [i0, i1) ; dBm[t] += sum_{i in [i0, min(t, i1-1)]} g_v(i, t).
+// One CTA per token t of the document; deterministic (no atomics).
+__global__ void __launch_bounds__(128) gv_reduce_kernel(const float* __restrict__ gv, int b, int n, int d, int i0, int i1,
+                                                        float* __restrict__ dab) {
+  const int t = blockIdx.x;
+  const int p0 = row_start(i0, n);
+  float* out = dab + ((int64_t)b * n + t) * 2 * d;
+  for (int f = threadIdx.x; f < d; f += 128) {
+    if (t >= i0 && t < i1) {
+      const float* src = gv + (int64_t)(row_start(t, n) - p0) * d + f;
+      float acc = 0.f;
+      for (int j = t; j < n; ++j) acc += src[(int64_t)(j - t) * d];
+      out[f] = acc;
+    }
+    const int ihi = min(t, i1 - 1);
+    if (ihi >= i0) {
+      float acc = 0.f;
+      for (int i = i0; i <= ihi; ++i) acc += gv[(int64_t)(row_start(i, n) - p0 + (t - i)) * d + f];
+      out[d + f] += acc;
+    }
+  }
+}
+
+inline size_t fl(size_t n) { return align_up(n * sizeof(float), 1024); }
+
+struct Plan {
+  int64_t tokens;
+  int chunk_rows_max;  // pair rows (flat) per chunk
+  int nU, nH;          // per-chunk [rows, d] buffers for pre-activations / hidden activations
+  size_t off_x, off_u1, off_y1, off_u2, off_y, off_ab, off_dab, off_dy, off_dy1;
+  size_t off_S, off_dS, off_G, off_U, off_H;
+  size_t total;
+};
+
+Plan make_plan(const peneo_dims& dm, int batch, int n) {
+  Plan p{};
+  p.tokens = (int64_t)batch * n;
+  const size_t T = p.tokens, d = dm.d, hid = dm.shrink ? dm.hid : 0, hin = dm.hin;
+  p.nU = dm.num_layers - 1;
+  p.nH = dm.num_layers >= 3 ? dm.num_layers - 2 : 0;
+  const int nbuf = 3 + p.nU + p.nH;  // S, dS, G
+  // ~512 MB of pair buffers, but never less than one full pair row (n pairs)
+  int64_t rows = (int64_t)(512ull << 20) / ((int64_t)nbuf * d * 4);
+  rows = std::min<int64_t>(rows, 65536);
+  if (const char* e = getenv("PENEO_BWD_CHUNK_ROWS")) rows = std::max(1, atoi(e));  // test hook: force small chunks
+  rows = std::max<int64_t>(n, rows);
+  rows = std::min<int64_t>(rows, pair_count(n));
+  p.chunk_rows_max = static_cast<int>(rows);
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    size_t at = off;
+    off += bytes;
+    return at;
+  };
+  p.off_x = take(fl(T * hin));
+  p.off_u1 = take(fl(T * hid)), p.off_y1 = take(fl(T * hid));
+  p.off_u2 = take(fl(T * (dm.shrink ? d : 0))), p.off_y = take(fl(T * (dm.shrink ? d : 0)));
+  p.off_ab = take(fl(T * 2 * d)), p.off_dab = take(fl(T * 2 * d));
+  p.off_dy = take(fl(T * d)), p.off_dy1 = take(fl(T * hid));
+  const size_t cb = fl((size_t)rows * d);
+  p.off_S = take(cb), p.off_dS = take(cb), p.off_G = take(cb);
+  p.off_U = take(cb * p.nU), p.off_H = take(cb * p.nH);
+  p.total = off + 1024;
+  return p;
+}
+
+}  // namespace
+
+size_t heads_bwd_workspace_bytes(const peneo_dims& dm, int batch, int n) { return make_plan(dm, batch, n).total; }
+
+int launch_heads_bwd_fp32(const peneo_dims& dm, const void* pack, const void* x, int x_dtype, int64_t x_row_stride,
+                          int batch, int n, const float* const dlogits[kNumHeads], const peneo_grads& gr, float* dx,
+                          void* workspace, cudaStream_t st) {
+  const PackLayout L = pack_layout(dm, PENEO_PREC_FP32);
+  const char* pk = static_cast<const char*>(pack);
+  const Plan pl = make_plan(dm, batch, n);
+  char* ws = static_cast<char*>(workspace);
+  const int d = dm.d, hid = dm.hid, hin = dm.hin, T = static_cast<int>(pl.tokens), NL = dm.num_layers;
+  const int64_t P = pair_count(n);
+  int rc;
+#define TRY(x_)                              \
+  do {                                       \
+    if ((rc = (x_)) != PENEO_OK) return rc;  \
+  } while (0)
+  auto F = [&](size_t off) { return reinterpret_cast<float*>(ws + off); };
+  auto W = [&](size_t off) { return reinterpret_cast<const float*>(pk + off); };
+  auto zero = [&](float* p, size_t count) -> int {
+    if (p && count) PENEO_CUDA_TRY(cudaMemsetAsync(p, 0, count * sizeof(float), st));
+    return PENEO_OK;
+  };
+
+  // ---- zero the gradient outputs (everything below accumulates)
+  if (dm.shrink) {
+    TRY(zero(gr.shrink_w1, (size_t)hid * hin));
+    TRY(zero(gr.shrink_b1, hid));
+    TRY(zero(gr.shrink_w2, (size_t)d * hid));
+    TRY(zero(gr.shrink_b2, d));
+  }
+  TRY(zero(gr.combine_w, (size_t)d * 2 * d));
+  TRY(zero(gr.combine_b, d));
+  for (int h = 0; h < kNumHeads; ++h) {
+    for (int l = 0; l + 1 < NL; ++l) {
+      TRY(zero(gr.mid_w[h * 8 + l], (size_t)d * d));
+      TRY(zero(gr.mid_b[h * 8 + l], d));
+    }
+    TRY(zero(gr.out_w[h], (size_t)head_classes(h) * d));
+    TRY(zero(gr.out_b[h], head_classes(h)));
+  }
+
+  // ---- recompute the per-token chain, keeping pre-activations
+  const float* xin;
+  int64_t ldx;
+  if (x_dtype == PENEO_DT_F32 && x_row_stride % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+    xin = static_cast<const float*>(x), ldx = x_row_stride;
+  } else {
+    TRY(launch_cast_rows(x, x_dtype, x_row_stride, F(pl.off_x), PENEO_DT_F32, T, hin, st));
+    xin = F(pl.off_x), ldx = hin;
+  }
+  const float* y = xin;
+  int64_t ldy = ldx;
+  Gemm g;
+  if (dm.shrink) {
+    g = Gemm{}, g.tb = true, g.A = xin, g.lda = ldx, g.B = W(L.f_w1), g.ldb = hin, g.C = F(pl.off_u1), g.ldc = hid;
+    g.M = T, g.N = hid, g.K = hin, g.bias = W(L.f_b1), g.C2 = F(pl.off_y1), g.ldc2 = hid;
+    TRY(run_gemm(g, st));
+    g = Gemm{}, g.tb = true, g.A = F(pl.off_y1), g.lda = hid, g.B = W(L.f_w2), g.ldb = hid, g.C = F(pl.off_u2), g.ldc = d;
+    g.M = T, g.N = d, g.K = hid, g.bias = W(L.f_b2), g.C2 = F(pl.off_y), g.ldc2 = d;
+    TRY(run_gemm(g, st));
+    y = F(pl.off_y), ldy = d;
+  }
+  float* ab = F(pl.off_ab);
+  g = Gemm{}, g.tb = true, g.A = y, g.lda = ldy, g.B = W(L.f_wc), g.ldb = 2 * d, g.C = ab, g.ldc = 2 * d;
+  g.M = T, g.N = d, g.K = d;
+  TRY(run_gemm(g, st));
+  g.B = W(L.f_wc) + d, g.C = ab + d, g.bias = W(L.f_bc);
+  TRY(run_gemm(g, st));
+
+  // ---- pair part, one chunk of whole pair-rows at a time
+  float* dab = F(pl.off_dab);
+  TRY(zero(dab, (size_t)T * 2 * d));
+  float *S = F(pl.off_S), *dS = F(pl.off_dS), *G = F(pl.off_G);
+  const size_t cstride = fl((size_t)pl.chunk_rows_max * d) / sizeof(float);
+  for (int b = 0; b < batch; ++b) {
+    int i0 = 0;
+    while (i0 < n) {
+      int i1 = i0 + 1;
+      while (i1 < n && row_start(i1 + 1, n) - row_start(i0, n) <= pl.chunk_rows_max) ++i1;
+      const int p0 = row_start(i0, n), rows = row_start(i1, n) - p0;  // row_start(n, n) == P
+      build_s_kernel<<<rows, 128, 0, st>>>(ab, b, n, d, p0, S);
+      PENEO_CUDA_TRY(cudaGetLastError());
+      const int rb = (rows + 127) / 128;
+      for (int h = 0; h < kNumHeads; ++h) {
+        const int C = head_classes(h);
+        const float* dz = dlogits[h] + ((int64_t)b * P + p0) * C;
+        if (NL == 1) {
+          if (C == 2)
+            out_only_bwd_kernel<2><<<rb, 128, 0, st>>>(S, dz, W(L.f_out_w[h]), rows, d, dS, h > 0, gr.out_w[h], gr.out_b[h]);
+          else
+            out_only_bwd_kernel<3><<<rb, 128, 0, st>>>(S, dz, W(L.f_out_w[h]), rows, d, dS, h > 0, gr.out_w[h], gr.out_b[h]);
+          PENEO_CUDA_TRY(cudaGetLastError());
+          continue;
+        }
+        // forward recompute through the hidden layers: U_l = H_l W_l^T + b_l ; H_{l+1} = SiLU(U_l)
+        const float* in = S;
+        for (int l = 0; l + 1 < NL; ++l) {
+          float* U = F(pl.off_U) + (size_t)l * cstride;
+          float* Hn = (l + 2 < NL) ? F(pl.off_H) + (size_t)l * cstride : nullptr;
+          g = Gemm{}, g.tb = true, g.A = in, g.lda = d, g.B = W(L.f_mid_w[h][l]), g.ldb = d, g.C = U, g.ldc = d;
+          g.M = rows, g.N = d, g.K = d, g.bias = W(L.f_mid_b[h][l]), g.C2 = Hn, g.ldc2 = d;
+          TRY(run_gemm(g, st));
+          in = Hn;
+        }
+        {
+          const float* U = F(pl.off_U) + (size_t)(NL - 2) * cstride;
+          if (C == 2)
+            head_out_bwd_kernel<2><<<rb, 128, 0, st>>>(U, dz, W(L.f_out_w[h]), rows, d, G, gr.out_w[h], gr.out_b[h],
+                                                       gr.mid_b[h * 8 + NL - 2]);
+          else
+            head_out_bwd_kernel<3><<<rb, 128, 0, st>>>(U, dz, W(L.f_out_w[h]), rows, d, G, gr.out_w[h], gr.out_b[h],
+                                                       gr.mid_b[h * 8 + NL - 2]);
+          PENEO_CUDA_TRY(cudaGetLastError());
+        }
+        // G_l = gradient w.r.t. the pre-activation of hidden layer l.  Once G_l exists U_l is dead, so
+        // dH_l = G_l W_l is written into U_l's buffer and turned into G_{l-1} in place.
+        const float* Gcur = G;
+        for (int l = NL - 2; l >= 0; --l) {
+          const float* Hin = (l == 0) ? S : F(pl.off_H) + (size_t)(l - 1) * cstride;
+          // dW_l[out, in] += sum_r G_l[r, out] Hin[r, in]
+          g = Gemm{}, g.ta = true, g.A = Gcur, g.lda = d, g.B = Hin, g.ldb = d, g.C = gr.mid_w[h * 8 + l], g.ldc = d;
+          g.M = d, g.N = d, g.K = rows, g.mode = 2;
+          TRY(run_gemm(g, st));
+          // dHin = G_l W_l
+          g = Gemm{}, g.A = Gcur, g.lda = d, g.B = W(L.f_mid_w[h][l]), g.ldb = d, g.M = rows, g.N = d, g.K = d;
+          if (l == 0) {
+            g.C = dS, g.ldc = d, g.mode = h > 0 ? 1 : 0;
+            TRY(run_gemm(g, st));
+          } else {
+            float* Ul = F(pl.off_U) + (size_t)l * cstride;
+            g.C = Ul, g.ldc = d, g.mode = 0;
+            TRY(run_gemm(g, st));
+            act_bwd_kernel<<<rb, 128, 0, st>>>(Ul, F(pl.off_U) + (size_t)(l - 1) * cstride, rows, d, d, d,
+                                               gr.mid_b[h * 8 + l - 1]);
+            PENEO_CUDA_TRY(cudaGetLastError());
+            Gcur = Ul;
+          }
+        }
+      }
+      gv_kernel<<<rows, 128, 0, st>>>(dS, ab, b, n, d, p0);
+      PENEO_CUDA_TRY(cudaGetLastError());
+      gv_reduce_kernel<<<n, 128, 0, st>>>(dS, b, n, d, i0, i1, dab);
+      PENEO_CUDA_TRY(cudaGetLastError());
+      i0 = i1;
+    }
+  }
+
+  // ---- per-token chain backward
+  const int tb = (T + 127) / 128;
+  // db_c = column sums of dBm
+  colsum_kernel<<<tb, 128, 0, st>>>(dab + d, T, d, 2 * d, gr.combine_b);
+  PENEO_CUDA_TRY(cudaGetLastError());
+  // dW_c[:, :d] = dA^T y ; dW_c[:, d:] = dBm^T y
+  g = Gemm{}, g.ta = true, g.A = dab, g.lda = 2 * d, g.B = y, g.ldb = ldy, g.C = gr.combine_w, g.ldc = 2 * d;
+  g.M = d, g.N = d, g.K = T, g.mode = 2;
+  TRY(run_gemm(g, st));
+  g.A = dab + d, g.C = gr.combine_w + d;
+  TRY(run_gemm(g, st));
+  // dy = dA W_c[:, :d] + dBm W_c[:, d:]
+  float* dy = (dm.shrink || dx == nullptr) ? F(pl.off_dy) : dx;
+  const int64_t lddy = (dm.shrink || dx == nullptr) ? d : hin;
+  g = Gemm{}, g.A = dab, g.lda = 2 * d, g.B = W(L.f_wc), g.ldb = 2 * d, g.C = dy, g.ldc = lddy, g.M = T, g.N = d, g.K = d;
+  TRY(run_gemm(g, st));
+  g.A = dab + d, g.B = W(L.f_wc) + d, g.mode = 1;
+  TRY(run_gemm(g, st));
+  if (dm.shrink) {
+    // G2 = dy * SiLU'(u2) ; db2 ; dW2 = G2^T y1 ; dy1 = G2 W2
+    act_bwd_kernel<<<tb, 128, 0, st>>>(dy, F(pl.off_u2), T, d, d, d, gr.shrink_b2);
+    PENEO_CUDA_TRY(cudaGetLastError());
+    g = Gemm{}, g.ta = true, g.A = dy, g.lda = d, g.B = F(pl.off_y1), g.ldb = hid, g.C = gr.shrink_w2, g.ldc = hid;
+    g.M = d, g.N = hid, g.K = T, g.mode = 2;
+    TRY(run_gemm(g, st));
+    float* dy1 = F(pl.off_dy1);
+    g = Gemm{}, g.A = dy, g.lda = d, g.B = W(L.f_w2), g.ldb = hid, g.C = dy1, g.ldc = hid, g.M = T, g.N = hid, g.K = d;
+    TRY(run_gemm(g, st));
+    // G1 = dy1 * SiLU'(u1) ; db1 ; dW1 = G1^T x ; dx = G1 W1
+    act_bwd_kernel<<<tb, 128, 0, st>>>(dy1, F(pl.off_u1), T, hid, hid, hid, gr.shrink_b1);
+    PENEO_CUDA_TRY(cudaGetLastError());
+    g = Gemm{}, g.ta = true, g.A = dy1, g.lda = hid, g.B = xin, g.ldb = ldx, g.C = gr.shrink_w1, g.ldc = hin;
+    g.M = hid, g.N = hin, g.K = T, g.mode = 2;
+    TRY(run_gemm(g, st));
+    if (dx) {
+      g = Gemm{}, g.A = dy1, g.lda = hid, g.B = W(L.f_w1), g.ldb = hin, g.C = dx, g.ldc = hin, g.M = T, g.N = hin, g.K = hid;
+      TRY(run_gemm(g, st));
+    }
+  }
+#undef TRY
+  return PENEO_OK;
+}
+
+}  // namespace peneo

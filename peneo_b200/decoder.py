@@ -151,6 +151,19 @@ class PEneoDecoderB200(nn.Module):
             self._pack_key = key
         return self._pack
 
+    def _fp32_pack(self, device) -> WeightPack:
+        """fp32 kernel-layout weights (the backward pass always runs in fp32)."""
+        if self.precision == "fp32":
+            return self._weight_pack(device)
+        state = {k: v for k, v in self.named_parameters()}
+        key = (str(device), tuple((p.data_ptr(), p._version) for p in state.values()))
+        if getattr(self, "_pack32", None) is None or self._pack32_key != key or self._pack32.buf.device != device:
+            if getattr(self, "_pack32", None) is None or self._pack32.buf.device != device:
+                self._pack32 = WeightPack(self.dims, PREC_FP32, device)
+            self._pack32.update({k: v.detach() for k, v in state.items()})
+            self._pack32_key = key
+        return self._pack32
+
     # ------------------------------------------------------------------ forward
     def forward(
         self,

@@ -1,0 +1,97 @@
+"""Training path of ``PEneoDecoderB200``: one ``torch.autograd.Function`` around the whole decoder.
+
+Forward runs the inference kernels (K1 + K2) and returns the five logits tensors; nothing of size
+``[P, D]`` is saved.  Backward receives d loss / d logits (from the fused loss's own backward, plus
+whatever else the caller hung on the logits), and calls ``peneo_heads_bwd`` which recomputes the pair
+activations chunk by chunk and produces every parameter gradient and d sequence_output — what
+autograd does for model/peneo_decoder.py:349-363 in the reference.
+"""
+from __future__ import annotations
+
+from typing import Dict, List
+
+import torch
+
+from . import _lib, ops
+from ._lib import PREC_FP32
+from .ops import HEAD_NAMES, WeightPack
+
+
+def _param_items(decoder) -> List:
+    return [(k, p) for k, p in decoder.named_parameters()]
+
+
+def _grad_struct(dims, grads: Dict[str, torch.Tensor]) -> _lib.Grads:
+    g = _lib.Grads()
+    ptr = lambda key: grads[key].data_ptr()  # noqa: E731
+    if dims.shrink:
+        g.shrink_w1, g.shrink_b1 = ptr("shrink_projection.0.weight"), ptr("shrink_projection.0.bias")
+        g.shrink_w2, g.shrink_b2 = ptr("shrink_projection.3.weight"), ptr("shrink_projection.3.bias")
+    g.combine_w, g.combine_b = ptr("handshaking_kernel.combine_fc.weight"), ptr("handshaking_kernel.combine_fc.bias")
+    for h, name in enumerate(HEAD_NAMES):
+        if dims.num_layers == 1:
+            g.out_w[h], g.out_b[h] = ptr(f"{name}_fc.weight"), ptr(f"{name}_fc.bias")
+        else:
+            for l in range(dims.num_layers - 1):
+                g.mid_w[h * 8 + l], g.mid_b[h * 8 + l] = ptr(f"{name}_fc.{3 * l}.weight"), ptr(f"{name}_fc.{3 * l}.bias")
+            last = 3 * (dims.num_layers - 1)
+            g.out_w[h], g.out_b[h] = ptr(f"{name}_fc.{last}.weight"), ptr(f"{name}_fc.{last}.bias")
+    return g
+
+
+def heads_backward(decoder, x: torch.Tensor, dlogits: List[torch.Tensor], need_dx: bool):
+    """x: [B, N, hin] CUDA; dlogits: five fp32 [B, P, C_h].  Returns ({param_key: grad}, dx | None)."""
+    lib = _lib.load()
+    dims = decoder.dims
+    b, n, hin = x.shape
+    dev = x.device
+    pack = decoder._fp32_pack(dev)
+    grads = {k: torch.empty_like(p, dtype=torch.float32) for k, p in _param_items(decoder)}
+    x2 = x.detach()
+    if x2.dtype not in (torch.float32, torch.bfloat16, torch.float16):
+        x2 = x2.float()
+    x2 = x2.reshape(b * n, hin)
+    if x2.stride(-1) != 1:
+        x2 = x2.contiguous()
+    dl = [g if (g.dtype == torch.float32 and g.is_contiguous()) else g.float().contiguous() for g in dlogits]
+    dx = torch.empty(b * n, hin, dtype=torch.float32, device=dev) if need_dx else None
+    ws = torch.empty(lib.peneo_heads_bwd_workspace_bytes(dims.c(), PREC_FP32, b, n), dtype=torch.uint8, device=dev)
+    gs = _grad_struct(dims, grads)
+    ops.COUNTERS["kernels"] += 1
+    _lib.check(
+        lib.peneo_heads_bwd(dims.c(), PREC_FP32, pack.buf.data_ptr(), x2.data_ptr(), ops._TORCH_DT[x2.dtype],
+                            x2.stride(0) if b * n > 1 else hin, b, n, _lib.ptrs5(dl), gs,
+                            dx.data_ptr() if dx is not None else None, ws.data_ptr(), ops._stream(dev)),
+        "peneo_heads_bwd",
+    )
+    return grads, (dx.view(b, n, hin) if dx is not None else None)
+
+
+class _DecoderHeads(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, decoder, x, *params):
+        pack = decoder._weight_pack(x.device)
+        logits = ops.heads_forward(pack, x.detach())
+        ctx.decoder = decoder
+        ctx.save_for_backward(x)
+        ctx.need_dx = x.requires_grad
+        ctx.param_keys = [k for k, _ in _param_items(decoder)]
+        return tuple(logits)
+
+    @staticmethod
+    def backward(ctx, *glogits):
+        (x,) = ctx.saved_tensors
+        dec = ctx.decoder
+        shapes = [(x.shape[0], ops.shaking_len(x.shape[1]), c) for c in ops.HEAD_CLASSES]
+        dl = [g if g is not None else torch.zeros(s, dtype=torch.float32, device=x.device)
+              for g, s in zip(glogits, shapes)]
+        grads, dx = heads_backward(dec, x, dl, ctx.need_dx)
+        out = [None, dx.to(x.dtype) if dx is not None else None]
+        for k, p in _param_items(dec):
+            out.append(grads[k].to(p.dtype) if p.requires_grad else None)
+        return tuple(out)
+
+
+def heads_with_grad(decoder, sequence_output: torch.Tensor) -> List[torch.Tensor]:
+    params = [p for _, p in _param_items(decoder)]
+    return list(_DecoderHeads.apply(decoder, sequence_output, *params))

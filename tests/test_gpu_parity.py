@@ -258,3 +258,87 @@ def test_module_interface_matches_reference_contract():
     assert out.line_extraction_shaking_outputs.shape == (b, n * (n + 1) // 2, 2)
     with pytest.raises(RuntimeError):
         dec(x.cpu())
+
+
+# ------------------------------------------------------------------------------------------------
+# training path: fused loss + backward (implicit autograd of model/peneo_decoder.py:349-428)
+# ------------------------------------------------------------------------------------------------
+GRAD_TOL_FP32 = 1e-3  # same per-tensor relative-to-max definition as the logits tolerance
+
+
+def _train_step(dec, x, tags):
+    dec.zero_grad(set_to_none=True)
+    x = x.clone().requires_grad_(True)
+    out = dec(x, None, *tags)
+    out.loss.backward()
+    return out, x.grad, {k: p.grad for k, p in dec.named_parameters()}
+
+
+def test_training_step_matches_reference_autograd_golden(golden):
+    """Loss, sub-losses, every parameter gradient and d sequence_output against the gradients the
+    reference's own autograd produced (tests/golden/train.pt), fp32 kernels."""
+    for case in golden("train.pt"):
+        sd = synth.init_decoder_state(case["hin"], case["hidden"], case["shrink"], case["num_layers"], seed=case["seed"],
+                                      trained_like=True)
+        dec = PEneoDecoderB200(Cfg(case["hidden"], case["shrink"], case["num_layers"], inference_mode=False,
+                                   precision="fp32", ratios=case["ratios"]), case["hin"])
+        dec.load_state_dict(sd)
+        dec = dec.cuda().eval()  # eval(): dropout off, as in the golden run
+        x = synth.hidden_states(case["batch"], case["seq_len"], case["hin"], doc_id0=case["x_doc_id0"]).cuda()
+        docs = [synth.make_document(case["seq_len"], doc_id=case["doc_id0"] + b) for b in range(case["batch"])]
+        tags = [torch.stack([d.tags()[k] for d in docs]).cuda() for k in range(5)]
+        out, dx, grads = _train_step(dec, x, tags)
+        assert abs(out.loss.item() - case["loss"].item()) <= 1e-5 * max(1.0, abs(case["loss"].item())), case["name"]
+        for k in range(5):
+            assert rel_err(out[f"{ops.HEAD_NAMES[k]}_shaking_outputs"], case["logits"][k]) <= FP32_TOL
+        e = rel_err(dx, case["dx"])
+        assert e <= GRAD_TOL_FP32, (case["name"], "dx", e)
+        assert set(grads) == set(case["grads"])
+        for key, g in case["grads"].items():
+            assert grads[key] is not None, key
+            e = rel_err(grads[key], g)
+            assert e <= GRAD_TOL_FP32, (case["name"], key, e)
+
+
+@pytest.mark.parametrize("prec,tol", [("fp32", GRAD_TOL_FP32), ("bf16", 3e-2)])
+def test_training_step_default_dims_vs_fp64_oracle(prec, tol):
+    """Shipped configuration (hidden 768 -> d 384, 2 layers), N = 37, batch 2 against the fp64 autograd
+    oracle.  bf16: the forward runs on tcgen05 (logits within 2e-2), the backward in fp32."""
+    n, b = 37, 2
+    sd = synth.init_decoder_state(seed=6, trained_like=True)
+    dec = PEneoDecoderB200(Cfg(768, inference_mode=False, precision=prec, ratios=(1.0, 0.5, 2.0, 1.0, 1.5)), 768)
+    dec.load_state_dict(sd)
+    dec = dec.cuda().eval()
+    x = synth.hidden_states(b, n, 768, doc_id0=3)
+    docs = [synth.make_document(n, doc_id=200 + i) for i in range(b)]
+    tags = [torch.stack([d.tags()[k] for d in docs]) for k in range(5)]
+    ref_loss, ref_subs, ref_grads, ref_dx = orc.loss_and_grads(sd, x, tags, [1.0, 10.0, 10.0], (1.0, 0.5, 2.0, 1.0, 1.5))
+    out, dx, grads = _train_step(dec, x.cuda(), [t.cuda() for t in tags])
+    assert abs(out.loss.item() - ref_loss.item()) <= tol * max(1.0, abs(ref_loss.item()))
+    worst = {}
+    worst["dx"] = rel_err(dx, ref_dx)
+    for key, g in ref_grads.items():
+        worst[key] = rel_err(grads[key], g)
+    print(prec, {k: f"{v:.2e}" for k, v in worst.items()})
+    bad = {k: v for k, v in worst.items() if v > tol}
+    assert not bad, bad
+
+
+def test_training_rows_cross_chunk_boundaries(monkeypatch):
+    """Several pair-row chunks per document in the backward pass (chunk size forced down through the
+    PENEO_BWD_CHUNK_ROWS test hook); gradients must not depend on the chunking."""
+    monkeypatch.setenv("PENEO_BWD_CHUNK_ROWS", "1000")
+    n, b = 150, 2
+    sd = synth.init_decoder_state(64, 64, True, 2, seed=8, trained_like=True)
+    dec = PEneoDecoderB200(Cfg(64, inference_mode=False, precision="fp32"), 64)
+    dec.load_state_dict(sd)
+    dec = dec.cuda().eval()
+    x = synth.hidden_states(b, n, 64, doc_id0=4)
+    docs = [synth.make_document(n, doc_id=300 + i) for i in range(b)]
+    tags = [torch.stack([d.tags()[k] for d in docs]) for k in range(5)]
+    ref_loss, _, ref_grads, ref_dx = orc.loss_and_grads(sd, x, tags, [1.0, 10.0, 10.0])
+    out, dx, grads = _train_step(dec, x.cuda(), [t.cuda() for t in tags])
+    assert abs(out.loss.item() - ref_loss.item()) <= 1e-4 * max(1.0, abs(ref_loss.item()))
+    assert rel_err(dx, ref_dx) <= GRAD_TOL_FP32
+    for key, g in ref_grads.items():
+        assert rel_err(grads[key], g) <= GRAD_TOL_FP32, key
