@@ -11,7 +11,7 @@
  *                                   + the five classifier heads             model/peneo_decoder.py:149-177, 355-363
  *   peneo_pair_loss_fwd ........... calculate_peneo_loss / CrossEntropyLossOHEM
  *                                   (OHEM off) + the ratio-weighted sum     model/peneo_decoder.py:315-336, 375-428; model/custom_loss.py:189-202
- *   peneo_pair_loss_ohem .......... CrossEntropyLossOHEM with hard-example
+ *   peneo_pair_loss_ohem_fwd/bwd .. CrossEntropyLossOHEM with hard-example
  *                                   selection (forward value + d loss/d logits) model/custom_loss.py:204-288
  *   peneo_heads_bwd ............... autograd backward of token_proj + pair_heads (implicit in the reference:
  *                                   loss.backward() through model/peneo_decoder.py:349-363)
@@ -120,6 +120,21 @@ int peneo_pair_loss_bwd(int32_t batch, int32_t n, const float* const logits[PENE
                         const int64_t* const tags[PENEO_NUM_HEADS], const float* class_w_host,
                         const float* ratio_host, const float* grad_out, const void* workspace,
                         float* const dlogits[PENEO_NUM_HEADS], void* stream);
+
+/* Same five sub-losses with online hard-example mining (num_hard_positive / num_hard_negative as in
+ * PEneoConfig.peneo_ohem_num_positive / _negative; -1 = keep the whole side).  Reproduces the reference's
+ * selection rule exactly, including its indexing quirk and the raw (k_pos + k_neg) divisor
+ * (model/custom_loss.py:255-280).  The workspace keeps the kept-element masks for the backward call.
+ * Synchronises `stream` (the side sizes are needed on the host, as in the reference). */
+size_t peneo_pair_loss_ohem_workspace_bytes(int32_t batch, int32_t n);
+int peneo_pair_loss_ohem_fwd(int32_t batch, int32_t n, const float* const logits[PENEO_NUM_HEADS],
+                             const int64_t* const tags[PENEO_NUM_HEADS], const float* class_w_host,
+                             const float* ratio_host, int32_t num_hard_positive, int32_t num_hard_negative, float* out6,
+                             void* workspace, void* stream);
+int peneo_pair_loss_ohem_bwd(int32_t batch, int32_t n, const float* const logits[PENEO_NUM_HEADS],
+                             const int64_t* const tags[PENEO_NUM_HEADS], const float* class_w_host,
+                             const float* ratio_host, const float* grad_out, const void* workspace,
+                             float* const dlogits[PENEO_NUM_HEADS], void* stream);
 
 /* ------------------------------------------------------------------ heads, backward */
 /* Gradient outputs, fp32, same layouts as peneo_params (all OVERWRITTEN by peneo_heads_bwd). */

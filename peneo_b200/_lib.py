@@ -32,6 +32,9 @@ SYMBOLS = (
     "peneo_pair_loss_workspace_bytes",
     "peneo_pair_loss_fwd",
     "peneo_pair_loss_bwd",
+    "peneo_pair_loss_ohem_workspace_bytes",
+    "peneo_pair_loss_ohem_fwd",
+    "peneo_pair_loss_ohem_bwd",
     "peneo_scatter_tags",
     "peneo_decode_spots_workspace_bytes",
     "peneo_decode_spots",
@@ -98,6 +101,12 @@ def load() -> C.CDLL:
                                         vp, vp]
     lib.peneo_pair_loss_bwd.argtypes = [i32, i32, PtrArray5, PtrArray5, C.POINTER(C.c_float), C.POINTER(C.c_float), vp,
                                         vp, PtrArray5, vp]
+    lib.peneo_pair_loss_ohem_workspace_bytes.restype = sz
+    lib.peneo_pair_loss_ohem_workspace_bytes.argtypes = [i32, i32]
+    lib.peneo_pair_loss_ohem_fwd.argtypes = [i32, i32, PtrArray5, PtrArray5, C.POINTER(C.c_float), C.POINTER(C.c_float),
+                                             i32, i32, vp, vp, vp]
+    lib.peneo_pair_loss_ohem_bwd.argtypes = [i32, i32, PtrArray5, PtrArray5, C.POINTER(C.c_float), C.POINTER(C.c_float),
+                                             vp, vp, PtrArray5, vp]
     lib.peneo_scatter_tags.argtypes = [vp, i64, i32, i32, vp, vp]
     lib.peneo_decode_spots_workspace_bytes.restype = sz
     lib.peneo_decode_spots_workspace_bytes.argtypes = [i32, i32]

@@ -17,7 +17,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libpeneo_b200.so")
 STAMP = os.path.join(HERE, "csrc", ".build_stamp")
 
-SOURCES = ["api.cu", "simt_kernels.cu", "gemm_tc.cu", "pair_heads_tc.cu", "loss.cu", "train.cu", "decode.cu", "selftest.cu"]
+SOURCES = ["api.cu", "simt_kernels.cu", "gemm_tc.cu", "pair_heads_tc.cu", "loss.cu", "ohem.cu", "train.cu", "decode.cu", "selftest.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",

@@ -217,6 +217,31 @@ int peneo_pair_loss_bwd(int32_t batch, int32_t n, const float* const logits[PENE
                               static_cast<cudaStream_t>(stream));
 }
 
+size_t peneo_pair_loss_ohem_workspace_bytes(int32_t batch, int32_t n) {
+  return batch >= 1 && n >= 1 ? pair_loss_ohem_workspace_bytes(batch, n) : 0;
+}
+
+int peneo_pair_loss_ohem_fwd(int32_t batch, int32_t n, const float* const logits[PENEO_NUM_HEADS],
+                             const int64_t* const tags[PENEO_NUM_HEADS], const float* class_w_host, const float* ratio_host,
+                             int32_t num_hard_positive, int32_t num_hard_negative, float* out6, void* workspace,
+                             void* stream) {
+  PENEO_REQUIRE(logits && tags && class_w_host && out6 && workspace, "pair_loss_ohem_fwd: NULL pointer");
+  for (int h = 0; h < kNumHeads; ++h) PENEO_REQUIRE(logits[h] && tags[h], "pair_loss_ohem_fwd: head %d pointer is NULL", h);
+  return launch_pair_loss_ohem_fwd(batch, n, logits, tags, class_w_host, ratio_host, num_hard_positive, num_hard_negative,
+                                   out6, workspace, static_cast<cudaStream_t>(stream));
+}
+
+int peneo_pair_loss_ohem_bwd(int32_t batch, int32_t n, const float* const logits[PENEO_NUM_HEADS],
+                             const int64_t* const tags[PENEO_NUM_HEADS], const float* class_w_host, const float* ratio_host,
+                             const float* grad_out, const void* workspace, float* const dlogits[PENEO_NUM_HEADS],
+                             void* stream) {
+  PENEO_REQUIRE(logits && tags && class_w_host && grad_out && workspace && dlogits, "pair_loss_ohem_bwd: NULL pointer");
+  for (int h = 0; h < kNumHeads; ++h)
+    PENEO_REQUIRE(logits[h] && tags[h] && dlogits[h], "pair_loss_ohem_bwd: head %d pointer is NULL", h);
+  return launch_pair_loss_ohem_bwd(batch, n, logits, tags, class_w_host, ratio_host, grad_out, workspace, dlogits,
+                                   static_cast<cudaStream_t>(stream));
+}
+
 int peneo_scatter_tags(const int32_t* spots_bijt, int64_t num_spots, int32_t batch, int32_t n, int64_t* tags,
                        void* stream) {
   PENEO_REQUIRE(tags && (spots_bijt || num_spots == 0) && batch >= 0 && n >= 1 && num_spots >= 0,

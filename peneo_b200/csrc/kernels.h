@@ -30,6 +30,15 @@ int launch_pair_loss_bwd(int batch, int n, const float* const logits[kNumHeads],
                          float* const dlogits[kNumHeads], cudaStream_t st);
 int launch_scatter_tags(const int32_t* spots, int64_t num_spots, int batch, int n, int64_t* tags, cudaStream_t st);
 
+// ohem.cu
+size_t pair_loss_ohem_workspace_bytes(int batch, int n);
+int launch_pair_loss_ohem_fwd(int batch, int n, const float* const logits[kNumHeads], const int64_t* const tags[kNumHeads],
+                              const float* class_w, const float* ratio, int num_hard_pos, int num_hard_neg, float* out6,
+                              void* workspace, cudaStream_t st);
+int launch_pair_loss_ohem_bwd(int batch, int n, const float* const logits[kNumHeads], const int64_t* const tags[kNumHeads],
+                              const float* class_w, const float* ratio, const float* grad_out, const void* workspace,
+                              float* const dlogits[kNumHeads], cudaStream_t st);
+
 // train.cu
 size_t heads_bwd_workspace_bytes(const peneo_dims& dm, int batch, int n);
 int launch_heads_bwd_fp32(const peneo_dims& dm, const void* pack, const void* x, int x_dtype, int64_t x_row_stride,
