@@ -84,46 +84,94 @@ def calibrate_bias(sd, n_eff, device):
 
 
 class ClockSampler:
-    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-             "clocks_event_reasons.sw_power_cap")
+    """SM clock / throttle-reason samples DURING the timed region: NVML polled from a thread every few
+    milliseconds (nvidia-smi -lms cannot sample a sub-second region densely enough); falls back to
+    nvidia-smi when pynvml is unavailable."""
 
-    def __init__(self, gpu_index: int):
-        self.rows, self.proc, self.gpu = [], None, gpu_index
+    REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20),
+               ("sw_power_cap", 0x4))
+
+    def __init__(self, gpu_index: int, period_s: float = 0.004):
+        self.gpu, self.period = gpu_index, period_s
+        self.sm, self.reasons, self.power = [], set(), []
+        self.sm_max, self.stop_flag, self.thread, self.mode = None, False, None, None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "100", "-i",
-                 str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
+            import pynvml
+
+            pynvml.nvmlInit()
+            # CUDA_VISIBLE_DEVICES may remap indices: resolve through the PCI bus id of the torch device
+            bus = torch.cuda.get_device_properties(self.gpu).pci_bus_id if hasattr(
+                torch.cuda.get_device_properties(self.gpu), "pci_bus_id") else None
+            h = None
+            if bus is not None:
+                for i in range(pynvml.nvmlDeviceGetCount()):
+                    hh = pynvml.nvmlDeviceGetHandleByIndex(i)
+                    if pynvml.nvmlDeviceGetPciInfo(hh).bus == bus:
+                        h = hh
+                        break
+            if h is None:
+                h = pynvml.nvmlDeviceGetHandleByIndex(self.gpu)
+            self.sm_max = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            self.mode = "nvml"
+
+            def loop():
+                while not self.stop_flag:
+                    try:
+                        self.sm.append(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+                        mask = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
+                        for name, bit in self.REASONS:
+                            if mask & bit:
+                                self.reasons.add(name)
+                        self.power.append(pynvml.nvmlDeviceGetPowerUsage(h) / 1000.0)
+                    except Exception:
+                        pass
+                    time.sleep(self.period)
+
+            self.thread = threading.Thread(target=loop, daemon=True)
             self.thread.start()
         except Exception:
-            self.proc = None
+            self.mode = "smi"
+            self._start_smi()
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+    def _start_smi(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "20",
+                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc, self.mode = None, None
+            return
+
+        def read():
+            for line in self.proc.stdout:
+                c = [v.strip() for v in line.split(",")]
+                if len(c) >= 7 and c[0].isdigit():
+                    self.sm.append(int(c[0]))
+                    self.sm_max = int(c[1]) if c[1].isdigit() else self.sm_max
+                    for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[3:7]):
+                        if v.lower().startswith("active"):
+                            self.reasons.add(name)
+
+        self.thread = threading.Thread(target=read, daemon=True)
+        self.thread.start()
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm = sorted(int(r[1]) for r in self.rows if len(r) >= 9 and r[1].isdigit())
-        mx = [int(r[2]) for r in self.rows if len(r) >= 9 and r[2].isdigit()]
-        reasons = set()
-        for r in self.rows:
-            if len(r) < 9:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        self.stop_flag = True
+        if self.mode == "smi" and getattr(self, "proc", None) is not None:
+            self.proc.terminate()
+        if self.thread is not None:
+            self.thread.join(timeout=2)
+        if not self.sm:
+            return {"sm_mhz": None, "sm_max_mhz": self.sm_max, "reasons": ["no samples"], "samples": 0}
+        sm = sorted(self.sm)
+        out = {"sm_mhz": sm[len(sm) // 2], "sm_min_mhz": sm[0], "sm_max_mhz": self.sm_max, "reasons": sorted(self.reasons),
+               "samples": len(sm), "source": self.mode}
+        if self.power:
+            out["power_w_max"] = max(self.power)
+        return out
 
 
 # ------------------------------------------------------------------------------------------------
@@ -154,62 +202,59 @@ def run_ours(args):
     xs_dev = [x.to(dev) for x in xs_host]
     texts = [[f"w{t} " for t in range(n_eff)] for _ in range(args.batch)]
 
-    k2_events = []
+    from peneo_b200 import HeadsDecodePipeline
 
-    def step(x_dev, timed):
-        pack = dec._weight_pack(dev)
-        ab = ops.token_projections(pack, x_dev)
-        if timed:
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-        logits = ops.pair_heads(pack, ab, args.batch, n_eff)
-        if timed:
-            e1.record()
-            k2_events.append((e0, e1))
-        return decode.device_decode(logits, n_eff)
+    pipe = HeadsDecodePipeline(dec, dev)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    with torch.no_grad():
-        for w in range(args.warmup):
-            step(xs_dev[w % args.rotate], False)
-        sampler = ClockSampler(local_rank)
-        sampler.start()
-        barrier()
-        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        t0.record()
-        launches0 = ops.COUNTERS["kernels"]
-        for s in range(args.steps):
-            dd = step(xs_dev[s % args.rotate], True)
-        launches = ops.COUNTERS["kernels"] - launches0
-        t1.record()
-        barrier()
-        ms_dev = t0.elapsed_time(t1)
-        clocks = sampler.stop()
-        k2_ms = sum(a.elapsed_time(b) for a, b in k2_events) / len(k2_events)
-        spots_per_head = float(dd.counts.mean())
+    def run_steps(inputs, steps, assemble, depth=2):
+        """`steps` passes of the hot path with `depth` batches in flight; returns the last result."""
+        last = None
+        for s in range(steps):
+            pipe.submit(inputs[s % args.rotate], texts)
+            if len(pipe) >= depth:
+                last = pipe.result(assemble=assemble)
+        while len(pipe):
+            last = pipe.result(assemble=assemble)
+        return last
 
-        # ---- end-to-end: pinned host hidden states -> H2D -> heads -> decode -> Python objects
-        for w in range(2):
-            x = xs_host[w % args.rotate].to(dev, non_blocking=True)
-            res = [decode._assemble(step(x, False), b, texts[b], None) for b in range(1)]
-        barrier()
-        wall0 = time.perf_counter()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        d2h = 0
-        for s in range(args.steps):
-            x = xs_host[s % args.rotate].to(dev, non_blocking=True)
-            dd = step(x, False)
-            res = [decode._assemble(dd, b, texts[b], None) for b in range(args.batch)]
-            d2h = dd.records.nbytes + dd.counts.nbytes
-        e1.record()
-        barrier()
-        ms_e2e = e0.elapsed_time(e1)
-        wall_e2e = (time.perf_counter() - wall0) * 1e3
+    # ---- device-resident leg: inputs already in HBM, records copied back, no Python objects
+    run_steps(xs_dev, args.warmup, False)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    pipe.k2_events = []
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = ops.COUNTERS["kernels"]
+    t0.record(pipe.compute)
+    dd = run_steps(xs_dev, args.steps, False)
+    t1.record(pipe.compute)
+    launches = ops.COUNTERS["kernels"] - launches0
+    barrier()
+    ms_dev = t0.elapsed_time(t1)
+    clocks = sampler.stop()
+    k2_ms = sum(a.elapsed_time(b) for a, b in pipe.k2_events) / len(pipe.k2_events)
+    pipe.k2_events = None
+    spots_per_head = float(dd.counts.mean())
+
+    # ---- end-to-end leg: pinned host hidden states -> H2D -> heads -> decode -> D2H -> Python objects
+    run_steps(xs_host, 2, True)
+    barrier()
+    pipe.h2d_bytes = pipe.d2h_bytes = 0
+    wall0 = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(pipe.compute)
+    res = run_steps(xs_host, args.steps, True)
+    e1.record(pipe.compute)
+    barrier()
+    ms_e2e = e0.elapsed_time(e1)
+    wall_e2e = (time.perf_counter() - wall0) * 1e3
+    assert len(res) == args.batch and len(res[0]) == 7
+    h2d, d2h = pipe.h2d_bytes // args.steps, pipe.d2h_bytes // args.steps
 
     if world > 1:
         t = torch.tensor([ms_dev, ms_e2e, wall_e2e], device=dev, dtype=torch.float64)
@@ -241,8 +286,9 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic", "config": workload_config(args, world),
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(xs_host[0].numel() * 2),
-                "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms / args.steps},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "ms_per_step": e2e_ms / args.steps,
+                "api": "peneo_b200.HeadsDecodePipeline.submit()/result(): pinned host hidden states in, reference 7-tuples out, 2 batches in flight"},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "tensor", "kernel": "pair_heads_tc_kernel", "achieved": achieved, "peak": peak_tf,
@@ -336,7 +382,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=32)

@@ -7,12 +7,14 @@ Public surface mirrors the reference (ZeningLin/PEneo):
 """
 from .decode import decode_peneo, parse_matrix_spots, sample_decode_peneo  # noqa: F401
 from .decoder import PEneoDecoderB200, PEneoOutput  # noqa: F401
+from .pipeline import HeadsDecodePipeline  # noqa: F401
 from .tagging import HandshakingTaggingScheme  # noqa: F401
 
 __all__ = [
     "PEneoDecoderB200",
     "PEneoOutput",
     "HandshakingTaggingScheme",
+    "HeadsDecodePipeline",
     "decode_peneo",
     "sample_decode_peneo",
     "parse_matrix_spots",

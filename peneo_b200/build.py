@@ -11,10 +11,12 @@ import hashlib
 import os
 import subprocess
 import sys
+import sysconfig
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libpeneo_b200.so")
+GLUE = os.path.join(HERE, "_hostglue" + (sysconfig.get_config_var("EXT_SUFFIX") or ".so"))
 STAMP = os.path.join(HERE, "csrc", ".build_stamp")
 
 SOURCES = ["api.cu", "simt_kernels.cu", "gemm_tc.cu", "pair_heads_tc.cu", "loss.cu", "ohem.cu", "train.cu", "decode.cu", "selftest.cu"]
@@ -37,7 +39,7 @@ def _nvcc() -> str:
 def _digest() -> str:
     h = hashlib.sha256()
     for name in sorted(os.listdir(CSRC)):
-        if name.endswith((".cu", ".cuh", ".h")):
+        if name.endswith((".cu", ".cuh", ".h", ".c")):
             with open(os.path.join(CSRC, name), "rb") as f:
                 h.update(name.encode() + b"\0" + f.read())
     with open(os.path.join(os.path.dirname(HERE), "include", "peneo_b200.h"), "rb") as f:
@@ -48,7 +50,7 @@ def _digest() -> str:
 
 def build(force: bool = False, verbose: bool = False) -> str:
     digest = _digest()
-    if not force and os.path.exists(LIB) and os.path.exists(STAMP):
+    if not force and os.path.exists(LIB) and os.path.exists(GLUE) and os.path.exists(STAMP):
         with open(STAMP) as f:
             if f.read().strip() == digest:
                 return LIB
@@ -73,6 +75,10 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if failed:
         raise RuntimeError("nvcc failed; see log above")
     cmd = [_nvcc(), "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a"]
+    subprocess.run(cmd, check=True)
+    # CPython extension with the decode host glue (record blocks -> Python objects)
+    cmd = [os.environ.get("CC", "gcc"), "-O2", "-shared", "-fPIC", "-Wall", "-I", sysconfig.get_paths()["include"],
+           os.path.join(CSRC, "hostglue.c"), "-o", GLUE]
     subprocess.run(cmd, check=True)
     with open(STAMP, "w") as f:
         f.write(digest)

@@ -81,51 +81,85 @@ def _as_batched_inputs(shakings: Sequence[torch.Tensor]):
     return outs, tag_mode
 
 
-def device_decode(shakings: Sequence[torch.Tensor], n: int, decode_gt: bool = False, score_thresh: float = 0,
-                  cap: Optional[int] = None, want_spots: bool = False) -> DeviceDecode:
-    """Run K3 (spots) + K4 (resolve) for a batch and bring the compact result to the host."""
-    lib = _lib.load()
-    ins, tag_mode = _as_batched_inputs(shakings)
-    b = ins[0].shape[0]
-    p = shaking_len(n)
-    for k, t in enumerate(ins):
-        if t.shape[1] != p:
-            raise ValueError(f"shaking tensor {k} has {t.shape[1]} rows, expected {p} for seq_len {n}")
-    dev = ins[0].device
-    dt = _TORCH_DT[ins[0].dtype]
-    if cap is None:
-        cap = min(p, max(8 * n, 1024))
-    while True:
-        spot_p = torch.empty(b * NUM_HEADS * cap, dtype=torch.int32, device=dev)
-        spot_tag = torch.empty_like(spot_p)
-        spot_score = torch.empty(b * NUM_HEADS * cap, dtype=torch.float32, device=dev)
+class PendingDecode:
+    """K3 + K4 enqueued for a batch; the compact result is on its way to pinned host memory.
+    ``finish()`` waits for it (and transparently re-runs with the worst-case capacity in the rare
+    case a spot list overflowed)."""
+
+    def __init__(self, ins, n, cap, decode_gt, score_thresh, want_spots):
+        self.ins, self.n, self.cap = ins, n, cap
+        self.decode_gt, self.score_thresh, self.want_spots = decode_gt, score_thresh, want_spots
+        self._launch()
+
+    def _launch(self):
+        lib = _lib.load()
+        ins, n, cap = self.ins, self.n, self.cap
+        b = ins[0].shape[0]
+        dev = ins[0].device
+        dt = _TORCH_DT[ins[0].dtype]
+        self.spot_p = torch.empty(b * NUM_HEADS * cap, dtype=torch.int32, device=dev)
+        self.spot_tag = torch.empty_like(self.spot_p)
+        self.spot_score = torch.empty(b * NUM_HEADS * cap, dtype=torch.float32, device=dev)
         counts = torch.empty(b * NUM_HEADS, dtype=torch.int32, device=dev)
         ws = torch.empty(max(16, lib.peneo_decode_spots_workspace_bytes(b, n)), dtype=torch.uint8, device=dev)
         _lib.check(
-            lib.peneo_decode_spots(b, n, _lib.ptrs5(ins), dt, cap, spot_p.data_ptr(), spot_tag.data_ptr(),
-                                   spot_score.data_ptr(), counts.data_ptr(), ws.data_ptr(), _stream(dev)),
+            lib.peneo_decode_spots(b, n, _lib.ptrs5(ins), dt, cap, self.spot_p.data_ptr(), self.spot_tag.data_ptr(),
+                                   self.spot_score.data_ptr(), counts.data_ptr(), ws.data_ptr(), _stream(dev)),
             "peneo_decode_spots",
         )
         doc_ints = lib.peneo_decode_resolve_doc_ints(n, cap)
         rec = torch.empty(b, doc_ints, dtype=torch.int32, device=dev)
         ws2 = torch.empty(max(16, lib.peneo_decode_resolve_workspace_bytes(b, n)), dtype=torch.uint8, device=dev)
         _lib.check(
-            lib.peneo_decode_resolve(b, n, cap, spot_p.data_ptr(), spot_tag.data_ptr(), spot_score.data_ptr(),
-                                     counts.data_ptr(), int(decode_gt), _thresh_f32(score_thresh), rec.data_ptr(),
-                                     ws2.data_ptr(), _stream(dev)),
+            lib.peneo_decode_resolve(b, n, cap, self.spot_p.data_ptr(), self.spot_tag.data_ptr(),
+                                     self.spot_score.data_ptr(), counts.data_ptr(), int(self.decode_gt),
+                                     _thresh_f32(self.score_thresh), rec.data_ptr(), ws2.data_ptr(), _stream(dev)),
             "peneo_decode_resolve",
         )
         COUNTERS["kernels"] += 2
-        counts_h = counts.cpu().numpy()
-        if counts_h.max(initial=0) <= cap:
-            break
-        cap = p  # a list overflowed: redo with the worst-case capacity
-    records = rec.cpu().numpy()
-    spots = None
-    if want_spots:
-        spots = (spot_p.cpu().numpy().reshape(b, NUM_HEADS, cap), spot_tag.cpu().numpy().reshape(b, NUM_HEADS, cap),
-                 spot_score.cpu().numpy().reshape(b, NUM_HEADS, cap))
-    return DeviceDecode(n, cap, b, records, counts_h.reshape(b, NUM_HEADS), spots)
+        self.counts_h = torch.empty(counts.shape, dtype=torch.int32, pin_memory=True)
+        self.rec_h = torch.empty(rec.shape, dtype=torch.int32, pin_memory=True)
+        self.counts_h.copy_(counts, non_blocking=True)
+        self.rec_h.copy_(rec, non_blocking=True)
+        self.d2h_bytes = self.counts_h.numel() * 4 + self.rec_h.numel() * 4
+        self.event = torch.cuda.Event()
+        self.event.record(torch.cuda.current_stream(dev))
+        self._keep = (counts, rec, ws, ws2)  # alive until the copies have run
+
+    def finish(self) -> "DeviceDecode":
+        self.event.synchronize()
+        b = self.ins[0].shape[0]
+        p = shaking_len(self.n)
+        if int(self.counts_h.max()) > self.cap and self.cap < p:
+            self.cap = p  # a list overflowed: redo with the worst-case capacity
+            self._launch()
+            self.event.synchronize()
+        spots = None
+        if self.want_spots:
+            cap = self.cap
+            spots = (self.spot_p.cpu().numpy().reshape(b, NUM_HEADS, cap), self.spot_tag.cpu().numpy().reshape(b, NUM_HEADS, cap),
+                     self.spot_score.cpu().numpy().reshape(b, NUM_HEADS, cap))
+        self._keep = None
+        return DeviceDecode(self.n, self.cap, b, self.rec_h.numpy(), self.counts_h.numpy().reshape(b, NUM_HEADS), spots)
+
+
+def device_decode_async(shakings: Sequence[torch.Tensor], n: int, decode_gt: bool = False, score_thresh: float = 0,
+                        cap: Optional[int] = None, want_spots: bool = False) -> PendingDecode:
+    """Enqueue K3 (spots) + K4 (resolve) + the D2H copy of the compact records on the current stream."""
+    ins, _tag_mode = _as_batched_inputs(shakings)
+    p = shaking_len(n)
+    for k, t in enumerate(ins):
+        if t.shape[1] != p:
+            raise ValueError(f"shaking tensor {k} has {t.shape[1]} rows, expected {p} for seq_len {n}")
+    if cap is None:
+        cap = min(p, max(8 * n, 1024))
+    return PendingDecode(ins, n, cap, decode_gt, score_thresh, want_spots)
+
+
+def device_decode(shakings: Sequence[torch.Tensor], n: int, decode_gt: bool = False, score_thresh: float = 0,
+                  cap: Optional[int] = None, want_spots: bool = False) -> DeviceDecode:
+    """Run K3 (spots) + K4 (resolve) for a batch and bring the compact result to the host."""
+    return device_decode_async(shakings, n, decode_gt, score_thresh, cap, want_spots).finish()
 
 
 def _unflatten(p: np.ndarray, n: int):
@@ -146,46 +180,36 @@ def spots_from_device(dd: DeviceDecode, b: int, head: int) -> List[Tuple[int, in
     return [(int(i), int(j), int(t), s.item()) for i, j, t, s in zip(ii, jj, st[b, head, :cnt], ss[b, head, :cnt])]
 
 
+def _glue():
+    """The CPython extension built next to this file (csrc/hostglue.c)."""
+    try:
+        from . import _hostglue
+    except ImportError as e:  # pragma: no cover
+        raise RuntimeError("peneo_b200._hostglue is not built: run `python -m peneo_b200.build`") from e
+    return _hostglue
+
+
+def _plain_bbox(bbox):
+    if bbox is None:
+        return None
+    return bbox.tolist() if hasattr(bbox, "tolist") else bbox
+
+
+def assemble_many(dd: DeviceDecode, docs: Sequence[int], texts: Sequence[List[str]], bboxes=None) -> List[Tuple]:
+    """Host glue for several documents of one decoded batch: ordered dicts, line strings / boxes and
+    key-value strings from the kernels' records (pipeline/decode.py:205-212, 353-378), built through
+    the C API in ``_hostglue``."""
+    texts = [t if isinstance(t, list) else list(t) for t in texts]
+    if bboxes is not None:
+        bboxes = [_plain_bbox(bx) for bx in bboxes]
+        if all(bx is None for bx in bboxes):
+            bboxes = None
+    rec = dd.records
+    return _glue().assemble(memoryview(rec).cast("B"), rec.shape[1], dd.n, dd.cap, list(docs), texts, bboxes)
+
+
 def _assemble(dd: DeviceDecode, b: int, text: List[str], bbox):
-    """Host glue: ordered dicts, line strings / boxes and key-value strings from the kernels' records."""
-    le_a, lgh_a, lgt_a, elh_a, elt_a, kv_a = dd.doc(b)
-    le = {int(h): int(t) for h, t in le_a}
-    lg_head = {int(h): int(t) for h, t in lgh_a}
-    lg_tail = {int(h): int(t) for h, t in lgt_a}
-    el_head: Dict[int, List[int]] = {}
-    for h, t in elh_a:
-        el_head.setdefault(int(h), []).append(int(t))
-    el_tail: Dict[int, List[int]] = {}
-    for h, t in elt_a:
-        el_tail.setdefault(int(h), []).append(int(t))
-    if bbox is not None and hasattr(bbox, "tolist"):
-        bbox = bbox.tolist()
-
-    lines = []
-    for h, t in le.items():
-        s = "".join(text[h : t + 1])
-        lines.append((s, merge_bbox(bbox[h : t + 1])) if bbox is not None else s)
-
-    def chain(head: int, nseg: int):
-        segs = [(head, le[head])]
-        cur = head
-        for _ in range(nseg - 1):
-            cur = lg_head[cur]
-            segs.append((cur, le[cur]))
-        return segs
-
-    pairs = []
-    for kh, vh, nk, nv in kv_a:
-        ks, vs = chain(int(kh), int(nk)), chain(int(vh), int(nv))
-        ktxt = "".join("".join(text[h : t + 1]) for h, t in ks).strip()
-        vtxt = "".join("".join(text[h : t + 1]) for h, t in vs).strip()
-        if bbox is not None:
-            kbox = merge_bbox([merge_bbox(bbox[h : t + 1]) for h, t in ks])
-            vbox = merge_bbox([merge_bbox(bbox[h : t + 1]) for h, t in vs])
-            pairs.append((ktxt, vtxt, kbox, vbox))
-        else:
-            pairs.append((ktxt, vtxt))
-    return pairs, lines, le, el_head, el_tail, lg_head, lg_tail
+    return assemble_many(dd, [b], [text], None if bbox is None else [bbox])[0]
 
 
 def parse_matrix_spots(matrix_spots, top_score_only: bool = False, triu_mode: bool = False, score_thresh: float = 0):
@@ -284,8 +308,9 @@ def decode_peneo(
         gt_in = [torch.stack([_to_device(t[s], device) for s in idxs]) for t in tags]
         dp = device_decode(pred_in, n, decode_gt=False)
         dg = device_decode(gt_in, n, decode_gt=True)
-        for r, s in enumerate(idxs):
-            all_pred[s] = _assemble(dp, r, texts[s], None)
-            all_gt[s] = _assemble(dg, r, texts[s], None)
+        rows = list(range(len(idxs)))
+        tx = [texts[s] for s in idxs]
+        for s, pr, gt in zip(idxs, assemble_many(dp, rows, tx), assemble_many(dg, rows, tx)):
+            all_pred[s], all_gt[s] = pr, gt
     all_ids = [file_ids[s] for s in range(count)]
     return all_pred, all_gt, all_ids

@@ -1,0 +1,84 @@
+"""Streaming heads + decode: the decoder-side loop of deploy/inference.py (``inference()`` ->
+``postprocess()``, deploy/inference.py:375-386, 388-462) with the GPU and the host overlapped.
+
+``submit()`` enqueues, without blocking, the H2D copy of a batch of hidden states (copy stream), the
+per-token projections, pair heads, spot extraction and link resolution (compute stream) and the D2H copy
+of the compact records; ``result()`` waits for that batch only and builds the reference's Python
+objects while the GPU already works on the next batch.  Documents are independent, so this is also the
+unit that is sharded across GPUs (one pipeline per process / GPU, no collective).
+"""
+from __future__ import annotations
+
+from collections import deque
+from typing import List, Optional, Sequence
+
+import torch
+
+from . import decode, ops
+
+
+class HeadsDecodePipeline:
+    def __init__(self, decoder, device=None, score_thresh: float = 0.0):
+        self.decoder = decoder
+        self.device = torch.device(device) if device is not None else next(decoder.parameters()).device
+        if self.device.type != "cuda":
+            raise RuntimeError("HeadsDecodePipeline needs the decoder on a CUDA device (no CPU path)")
+        self.compute = torch.cuda.Stream(self.device)
+        self.copy = torch.cuda.Stream(self.device)
+        self.score_thresh = score_thresh
+        self._queue = deque()
+        self.h2d_bytes = 0
+        self.d2h_bytes = 0
+        self.k2_events = None  # set to a list to collect (start, stop) CUDA events around K2
+
+    def submit(self, hidden: torch.Tensor, texts: Sequence[List[str]], bboxes=None):
+        """hidden: [B, N, Hin] on the host (pinned for a truly asynchronous copy) or on the device."""
+        b, n, _ = hidden.shape
+        if hidden.is_cuda:
+            x = hidden
+            ready = None
+        else:
+            with torch.cuda.stream(self.copy):
+                x = hidden.to(self.device, non_blocking=True)
+                ready = torch.cuda.Event()
+                ready.record(self.copy)
+            self.h2d_bytes += hidden.numel() * hidden.element_size()
+        with torch.cuda.stream(self.compute), torch.no_grad():
+            if ready is not None:
+                self.compute.wait_event(ready)
+            pack = self.decoder._weight_pack(self.device)
+            ab = ops.token_projections(pack, x)
+            if self.k2_events is not None:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(self.compute)
+            logits = ops.pair_heads(pack, ab, b, n)
+            if self.k2_events is not None:
+                e1.record(self.compute)
+                self.k2_events.append((e0, e1))
+            pending = decode.device_decode_async(logits, n, score_thresh=self.score_thresh)
+            x.record_stream(self.compute)
+        self.d2h_bytes += pending.d2h_bytes
+        self._queue.append((pending, list(texts), bboxes))
+        return len(self._queue)
+
+    def result(self, assemble: bool = True):
+        """Python results (one reference 7-tuple per document) of the oldest submitted batch.
+        ``assemble=False`` returns the raw :class:`decode.DeviceDecode` (records on the host)."""
+        pending, texts, bboxes = self._queue.popleft()
+        with torch.cuda.stream(self.compute):
+            dd = pending.finish()
+        if not assemble:
+            return dd
+        return decode.assemble_many(dd, range(dd.batch), texts, bboxes)
+
+    def __len__(self):
+        return len(self._queue)
+
+    def run(self, batches, depth: int = 2):
+        """Generator over ``(hidden, texts[, bboxes])`` batches with ``depth`` batches in flight."""
+        for item in batches:
+            self.submit(*item)
+            if len(self._queue) >= depth:
+                yield self.result()
+        while self._queue:
+            yield self.result()

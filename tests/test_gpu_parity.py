@@ -440,3 +440,28 @@ def test_module_training_with_ohem_matches_oracle():
     for key, p in sd64.items():
         if p.requires_grad:
             assert rel_err(grads[key], p.grad) <= GRAD_TOL_FP32, key
+
+
+# ------------------------------------------------------------------------------------------------
+# streaming pipeline (overlapped H2D / kernels / D2H / host glue) == the synchronous reference-shaped calls
+# ------------------------------------------------------------------------------------------------
+def test_pipeline_matches_synchronous_decode_and_oracle():
+    from peneo_b200 import HeadsDecodePipeline
+
+    n, b = 95, 3
+    sd = synth.init_decoder_state(seed=12, trained_like=True)
+    dec = build(sd, 768, 768, True, 2, "fp32")
+    pipe = HeadsDecodePipeline(dec)
+    texts = [[f"t{i} " for i in range(n)] for _ in range(b)]
+    batches = [synth.hidden_states(b, n, 768, doc_id0=50 + 10 * s).pin_memory() for s in range(4)]
+    results = list(pipe.run(((x, texts) for x in batches), depth=2))
+    assert len(results) == 4 and pipe.h2d_bytes == 4 * batches[0].numel() * 4 and pipe.d2h_bytes > 0
+    tagger = HandshakingTaggingScheme()
+    for x, res in zip(batches, results):
+        with torch.no_grad():
+            logits = dec(x.cuda())[:5]
+        for d in range(b):
+            sync = sample_decode_peneo(tagger, texts[d], *[l[d] for l in logits], seq_len=n)
+            _same_result(res[d], sync)
+            ref = orc.sample_decode(texts[d], [l[d].cpu() for l in logits], n)
+            _same_result(res[d], ref)
