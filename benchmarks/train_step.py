@@ -1,0 +1,81 @@
+"""Fine-tuning step of the decoder (BASELINE configs[2] shape): forward + fused loss + backward on synthetic
+SIBR-shaped documents, timed with CUDA events.  Reports ms / step and the fraction of the tensor roofline
+against 3 x F_heads (what autograd would execute with stored activations).
+
+    python benchmarks/train_step.py --seq-len 1024 --batch 4 --precision bf16
+"""
+import argparse
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+from peneo_b200 import PEneoDecoderB200, synth  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--seq-len", type=int, default=1024)
+    ap.add_argument("--batch", type=int, default=4)
+    ap.add_argument("--precision", default="bf16")
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=2)
+    args = ap.parse_args()
+
+    class Cfg:
+        backbone_config = {"hidden_size": 768, "hidden_dropout_prob": 0.1}
+        peneo_decoder_shrink = True
+        peneo_classifier_num_layers = 2
+        peneo_loss_ratio = [1.0] * 5
+        peneo_category_weights = [1.0, 10.0, 10.0]
+        peneo_ohem_num_positive = -1
+        peneo_ohem_num_negative = -1
+        inference_mode = False
+        peneo_b200_precision = args.precision
+
+    n = args.seq_len - 1
+    dec = PEneoDecoderB200(Cfg, 768)
+    dec.load_state_dict(synth.init_decoder_state(seed=0))
+    dec = dec.cuda().eval()
+    x = synth.hidden_states(args.batch, n, 768).cuda().requires_grad_(True)
+    docs = [synth.make_document(n, doc_id=i, style="sibr") for i in range(args.batch)]
+    tags = [torch.stack([d.tags()[k] for d in docs]).cuda() for k in range(5)]
+
+    def step():
+        dec.zero_grad(set_to_none=True)
+        x.grad = None
+        out = dec(x, None, *tags)
+        out.loss.backward()
+        return out.loss
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    fwd_ms = 0.0
+    ev[0].record()
+    for _ in range(args.steps):
+        loss = step()
+    ev[1].record()
+    torch.cuda.synchronize()
+    ms = ev[0].elapsed_time(ev[1]) / args.steps
+    p = n * (n + 1) // 2
+    f_heads = 2.0 * n * (768 * 768 + 768 * 384 + 2 * 384 * 384) + 10.0 * p * 384 * 384 + 28.0 * p * 384
+    peak = 1427.8
+    try:
+        peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops_sustained"]
+    except Exception:
+        pass
+    tf = 3.0 * f_heads * args.batch / (ms * 1e-3) / 1e12
+    print(json.dumps({"what": "decoder fine-tuning step (fwd + loss + bwd)", "precision": args.precision, "seq_len": args.seq_len,
+                      "batch": args.batch, "ms_per_step": ms, "docs_per_s": args.batch / (ms * 1e-3), "loss": float(loss),
+                      "tflops_vs_3F": tf, "frac_of_sustained_bf16_peak": tf / peak,
+                      "peak_mem_gb": torch.cuda.max_memory_allocated() / 2**30}))
+
+
+if __name__ == "__main__":
+    main()

@@ -168,17 +168,15 @@ int peneo_pair_heads_fwd(const peneo_dims* dims, int prec, const void* pack, con
 }
 
 size_t peneo_heads_bwd_workspace_bytes(const peneo_dims* dims, int prec, int32_t batch, int32_t n) {
-  if (check_dims(dims) != PENEO_OK || batch < 0 || n < 1) return 0;
-  (void)prec;
-  return heads_bwd_workspace_bytes(*dims, batch, n);
+  if (check_dims(dims) != PENEO_OK || check_prec(dims, prec) != PENEO_OK || batch < 0 || n < 1) return 0;
+  return heads_bwd_workspace_bytes(*dims, prec, batch, n);
 }
 
 int peneo_heads_bwd(const peneo_dims* dims, int prec, const void* pack, const void* x, int x_dtype, int64_t x_row_stride,
                     int32_t batch, int32_t n, const float* const dlogits[PENEO_NUM_HEADS], const peneo_grads* grads,
                     float* dx, void* workspace, void* stream) {
   int rc;
-  if ((rc = check_dims(dims)) != PENEO_OK) return rc;
-  PENEO_REQUIRE(prec == PENEO_PREC_FP32, "heads_bwd: only PENEO_PREC_FP32 is implemented for the backward pass");
+  if ((rc = check_dims(dims)) != PENEO_OK || (rc = check_prec(dims, prec)) != PENEO_OK) return rc;
   PENEO_REQUIRE(pack && x && dlogits && grads && workspace, "heads_bwd: NULL pointer");
   PENEO_REQUIRE(batch >= 1 && n >= 1 && n <= 46340, "heads_bwd: bad sizes batch=%d n=%d", batch, n);
   PENEO_REQUIRE((int64_t)batch * n < (1ll << 31), "heads_bwd: too many tokens");
@@ -192,7 +190,7 @@ int peneo_heads_bwd(const peneo_dims* dims, int prec, const void* pack, const vo
     for (int l = 0; l + 1 < dims->num_layers; ++l)
       PENEO_REQUIRE(grads->mid_w[h * 8 + l] && grads->mid_b[h * 8 + l], "heads_bwd: head %d layer %d buffers missing", h, l);
   }
-  return launch_heads_bwd_fp32(*dims, pack, x, x_dtype, x_row_stride, batch, n, dlogits, *grads, dx, workspace,
+  return launch_heads_bwd(*dims, prec, pack, x, x_dtype, x_row_stride, batch, n, dlogits, *grads, dx, workspace,
                                static_cast<cudaStream_t>(stream));
 }
 

@@ -77,6 +77,10 @@ struct PackLayout {
   size_t bmid_half;  // [5d] fp32 0.5 * b_mid
   size_t wout_bf16;  // [15*16, 128] bf16: chunk c = (head c/3, features 128*(c%3)..), rows >= C zero
   size_t bout;       // [5*4] fp32
+  // backward pass of the bf16 mode: unscaled bf16 W_mid ([5d, d], heads stacked) and its per-head transpose
+  // ([5][d_in, d_out]), fp32 b_mid [5d]; the per-token chain and W_out use the fp32 fields above (f_w1 .. f_bc,
+  // f_out_w, f_out_b), which the bf16 pack also carries.
+  size_t wmid_full_bf16, wmidT_bf16, bmid_full;
   size_t total;
 };
 
@@ -107,6 +111,11 @@ inline PackLayout pack_layout(const peneo_dims& dm, int prec) {
     L.wc_bf16 = take(2 * d * d * 2), L.bc_half = take(2 * d * 4);
     L.wmid_bf16 = take(5 * d * d * 2), L.bmid_half = take(5 * d * 4);
     L.wout_bf16 = take(15 * 16 * 128 * 2), L.bout = take(5 * 4 * 4);
+    L.wmid_full_bf16 = take(5 * d * d * 2), L.wmidT_bf16 = take(5 * d * d * 2), L.bmid_full = take(5 * d * 4);
+    L.f_w1 = take(hid * hin * 4), L.f_b1 = take(hid * 4);
+    L.f_w2 = take(d * hid * 4), L.f_b2 = take(d * 4);
+    L.f_wc = take(d * 2 * d * 4), L.f_bc = take(d * 4);
+    for (int h = 0; h < kNumHeads; ++h) L.f_out_w[h] = take(head_classes(h) * d * 4), L.f_out_b[h] = take(16);
   }
   L.total = off;
   return L;

@@ -174,4 +174,214 @@ int launch_gemm_tc(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* W, 
   return PENEO_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// gemm_tc2: persistent 128x128-tile tcgen05 GEMM with the output modes the backward pass needs.
+//   C[M, N] (op)= A[M, K] W[N, K]^T      A, W bf16, K contiguous (TMA zero-fills the K / M / N tails)
+//   OUT 0: bf16 store of (acc + bias)      OUT 1: fp32 store      OUT 2: fp32 C += acc
+//   OUT 3: fp32 atomicAdd (split-K; C pre-initialised by the caller)
+// One CTA per SM loops over work items (m block, n block, k split); the accumulator is double-buffered in
+// TMEM so the epilogue of item i overlaps the main loop of item i + 1 — what makes the short-K (K = 384)
+// GEMMs of the backward pass efficient.  warp 0 TMA, warp 1 MMA (+TMEM alloc), warps 2-5 epilogue.
+// ------------------------------------------------------------------------------------------------
+constexpr int kG2Stages = 5;
+constexpr int kG2Smem = kG2Stages * kGemmStageBytes + 1024 + 256;
+
+template <int OUT>
+__global__ void __launch_bounds__(192, 1)
+    gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+                    const float* __restrict__ bias, void* __restrict__ Cv, int64_t ldc, int64_t M, int N, int K,
+                    int kb_per_split, int splits, int n_blocks, int64_t num_items) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kG2Stages * kGemmStageBytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + kG2Stages;
+  uint64_t* acc_full = bars + 2 * kG2Stages;       // [2]
+  uint64_t* acc_empty = bars + 2 * kG2Stages + 2;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kG2Stages + 4);
+
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int num_k_total = (K + 63) / 64;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmA);
+    ptx::prefetch_tmap(&tmW);
+    for (int s = 0; s < kG2Stages; ++s) ptx::mbar_init(&full[s], 1), ptx::mbar_init(&empty[s], 1);
+    for (int s = 0; s < 2; ++s) ptx::mbar_init(&acc_full[s], 1), ptx::mbar_init(&acc_empty[s], 4);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_slot, 256);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  auto decode = [&](int64_t item, int64_t& m0, int& n0, int& kb0, int& nk) {
+    const int split = static_cast<int>(item % splits);
+    const int64_t tile = item / splits;
+    n0 = static_cast<int>(tile % n_blocks) * 128;
+    m0 = (tile / n_blocks) * 128;
+    kb0 = split * kb_per_split;
+    nk = min(kb_per_split, num_k_total - kb0);
+  };
+
+  if (warp == 0) {
+    if (ptx::elect_one()) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int64_t item = blockIdx.x; item < num_items; item += gridDim.x) {
+        int64_t m0;
+        int n0, kb0, nk;
+        decode(item, m0, n0, kb0, nk);
+        for (int kb = 0; kb < nk; ++kb) {
+          ptx::mbar_wait(&empty[s], ph ^ 1);
+          ptx::mbar_arrive_expect_tx(&full[s], kGemmStageBytes);
+          unsigned char* st = smem + s * kGemmStageBytes;
+          ptx::tma_load_2d(st, &tmA, &full[s], (kb0 + kb) * 64, static_cast<int32_t>(m0));
+          ptx::tma_load_2d(st + 128 * 64 * 2, &tmW, &full[s], (kb0 + kb) * 64, n0);
+          if (++s == kG2Stages) s = 0, ph ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (ptx::elect_one()) {
+      constexpr uint32_t idesc = ptx::umma_idesc_bf16(128, 128);
+      int s = 0;
+      uint32_t ph = 0;
+      int it = 0;
+      for (int64_t item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
+        int64_t m0;
+        int n0, kb0, nk;
+        decode(item, m0, n0, kb0, nk);
+        const int buf = it & 1;
+        ptx::mbar_wait(&acc_empty[buf], ((it >> 1) & 1) ^ 1);
+        ptx::tc_fence_after();
+        const uint32_t acc = tmem + 128 * buf;
+        for (int kb = 0; kb < nk; ++kb) {
+          ptx::mbar_wait(&full[s], ph);
+          ptx::tc_fence_after();
+          const uint32_t a_addr = ptx::smem_u32(smem + s * kGemmStageBytes);
+          const uint32_t w_addr = a_addr + 128 * 64 * 2;
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks)
+            ptx::umma_ss(acc, ptx::umma_desc_sw128(a_addr + ks * 32), ptx::umma_desc_sw128(w_addr + ks * 32), idesc,
+                         (kb | ks) != 0);
+          ptx::tc_commit(&empty[s]);
+          if (++s == kG2Stages) s = 0, ph ^= 1;
+        }
+        ptx::tc_commit(&acc_full[buf]);
+      }
+    }
+  } else {
+    const int q = warp % 4;  // TMEM lane quarter this warp may access
+    int it = 0;
+    for (int64_t item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
+      int64_t m0;
+      int n0, kb0, nk;
+      decode(item, m0, n0, kb0, nk);
+      const int buf = it & 1;
+      ptx::mbar_wait(&acc_full[buf], (it >> 1) & 1);
+      ptx::tc_fence_after();
+      const int64_t m = m0 + q * 32 + lane;
+#pragma unroll 1
+      for (int piece = 0; piece < 4; ++piece) {
+        uint32_t r[32];
+        ptx::tmem_ld_x32(tmem + (static_cast<uint32_t>(q * 32) << 16) + 128 * buf + piece * 32, r);
+        ptx::tmem_ld_wait();
+        if (piece == 3) {  // accumulator drained: hand the buffer back before the (slow) global stores
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&acc_empty[buf]);
+        }
+        const int nb = n0 + piece * 32;
+        if (m < M && nb < N) {
+          if (OUT == 0) {
+            uint32_t packed[16];
+#pragma unroll
+            for (int x = 0; x < 32; x += 2) {
+              const float v0 = __uint_as_float(r[x]) + (bias ? bias[nb + x] : 0.f);
+              const float v1 = __uint_as_float(r[x + 1]) + (bias ? bias[nb + x + 1] : 0.f);
+              packed[x / 2] = ptx::pack_bf16x2(v0, v1);
+            }
+            uint4* dst = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(Cv) + m * ldc + nb);
+#pragma unroll
+            for (int v = 0; v < 4; ++v)
+              dst[v] = make_uint4(packed[4 * v], packed[4 * v + 1], packed[4 * v + 2], packed[4 * v + 3]);
+          } else {
+            float* dst = static_cast<float*>(Cv) + m * ldc + nb;
+            if (OUT == 3) {
+#pragma unroll
+              for (int x = 0; x < 32; ++x) atomicAdd(dst + x, __uint_as_float(r[x]));
+            } else {
+#pragma unroll
+              for (int x = 0; x < 32; x += 4) {
+                float4 v = make_float4(__uint_as_float(r[x]), __uint_as_float(r[x + 1]), __uint_as_float(r[x + 2]),
+                                       __uint_as_float(r[x + 3]));
+                float4* d4 = reinterpret_cast<float4*>(dst + x);
+                if (OUT == 2) {
+                  const float4 o = *d4;
+                  v.x += o.x, v.y += o.y, v.z += o.z, v.w += o.w;
+                }
+                *d4 = v;
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc(tmem, 256);
+}
+
+int launch_gemm_tc2(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* W, int64_t ldw, const float* bias, void* C,
+                    int64_t ldc, int64_t M, int N, int K, int out_mode, int splits, cudaStream_t st) {
+  PENEO_REQUIRE(N % 32 == 0 && K >= 1, "gemm_tc2: N %% 32 required (N=%d K=%d)", N, K);
+  PENEO_REQUIRE(lda % 8 == 0 && ldw % 8 == 0 && ldc % (out_mode == 0 ? 8 : 4) == 0,
+                "gemm_tc2: leading dimensions not vector aligned (lda=%lld ldw=%lld ldc=%lld)", (long long)lda, (long long)ldw,
+                (long long)ldc);
+  PENEO_REQUIRE(out_mode >= 0 && out_mode <= 3 && (out_mode == 3 || splits == 1), "gemm_tc2: bad output mode / splits");
+  if (M == 0) return PENEO_OK;
+  alignas(64) CUtensorMap tmA, tmW;
+  int rc;
+  if ((rc = make_tensor_map_bf16(&tmA, A, K, M, lda * 2, 64, 128)) != PENEO_OK) return rc;
+  if ((rc = make_tensor_map_bf16(&tmW, W, K, N, ldw * 2, 64, 128)) != PENEO_OK) return rc;
+  const int num_k = (K + 63) / 64;
+  splits = std::max(1, std::min(splits, num_k));
+  const int kb_per_split = (num_k + splits - 1) / splits;
+  splits = (num_k + kb_per_split - 1) / kb_per_split;
+  const int n_blocks = (N + 127) / 128;
+  const int64_t items = ((M + 127) / 128) * n_blocks * splits;
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    PENEO_CUDA_TRY(cudaGetDevice(&dev));
+    PENEO_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const int grid = static_cast<int>(std::min<int64_t>(items, sms));
+#define GO(OUT)                                                                                                      \
+  {                                                                                                                  \
+    static bool attr_set = false;                                                                                    \
+    if (!attr_set) {                                                                                                 \
+      PENEO_CUDA_TRY(cudaFuncSetAttribute(gemm_tc2_kernel<OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kG2Smem)); \
+      attr_set = true;                                                                                               \
+    }                                                                                                                \
+    gemm_tc2_kernel<OUT><<<grid, 192, kG2Smem, st>>>(tmA, tmW, bias, C, ldc, M, N, K, kb_per_split, splits, n_blocks,  \
+                                                     items);                                                         \
+  }
+  switch (out_mode) {
+    case 0: GO(0) break;
+    case 1: GO(1) break;
+    case 2: GO(2) break;
+    default: GO(3) break;
+  }
+#undef GO
+  PENEO_CUDA_TRY(cudaGetLastError());
+  return PENEO_OK;
+}
+
 }  // namespace peneo

@@ -17,6 +17,10 @@ int launch_pair_heads_simt(const peneo_dims& dm, const void* pack, const float* 
 int launch_gemm_tc(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* W, int64_t ldw, const float* bias,
                    __nv_bfloat16* C, int64_t ldc, int64_t M, int N, int K, int act, cudaStream_t st);
 
+// C[M, N] (op)= A W^T ; out_mode 0 bf16 store (+bias), 1 fp32 store, 2 fp32 +=, 3 fp32 atomicAdd with split-K
+int launch_gemm_tc2(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* W, int64_t ldw, const float* bias, void* C,
+                    int64_t ldc, int64_t M, int N, int K, int out_mode, int splits, cudaStream_t st);
+
 // pair_heads_tc.cu
 int launch_pair_heads_tc(const void* pack, const PackLayout& L, const __nv_bfloat16* ab, int batch, int n,
                          float* const logits[kNumHeads], cudaStream_t st);
@@ -40,10 +44,10 @@ int launch_pair_loss_ohem_bwd(int batch, int n, const float* const logits[kNumHe
                               float* const dlogits[kNumHeads], cudaStream_t st);
 
 // train.cu
-size_t heads_bwd_workspace_bytes(const peneo_dims& dm, int batch, int n);
-int launch_heads_bwd_fp32(const peneo_dims& dm, const void* pack, const void* x, int x_dtype, int64_t x_row_stride,
-                          int batch, int n, const float* const dlogits[kNumHeads], const peneo_grads& gr, float* dx,
-                          void* workspace, cudaStream_t st);
+size_t heads_bwd_workspace_bytes(const peneo_dims& dm, int prec, int batch, int n);
+int launch_heads_bwd(const peneo_dims& dm, int prec, const void* pack, const void* x, int x_dtype, int64_t x_row_stride,
+                     int batch, int n, const float* const dlogits[kNumHeads], const peneo_grads& gr, float* dx,
+                     void* workspace, cudaStream_t st);
 
 // decode.cu
 size_t decode_spots_workspace_bytes(int batch, int n);

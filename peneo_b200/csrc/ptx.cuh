@@ -101,6 +101,19 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
   d |= static_cast<uint64_t>(2) << 61;                     // SWIZZLE_128B
   return d;
 }
+// Shared-memory matrix descriptor, MN-major operand (the MN index is contiguous in memory), SWIZZLE_128B:
+// 64-element (128 B) rows indexed by K; 8 K-rows form a 1024-B swizzle atom; `sbo_bytes` is the distance
+// between consecutive 8-row atoms along K, `lbo_bytes` the distance between consecutive 64-element blocks
+// along MN (canonical layout ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units).
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
 // Instruction descriptor for kind::f16, bf16 x bf16 -> fp32, both operands K-major.
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(uint32_t M, uint32_t N) {
   return (1u << 4)            // D format: f32
@@ -108,6 +121,11 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(uint32_t M, uint32_t N) {
          | (1u << 10)         // B format: bf16
          | ((N >> 3) << 17)   // N
          | ((M >> 4) << 24);  // M
+}
+
+// same, with the majorness of each operand: bit 15 = A is MN-major, bit 16 = B is MN-major
+__host__ __device__ constexpr uint32_t umma_idesc_bf16_major(uint32_t M, uint32_t N, bool a_mn, bool b_mn) {
+  return umma_idesc_bf16(M, N) | (a_mn ? (1u << 15) : 0u) | (b_mn ? (1u << 16) : 0u);
 }
 
 // D[tmem] (+)= A[smem] * B[smem]^T

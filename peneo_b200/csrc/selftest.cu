@@ -3,6 +3,7 @@
 #include <cuda.h>
 
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -77,6 +78,67 @@ __global__ void __launch_bounds__(128, 1)
   if (warp == 0) ptx::tmem_dealloc(tmem, 512);
 }
 
+// D[128, N] = sum_k At[k, m] Bt[k, n]: both operands MN-major, loaded as [64 k-rows x 64 cols] SWIZZLE_128B boxes.
+// At: [K, 128], Bt: [K, N] row-major; K = 64 * kblocks.  `swap` exchanges the roles of LBO / SBO (diagnostic).
+__global__ void __launch_bounds__(128, 1)
+    mn_mma_test_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                       float* __restrict__ d_out, int N, int kblocks, int swap) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ uint64_t bar_full, bar_done;
+  __shared__ uint32_t tmem_slot;
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  if (threadIdx.x == 0) {
+    ptx::mbar_init(&bar_full, 1);
+    ptx::mbar_init(&bar_done, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 0) {
+    ptx::tmem_alloc(&tmem_slot, 512);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  const int nbB = N / 64;                        // 64-column blocks of B
+  const uint32_t blk = 64 * 128;                 // one [64 k x 64 col] box = 8 KB
+  const uint32_t stage = (2 + nbB) * blk;        // per k-block: 2 A boxes then nbB B boxes
+  if (threadIdx.x == 0) {
+    ptx::mbar_arrive_expect_tx(&bar_full, stage * kblocks);
+    for (int kb = 0; kb < kblocks; ++kb) {
+      unsigned char* st = smem + kb * stage;
+      for (int mb = 0; mb < 2; ++mb) ptx::tma_load_2d(st + mb * blk, &tmA, &bar_full, mb * 64, kb * 64);
+      for (int nb = 0; nb < nbB; ++nb) ptx::tma_load_2d(st + (2 + nb) * blk, &tmB, &bar_full, nb * 64, kb * 64);
+    }
+    ptx::mbar_wait(&bar_full, 0);
+    ptx::tc_fence_after();
+    const uint32_t idesc = ptx::umma_idesc_bf16_major(128, N, true, true);
+    const uint32_t lbo = swap ? 1024u : blk, sbo = swap ? blk : 1024u;
+    for (int kb = 0; kb < kblocks; ++kb)
+      for (int ks = 0; ks < 4; ++ks) {
+        const uint32_t a = ptx::smem_u32(smem + kb * stage) + ks * 2048;
+        const uint32_t b = ptx::smem_u32(smem + kb * stage + 2 * blk) + ks * 2048;
+        ptx::umma_ss(tmem, ptx::umma_desc_mn_sw128(a, lbo, sbo), ptx::umma_desc_mn_sw128(b, lbo, sbo), idesc,
+                     (kb | ks) != 0);
+      }
+    ptx::tc_commit(&bar_done);
+  }
+  ptx::mbar_wait(&bar_done, 0);
+  ptx::tc_fence_after();
+  const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
+  const int row = warp * 32 + lane;
+  for (int c0 = 0; c0 < N; c0 += 16) {
+    uint32_t r[16];
+    ptx::tmem_ld_x16(tmem + lane_base + c0, r);
+    ptx::tmem_ld_wait();
+    for (int x = 0; x < 16; ++x) d_out[row * N + c0 + x] = __uint_as_float(r[x]);
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) ptx::tmem_dealloc(tmem, 512);
+}
+
 static float bf16_round(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
 static uint16_t bf16_bits(float v) {
   __nv_bfloat16 b = __float2bfloat16_rn(v);
@@ -138,6 +200,46 @@ static int check_ts(int N, int kblocks, double& max_err, std::string& note) {
   return PENEO_OK;
 }
 
+static int check_mn(int N, int kblocks, int swap, double& max_err) {
+  const int K = 64 * kblocks;
+  Lcg rng{4242ull + N * 17 + kblocks};
+  std::vector<float> A((size_t)K * 128), B((size_t)K * N);
+  for (auto& v : A) v = bf16_round(rng.next());
+  for (auto& v : B) v = bf16_round(rng.next());
+  std::vector<uint16_t> ab(A.size()), bb(B.size());
+  for (size_t i = 0; i < A.size(); ++i) ab[i] = bf16_bits(A[i]);
+  for (size_t i = 0; i < B.size(); ++i) bb[i] = bf16_bits(B[i]);
+  uint16_t *d_a = nullptr, *d_b = nullptr;
+  float* d_d = nullptr;
+  PENEO_CUDA_TRY(cudaMalloc(&d_a, ab.size() * 2));
+  PENEO_CUDA_TRY(cudaMalloc(&d_b, bb.size() * 2));
+  PENEO_CUDA_TRY(cudaMalloc(&d_d, 128 * N * 4));
+  PENEO_CUDA_TRY(cudaMemcpy(d_a, ab.data(), ab.size() * 2, cudaMemcpyHostToDevice));
+  PENEO_CUDA_TRY(cudaMemcpy(d_b, bb.data(), bb.size() * 2, cudaMemcpyHostToDevice));
+  PENEO_CUDA_TRY(cudaMemset(d_d, 0xFF, 128 * N * 4));
+  alignas(64) CUtensorMap tmA, tmB;
+  int rc;
+  if ((rc = make_tensor_map_bf16(&tmA, d_a, 128, K, 128 * 2, 64, 64)) != PENEO_OK) return rc;
+  if ((rc = make_tensor_map_bf16(&tmB, d_b, N, K, N * 2, 64, 64)) != PENEO_OK) return rc;
+  const int smem = (2 + N / 64) * 64 * 128 * kblocks + 1024;
+  PENEO_CUDA_TRY(cudaFuncSetAttribute(mn_mma_test_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  mn_mma_test_kernel<<<1, 128, smem>>>(tmA, tmB, d_d, N, kblocks, swap);
+  PENEO_CUDA_TRY(cudaGetLastError());
+  PENEO_CUDA_TRY(cudaDeviceSynchronize());
+  std::vector<float> D(128 * N);
+  PENEO_CUDA_TRY(cudaMemcpy(D.data(), d_d, D.size() * 4, cudaMemcpyDeviceToHost));
+  cudaFree(d_a), cudaFree(d_b), cudaFree(d_d);
+  max_err = 0.0;
+  for (int m = 0; m < 128; ++m)
+    for (int c = 0; c < N; ++c) {
+      double ref = 0.0;
+      for (int k = 0; k < K; ++k) ref += static_cast<double>(A[(size_t)k * 128 + m]) * B[(size_t)k * N + c];
+      const double e = std::fabs(ref - D[m * N + c]);
+      if (!(e <= max_err)) max_err = e;
+    }
+  return PENEO_OK;
+}
+
 static int check_ss(int M, int N, int K, double& max_err) {
   Lcg rng{777ull + M + N * 3 + K * 7};
   std::vector<float> A((size_t)M * K), W((size_t)N * K), bias(N);
@@ -188,16 +290,23 @@ int run_selftest(uint32_t* failed_mask, char* report, size_t report_bytes) {
       {"ss_gemm_128x128x64", 0, 128, 128, 64, 1e-2},   {"ss_gemm_200x256x384", 0, 200, 256, 384, 1e-2},
       {"ts_mma_n128_k64", 1, 128, 1, 0, 1e-3},          {"ts_mma_n128_k384", 1, 128, 6, 0, 2e-3},
       {"ts_mma_n16_k128", 1, 16, 2, 0, 1e-3},
+      {"mn_major_n128_k64", 2, 128, 1, 0, 1e-3},         {"mn_major_n256_k192", 2, 256, 3, 0, 2e-3},
   };
   int idx = 0;
   for (auto& cs : cases) {
     double err = 0.0;
     std::string note;
-    int rc = cs.kind == 0 ? check_ss(cs.a, cs.b, cs.c, err) : check_ts(cs.a, cs.b, err, note);
+    int rc = cs.kind == 0 ? check_ss(cs.a, cs.b, cs.c, err)
+             : cs.kind == 1 ? check_ts(cs.a, cs.b, err, note)
+                            : check_mn(cs.a, cs.b, cs.c, err);
+    if (cs.kind == 2 && rc == PENEO_OK && !(err <= cs.tol) && getenv("PENEO_SELFTEST_MN_SWAP")) {
+      double err2 = 0.0;  // diagnostic: LBO / SBO exchanged
+      if (check_mn(cs.a, cs.b, 1, err2) == PENEO_OK) note = " (swapped LBO/SBO: max_err=" + std::to_string(err2) + ")";
+    }
     bool ok = rc == PENEO_OK && err <= cs.tol;
     if (!ok) mask |= 1u << idx;
-    snprintf(line, sizeof line, "%-24s %s max_err=%.3e%s%s\n", cs.name, ok ? "ok  " : "FAIL", err,
-             rc != PENEO_OK ? " error: " : "", rc != PENEO_OK ? get_error() : "");
+    snprintf(line, sizeof line, "%-24s %s max_err=%.3e%s%s%s\n", cs.name, ok ? "ok  " : "FAIL", err,
+             rc != PENEO_OK ? " error: " : "", rc != PENEO_OK ? get_error() : "", note.c_str());
     rep += line;
     if (rc == PENEO_E_CUDA) {  // sticky CUDA error: stop, later checks would only echo it
       for (int rest = idx + 1; rest < (int)(sizeof cases / sizeof cases[0]); ++rest) mask |= 1u << rest;

@@ -117,6 +117,15 @@ __global__ void pack_bf16_kernel(const float* __restrict__ src, int64_t ld, int 
     dst[e] = __float2bfloat16_rn(scale * src[(int64_t)r * ld + col0 + c]);
   }
 }
+// dst[c, r] = bf16(src[r * ld + c])   (transpose of a [rows, cols] matrix)
+__global__ void pack_bf16_T_kernel(const float* __restrict__ src, int64_t ld, __nv_bfloat16* __restrict__ dst, int rows,
+                                   int cols) {
+  const int64_t total = (int64_t)rows * cols;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int c = static_cast<int>(e / rows), r = static_cast<int>(e % rows);
+    dst[e] = __float2bfloat16_rn(src[(int64_t)r * ld + c]);
+  }
+}
 __global__ void pack_f32_kernel(const float* __restrict__ src, float* __restrict__ dst, int64_t n, float scale) {
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x)
     dst[e] = src ? scale * src[e] : 0.f;
@@ -196,6 +205,22 @@ int pack_weights_impl(const peneo_dims& dm, int prec, const peneo_params& P, voi
     pack_wout_kernel<<<(15 * 16 * 128 + 255) / 256, 256, 0, st>>>(
         wp, reinterpret_cast<__nv_bfloat16*>(base + L.wout_bf16), reinterpret_cast<float*>(base + L.bout), d);
     PENEO_CUDA_TRY(cudaGetLastError());
+    // operands of the backward pass
+    for (int h = 0; h < kNumHeads; ++h) {
+      TRY(bf(P.mid_w[h * 8], d, 0, L.wmid_full_bf16 + (size_t)h * d * d * 2, d, d, 1.f));
+      pack_bf16_T_kernel<<<(d * d + 255) / 256, 256, 0, st>>>(
+          P.mid_w[h * 8], d, reinterpret_cast<__nv_bfloat16*>(base + L.wmidT_bf16 + (size_t)h * d * d * 2), d, d);
+      PENEO_CUDA_TRY(cudaGetLastError());
+      TRY(f32(P.mid_b[h * 8], L.bmid_full + (size_t)h * d * 4, d, 1.f));
+      TRY(f32(P.out_w[h], L.f_out_w[h], (int64_t)head_classes(h) * d, 1.f));
+      TRY(f32(P.out_b[h], L.f_out_b[h], head_classes(h), 1.f));
+    }
+    TRY(f32(P.shrink_w1, L.f_w1, (int64_t)hid * hin, 1.f));
+    TRY(f32(P.shrink_b1, L.f_b1, hid, 1.f));
+    TRY(f32(P.shrink_w2, L.f_w2, (int64_t)d * hid, 1.f));
+    TRY(f32(P.shrink_b2, L.f_b2, d, 1.f));
+    TRY(f32(P.combine_w, L.f_wc, (int64_t)d * 2 * d, 1.f));
+    TRY(f32(P.combine_b, L.f_bc, d, 1.f));
   }
 #undef TRY
   return PENEO_OK;

@@ -235,30 +235,32 @@ __global__ void __launch_bounds__(128) out_only_bwd_kernel(const float* __restri
   }
 }
 
-// G = dH * SiLU'(U) (in place over dH) ; db += column sums.  128 rows per CTA.
+// G = dH * SiLU'(U) (in place over dH) ; db += column sums.  Grid: (row blocks of 32, column blocks of 128).
 __global__ void __launch_bounds__(128) act_bwd_kernel(float* __restrict__ dH, const float* __restrict__ U, int rows,
                                                       int d, int64_t ld_dh, int64_t ld_u, float* __restrict__ db) {
-  const int r0 = blockIdx.x * 128, nr = min(128, rows - r0);
-  for (int f = threadIdx.x; f < d; f += 128) {
-    float acc = 0.f;
-    for (int r = 0; r < nr; ++r) {
-      const float g = dH[(int64_t)(r0 + r) * ld_dh + f] * dsilu_exact(U[(int64_t)(r0 + r) * ld_u + f]);
-      dH[(int64_t)(r0 + r) * ld_dh + f] = g;
-      acc += g;
-    }
-    if (db) atomicAdd(&db[f], acc);
+  const int r0 = blockIdx.x * 32, nr = min(32, rows - r0);
+  const int f = blockIdx.y * 128 + threadIdx.x;
+  if (f >= d) return;
+  float acc = 0.f;
+#pragma unroll 8
+  for (int r = 0; r < nr; ++r) {
+    const float g = dH[(int64_t)(r0 + r) * ld_dh + f] * dsilu_exact(U[(int64_t)(r0 + r) * ld_u + f]);
+    dH[(int64_t)(r0 + r) * ld_dh + f] = g;
+    acc += g;
   }
+  if (db) atomicAdd(&db[f], acc);
 }
 
-// column sums of X[rows, d] (ld) into out[d] (atomic)
+// column sums of X[rows, d] (ld) into out[d] (atomic); same grid
 __global__ void __launch_bounds__(128) colsum_kernel(const float* __restrict__ X, int rows, int d, int64_t ld,
                                                      float* __restrict__ out) {
-  const int r0 = blockIdx.x * 128, nr = min(128, rows - r0);
-  for (int f = threadIdx.x; f < d; f += 128) {
-    float acc = 0.f;
-    for (int r = 0; r < nr; ++r) acc += X[(int64_t)(r0 + r) * ld + f];
-    atomicAdd(&out[f], acc);
-  }
+  const int r0 = blockIdx.x * 32, nr = min(32, rows - r0);
+  const int f = blockIdx.y * 128 + threadIdx.x;
+  if (f >= d) return;
+  float acc = 0.f;
+#pragma unroll 8
+  for (int r = 0; r < nr; ++r) acc += X[(int64_t)(r0 + r) * ld + f];
+  atomicAdd(&out[f], acc);
 }
 
 // g_v = dS * SiLU'(a_i + b_j), in place
@@ -272,26 +274,146 @@ __global__ void gv_kernel(float* __restrict__ dS, const float* __restrict__ ab, 
 }
 
 // dA[t] = sum_{j >= t} g_v(t, j) for pair-rows t in [i0, i1) ; dBm[t] += sum_{i in [i0, min(t, i1-1)]} g_v(i, t).
-// One CTA per token t of the document; deterministic (no atomics).
+// Grid: (token t of the document, column blocks of 128); deterministic (no atomics).
 __global__ void __launch_bounds__(128) gv_reduce_kernel(const float* __restrict__ gv, int b, int n, int d, int i0, int i1,
                                                         float* __restrict__ dab) {
   const int t = blockIdx.x;
+  const int f = blockIdx.y * 128 + threadIdx.x;
+  if (f >= d) return;
   const int p0 = row_start(i0, n);
   float* out = dab + ((int64_t)b * n + t) * 2 * d;
-  for (int f = threadIdx.x; f < d; f += 128) {
-    if (t >= i0 && t < i1) {
-      const float* src = gv + (int64_t)(row_start(t, n) - p0) * d + f;
-      float acc = 0.f;
-      for (int j = t; j < n; ++j) acc += src[(int64_t)(j - t) * d];
-      out[f] = acc;
+  if (t >= i0 && t < i1) {
+    const float* src = gv + (int64_t)(row_start(t, n) - p0) * d + f;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    int j = t;
+    for (; j + 3 < n; j += 4) {
+      a0 += src[(int64_t)(j - t) * d], a1 += src[(int64_t)(j + 1 - t) * d];
+      a2 += src[(int64_t)(j + 2 - t) * d], a3 += src[(int64_t)(j + 3 - t) * d];
     }
-    const int ihi = min(t, i1 - 1);
-    if (ihi >= i0) {
-      float acc = 0.f;
-      for (int i = i0; i <= ihi; ++i) acc += gv[(int64_t)(row_start(i, n) - p0 + (t - i)) * d + f];
-      out[d + f] += acc;
+    for (; j < n; ++j) a0 += src[(int64_t)(j - t) * d];
+    out[f] = (a0 + a1) + (a2 + a3);
+  }
+  const int ihi = min(t, i1 - 1);
+  if (ihi >= i0) {
+    float a0 = 0.f, a1 = 0.f;
+    int i = i0;
+    for (; i + 1 <= ihi; i += 2) {
+      a0 += gv[(int64_t)(row_start(i, n) - p0 + (t - i)) * d + f];
+      a1 += gv[(int64_t)(row_start(i + 1, n) - p0 + (t - i - 1)) * d + f];
+    }
+    if (i <= ihi) a0 += gv[(int64_t)(row_start(i, n) - p0 + (t - i)) * d + f];
+    out[d + f] += a0 + a1;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// bf16 / tcgen05 pair part (PENEO_PREC_BF16: d == 384, num_layers == 2).  Same algorithm, but the three
+// [rows x 384] GEMMs of every head run on the tensor cores (gemm_tc2) with bf16 operands:
+//   U   = S W_mid^T + b            A = S   [rows, d]      W = W_mid   [d_out, d_in]      -> bf16
+//   dW += G^T S                    A = G^T [d, rows]      W = S^T     [d, rows]          -> fp32 atomic, split-K
+//   dS += G W_mid                  A = G   [rows, d]      W = W_mid^T [d_in, d_out]      -> fp32 (+)=
+// so the element-wise kernels emit every activation twice: row-major and transposed.
+// ------------------------------------------------------------------------------------------------
+constexpr int kD16 = 384;
+constexpr int kSubRows = 32;
+
+// S and S^T (ld = ldt) of the chunk; one CTA per 32 rows, 256 threads
+__global__ void __launch_bounds__(256) build_s_bf16_kernel(const float* __restrict__ ab, int b, int n, int p0, int rows,
+                                                           __nv_bfloat16* __restrict__ S, __nv_bfloat16* __restrict__ ST,
+                                                           int64_t ldt) {
+  __shared__ __nv_bfloat16 tile[kSubRows][kD16 + 8];
+  const int r0 = blockIdx.x * kSubRows, nr = min(kSubRows, rows - r0);
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  for (int r = warp; r < kSubRows; r += 8) {
+    if (r < nr) {
+      int i, j;
+      pair_from_flat(p0 + r0 + r, n, i, j);
+      const float* ai = ab + ((int64_t)b * n + i) * 2 * kD16;
+      const float* bj = ab + ((int64_t)b * n + j) * 2 * kD16 + kD16;
+      for (int f = 2 * lane; f < kD16; f += 64) {
+        const float2 a2 = *reinterpret_cast<const float2*>(ai + f), b2 = *reinterpret_cast<const float2*>(bj + f);
+        const __nv_bfloat162 v = __floats2bfloat162_rn(silu_exact(a2.x + b2.x), silu_exact(a2.y + b2.y));
+        *reinterpret_cast<__nv_bfloat162*>(&tile[r][f]) = v;
+        *reinterpret_cast<__nv_bfloat162*>(S + (int64_t)(r0 + r) * kD16 + f) = v;
+      }
+    } else {
+      for (int f = 2 * lane; f < kD16; f += 64) *reinterpret_cast<__nv_bfloat162*>(&tile[r][f]) = __floats2bfloat162_rn(0.f, 0.f);
     }
   }
+  __syncthreads();
+  // transposed store: 4 threads per feature row, 8 rows (16 B) each
+  for (int e = threadIdx.x; e < kD16 * 4; e += 256) {
+    const int f = e / 4, q = e % 4;
+    if (r0 + q * 8 >= rows) continue;
+    alignas(16) __nv_bfloat16 v[8];
+#pragma unroll
+    for (int x = 0; x < 8; ++x) v[x] = tile[q * 8 + x][f];
+    *reinterpret_cast<uint4*>(ST + (int64_t)f * ldt + r0 + q * 8) = *reinterpret_cast<const uint4*>(v);
+  }
+}
+
+// Last hidden layer + output layer of one head from bf16 pre-activations U:
+//   m = SiLU(U) ; G = (dz W_out) * SiLU'(U) -> G (row-major) and G^T ; dW_out += dz^T m ; db_out, db_mid
+// 192 threads, two adjacent features each (bf16x2 accesses); one CTA walks `sub_per_cta` consecutive
+// 32-row sub-tiles so that the fp32 atomics are amortised.
+template <int C>
+__global__ void __launch_bounds__(192) head_out_bwd_bf16_kernel(const __nv_bfloat16* __restrict__ U,
+                                                                const float* __restrict__ dz,
+                                                                const float* __restrict__ Wout, int rows, int sub_per_cta,
+                                                                __nv_bfloat16* __restrict__ G,
+                                                                __nv_bfloat16* __restrict__ GT, int64_t ldt,
+                                                                float* __restrict__ dWout, float* __restrict__ dbout,
+                                                                float* __restrict__ dbmid) {
+  __shared__ __nv_bfloat16 tile[kSubRows][kD16 + 8];
+  __shared__ float sdz[kSubRows][C];
+  const int f = 2 * threadIdx.x;
+  float w0[C], w1[C], aw0[C], aw1[C], ab0 = 0.f, ab1 = 0.f, dzsum = 0.f;
+#pragma unroll
+  for (int c = 0; c < C; ++c) w0[c] = Wout[c * kD16 + f], w1[c] = Wout[c * kD16 + f + 1], aw0[c] = 0.f, aw1[c] = 0.f;
+  for (int sub = 0; sub < sub_per_cta; ++sub) {
+    const int r0 = (blockIdx.x * sub_per_cta + sub) * kSubRows;
+    if (r0 >= rows) break;
+    const int nr = min(kSubRows, rows - r0);
+    __syncthreads();  // previous sub-tile's transposed store is done with `tile` / `sdz`
+    for (int e = threadIdx.x; e < kSubRows * C; e += 192) sdz[e / C][e % C] = e < nr * C ? dz[(int64_t)r0 * C + e] : 0.f;
+    __syncthreads();
+    if (threadIdx.x < C)
+      for (int r = 0; r < nr; ++r) dzsum += sdz[r][threadIdx.x];
+#pragma unroll 8
+    for (int r = 0; r < kSubRows; ++r) {
+      __nv_bfloat162 gb = __floats2bfloat162_rn(0.f, 0.f);
+      if (r < nr) {
+        const float2 u = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(U + (int64_t)(r0 + r) * kD16 + f));
+        const float s0 = sigmoid_exact(u.x), s1 = sigmoid_exact(u.y);
+        const float m0 = u.x * s0, m1 = u.y * s1;
+        float g0 = 0.f, g1 = 0.f;
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+          const float z = sdz[r][c];
+          g0 = fmaf(z, w0[c], g0), g1 = fmaf(z, w1[c], g1);
+          aw0[c] = fmaf(z, m0, aw0[c]), aw1[c] = fmaf(z, m1, aw1[c]);
+        }
+        gb = __floats2bfloat162_rn(g0 * (s0 * (1.0f + u.x * (1.0f - s0))), g1 * (s1 * (1.0f + u.y * (1.0f - s1))));
+        *reinterpret_cast<__nv_bfloat162*>(G + (int64_t)(r0 + r) * kD16 + f) = gb;
+        const float2 gf = __bfloat1622float2(gb);  // bias gradient of exactly what the GEMMs will see
+        ab0 += gf.x, ab1 += gf.y;
+      }
+      *reinterpret_cast<__nv_bfloat162*>(&tile[r][f]) = gb;
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < kD16 * 4; e += 192) {
+      const int ff = e / 4, q = e % 4;
+      if (r0 + q * 8 >= rows) continue;
+      alignas(16) __nv_bfloat16 v[8];
+#pragma unroll
+      for (int x = 0; x < 8; ++x) v[x] = tile[q * 8 + x][ff];
+      *reinterpret_cast<uint4*>(GT + (int64_t)ff * ldt + r0 + q * 8) = *reinterpret_cast<const uint4*>(v);
+    }
+  }
+  if (threadIdx.x < C) atomicAdd(&dbout[threadIdx.x], dzsum);
+#pragma unroll
+  for (int c = 0; c < C; ++c) atomicAdd(&dWout[c * kD16 + f], aw0[c]), atomicAdd(&dWout[c * kD16 + f + 1], aw1[c]);
+  atomicAdd(&dbmid[f], ab0), atomicAdd(&dbmid[f + 1], ab1);
 }
 
 inline size_t fl(size_t n) { return align_up(n * sizeof(float), 1024); }
@@ -302,16 +424,20 @@ struct Plan {
   int nU, nH;          // per-chunk [rows, d] buffers for pre-activations / hidden activations
   size_t off_x, off_u1, off_y1, off_u2, off_y, off_ab, off_dab, off_dy, off_dy1;
   size_t off_S, off_dS, off_G, off_U, off_H;
+  // bf16 pair part: row-major and transposed (ld = ldt) bf16 activations
+  size_t off_S16, off_ST16, off_U16, off_G16, off_GT16;
+  int64_t ldt;
   size_t total;
 };
 
-Plan make_plan(const peneo_dims& dm, int batch, int n) {
+Plan make_plan(const peneo_dims& dm, int prec, int batch, int n) {
   Plan p{};
   p.tokens = (int64_t)batch * n;
   const size_t T = p.tokens, d = dm.d, hid = dm.shrink ? dm.hid : 0, hin = dm.hin;
   p.nU = dm.num_layers - 1;
   p.nH = dm.num_layers >= 3 ? dm.num_layers - 2 : 0;
-  const int nbuf = 3 + p.nU + p.nH;  // S, dS, G
+  const bool tc = prec == PENEO_PREC_BF16;
+  const int nbuf = tc ? 4 : 3 + p.nU + p.nH;  // fp32: S, dS, G, U.., H.. ; bf16: dS (fp32) + 5 half-size buffers
   // ~512 MB of pair buffers, but never less than one full pair row (n pairs)
   int64_t rows = (int64_t)(512ull << 20) / ((int64_t)nbuf * d * 4);
   rows = std::min<int64_t>(rows, 65536);
@@ -331,22 +457,32 @@ Plan make_plan(const peneo_dims& dm, int batch, int n) {
   p.off_ab = take(fl(T * 2 * d)), p.off_dab = take(fl(T * 2 * d));
   p.off_dy = take(fl(T * d)), p.off_dy1 = take(fl(T * hid));
   const size_t cb = fl((size_t)rows * d);
-  p.off_S = take(cb), p.off_dS = take(cb), p.off_G = take(cb);
-  p.off_U = take(cb * p.nU), p.off_H = take(cb * p.nH);
+  p.off_dS = take(cb);
+  if (tc) {
+    p.ldt = (rows + 63) / 64 * 64;
+    const size_t hb = align_up((size_t)p.ldt * d * 2, 1024);
+    p.off_S16 = take(hb), p.off_ST16 = take(hb), p.off_U16 = take(hb), p.off_G16 = take(hb), p.off_GT16 = take(hb);
+  } else {
+    p.off_S = take(cb), p.off_G = take(cb);
+    p.off_U = take(cb * p.nU), p.off_H = take(cb * p.nH);
+  }
   p.total = off + 1024;
   return p;
 }
 
 }  // namespace
 
-size_t heads_bwd_workspace_bytes(const peneo_dims& dm, int batch, int n) { return make_plan(dm, batch, n).total; }
+size_t heads_bwd_workspace_bytes(const peneo_dims& dm, int prec, int batch, int n) {
+  return make_plan(dm, prec, batch, n).total;
+}
 
-int launch_heads_bwd_fp32(const peneo_dims& dm, const void* pack, const void* x, int x_dtype, int64_t x_row_stride,
-                          int batch, int n, const float* const dlogits[kNumHeads], const peneo_grads& gr, float* dx,
-                          void* workspace, cudaStream_t st) {
-  const PackLayout L = pack_layout(dm, PENEO_PREC_FP32);
+int launch_heads_bwd(const peneo_dims& dm, int prec, const void* pack, const void* x, int x_dtype, int64_t x_row_stride,
+                     int batch, int n, const float* const dlogits[kNumHeads], const peneo_grads& gr, float* dx,
+                     void* workspace, cudaStream_t st) {
+  const PackLayout L = pack_layout(dm, prec);
+  const bool tc = prec == PENEO_PREC_BF16;
   const char* pk = static_cast<const char*>(pack);
-  const Plan pl = make_plan(dm, batch, n);
+  const Plan pl = make_plan(dm, prec, batch, n);
   char* ws = static_cast<char*>(workspace);
   const int d = dm.d, hid = dm.hid, hin = dm.hin, T = static_cast<int>(pl.tokens), NL = dm.num_layers;
   const int64_t P = pair_count(n);
@@ -419,9 +555,38 @@ int launch_heads_bwd_fp32(const peneo_dims& dm, const void* pack, const void* x,
       int i1 = i0 + 1;
       while (i1 < n && row_start(i1 + 1, n) - row_start(i0, n) <= pl.chunk_rows_max) ++i1;
       const int p0 = row_start(i0, n), rows = row_start(i1, n) - p0;  // row_start(n, n) == P
+      const int rb = (rows + 127) / 128;
+      if (tc) {
+        __nv_bfloat16* S16 = reinterpret_cast<__nv_bfloat16*>(ws + pl.off_S16);
+        __nv_bfloat16* ST16 = reinterpret_cast<__nv_bfloat16*>(ws + pl.off_ST16);
+        __nv_bfloat16* U16 = reinterpret_cast<__nv_bfloat16*>(ws + pl.off_U16);
+        __nv_bfloat16* G16 = reinterpret_cast<__nv_bfloat16*>(ws + pl.off_G16);
+        __nv_bfloat16* GT16 = reinterpret_cast<__nv_bfloat16*>(ws + pl.off_GT16);
+        const int nsub = (rows + kSubRows - 1) / kSubRows;
+        build_s_bf16_kernel<<<nsub, 256, 0, st>>>(ab, b, n, p0, rows, S16, ST16, pl.ldt);
+        PENEO_CUDA_TRY(cudaGetLastError());
+        const int sub_per_cta = std::max(1, (nsub + 1183) / 1184);
+        const int ctas = (nsub + sub_per_cta - 1) / sub_per_cta;
+        const int splits = std::max(1, std::min((rows + 63) / 64, 296 / 9));
+        for (int h = 0; h < kNumHeads; ++h) {
+          const int C = head_classes(h);
+          const float* dz = dlogits[h] + ((int64_t)b * P + p0) * C;
+          const __nv_bfloat16* Wm = reinterpret_cast<const __nv_bfloat16*>(pk + L.wmid_full_bf16) + (size_t)h * d * d;
+          const __nv_bfloat16* WmT = reinterpret_cast<const __nv_bfloat16*>(pk + L.wmidT_bf16) + (size_t)h * d * d;
+          TRY(launch_gemm_tc2(S16, d, Wm, d, W(L.bmid_full) + (size_t)h * d, U16, d, rows, d, d, 0, 1, st));
+          if (C == 2)
+            head_out_bwd_bf16_kernel<2><<<ctas, 192, 0, st>>>(U16, dz, W(L.f_out_w[h]), rows, sub_per_cta, G16, GT16, pl.ldt,
+                                                              gr.out_w[h], gr.out_b[h], gr.mid_b[h * 8]);
+          else
+            head_out_bwd_bf16_kernel<3><<<ctas, 192, 0, st>>>(U16, dz, W(L.f_out_w[h]), rows, sub_per_cta, G16, GT16, pl.ldt,
+                                                              gr.out_w[h], gr.out_b[h], gr.mid_b[h * 8]);
+          PENEO_CUDA_TRY(cudaGetLastError());
+          TRY(launch_gemm_tc2(GT16, pl.ldt, ST16, pl.ldt, nullptr, gr.mid_w[h * 8], d, d, d, rows, 3, splits, st));
+          TRY(launch_gemm_tc2(G16, d, WmT, d, nullptr, dS, d, rows, d, d, h > 0 ? 2 : 1, 1, st));
+        }
+      } else {
       build_s_kernel<<<rows, 128, 0, st>>>(ab, b, n, d, p0, S);
       PENEO_CUDA_TRY(cudaGetLastError());
-      const int rb = (rows + 127) / 128;
       for (int h = 0; h < kNumHeads; ++h) {
         const int C = head_classes(h);
         const float* dz = dlogits[h] + ((int64_t)b * P + p0) * C;
@@ -471,25 +636,26 @@ int launch_heads_bwd_fp32(const peneo_dims& dm, const void* pack, const void* x,
             float* Ul = F(pl.off_U) + (size_t)l * cstride;
             g.C = Ul, g.ldc = d, g.mode = 0;
             TRY(run_gemm(g, st));
-            act_bwd_kernel<<<rb, 128, 0, st>>>(Ul, F(pl.off_U) + (size_t)(l - 1) * cstride, rows, d, d, d,
+            act_bwd_kernel<<<dim3((rows + 31) / 32, (d + 127) / 128), 128, 0, st>>>(Ul, F(pl.off_U) + (size_t)(l - 1) * cstride, rows, d, d, d,
                                                gr.mid_b[h * 8 + l - 1]);
             PENEO_CUDA_TRY(cudaGetLastError());
             Gcur = Ul;
           }
         }
       }
+      }  // fp32 pair part
       gv_kernel<<<rows, 128, 0, st>>>(dS, ab, b, n, d, p0);
       PENEO_CUDA_TRY(cudaGetLastError());
-      gv_reduce_kernel<<<n, 128, 0, st>>>(dS, b, n, d, i0, i1, dab);
+      gv_reduce_kernel<<<dim3(n, (d + 127) / 128), 128, 0, st>>>(dS, b, n, d, i0, i1, dab);
       PENEO_CUDA_TRY(cudaGetLastError());
       i0 = i1;
     }
   }
 
   // ---- per-token chain backward
-  const int tb = (T + 127) / 128;
+  const int tb = (T + 31) / 32;
   // db_c = column sums of dBm
-  colsum_kernel<<<tb, 128, 0, st>>>(dab + d, T, d, 2 * d, gr.combine_b);
+  colsum_kernel<<<dim3(tb, (d + 127) / 128), 128, 0, st>>>(dab + d, T, d, 2 * d, gr.combine_b);
   PENEO_CUDA_TRY(cudaGetLastError());
   // dW_c[:, :d] = dA^T y ; dW_c[:, d:] = dBm^T y
   g = Gemm{}, g.ta = true, g.A = dab, g.lda = 2 * d, g.B = y, g.ldb = ldy, g.C = gr.combine_w, g.ldc = 2 * d;
@@ -506,7 +672,7 @@ int launch_heads_bwd_fp32(const peneo_dims& dm, const void* pack, const void* x,
   TRY(run_gemm(g, st));
   if (dm.shrink) {
     // G2 = dy * SiLU'(u2) ; db2 ; dW2 = G2^T y1 ; dy1 = G2 W2
-    act_bwd_kernel<<<tb, 128, 0, st>>>(dy, F(pl.off_u2), T, d, d, d, gr.shrink_b2);
+    act_bwd_kernel<<<dim3(tb, (d + 127) / 128), 128, 0, st>>>(dy, F(pl.off_u2), T, d, d, d, gr.shrink_b2);
     PENEO_CUDA_TRY(cudaGetLastError());
     g = Gemm{}, g.ta = true, g.A = dy, g.lda = d, g.B = F(pl.off_y1), g.ldb = hid, g.C = gr.shrink_w2, g.ldc = hid;
     g.M = d, g.N = hid, g.K = T, g.mode = 2;
@@ -515,7 +681,7 @@ int launch_heads_bwd_fp32(const peneo_dims& dm, const void* pack, const void* x,
     g = Gemm{}, g.A = dy, g.lda = d, g.B = W(L.f_w2), g.ldb = hid, g.C = dy1, g.ldc = hid, g.M = T, g.N = hid, g.K = d;
     TRY(run_gemm(g, st));
     // G1 = dy1 * SiLU'(u1) ; db1 ; dW1 = G1^T x ; dx = G1 W1
-    act_bwd_kernel<<<tb, 128, 0, st>>>(dy1, F(pl.off_u1), T, hid, hid, hid, gr.shrink_b1);
+    act_bwd_kernel<<<dim3(tb, (hid + 127) / 128), 128, 0, st>>>(dy1, F(pl.off_u1), T, hid, hid, hid, gr.shrink_b1);
     PENEO_CUDA_TRY(cudaGetLastError());
     g = Gemm{}, g.ta = true, g.A = dy1, g.lda = hid, g.B = xin, g.ldb = ldx, g.C = gr.shrink_w1, g.ldc = hin;
     g.M = hid, g.N = hin, g.K = T, g.mode = 2;

@@ -13,7 +13,7 @@ from typing import Dict, List
 import torch
 
 from . import _lib, ops
-from ._lib import PREC_FP32
+from ._lib import PREC_BF16, PREC_FP32
 from .ops import HEAD_NAMES, WeightPack
 
 
@@ -45,7 +45,12 @@ def heads_backward(decoder, x: torch.Tensor, dlogits: List[torch.Tensor], need_d
     dims = decoder.dims
     b, n, hin = x.shape
     dev = x.device
-    pack = decoder._fp32_pack(dev)
+    # bf16 mode: the [rows x 384] GEMMs of the pair part run on tcgen05 (bf16 operands, fp32 accumulation);
+    # `backward_precision = "fp32"` on the module forces the exact CUDA-core path.
+    if decoder.precision == "bf16" and getattr(decoder, "backward_precision", "bf16") == "bf16":
+        pack, prec = decoder._weight_pack(dev), PREC_BF16
+    else:
+        pack, prec = decoder._fp32_pack(dev), PREC_FP32
     grads = {k: torch.empty_like(p, dtype=torch.float32) for k, p in _param_items(decoder)}
     x2 = x.detach()
     if x2.dtype not in (torch.float32, torch.bfloat16, torch.float16):
@@ -55,11 +60,11 @@ def heads_backward(decoder, x: torch.Tensor, dlogits: List[torch.Tensor], need_d
         x2 = x2.contiguous()
     dl = [g if (g.dtype == torch.float32 and g.is_contiguous()) else g.float().contiguous() for g in dlogits]
     dx = torch.empty(b * n, hin, dtype=torch.float32, device=dev) if need_dx else None
-    ws = torch.empty(lib.peneo_heads_bwd_workspace_bytes(dims.c(), PREC_FP32, b, n), dtype=torch.uint8, device=dev)
+    ws = torch.empty(lib.peneo_heads_bwd_workspace_bytes(dims.c(), prec, b, n), dtype=torch.uint8, device=dev)
     gs = _grad_struct(dims, grads)
     ops.COUNTERS["kernels"] += 1
     _lib.check(
-        lib.peneo_heads_bwd(dims.c(), PREC_FP32, pack.buf.data_ptr(), x2.data_ptr(), ops._TORCH_DT[x2.dtype],
+        lib.peneo_heads_bwd(dims.c(), prec, pack.buf.data_ptr(), x2.data_ptr(), ops._TORCH_DT[x2.dtype],
                             x2.stride(0) if b * n > 1 else hin, b, n, _lib.ptrs5(dl), gs,
                             dx.data_ptr() if dx is not None else None, ws.data_ptr(), ops._stream(dev)),
         "peneo_heads_bwd",

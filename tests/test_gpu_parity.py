@@ -324,6 +324,32 @@ def test_training_step_default_dims_vs_fp64_oracle(prec, tol):
     assert not bad, bad
 
 
+def test_training_bf16_tensor_core_backward_at_larger_n(monkeypatch):
+    """bf16 mode: forward and the backward GEMMs on tcgen05.  N = 120 with the chunk hook forcing several
+    chunks and ragged row counts (K tails of the split-K GEMM); compared with the fp32 CUDA path on the
+    same inputs (which is itself pinned against the reference autograd above)."""
+    monkeypatch.setenv("PENEO_BWD_CHUNK_ROWS", "3000")
+    n, b = 120, 2
+    sd = synth.init_decoder_state(seed=13, trained_like=True)
+    x = synth.hidden_states(b, n, 768, doc_id0=9).cuda()
+    docs = [synth.make_document(n, doc_id=600 + i) for i in range(b)]
+    tags = [torch.stack([d.tags()[k] for d in docs]).cuda() for k in range(5)]
+    res = {}
+    for prec in ("fp32", "bf16"):
+        dec = PEneoDecoderB200(Cfg(768, inference_mode=False, precision=prec), 768)
+        dec.load_state_dict(sd)
+        dec = dec.cuda().eval()
+        res[prec] = _train_step(dec, x, tags)
+    (o32, dx32, g32), (o16, dx16, g16) = res["fp32"], res["bf16"]
+    assert abs(o16.loss.item() - o32.loss.item()) <= 2e-2 * max(1.0, abs(o32.loss.item()))
+    worst = {"dx": rel_err(dx16, dx32.cpu())}
+    for key in g32:
+        worst[key] = rel_err(g16[key], g32[key].cpu())
+    print({k: f"{v:.2e}" for k, v in worst.items()})
+    bad = {k: v for k, v in worst.items() if v > 3e-2}
+    assert not bad, bad
+
+
 def test_training_rows_cross_chunk_boundaries(monkeypatch):
     """Several pair-row chunks per document in the backward pass (chunk size forced down through the
     PENEO_BWD_CHUNK_ROWS test hook); gradients must not depend on the chunking."""
