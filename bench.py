@@ -278,7 +278,10 @@ def run_ours(args):
     tpath = os.path.join(ROOT, "profiles", "k2_traffic.json")
     if os.path.exists(tpath):
         try:
-            traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+            prof = json.load(open(tpath))
+            # a per-launch ncu figure is only meaningful for the configuration it was captured on
+            if prof.get("config") == {"batch": args.batch, "pair_dim": n_eff}:
+                traffic = prof.get("dram_bytes_per_launch")
         except Exception:
             traffic = None
 

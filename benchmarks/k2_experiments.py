@@ -1,6 +1,8 @@
-"""Scratch: time K2 under PENEO_K2_DBG experiment bits (GPU box only)."""
+"""Bottleneck study of K2 (pair_heads_tc_kernel): times the kernel under the PENEO_K2_DBG experiment bits
+(1 = W_mid streaming disabled after the first tile, 2 = epilogue without the SiLU math; results are wrong when
+a bit is set, only the timing is meaningful).  GPU box only:  python benchmarks/k2_experiments.py 0 1 2 3"""
 import os, sys, subprocess, json
-ROOT = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 if len(sys.argv) > 1 and sys.argv[1] == "child":
     import torch
