@@ -81,6 +81,7 @@ struct PackLayout {
   // ([5][d_in, d_out]), fp32 b_mid [5d]; the per-token chain and W_out use the fp32 fields above (f_w1 .. f_bc,
   // f_out_w, f_out_b), which the bf16 pack also carries.
   size_t wmid_full_bf16, wmidT_bf16, bmid_full;
+  size_t wout_f32x4;  // [5d] float4: (W_out[0][f], W_out[1][f], W_out[2][f] or 0, 0) per stacked mid feature
   size_t total;
 };
 
@@ -112,6 +113,7 @@ inline PackLayout pack_layout(const peneo_dims& dm, int prec) {
     L.wmid_bf16 = take(5 * d * d * 2), L.bmid_half = take(5 * d * 4);
     L.wout_bf16 = take(15 * 16 * 128 * 2), L.bout = take(5 * 4 * 4);
     L.wmid_full_bf16 = take(5 * d * d * 2), L.wmidT_bf16 = take(5 * d * d * 2), L.bmid_full = take(5 * d * 4);
+    L.wout_f32x4 = take(5 * d * 16);
     L.f_w1 = take(hid * hin * 4), L.f_b1 = take(hid * 4);
     L.f_w2 = take(d * hid * 4), L.f_b2 = take(d * 4);
     L.f_wc = take(d * 2 * d * 4), L.f_bc = take(d * 4);

@@ -1,0 +1,235 @@
+// The two large GEMMs of the bf16 backward pass, on tcgen05 with a [128 x 384] fp32 accumulator tile in TMEM.
+// Both read the row-major bf16 matrices written by T1 (pair_bwd_tc.cu) directly — no transposed copies —
+// by using MN-major shared-memory descriptors where the contraction index is the ROW index in memory:
+//
+//   dS  [rows, 384]  = G [rows, 1920] * W_mid [1920, 384]        A K-major (row = m, contiguous = k = mid feature)
+//                                                                B MN-major (row = k = mid feature, contiguous = n)
+//   dWm [1920, 384] += G^T [1920, rows] * S [rows, 384]          A MN-major (row = k = pair, contiguous = m)
+//                                                                B MN-major (row = k = pair, contiguous = n)
+//
+// (autograd of the five Linear(D, D) layers in model/peneo_decoder.py:258-269: grad_input = grad_output W,
+// grad_weight = grad_output^T input.)  Stage = one 64-deep K block: A 16 KB + B 6 x 8 KB = 64 KB, 3 stages.
+// Persistent CTAs: warp 0 TMA, warp 1 MMA (+ TMEM alloc), warps 2-5 epilogue.  The dW GEMM is split along K
+// (= pairs) across CTAs and accumulated with fp32 atomics.
+#include <cuda.h>
+
+#include "common.cuh"
+#include "kernels.h"
+#include "ptx.cuh"
+
+namespace peneo {
+namespace gb {
+
+constexpr int kN = 384;
+constexpr int kBlk = 64 * 128;              // one [64 rows x 64 cols] swizzled box = 8 KB
+constexpr int kStageBytes = 2 * kBlk + 6 * kBlk;  // 64 KB
+constexpr int kStages = 3;
+constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
+
+struct Args {
+  int64_t m_total;   // rows of the output (dS: pairs in the chunk; dW: 1920)
+  int32_t k_total;   // contraction length (dS: 1920; dW: pairs in the chunk)
+  int32_t kb_per_split, splits;
+  int64_t num_items;  // m blocks * splits
+  float* out[kNumHeads];  // dS: out[0] = dS (ld 384); dW: five [384, 384] matrices, m block -> head = mb / 3
+};
+
+template <bool A_MN>
+__global__ void __launch_bounds__(192, 1)
+    gemm_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Args a) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + kStages;
+  uint64_t* acc_full = bars + 2 * kStages;
+  uint64_t* acc_empty = bars + 2 * kStages + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 2);
+
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int num_kb = (a.k_total + 63) / 64;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmA);
+    ptx::prefetch_tmap(&tmB);
+    for (int s = 0; s < kStages; ++s) ptx::mbar_init(&full[s], 1), ptx::mbar_init(&empty[s], 1);
+    ptx::mbar_init(acc_full, 1);
+    ptx::mbar_init(acc_empty, 4);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_slot, 512);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  auto decode = [&](int64_t item, int64_t& mb, int& kb0, int& nk) {
+    const int split = static_cast<int>(item % a.splits);
+    mb = item / a.splits;
+    kb0 = split * a.kb_per_split;
+    nk = min(a.kb_per_split, num_kb - kb0);
+  };
+
+  if (warp == 0) {
+    if (ptx::elect_one()) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int64_t item = blockIdx.x; item < a.num_items; item += gridDim.x) {
+        int64_t mb;
+        int kb0, nk;
+        decode(item, mb, kb0, nk);
+        for (int kb = 0; kb < nk; ++kb) {
+          const int k0 = (kb0 + kb) * 64;
+          ptx::mbar_wait(&empty[s], ph ^ 1);
+          ptx::mbar_arrive_expect_tx(&full[s], kStageBytes);
+          unsigned char* st = smem + s * kStageBytes;
+          if (A_MN) {  // two [64 k-rows x 64 m-cols] boxes
+            ptx::tma_load_2d(st, &tmA, &full[s], static_cast<int32_t>(mb * 128), k0);
+            ptx::tma_load_2d(st + kBlk, &tmA, &full[s], static_cast<int32_t>(mb * 128 + 64), k0);
+          } else {     // one [128 m-rows x 64 k-cols] box
+            ptx::tma_load_2d(st, &tmA, &full[s], k0, static_cast<int32_t>(mb * 128));
+          }
+          for (int nb = 0; nb < 6; ++nb) ptx::tma_load_2d(st + (2 + nb) * kBlk, &tmB, &full[s], nb * 64, k0);
+          if (++s == kStages) s = 0, ph ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (ptx::elect_one()) {
+      constexpr uint32_t idesc256 = ptx::umma_idesc_bf16_major(128, 256, A_MN, true);
+      constexpr uint32_t idesc128 = ptx::umma_idesc_bf16_major(128, 128, A_MN, true);
+      int s = 0;
+      uint32_t ph = 0;
+      int it = 0;
+      for (int64_t item = blockIdx.x; item < a.num_items; item += gridDim.x, ++it) {
+        int64_t mb;
+        int kb0, nk;
+        decode(item, mb, kb0, nk);
+        ptx::mbar_wait(acc_empty, (it & 1) ^ 1);
+        ptx::tc_fence_after();
+        for (int kb = 0; kb < nk; ++kb) {
+          ptx::mbar_wait(&full[s], ph);
+          ptx::tc_fence_after();
+          const uint32_t a_addr = ptx::smem_u32(smem + s * kStageBytes);
+          const uint32_t b_addr = a_addr + 2 * kBlk;
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            const uint64_t ad = A_MN ? ptx::umma_desc_mn_sw128(a_addr + ks * 2048, kBlk, 1024)
+                                     : ptx::umma_desc_sw128(a_addr + ks * 32);
+            ptx::umma_ss(tmem, ad, ptx::umma_desc_mn_sw128(b_addr + ks * 2048, kBlk, 1024), idesc256, (kb | ks) != 0);
+            ptx::umma_ss(tmem + 256, ad, ptx::umma_desc_mn_sw128(b_addr + 4 * kBlk + ks * 2048, kBlk, 1024), idesc128,
+                         (kb | ks) != 0);
+          }
+          ptx::tc_commit(&empty[s]);
+          if (++s == kStages) s = 0, ph ^= 1;
+        }
+        ptx::tc_commit(acc_full);
+      }
+    }
+  } else {
+    const int q = warp % 4;
+    int it = 0;
+    for (int64_t item = blockIdx.x; item < a.num_items; item += gridDim.x, ++it) {
+      int64_t mb;
+      int kb0, nk;
+      decode(item, mb, kb0, nk);
+      ptx::mbar_wait(acc_full, it & 1);
+      ptx::tc_fence_after();
+      const int64_t m = mb * 128 + q * 32 + lane;
+      float* dst;
+      if (A_MN) {  // dW: row m of the stacked [1920, 384] gradient = row (m % 384) of head m / 384
+        dst = a.out[static_cast<int>(m / kN)] + (m % kN) * kN;
+      } else {
+        dst = a.out[0] + m * kN;
+      }
+#pragma unroll 1
+      for (int piece = 0; piece < kN / 32; ++piece) {
+        uint32_t r[32];
+        ptx::tmem_ld_x32(tmem + (static_cast<uint32_t>(q * 32) << 16) + piece * 32, r);
+        ptx::tmem_ld_wait();
+        if (piece == kN / 32 - 1) {
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(acc_empty);
+        }
+        if (m < a.m_total) {
+          if (A_MN) {
+#pragma unroll
+            for (int x = 0; x < 32; x += 4)
+              atomicAdd(reinterpret_cast<float4*>(dst + piece * 32 + x),
+                        make_float4(__uint_as_float(r[x]), __uint_as_float(r[x + 1]), __uint_as_float(r[x + 2]),
+                                    __uint_as_float(r[x + 3])));
+          } else {
+#pragma unroll
+            for (int x = 0; x < 32; x += 4)
+              *reinterpret_cast<float4*>(dst + piece * 32 + x) = make_float4(
+                  __uint_as_float(r[x]), __uint_as_float(r[x + 1]), __uint_as_float(r[x + 2]), __uint_as_float(r[x + 3]));
+          }
+        }
+      }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc(tmem, 512);
+}
+
+static int sm_count() {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+      sms = 148;
+  }
+  return sms;
+}
+
+}  // namespace gb
+
+// dS[rows, 384] = G[rows, 1920] * Wmid[1920, 384]   (Wmid: the five [d_out, d_in] matrices stacked, bf16, unscaled)
+int launch_gemm_ds(const __nv_bfloat16* G, const __nv_bfloat16* wmid_full, float* dS, int rows, cudaStream_t st) {
+  using namespace gb;
+  if (rows == 0) return PENEO_OK;
+  alignas(64) CUtensorMap tmA, tmB;
+  int rc;
+  if ((rc = make_tensor_map_bf16(&tmA, G, 5 * kN, rows, 5 * kN * 2, 64, 128)) != PENEO_OK) return rc;
+  if ((rc = make_tensor_map_bf16(&tmB, wmid_full, kN, 5 * kN, kN * 2, 64, 64)) != PENEO_OK) return rc;
+  Args a{};
+  a.m_total = rows, a.k_total = 5 * kN;
+  a.splits = 1, a.kb_per_split = (a.k_total + 63) / 64;
+  a.num_items = (rows + 127) / 128;
+  a.out[0] = dS;
+  const int grid = static_cast<int>(std::min<int64_t>(a.num_items, sm_count()));
+  PENEO_CUDA_TRY(cudaFuncSetAttribute(gemm_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+  gemm_bwd_kernel<false><<<grid, 192, kSmemBytes, st>>>(tmA, tmB, a);
+  PENEO_CUDA_TRY(cudaGetLastError());
+  return PENEO_OK;
+}
+
+// dWmid[h][384, 384] += (G[:, 384 h : 384 (h + 1)])^T * S        (G [rows, 1920], S [rows, 384], bf16)
+int launch_gemm_dw(const __nv_bfloat16* G, const __nv_bfloat16* S, float* const dW[kNumHeads], int rows, cudaStream_t st) {
+  using namespace gb;
+  if (rows == 0) return PENEO_OK;
+  alignas(64) CUtensorMap tmA, tmB;
+  int rc;
+  if ((rc = make_tensor_map_bf16(&tmA, G, 5 * kN, rows, 5 * kN * 2, 64, 64)) != PENEO_OK) return rc;
+  if ((rc = make_tensor_map_bf16(&tmB, S, kN, rows, kN * 2, 64, 64)) != PENEO_OK) return rc;
+  Args a{};
+  a.m_total = 5 * kN, a.k_total = rows;
+  const int num_kb = (rows + 63) / 64, m_blocks = 5 * kN / 128;
+  int splits = std::max(1, std::min(num_kb, sm_count() / m_blocks));  // one work item per SM, a single wave
+  a.kb_per_split = (num_kb + splits - 1) / splits;
+  a.splits = (num_kb + a.kb_per_split - 1) / a.kb_per_split;
+  a.num_items = (int64_t)m_blocks * a.splits;
+  for (int h = 0; h < kNumHeads; ++h) a.out[h] = dW[h];
+  const int grid = static_cast<int>(std::min<int64_t>(a.num_items, sm_count()));
+  PENEO_CUDA_TRY(cudaFuncSetAttribute(gemm_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+  gemm_bwd_kernel<true><<<grid, 192, kSmemBytes, st>>>(tmA, tmB, a);
+  PENEO_CUDA_TRY(cudaGetLastError());
+  return PENEO_OK;
+}
+
+}  // namespace peneo

@@ -25,6 +25,15 @@ int launch_gemm_tc2(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* W,
 int launch_pair_heads_tc(const void* pack, const PackLayout& L, const __nv_bfloat16* ab, int batch, int n,
                          float* const logits[kNumHeads], cudaStream_t st);
 
+// pair_bwd_tc.cu : regenerated S, M = SiLU(u), G = (dz W_out) SiLU'(u) of a chunk of pairs (bf16 backward)
+int launch_pair_bwd_prep(const void* pack, const PackLayout& L, const __nv_bfloat16* ab, int n, int64_t g0, int rows,
+                         const float* const dz[kNumHeads], __nv_bfloat16* S, __nv_bfloat16* G, __nv_bfloat16* M,
+                         cudaStream_t st);
+
+// gemm_bwd_tc.cu
+int launch_gemm_ds(const __nv_bfloat16* G, const __nv_bfloat16* wmid_full, float* dS, int rows, cudaStream_t st);
+int launch_gemm_dw(const __nv_bfloat16* G, const __nv_bfloat16* S, float* const dW[kNumHeads], int rows, cudaStream_t st);
+
 // loss.cu
 size_t pair_loss_workspace_bytes(int batch, int n);
 int launch_pair_loss_fwd(int batch, int n, const float* const logits[kNumHeads], const int64_t* const tags[kNumHeads],

@@ -1,0 +1,330 @@
+// T1 — first kernel of the bf16 backward pass (PENEO_PREC_BF16, d = 384, num_layers = 2): the forward
+// structure of K2 (pair_heads_tc.cu) with a gradient epilogue.  For every pair of a chunk [g0, g0 + rows) of
+// the batch-flattened pair list and every head k:
+//   s   = SiLU(a_i + b_j)                         regenerated (CUDA cores -> TMEM), also stored: S  [rows, 384]
+//   u_k = W_mid,k s + b_mid,k                     tcgen05, 15 chunks of 128 mid features
+//   m_k = SiLU(u_k)                               stored: M [rows, 1920]   (dW_out = dz^T M)
+//   g_k = (dz_k W_out,k) * SiLU'(u_k)             stored: G [rows, 1920]   (dW_mid = G^T S, dS = G W_mid)
+// dz_k = d loss / d logits of head k (fp32, from the loss backward).  Nothing is accumulated here; the three
+// bf16 matrices feed the GEMMs of train.cu.  What autograd keeps alive between forward and backward in the
+// reference ([P, D] activations of every layer) is recomputed instead.
+//
+// Warp roles as in K2 minus the second MMA: warp 0 TMA (W_mid stream), warp 1 MMA issuer, warp 2 TMEM
+// allocator, warps 4-11 epilogue, warps 12-15 pair producers.
+// TMEM columns: [0,192) s | [192,320) u buffer 0 | [320,448) u buffer 1
+#include <cuda.h>
+
+#include "common.cuh"
+#include "kernels.h"
+#include "ptx.cuh"
+
+namespace peneo {
+namespace t1 {
+
+constexpr int D = 384;
+constexpr int kChunks = 15;       // 5 heads x 3 chunks of 128 mid features
+constexpr int kKChunks = 6;       // 384 / 64
+constexpr int kWStages = 6;
+constexpr int kWStageBytes = 128 * 64 * 2;  // 16 KB
+constexpr int kStageRowBytes = D * 2;       // staging: 128 rows x 768 B
+constexpr int kThreads = 512;
+constexpr int kLdG = 5 * D;                 // row stride of G / M
+
+constexpr uint32_t kColS = 0, kColU = 192;
+
+struct Smem {
+  static constexpr int w = 0;
+  static constexpr int stage = w + kWStages * kWStageBytes;
+  static constexpr int bmid = stage + 128 * kStageRowBytes;  // 1920 floats
+  static constexpr int bars = bmid + 5 * D * 4;
+  static constexpr int total = bars + 512;
+};
+constexpr int bWFull = 0, bWEmpty = bWFull + kWStages, bUFull = bWEmpty + kWStages, bUFree = bUFull + 2,
+              bSFull = bUFree + 2, bSFree = bSFull + kKChunks, bCount = bSFree + kKChunks;
+static_assert(bCount * 8 + 16 <= 512, "barrier area too small");
+constexpr int kSmemBytes = Smem::total + 1024;
+
+struct Args {
+  const __nv_bfloat16* ab;   // [batch*n, 768] : 0.5*A | 0.5*Bm
+  const float* bmid_half;    // [1920]
+  const float4* wout4;       // [5][384] : (W_out[0][f], W_out[1][f], W_out[2][f] or 0, 0)
+  const float* dz[kNumHeads];  // d loss / d logits, fp32 [batch*P, C_h]
+  __nv_bfloat16* S;          // [rows, 384]
+  __nv_bfloat16* G;          // [rows, 1920]
+  __nv_bfloat16* M;          // [rows, 1920]
+  int32_t n, pairs_per_doc;
+  int64_t g0;                // first flat pair of the chunk
+  int32_t rows, num_tiles;
+};
+
+__global__ void __launch_bounds__(kThreads, 1) pair_bwd_prep_kernel(const __grid_constant__ CUtensorMap tmW, const Args a) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Smem::bars);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + bCount);
+  float* s_bmid = reinterpret_cast<float*>(smem + Smem::bmid);
+
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+
+  if (threadIdx.x == 0) {
+    ptx::prefetch_tmap(&tmW);
+    for (int s = 0; s < kWStages; ++s) ptx::mbar_init(&bars[bWFull + s], 1), ptx::mbar_init(&bars[bWEmpty + s], 1);
+    for (int s = 0; s < 2; ++s) ptx::mbar_init(&bars[bUFull + s], 1), ptx::mbar_init(&bars[bUFree + s], 8);
+    for (int s = 0; s < kKChunks; ++s) ptx::mbar_init(&bars[bSFull + s], 4), ptx::mbar_init(&bars[bSFree + s], 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 2) {
+    ptx::tmem_alloc(tmem_slot, 512);
+    ptx::tmem_relinquish();
+  }
+  for (int e = threadIdx.x; e < 5 * D; e += kThreads) s_bmid[e] = a.bmid_half[e];
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  const int my_tiles = (a.num_tiles > static_cast<int>(blockIdx.x))
+                           ? (a.num_tiles - 1 - static_cast<int>(blockIdx.x)) / static_cast<int>(gridDim.x) + 1
+                           : 0;
+
+  if (warp == 0) {
+    // ============================== TMA producer ==============================
+    if (ptx::elect_one()) {
+      int ws = 0;
+      uint32_t wph = 0;
+      for (int it = 0; it < my_tiles; ++it)
+        for (int c = 0; c < kChunks; ++c)
+          for (int kc = 0; kc < kKChunks; ++kc) {
+            ptx::mbar_wait(&bars[bWEmpty + ws], wph ^ 1);
+            ptx::mbar_arrive_expect_tx(&bars[bWFull + ws], kWStageBytes);
+            ptx::tma_load_2d(smem + Smem::w + ws * kWStageBytes, &tmW, &bars[bWFull + ws], kc * 64, c * 128);
+            if (++ws == kWStages) ws = 0, wph ^= 1;
+          }
+    }
+  } else if (warp == 1) {
+    // ============================== MMA issuer ==============================
+    if (ptx::elect_one()) {
+      constexpr uint32_t idesc1 = ptx::umma_idesc_bf16(128, 128);
+      int ws = 0;
+      uint32_t wph = 0;
+      const uint32_t w_base = ptx::smem_u32(smem + Smem::w);
+      int g = 0;
+      for (int it = 0; it < my_tiles; ++it) {
+        for (int c = 0; c < kChunks; ++c, ++g) {
+          const int buf = g & 1;
+          // the epilogue has drained this accumulator (chunk g - 2)
+          ptx::mbar_wait(&bars[bUFree + buf], ((g >> 1) & 1) ^ 1);
+          ptx::tc_fence_after();
+          const uint32_t ut = tmem + kColU + 128 * buf;
+          for (int kc = 0; kc < kKChunks; ++kc) {
+            if (c == 0) ptx::mbar_wait(&bars[bSFull + kc], it & 1);
+            ptx::mbar_wait(&bars[bWFull + ws], wph);
+            ptx::tc_fence_after();
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)
+              ptx::umma_ts(ut, tmem + kColS + 32 * kc + 8 * ks, ptx::umma_desc_sw128(w_base + ws * kWStageBytes + ks * 32),
+                           idesc1, (kc | ks) != 0);
+            ptx::tc_commit(&bars[bWEmpty + ws]);
+            if (c == kChunks - 1) ptx::tc_commit(&bars[bSFree + kc]);
+            if (++ws == kWStages) ws = 0, wph ^= 1;
+          }
+          ptx::tc_commit(&bars[bUFull + buf]);
+        }
+      }
+    }
+  } else if (warp >= 4 && warp < 12) {
+    // ============================== epilogue ==============================
+    const int q = warp % 4, hsel = (warp - 4) / 4;
+    const uint32_t lane_base = static_cast<uint32_t>(q * 32) << 16;
+    const int row = q * 32 + lane;
+    int g = 0;
+    for (int it = 0; it < my_tiles; ++it) {
+      const int64_t tile = static_cast<int64_t>(blockIdx.x) + static_cast<int64_t>(it) * gridDim.x;
+      const int64_t lr = tile * 128 + row;          // row inside the chunk
+      const bool live = lr < a.rows;
+      const int64_t gp = a.g0 + lr;                 // flat pair index in the batch
+      float dz0 = 0.f, dz1 = 0.f, dz2 = 0.f;
+      for (int c = 0; c < kChunks; ++c, ++g) {
+        const int buf = g & 1, k = c / 3;
+        if (c - 3 * k == 0) {
+          dz0 = dz1 = dz2 = 0.f;
+          if (live) {
+            const int C = head_classes(k);
+            const float* p = a.dz[k] + gp * C;
+            dz0 = p[0], dz1 = p[1];
+            if (C == 3) dz2 = p[2];
+          }
+        }
+        ptx::mbar_wait(&bars[bUFull + buf], (g >> 1) & 1);
+        ptx::tc_fence_after();
+        const uint32_t ut = tmem + lane_base + kColU + 128 * buf + 64 * hsel;
+        const int f0 = c * 128 + 64 * hsel;  // column in the stacked [0, 1920) feature space
+        const float* hb = s_bmid + f0;
+        const float4* w4 = a.wout4 + f0;     // wout4 is indexed [k * 384 + f] = stacked feature index
+#pragma unroll
+        for (int piece = 0; piece < 2; ++piece) {
+          uint32_t r[32];
+          ptx::tmem_ld_x32(ut + 32 * piece, r);
+          ptx::tmem_ld_wait();
+          if (piece == 1) {  // accumulator drained: release it to the MMA warp before the math / stores
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&bars[bUFree + buf]);
+          }
+          uint32_t mp[16], gpk[16];
+#pragma unroll
+          for (int x = 0; x < 32; x += 2) {
+            float mv[2], gv[2];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int col = 32 * piece + x + e;
+              const float h = __uint_as_float(r[x + e]) + hb[col];  // u / 2
+              const float t = ptx::tanh_approx(h);
+              const float sg = fmaf(0.5f, t, 0.5f);                 // sigmoid(u)
+              const float u = h + h;
+              mv[e] = u * sg;
+              const float4 w = __ldg(w4 + col);
+              const float gm = fmaf(dz2, w.z, fmaf(dz1, w.y, dz0 * w.x));
+              gv[e] = gm * (sg * fmaf(u, 1.0f - sg, 1.0f));
+            }
+            mp[x / 2] = ptx::pack_bf16x2(mv[0], mv[1]);
+            gpk[x / 2] = ptx::pack_bf16x2(gv[0], gv[1]);
+          }
+          if (live) {
+            uint4* dm = reinterpret_cast<uint4*>(a.M + lr * kLdG + f0 + 32 * piece);
+            uint4* dg = reinterpret_cast<uint4*>(a.G + lr * kLdG + f0 + 32 * piece);
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+              dm[v] = make_uint4(mp[4 * v], mp[4 * v + 1], mp[4 * v + 2], mp[4 * v + 3]);
+              dg[v] = make_uint4(gpk[4 * v], gpk[4 * v + 1], gpk[4 * v + 2], gpk[4 * v + 3]);
+            }
+          }
+        }
+      }
+    }
+  } else if (warp >= 12) {
+    // ============================== pair producers ==============================
+    const int q = warp - 12;
+    const uint32_t lane_base = static_cast<uint32_t>(q * 32) << 16;
+    unsigned char* stg = smem + Smem::stage;
+    for (int it = 0; it < my_tiles; ++it) {
+      const int64_t tile = static_cast<int64_t>(blockIdx.x) + static_cast<int64_t>(it) * gridDim.x;
+      int64_t my_a = -1, my_b = -1;
+      const int64_t my_lr = tile * 128 + q * 32 + lane;
+      if (my_lr < a.rows) {
+        const int64_t gp = a.g0 + my_lr;
+        const int64_t b = gp / a.pairs_per_doc;
+        const int p = static_cast<int>(gp - b * a.pairs_per_doc);
+        int i, j;
+        pair_from_flat(p, a.n, i, j);
+        my_a = (b * a.n + i) * (2 * D);
+        my_b = (b * a.n + j) * (2 * D) + D;
+      }
+      // ---- generate s rows [32q, 32q+32) into staging; lane = 4-column group (3 groups per lane)
+#pragma unroll 1
+      for (int rr = 0; rr < 32; rr += 4) {
+        uint2 av[4][3], bv[4][3];
+        int64_t offa[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          offa[u] = __shfl_sync(0xffffffffu, my_a, rr + u);
+          const int64_t offb = __shfl_sync(0xffffffffu, my_b, rr + u);
+#pragma unroll
+          for (int mth = 0; mth < 3; ++mth) {
+            const int col = 4 * (lane + 32 * mth);
+            if (offa[u] >= 0) {
+              av[u][mth] = __ldg(reinterpret_cast<const uint2*>(a.ab + offa[u] + col));
+              bv[u][mth] = __ldg(reinterpret_cast<const uint2*>(a.ab + offb + col));
+            } else {
+              av[u][mth] = make_uint2(0u, 0u), bv[u][mth] = make_uint2(0u, 0u);
+            }
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int r = q * 32 + rr + u;
+#pragma unroll
+          for (int mth = 0; mth < 3; ++mth) {
+            const int cg = lane + 32 * mth;  // 4-column group index, 0..95
+            const float a0 = __uint_as_float(av[u][mth].x << 16), a1 = __uint_as_float(av[u][mth].x & 0xFFFF0000u);
+            const float a2 = __uint_as_float(av[u][mth].y << 16), a3 = __uint_as_float(av[u][mth].y & 0xFFFF0000u);
+            const float b0 = __uint_as_float(bv[u][mth].x << 16), b1 = __uint_as_float(bv[u][mth].x & 0xFFFF0000u);
+            const float b2 = __uint_as_float(bv[u][mth].y << 16), b3 = __uint_as_float(bv[u][mth].y & 0xFFFF0000u);
+            uint2 o;
+            o.x = ptx::pack_bf16x2(ptx::silu_from_half(a0 + b0), ptx::silu_from_half(a1 + b1));
+            o.y = ptx::pack_bf16x2(ptx::silu_from_half(a2 + b2), ptx::silu_from_half(a3 + b3));
+            const int chunk16 = (cg >> 1) ^ (r & 7);
+            *reinterpret_cast<uint2*>(stg + r * kStageRowBytes + chunk16 * 16 + (cg & 1) * 8) = o;
+          }
+        }
+      }
+      __syncwarp();
+      // ---- copy into TMEM (and to the S matrix in global memory), one 64-feature K chunk at a time
+      const int r = q * 32 + lane;
+#pragma unroll 1
+      for (int kc = 0; kc < kKChunks; ++kc) {
+        uint32_t v[32];
+#pragma unroll
+        for (int ch = 0; ch < 8; ++ch) {
+          const int chunk16 = (kc * 8 + ch) ^ (r & 7);
+          const uint4 t = *reinterpret_cast<const uint4*>(stg + r * kStageRowBytes + chunk16 * 16);
+          v[4 * ch] = t.x, v[4 * ch + 1] = t.y, v[4 * ch + 2] = t.z, v[4 * ch + 3] = t.w;
+        }
+        if (my_lr < a.rows) {
+          uint4* ds = reinterpret_cast<uint4*>(a.S + my_lr * D + kc * 64);
+#pragma unroll
+          for (int ch = 0; ch < 8; ++ch) ds[ch] = make_uint4(v[4 * ch], v[4 * ch + 1], v[4 * ch + 2], v[4 * ch + 3]);
+        }
+        if (it > 0) ptx::mbar_wait(&bars[bSFree + kc], (it - 1) & 1);
+        ptx::tc_fence_after();
+        uint32_t lo[16], hi[16];
+#pragma unroll
+        for (int x = 0; x < 16; ++x) lo[x] = v[x], hi[x] = v[16 + x];
+        ptx::tmem_st_x16(tmem + lane_base + kColS + 32 * kc, lo);
+        ptx::tmem_st_x16(tmem + lane_base + kColS + 32 * kc + 16, hi);
+        ptx::tmem_st_wait();
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&bars[bSFull + kc]);
+      }
+      __syncwarp();
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) ptx::tmem_dealloc(tmem, 512);
+}
+
+}  // namespace t1
+
+int launch_pair_bwd_prep(const void* pack, const PackLayout& L, const __nv_bfloat16* ab, int n, int64_t g0, int rows,
+                         const float* const dz[kNumHeads], __nv_bfloat16* S, __nv_bfloat16* G, __nv_bfloat16* M,
+                         cudaStream_t st) {
+  using namespace t1;
+  const char* base = static_cast<const char*>(pack);
+  Args a{};
+  a.ab = ab;
+  a.bmid_half = reinterpret_cast<const float*>(base + L.bmid_half);
+  a.wout4 = reinterpret_cast<const float4*>(base + L.wout_f32x4);
+  for (int h = 0; h < kNumHeads; ++h) a.dz[h] = dz[h];
+  a.S = S, a.G = G, a.M = M;
+  a.n = n;
+  a.pairs_per_doc = static_cast<int32_t>(pair_count(n));
+  a.g0 = g0, a.rows = rows;
+  a.num_tiles = (rows + 127) / 128;
+  if (rows == 0) return PENEO_OK;
+  alignas(64) CUtensorMap tmW;
+  int rc;
+  if ((rc = make_tensor_map_bf16(&tmW, base + L.wmid_bf16, D, 5 * D, D * 2, 64, 128)) != PENEO_OK) return rc;
+  int dev = 0, sms = 148;
+  PENEO_CUDA_TRY(cudaGetDevice(&dev));
+  PENEO_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int grid = std::min(a.num_tiles, sms);
+  PENEO_CUDA_TRY(cudaFuncSetAttribute(pair_bwd_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+  pair_bwd_prep_kernel<<<grid, kThreads, kSmemBytes, st>>>(tmW, a);
+  PENEO_CUDA_TRY(cudaGetLastError());
+  return PENEO_OK;
+}
+
+}  // namespace peneo

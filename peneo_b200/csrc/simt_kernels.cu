@@ -150,6 +150,15 @@ __global__ void pack_wout_kernel(WoutPtrs p, __nv_bfloat16* __restrict__ dst, fl
   }
 }
 
+// wout4[h * d + f] = (W_out_h[0][f], W_out_h[1][f], C_h == 3 ? W_out_h[2][f] : 0, 0)
+__global__ void pack_wout4_kernel(WoutPtrs p, float4* __restrict__ dst, int d) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= kNumHeads * d) return;
+  const int h = e / d, f = e % d;
+  const float* w = p.w[h];
+  dst[e] = make_float4(w[f], w[d + f], head_classes(h) == 3 ? w[2 * d + f] : 0.f, 0.f);
+}
+
 int pack_weights_impl(const peneo_dims& dm, int prec, const peneo_params& P, void* pack, cudaStream_t st) {
   char* base = static_cast<char*>(pack);
   const PackLayout L = pack_layout(dm, prec);
@@ -206,6 +215,8 @@ int pack_weights_impl(const peneo_dims& dm, int prec, const peneo_params& P, voi
         wp, reinterpret_cast<__nv_bfloat16*>(base + L.wout_bf16), reinterpret_cast<float*>(base + L.bout), d);
     PENEO_CUDA_TRY(cudaGetLastError());
     // operands of the backward pass
+    pack_wout4_kernel<<<(kNumHeads * d + 255) / 256, 256, 0, st>>>(wp, reinterpret_cast<float4*>(base + L.wout_f32x4), d);
+    PENEO_CUDA_TRY(cudaGetLastError());
     for (int h = 0; h < kNumHeads; ++h) {
       TRY(bf(P.mid_w[h * 8], d, 0, L.wmid_full_bf16 + (size_t)h * d * d * 2, d, d, 1.f));
       pack_bf16_T_kernel<<<(d * d + 255) / 256, 256, 0, st>>>(

@@ -416,6 +416,45 @@ __global__ void __launch_bounds__(192) head_out_bwd_bf16_kernel(const __nv_bfloa
   atomicAdd(&dbmid[f], ab0), atomicAdd(&dbmid[f + 1], ab1);
 }
 
+// dW_out, db_out, db_mid of all five heads from the bf16 matrices T1 wrote:
+//   dW_out[k][c][f] += sum_r dz_k[r][c] M[r][384 k + f] ; db_mid[k][f] += sum_r G[r][384 k + f] ; db_out[k][c] += sum_r dz_k[r][c]
+// Grid: (blocks of 256 rows, 15 blocks of 128 stacked mid features); one thread per feature.
+struct DzPtrs {
+  const float* p[kNumHeads];
+};
+__global__ void __launch_bounds__(128) dwout_bf16_kernel(const __nv_bfloat16* __restrict__ M, const __nv_bfloat16* __restrict__ G,
+                                                         DzPtrs dz, int rows, float* const* __restrict__ dWout,
+                                                         float* const* __restrict__ dbout, float* const* __restrict__ dbmid) {
+  __shared__ float sdz[256][3];
+  const int r0 = blockIdx.x * 256, nr = min(256, rows - r0);
+  const int fs = blockIdx.y * 128 + threadIdx.x;  // stacked feature index in [0, 1920)
+  const int k = fs / kD16, f = fs - k * kD16, C = head_classes(k);
+  const float* dzk = dz.p[k];
+  for (int e = threadIdx.x; e < 256 * 3; e += 128) {
+    const int r = e / 3, c = e - 3 * r;
+    sdz[r][c] = (r < nr && c < C) ? dzk[(int64_t)(r0 + r) * C + c] : 0.f;
+  }
+  __syncthreads();
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, ab_ = 0.f;
+  const __nv_bfloat16* pm = M + (int64_t)r0 * (5 * kD16) + fs;
+  const __nv_bfloat16* pg = G + (int64_t)r0 * (5 * kD16) + fs;
+#pragma unroll 8
+  for (int r = 0; r < nr; ++r) {
+    const float m = __bfloat162float(pm[(int64_t)r * (5 * kD16)]);
+    ab_ += __bfloat162float(pg[(int64_t)r * (5 * kD16)]);
+    a0 = fmaf(sdz[r][0], m, a0), a1 = fmaf(sdz[r][1], m, a1), a2 = fmaf(sdz[r][2], m, a2);
+  }
+  atomicAdd(&dWout[k][f], a0);
+  atomicAdd(&dWout[k][kD16 + f], a1);
+  if (C == 3) atomicAdd(&dWout[k][2 * kD16 + f], a2);
+  atomicAdd(&dbmid[k][f], ab_);
+  if (blockIdx.y % 3 == 0 && threadIdx.x < C) {
+    float s = 0.f;
+    for (int r = 0; r < nr; ++r) s += sdz[r][threadIdx.x];
+    atomicAdd(&dbout[k][threadIdx.x], s);
+  }
+}
+
 inline size_t fl(size_t n) { return align_up(n * sizeof(float), 1024); }
 
 struct Plan {
@@ -427,6 +466,8 @@ struct Plan {
   // bf16 pair part: row-major and transposed (ld = ldt) bf16 activations
   size_t off_S16, off_ST16, off_U16, off_G16, off_GT16;
   int64_t ldt;
+  // v2 (T1 + MN-major GEMMs): G / M [rows, 1920] bf16, bf16 per-token projections and their scratch
+  size_t off_Gc, off_Mc, off_ab16, off_tokws, tokws_bytes;
   size_t total;
 };
 
@@ -437,7 +478,7 @@ Plan make_plan(const peneo_dims& dm, int prec, int batch, int n) {
   p.nU = dm.num_layers - 1;
   p.nH = dm.num_layers >= 3 ? dm.num_layers - 2 : 0;
   const bool tc = prec == PENEO_PREC_BF16;
-  const int nbuf = tc ? 4 : 3 + p.nU + p.nH;  // fp32: S, dS, G, U.., H.. ; bf16: dS (fp32) + 5 half-size buffers
+  const int nbuf = tc ? 7 : 3 + p.nU + p.nH;  // fp32: S, dS, G, U.., H.. ; bf16: dS (fp32) + S, G, M (bf16, 1 + 5 + 5 halves)
   // ~512 MB of pair buffers, but never less than one full pair row (n pairs)
   int64_t rows = (int64_t)(512ull << 20) / ((int64_t)nbuf * d * 4);
   rows = std::min<int64_t>(rows, 65536);
@@ -461,7 +502,13 @@ Plan make_plan(const peneo_dims& dm, int prec, int batch, int n) {
   if (tc) {
     p.ldt = (rows + 63) / 64 * 64;
     const size_t hb = align_up((size_t)p.ldt * d * 2, 1024);
-    p.off_S16 = take(hb), p.off_ST16 = take(hb), p.off_U16 = take(hb), p.off_G16 = take(hb), p.off_GT16 = take(hb);
+    const size_t gb = align_up((size_t)p.ldt * 5 * d * 2, 1024);
+    p.off_S16 = take(hb), p.off_Gc = take(gb), p.off_Mc = take(gb);
+    // the v1 path (PENEO_BWD_TC=1) carves its four [ldt, d] buffers out of the G / M regions
+    p.off_U16 = p.off_Gc, p.off_G16 = p.off_Gc + hb, p.off_GT16 = p.off_Mc, p.off_ST16 = p.off_Mc + hb;
+    p.off_ab16 = take(align_up(T * 2 * d * 2, 1024));
+    p.tokws_bytes = peneo_token_proj_workspace_bytes(&dm, PENEO_PREC_BF16, p.tokens);
+    p.off_tokws = take(align_up(p.tokws_bytes, 1024));
   } else {
     p.off_S = take(cb), p.off_G = take(cb);
     p.off_U = take(cb * p.nU), p.off_H = take(cb * p.nH);
@@ -547,6 +594,21 @@ int launch_heads_bwd(const peneo_dims& dm, int prec, const void* pack, const voi
   // ---- pair part, one chunk of whole pair-rows at a time
   float* dab = F(pl.off_dab);
   TRY(zero(dab, (size_t)T * 2 * d));
+  int tc_version = 2;
+  if (const char* e = getenv("PENEO_BWD_TC")) tc_version = atoi(e) == 1 ? 1 : 2;
+  float **d_outw = nullptr, **d_outb = nullptr, **d_midb = nullptr;
+  if (tc && tc_version == 2) {
+    // bf16 per-token projections (0.5-scaled A | Bm) for T1, exactly what the forward pass used
+    rc = peneo_token_proj_fwd(&dm, PENEO_PREC_BF16, pack, x, x_dtype, x_row_stride, T, ws + pl.off_ab16, ws + pl.off_tokws, st);
+    if (rc != PENEO_OK) return rc;
+    // device tables of the per-head gradient pointers (15 pointers at the start of the token scratch tail)
+    float* h_tab[15];
+    for (int h = 0; h < kNumHeads; ++h) h_tab[h] = gr.out_w[h], h_tab[5 + h] = gr.out_b[h], h_tab[10 + h] = gr.mid_b[h * 8];
+    float** tab = reinterpret_cast<float**>(ws + pl.off_tokws + pl.tokws_bytes - 1024);
+    PENEO_CUDA_TRY(cudaMemcpyAsync(tab, h_tab, sizeof h_tab, cudaMemcpyHostToDevice, st));
+    PENEO_CUDA_TRY(cudaStreamSynchronize(st));  // h_tab lives on this stack frame
+    d_outw = tab, d_outb = tab + 5, d_midb = tab + 10;
+  }
   float *S = F(pl.off_S), *dS = F(pl.off_dS), *G = F(pl.off_G);
   const size_t cstride = fl((size_t)pl.chunk_rows_max * d) / sizeof(float);
   for (int b = 0; b < batch; ++b) {
@@ -556,7 +618,25 @@ int launch_heads_bwd(const peneo_dims& dm, int prec, const void* pack, const voi
       while (i1 < n && row_start(i1 + 1, n) - row_start(i0, n) <= pl.chunk_rows_max) ++i1;
       const int p0 = row_start(i0, n), rows = row_start(i1, n) - p0;  // row_start(n, n) == P
       const int rb = (rows + 127) / 128;
-      if (tc) {
+      if (tc && tc_version == 2) {
+        __nv_bfloat16* S16 = reinterpret_cast<__nv_bfloat16*>(ws + pl.off_S16);
+        __nv_bfloat16* Gc = reinterpret_cast<__nv_bfloat16*>(ws + pl.off_Gc);
+        __nv_bfloat16* Mc = reinterpret_cast<__nv_bfloat16*>(ws + pl.off_Mc);
+        const __nv_bfloat16* ab16 = reinterpret_cast<const __nv_bfloat16*>(ws + pl.off_ab16);
+        // T1: regenerate S, M = SiLU(u), G = (dz W_out) SiLU'(u) for the five heads (tcgen05, K2's structure)
+        TRY(launch_pair_bwd_prep(pack, L, ab16, n, (int64_t)b * P + p0, rows, dlogits, S16, Gc, Mc, st));
+        // dS = G W_mid (all heads in one K = 1920 GEMM) ; dW_mid += G^T S
+        TRY(launch_gemm_ds(Gc, reinterpret_cast<const __nv_bfloat16*>(pk + L.wmid_full_bf16), dS, rows, st));
+        float* dwm[kNumHeads];
+        DzPtrs dzp;
+        for (int h = 0; h < kNumHeads; ++h) {
+          dwm[h] = gr.mid_w[h * 8];
+          dzp.p[h] = dlogits[h] + ((int64_t)b * P + p0) * head_classes(h);
+        }
+        TRY(launch_gemm_dw(Gc, S16, dwm, rows, st));
+        dwout_bf16_kernel<<<dim3((rows + 255) / 256, 15), 128, 0, st>>>(Mc, Gc, dzp, rows, d_outw, d_outb, d_midb);
+        PENEO_CUDA_TRY(cudaGetLastError());
+      } else if (tc) {
         __nv_bfloat16* S16 = reinterpret_cast<__nv_bfloat16*>(ws + pl.off_S16);
         __nv_bfloat16* ST16 = reinterpret_cast<__nv_bfloat16*>(ws + pl.off_ST16);
         __nv_bfloat16* U16 = reinterpret_cast<__nv_bfloat16*>(ws + pl.off_U16);
