@@ -24,19 +24,23 @@ namespace t1 {
 constexpr int D = 384;
 constexpr int kChunks = 15;       // 5 heads x 3 chunks of 128 mid features
 constexpr int kKChunks = 6;       // 384 / 64
-constexpr int kWStages = 6;
+constexpr int kWStages = 5;
 constexpr int kWStageBytes = 128 * 64 * 2;  // 16 KB
 constexpr int kStageRowBytes = D * 2;       // staging: 128 rows x 768 B
 constexpr int kThreads = 512;
 constexpr int kLdG = 5 * D;                 // row stride of G / M
 
 constexpr uint32_t kColS = 0, kColU = 192;
+constexpr int kOutRowBytes = 64 + 16;            // 32 bf16 + pad (conflict-free 16-B accesses)
+constexpr int kOutWarpBytes = 32 * kOutRowBytes;  // 2560 B
 
 struct Smem {
   static constexpr int w = 0;
   static constexpr int stage = w + kWStages * kWStageBytes;
   static constexpr int bmid = stage + 128 * kStageRowBytes;  // 1920 floats
-  static constexpr int bars = bmid + 5 * D * 4;
+  static constexpr int out = bmid + 5 * D * 4;               // 8 epilogue warps x [32 rows][64 + 16 B]
+  static constexpr int wout = out + 8 * kOutWarpBytes;       // [1920] x (bf16 W_out[0..2][f], 0) = 15 KB
+  static constexpr int bars = wout + 5 * D * 8;
   static constexpr int total = bars + 512;
 };
 constexpr int bWFull = 0, bWEmpty = bWFull + kWStages, bUFull = bWEmpty + kWStages, bUFree = bUFull + 2,
@@ -78,6 +82,11 @@ __global__ void __launch_bounds__(kThreads, 1) pair_bwd_prep_kernel(const __grid
     ptx::tmem_relinquish();
   }
   for (int e = threadIdx.x; e < 5 * D; e += kThreads) s_bmid[e] = a.bmid_half[e];
+  uint2* s_wout = reinterpret_cast<uint2*>(smem + Smem::wout);
+  for (int e = threadIdx.x; e < 5 * D; e += kThreads) {
+    const float4 w = a.wout4[e];
+    s_wout[e] = make_uint2(ptx::pack_bf16x2(w.x, w.y), ptx::pack_bf16x2(w.z, 0.f));
+  }
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
@@ -160,7 +169,7 @@ __global__ void __launch_bounds__(kThreads, 1) pair_bwd_prep_kernel(const __grid
         const uint32_t ut = tmem + lane_base + kColU + 128 * buf + 64 * hsel;
         const int f0 = c * 128 + 64 * hsel;  // column in the stacked [0, 1920) feature space
         const float* hb = s_bmid + f0;
-        const float4* w4 = a.wout4 + f0;     // wout4 is indexed [k * 384 + f] = stacked feature index
+        const uint2* w4 = s_wout + f0;       // indexed by the stacked feature index k * 384 + f
 #pragma unroll
         for (int piece = 0; piece < 2; ++piece) {
           uint32_t r[32];
@@ -183,20 +192,34 @@ __global__ void __launch_bounds__(kThreads, 1) pair_bwd_prep_kernel(const __grid
               const float sg = fmaf(0.5f, t, 0.5f);                 // sigmoid(u)
               const float u = h + h;
               mv[e] = u * sg;
-              const float4 w = __ldg(w4 + col);
-              const float gm = fmaf(dz2, w.z, fmaf(dz1, w.y, dz0 * w.x));
+              const uint2 wp = w4[col];  // (bf16 W_out[0][f], W_out[1][f]), (W_out[2][f], 0)
+              const float gm = fmaf(dz2, __uint_as_float(wp.y << 16),
+                                    fmaf(dz1, __uint_as_float(wp.x & 0xFFFF0000u), dz0 * __uint_as_float(wp.x << 16)));
               gv[e] = gm * (sg * fmaf(u, 1.0f - sg, 1.0f));
             }
             mp[x / 2] = ptx::pack_bf16x2(mv[0], mv[1]);
             gpk[x / 2] = ptx::pack_bf16x2(gv[0], gv[1]);
           }
-          if (live) {
-            uint4* dm = reinterpret_cast<uint4*>(a.M + lr * kLdG + f0 + 32 * piece);
-            uint4* dg = reinterpret_cast<uint4*>(a.G + lr * kLdG + f0 + 32 * piece);
+          // Coalesced stores: lane = row in TMEM, so each lane holds 64 B of its own row; going through a
+          // per-warp smem tile lets one store instruction write 8 rows x 64 B (full sectors) instead of
+          // 32 rows x 16 B (one LSU transaction per lane).
+          unsigned char* ob = smem + Smem::out + (warp - 4) * kOutWarpBytes;
+          const int64_t row0 = tile * 128 + q * 32;  // first chunk-row of this warp
 #pragma unroll
-            for (int v = 0; v < 4; ++v) {
-              dm[v] = make_uint4(mp[4 * v], mp[4 * v + 1], mp[4 * v + 2], mp[4 * v + 3]);
-              dg[v] = make_uint4(gpk[4 * v], gpk[4 * v + 1], gpk[4 * v + 2], gpk[4 * v + 3]);
+          for (int arr = 0; arr < 2; ++arr) {
+            const uint32_t* src = arr == 0 ? mp : gpk;
+            __nv_bfloat16* dstm = (arr == 0 ? a.M : a.G) + f0 + 32 * piece;
+            __syncwarp();
+#pragma unroll
+            for (int v = 0; v < 4; ++v)
+              *reinterpret_cast<uint4*>(ob + lane * kOutRowBytes + v * 16) =
+                  make_uint4(src[4 * v], src[4 * v + 1], src[4 * v + 2], src[4 * v + 3]);
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int rr = 8 * i + (lane >> 2), c16 = lane & 3;
+              const uint4 val = *reinterpret_cast<const uint4*>(ob + rr * kOutRowBytes + c16 * 16);
+              if (row0 + rr < a.rows) *reinterpret_cast<uint4*>(dstm + (row0 + rr) * kLdG + c16 * 8) = val;
             }
           }
         }
@@ -259,7 +282,19 @@ __global__ void __launch_bounds__(kThreads, 1) pair_bwd_prep_kernel(const __grid
         }
       }
       __syncwarp();
-      // ---- copy into TMEM (and to the S matrix in global memory), one 64-feature K chunk at a time
+      // ---- S matrix to global memory: the warp's 32 rows are 24 KB contiguous in S [rows, 384]; read the
+      //      swizzled staging tile 16 B at a time so that every store instruction covers 512 contiguous bytes
+      {
+        const int64_t row0 = tile * 128 + q * 32;
+#pragma unroll 4
+        for (int itc = 0; itc < 48; ++itc) {
+          const int id = itc * 32 + lane, rr = id / 48, c16 = id - rr * 48;
+          const int r2 = q * 32 + rr;
+          const uint4 t = *reinterpret_cast<const uint4*>(stg + r2 * kStageRowBytes + ((c16 ^ (r2 & 7)) * 16));
+          if (row0 + rr < a.rows) *reinterpret_cast<uint4*>(a.S + (row0 + rr) * D + c16 * 8) = t;
+        }
+      }
+      // ---- copy into TMEM, one 64-feature K chunk at a time, as the MMA warp releases them
       const int r = q * 32 + lane;
 #pragma unroll 1
       for (int kc = 0; kc < kKChunks; ++kc) {
@@ -269,11 +304,6 @@ __global__ void __launch_bounds__(kThreads, 1) pair_bwd_prep_kernel(const __grid
           const int chunk16 = (kc * 8 + ch) ^ (r & 7);
           const uint4 t = *reinterpret_cast<const uint4*>(stg + r * kStageRowBytes + chunk16 * 16);
           v[4 * ch] = t.x, v[4 * ch + 1] = t.y, v[4 * ch + 2] = t.z, v[4 * ch + 3] = t.w;
-        }
-        if (my_lr < a.rows) {
-          uint4* ds = reinterpret_cast<uint4*>(a.S + my_lr * D + kc * 64);
-#pragma unroll
-          for (int ch = 0; ch < 8; ++ch) ds[ch] = make_uint4(v[4 * ch], v[4 * ch + 1], v[4 * ch + 2], v[4 * ch + 3]);
         }
         if (it > 0) ptx::mbar_wait(&bars[bSFree + kc], (it - 1) & 1);
         ptx::tc_fence_after();

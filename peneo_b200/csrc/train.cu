@@ -263,45 +263,47 @@ __global__ void __launch_bounds__(128) colsum_kernel(const float* __restrict__ X
   atomicAdd(&out[f], acc);
 }
 
-// g_v = dS * SiLU'(a_i + b_j), in place
-__global__ void gv_kernel(float* __restrict__ dS, const float* __restrict__ ab, int b, int n, int d, int p0) {
-  const int r = blockIdx.x;
-  int i, j;
-  pair_from_flat(p0 + r, n, i, j);
-  const float* ai = ab + ((int64_t)b * n + i) * 2 * d;
-  const float* bj = ab + ((int64_t)b * n + j) * 2 * d + d;
-  for (int f = threadIdx.x; f < d; f += blockDim.x) dS[(int64_t)r * d + f] *= dsilu_exact(ai[f] + bj[f]);
-}
-
-// dA[t] = sum_{j >= t} g_v(t, j) for pair-rows t in [i0, i1) ; dBm[t] += sum_{i in [i0, min(t, i1-1)]} g_v(i, t).
-// Grid: (token t of the document, column blocks of 128); deterministic (no atomics).
-__global__ void __launch_bounds__(128) gv_reduce_kernel(const float* __restrict__ gv, int b, int n, int d, int i0, int i1,
-                                                        float* __restrict__ dab) {
+// g_v(i, j) = dS(i, j) * SiLU'(a_i + b_j), reduced on the fly:
+//   dA[t]   = sum_{j >= t} g_v(t, j)                      for pair-rows t in [i0, i1)
+//   dBm[t] += sum_{i in [i0, min(t, i1 - 1)]} g_v(i, t)
+// SiLU' is evaluated where it is consumed (twice per pair) instead of in a separate read-modify-write pass
+// over dS.  Grid: (token t of the document, column blocks of 128); deterministic (no atomics).
+__global__ void __launch_bounds__(128) gv_reduce_kernel(const float* __restrict__ dS, const float* __restrict__ ab, int b,
+                                                        int n, int d, int i0, int i1, float* __restrict__ dab) {
   const int t = blockIdx.x;
   const int f = blockIdx.y * 128 + threadIdx.x;
   if (f >= d) return;
   const int p0 = row_start(i0, n);
+  const float* abd = ab + (int64_t)b * n * 2 * d;  // this document's [n, 2d] projections
   float* out = dab + ((int64_t)b * n + t) * 2 * d;
   if (t >= i0 && t < i1) {
-    const float* src = gv + (int64_t)(row_start(t, n) - p0) * d + f;
+    const float at = abd[(int64_t)t * 2 * d + f];
+    const float* src = dS + (int64_t)(row_start(t, n) - p0) * d + f;
+    const float* bj = abd + (int64_t)t * 2 * d + d + f;
     float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
     int j = t;
     for (; j + 3 < n; j += 4) {
-      a0 += src[(int64_t)(j - t) * d], a1 += src[(int64_t)(j + 1 - t) * d];
-      a2 += src[(int64_t)(j + 2 - t) * d], a3 += src[(int64_t)(j + 3 - t) * d];
+      const int64_t o = (int64_t)(j - t);
+      a0 = fmaf(src[o * d], dsilu_exact(at + bj[o * 2 * d]), a0);
+      a1 = fmaf(src[(o + 1) * d], dsilu_exact(at + bj[(o + 1) * 2 * d]), a1);
+      a2 = fmaf(src[(o + 2) * d], dsilu_exact(at + bj[(o + 2) * 2 * d]), a2);
+      a3 = fmaf(src[(o + 3) * d], dsilu_exact(at + bj[(o + 3) * 2 * d]), a3);
     }
-    for (; j < n; ++j) a0 += src[(int64_t)(j - t) * d];
+    for (; j < n; ++j) a0 = fmaf(src[(int64_t)(j - t) * d], dsilu_exact(at + bj[(int64_t)(j - t) * 2 * d]), a0);
     out[f] = (a0 + a1) + (a2 + a3);
   }
   const int ihi = min(t, i1 - 1);
   if (ihi >= i0) {
+    const float bt = abd[(int64_t)t * 2 * d + d + f];
     float a0 = 0.f, a1 = 0.f;
     int i = i0;
     for (; i + 1 <= ihi; i += 2) {
-      a0 += gv[(int64_t)(row_start(i, n) - p0 + (t - i)) * d + f];
-      a1 += gv[(int64_t)(row_start(i + 1, n) - p0 + (t - i - 1)) * d + f];
+      a0 = fmaf(dS[(int64_t)(row_start(i, n) - p0 + (t - i)) * d + f], dsilu_exact(abd[(int64_t)i * 2 * d + f] + bt), a0);
+      a1 = fmaf(dS[(int64_t)(row_start(i + 1, n) - p0 + (t - i - 1)) * d + f],
+                dsilu_exact(abd[(int64_t)(i + 1) * 2 * d + f] + bt), a1);
     }
-    if (i <= ihi) a0 += gv[(int64_t)(row_start(i, n) - p0 + (t - i)) * d + f];
+    if (i <= ihi)
+      a0 = fmaf(dS[(int64_t)(row_start(i, n) - p0 + (t - i)) * d + f], dsilu_exact(abd[(int64_t)i * 2 * d + f] + bt), a0);
     out[d + f] += a0 + a1;
   }
 }
@@ -724,9 +726,7 @@ int launch_heads_bwd(const peneo_dims& dm, int prec, const void* pack, const voi
         }
       }
       }  // fp32 pair part
-      gv_kernel<<<rows, 128, 0, st>>>(dS, ab, b, n, d, p0);
-      PENEO_CUDA_TRY(cudaGetLastError());
-      gv_reduce_kernel<<<dim3(n, (d + 127) / 128), 128, 0, st>>>(dS, b, n, d, i0, i1, dab);
+      gv_reduce_kernel<<<dim3(n, (d + 127) / 128), 128, 0, st>>>(dS, ab, b, n, d, i0, i1, dab);
       PENEO_CUDA_TRY(cudaGetLastError());
       i0 = i1;
     }
