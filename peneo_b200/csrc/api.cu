@@ -143,15 +143,16 @@ int peneo_token_proj_fwd(const peneo_dims* dims, int prec, const void* pack, con
     if ((rc = launch_cast_rows(x, x_dtype, x_row_stride, xc, PENEO_DT_BF16, tokens, dm.hin, st)) != PENEO_OK) return rc;
     xin = xc, ldx = dm.hin;
   }
-  if ((rc = launch_gemm_tc(xin, ldx, reinterpret_cast<const __nv_bfloat16*>(pk + L.w1_bf16), dm.hin,
-                           reinterpret_cast<const float*>(pk + L.b1), y1, dm.hid, tokens, dm.hid, dm.hin, 1, st)) != PENEO_OK)
+  // persistent tcgen05 GEMM chain (gemm_tc2): x -> y1 -> y -> (0.5 A | 0.5 Bm)
+  if ((rc = launch_gemm_tc2(xin, ldx, reinterpret_cast<const __nv_bfloat16*>(pk + L.w1_bf16), dm.hin,
+                            reinterpret_cast<const float*>(pk + L.b1), y1, dm.hid, tokens, dm.hid, dm.hin, 0, 1, st, 1)) != PENEO_OK)
     return rc;
-  if ((rc = launch_gemm_tc(y1, dm.hid, reinterpret_cast<const __nv_bfloat16*>(pk + L.w2_bf16), dm.hid,
-                           reinterpret_cast<const float*>(pk + L.b2), y, dm.d, tokens, dm.d, dm.hid, 1, st)) != PENEO_OK)
+  if ((rc = launch_gemm_tc2(y1, dm.hid, reinterpret_cast<const __nv_bfloat16*>(pk + L.w2_bf16), dm.hid,
+                            reinterpret_cast<const float*>(pk + L.b2), y, dm.d, tokens, dm.d, dm.hid, 0, 1, st, 1)) != PENEO_OK)
     return rc;
-  return launch_gemm_tc(y, dm.d, reinterpret_cast<const __nv_bfloat16*>(pk + L.wc_bf16), dm.d,
-                        reinterpret_cast<const float*>(pk + L.bc_half), static_cast<__nv_bfloat16*>(ab), 2 * dm.d, tokens,
-                        2 * dm.d, dm.d, 0, st);
+  return launch_gemm_tc2(y, dm.d, reinterpret_cast<const __nv_bfloat16*>(pk + L.wc_bf16), dm.d,
+                         reinterpret_cast<const float*>(pk + L.bc_half), static_cast<__nv_bfloat16*>(ab), 2 * dm.d, tokens,
+                         2 * dm.d, dm.d, 0, 1, st, 0);
 }
 
 int peneo_pair_heads_fwd(const peneo_dims* dims, int prec, const void* pack, const void* ab, int32_t batch, int32_t n,

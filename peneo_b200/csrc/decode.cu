@@ -92,10 +92,19 @@ __global__ void __launch_bounds__(256) decode_spots_kernel(const SpotArgs a) {
     if (p < a.pairs) {
       if constexpr (DT == PENEO_DT_I64) {
         pred = static_cast<int>(reinterpret_cast<const int64_t*>(base)[doc_row0 + p]);
-      } else if (C == 2) {
-        classify<DT, 2>(base, doc_row0 + p, pred, score);
       } else {
-        classify<DT, 3>(base, doc_row0 + p, pred, score);
+        // Fast reject: when the class-0 logit is >= every other logit, its probability is >= theirs after any
+        // monotone rounding and argmax returns the first maximum, i.e. class 0 -> not a spot.  Only the rare
+        // rows that can be spots pay for the exact softmax (exp, sum, divide, round) of the reference.
+        const float x0 = load_as_float<DT>(base, (doc_row0 + p) * C);
+        float xo = load_as_float<DT>(base, (doc_row0 + p) * C + 1);
+        if (C == 3) xo = fmaxf(xo, load_as_float<DT>(base, (doc_row0 + p) * C + 2));
+        if (!(x0 >= xo)) {
+          if (C == 2)
+            classify<DT, 2>(base, doc_row0 + p, pred, score);
+          else
+            classify<DT, 3>(base, doc_row0 + p, pred, score);
+        }
       }
     }
     const bool hit = pred != 0;

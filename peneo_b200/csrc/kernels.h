@@ -17,9 +17,9 @@ int launch_pair_heads_simt(const peneo_dims& dm, const void* pack, const float* 
 int launch_gemm_tc(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* W, int64_t ldw, const float* bias,
                    __nv_bfloat16* C, int64_t ldc, int64_t M, int N, int K, int act, cudaStream_t st);
 
-// C[M, N] (op)= A W^T ; out_mode 0 bf16 store (+bias), 1 fp32 store, 2 fp32 +=, 3 fp32 atomicAdd with split-K
+// C[M, N] (op)= A W^T ; out_mode 0 bf16 store (+bias, SiLU when act), 1 fp32 store, 2 fp32 +=, 3 fp32 atomicAdd with split-K
 int launch_gemm_tc2(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* W, int64_t ldw, const float* bias, void* C,
-                    int64_t ldc, int64_t M, int N, int K, int out_mode, int splits, cudaStream_t st);
+                    int64_t ldc, int64_t M, int N, int K, int out_mode, int splits, cudaStream_t st, int act = 0);
 
 // pair_heads_tc.cu
 int launch_pair_heads_tc(const void* pack, const PackLayout& L, const __nv_bfloat16* ab, int batch, int n,

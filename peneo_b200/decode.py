@@ -86,9 +86,10 @@ class PendingDecode:
     ``finish()`` waits for it (and transparently re-runs with the worst-case capacity in the rare
     case a spot list overflowed)."""
 
-    def __init__(self, ins, n, cap, decode_gt, score_thresh, want_spots):
+    def __init__(self, ins, n, cap, decode_gt, score_thresh, want_spots, d2h_stream=None):
         self.ins, self.n, self.cap = ins, n, cap
         self.decode_gt, self.score_thresh, self.want_spots = decode_gt, score_thresh, want_spots
+        self.d2h_stream = d2h_stream  # optional side stream so the record copy does not stall the next batch
         self._launch()
 
     def _launch(self):
@@ -119,11 +120,24 @@ class PendingDecode:
         COUNTERS["kernels"] += 2
         self.counts_h = torch.empty(counts.shape, dtype=torch.int32, pin_memory=True)
         self.rec_h = torch.empty(rec.shape, dtype=torch.int32, pin_memory=True)
-        self.counts_h.copy_(counts, non_blocking=True)
-        self.rec_h.copy_(rec, non_blocking=True)
+        cur = torch.cuda.current_stream(dev)
+        if self.d2h_stream is not None and self.d2h_stream != cur:
+            ready = torch.cuda.Event()
+            ready.record(cur)
+            with torch.cuda.stream(self.d2h_stream):
+                self.d2h_stream.wait_event(ready)
+                self.counts_h.copy_(counts, non_blocking=True)
+                self.rec_h.copy_(rec, non_blocking=True)
+                counts.record_stream(self.d2h_stream)
+                rec.record_stream(self.d2h_stream)
+                self.event = torch.cuda.Event()
+                self.event.record(self.d2h_stream)
+        else:
+            self.counts_h.copy_(counts, non_blocking=True)
+            self.rec_h.copy_(rec, non_blocking=True)
+            self.event = torch.cuda.Event()
+            self.event.record(cur)
         self.d2h_bytes = self.counts_h.numel() * 4 + self.rec_h.numel() * 4
-        self.event = torch.cuda.Event()
-        self.event.record(torch.cuda.current_stream(dev))
         self._keep = (counts, rec, ws, ws2)  # alive until the copies have run
 
     def finish(self) -> "DeviceDecode":
@@ -144,7 +158,7 @@ class PendingDecode:
 
 
 def device_decode_async(shakings: Sequence[torch.Tensor], n: int, decode_gt: bool = False, score_thresh: float = 0,
-                        cap: Optional[int] = None, want_spots: bool = False) -> PendingDecode:
+                        cap: Optional[int] = None, want_spots: bool = False, d2h_stream=None) -> PendingDecode:
     """Enqueue K3 (spots) + K4 (resolve) + the D2H copy of the compact records on the current stream."""
     ins, _tag_mode = _as_batched_inputs(shakings)
     p = shaking_len(n)
@@ -153,7 +167,7 @@ def device_decode_async(shakings: Sequence[torch.Tensor], n: int, decode_gt: boo
             raise ValueError(f"shaking tensor {k} has {t.shape[1]} rows, expected {p} for seq_len {n}")
     if cap is None:
         cap = min(p, max(8 * n, 1024))
-    return PendingDecode(ins, n, cap, decode_gt, score_thresh, want_spots)
+    return PendingDecode(ins, n, cap, decode_gt, score_thresh, want_spots, d2h_stream)
 
 
 def device_decode(shakings: Sequence[torch.Tensor], n: int, decode_gt: bool = False, score_thresh: float = 0,

@@ -25,6 +25,7 @@ class HeadsDecodePipeline:
             raise RuntimeError("HeadsDecodePipeline needs the decoder on a CUDA device (no CPU path)")
         self.compute = torch.cuda.Stream(self.device)
         self.copy = torch.cuda.Stream(self.device)
+        self.d2h = torch.cuda.Stream(self.device)
         self.score_thresh = score_thresh
         self._queue = deque()
         self.h2d_bytes = 0
@@ -55,7 +56,7 @@ class HeadsDecodePipeline:
             if self.k2_events is not None:
                 e1.record(self.compute)
                 self.k2_events.append((e0, e1))
-            pending = decode.device_decode_async(logits, n, score_thresh=self.score_thresh)
+            pending = decode.device_decode_async(logits, n, score_thresh=self.score_thresh, d2h_stream=self.d2h)
             x.record_stream(self.compute)
         self.d2h_bytes += pending.d2h_bytes
         self._queue.append((pending, list(texts), bboxes))
