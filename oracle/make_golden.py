@@ -250,6 +250,26 @@ def tag_cases(ns):
     return cases
 
 
+def eval_cases(ns):
+    """pipeline/evaluation.py on decoded synthetic documents: predictions = decode of planted logits of a
+    *perturbed* document (so that TP / FP / FN all occur), ground truth = GT decode of the document."""
+    tagger = ns.HandshakingTaggingScheme()
+    preds, gts, names = [], [], []
+    for did, n in [(1, 63), (2, 95), (3, 40), (4, 63), (5, 127)]:
+        doc = synth.make_document(n, doc_id=did)
+        other = synth.make_document(n, doc_id=did + (0 if did % 2 else 50))  # odd ids: perfect prediction
+        pred = ns.sample_decode_peneo(tagger, doc.text, *synth.planted_logits(other, seed=did), seq_len=n)
+        gt = ns.sample_decode_peneo(tagger, doc.text, *doc.tags(), seq_len=n, decode_gt=True)
+        preds.append(pred), gts.append(gt), names.append(f"file_{did}.json")
+    # a duplicated file name (distributed sampler padding) and an empty sample
+    preds.append(preds[0]), gts.append(gts[0]), names.append(names[0])
+    empty = ([], [], {}, {}, {}, {}, {})
+    preds.append(empty), gts.append(empty), names.append("empty.json")
+    kv = ns.calculate_KVPE_metric(preds, gts, names)
+    detail = ns.calculate_detail_KVPE_metric(preds, gts, names)
+    return dict(preds=preds, gts=gts, names=names, kvpe=kv, detail=detail)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ns = ref_shim.load_reference()
@@ -259,6 +279,8 @@ def main():
     torch.save(train_cases(ns), os.path.join(OUT, "train.pt"))
     torch.save(decode_cases(ns), os.path.join(OUT, "decode.pt"))
     torch.save(tag_cases(ns), os.path.join(OUT, "tags.pt"))
+    if os.environ.get("PENEO_GOLDEN_ONLY", "") in ("", "eval"):
+        torch.save(eval_cases(ns), os.path.join(OUT, "eval.pt"))
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

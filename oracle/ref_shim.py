@@ -39,6 +39,7 @@ def load_reference():
     from model.custom_loss import CrossEntropyLossOHEM
     from pipeline.decode import decode_peneo, sample_decode_peneo, parse_matrix_spots
     from data.data_utils import merge_bbox
+    from pipeline.evaluation import calculate_KVPE_metric, calculate_detail_KVPE_metric
 
     ns = types.SimpleNamespace(
         PEneoConfig=PEneoConfig,
@@ -51,5 +52,7 @@ def load_reference():
         sample_decode_peneo=sample_decode_peneo,
         parse_matrix_spots=parse_matrix_spots,
         merge_bbox=merge_bbox,
+        calculate_KVPE_metric=calculate_KVPE_metric,
+        calculate_detail_KVPE_metric=calculate_detail_KVPE_metric,
     )
     return ns
