@@ -117,21 +117,38 @@ __global__ void __launch_bounds__(256) decode_spots_kernel(const SpotArgs a) {
   }
   if (lane == 0) wcount[warp] = cnt;
   __syncthreads();
-  if (threadIdx.x == 0) {
+  if (warp == 0) {
+    // Decoupled look-back (single-pass scan): publish this chunk's own count first, then walk back over the
+    // predecessors 32 at a time, adding their counts until one that already knows its inclusive prefix.
+    // status word: (value << 2) | flag, flag 1 = chunk count, 2 = inclusive prefix, 0 = nothing yet.
     int total = 0;
     for (int w = 0; w < 8; ++w) total += wcount[w];
-    int prefix = 0;
-    if (chunk > 0) {
-      volatile int32_t* st = a.status + (int64_t)list * a.chunks + chunk - 1;
-      int v;
-      while ((v = *st) == 0) {
-      }
-      prefix = v - 1;
+    int32_t* st = a.status + (int64_t)list * a.chunks;
+    if (lane == 0 && chunk + 1 < a.chunks) {
+      __threadfence();
+      atomicExch(&st[chunk], (total << 2) | 1);
     }
-    __threadfence();
-    atomicExch(&a.status[(int64_t)list * a.chunks + chunk], prefix + total + 1);
-    if (chunk == a.chunks - 1) a.counts[list] = prefix + total;
-    s_base = prefix;
+    int prefix = 0, look = chunk - 1;
+    while (look >= 0) {
+      const int idx = look - lane;  // lane 0 = nearest predecessor; before the first chunk: prefix 0
+      const int v = idx >= 0 ? *reinterpret_cast<volatile int32_t*>(&st[idx]) : 2;
+      const unsigned ready = __ballot_sync(0xffffffffu, v != 0);
+      const unsigned is_p = __ballot_sync(0xffffffffu, (v & 3) == 2);
+      const int first_p = is_p ? __ffs(is_p) - 1 : 32;
+      const unsigned need = first_p >= 31 ? 0xffffffffu : ((1u << (first_p + 1)) - 1u);
+      if ((ready & need) != need) continue;  // a predecessor inside the window has not published yet
+      int contrib = lane <= first_p ? (v >> 2) : 0;
+      for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, o);
+      prefix += contrib;
+      if (first_p < 32) break;
+      look -= 32;
+    }
+    if (lane == 0) {
+      __threadfence();
+      atomicExch(&st[chunk], ((prefix + total) << 2) | 2);
+      if (chunk == a.chunks - 1) a.counts[list] = prefix + total;
+      s_base = prefix;
+    }
   }
   __syncthreads();
   int off = s_base;
