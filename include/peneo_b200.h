@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define PENEO_ABI_VERSION 1
+#define PENEO_ABI_VERSION 2
 
 #define PENEO_OK 0
 #define PENEO_E_INVALID -1     /* bad argument / unsupported configuration */
@@ -84,6 +84,14 @@ typedef struct peneo_params {
   const float* out_b[PENEO_NUM_HEADS]; /* [C_h]                   */
 } peneo_params;
 
+/* Dropout of the decoder's own nn.Dropout modules in training mode (model/peneo_decoder.py:218, 221, 261).
+ * NULL or p == 0 means eval-mode behaviour (identity).  The mask is a pure function of (seed, site, element),
+ * so the backward pass regenerates it: pass the SAME struct to the forward calls and to peneo_heads_bwd. */
+typedef struct peneo_dropout {
+  float p;       /* drop probability, backbone_config["hidden_dropout_prob"] */
+  uint64_t seed; /* fresh per training step */
+} peneo_dropout;
+
 /* Bytes of the packed-weight buffer for (dims, prec).  0 if the combination is unsupported
  * (PENEO_PREC_BF16 needs shrink-style d == 384 and num_layers == 2). */
 size_t peneo_pack_bytes(const peneo_dims* dims, int prec);
@@ -100,12 +108,13 @@ size_t peneo_token_proj_workspace_bytes(const peneo_dims* dims, int prec, int64_
  * (fp32 for PENEO_PREC_FP32; bf16, pre-multiplied by 1/2, for PENEO_PREC_BF16).
  * If y_out != NULL also stores y (shrink output, same type as ab) for the backward pass. */
 int peneo_token_proj_fwd(const peneo_dims* dims, int prec, const void* pack, const void* x, int x_dtype,
-                         int64_t x_row_stride, int64_t tokens, void* ab, void* workspace, void* stream);
+                         int64_t x_row_stride, int64_t tokens, void* ab, void* workspace, const peneo_dropout* dropout,
+                         void* stream);
 
 /* Pair scoring + classifier heads for `batch` documents of `n` tokens each.
  * logits[h]: fp32 [batch, n(n+1)/2, C_h], row p(i,j) = i*n - i(i-1)/2 + (j-i). */
 int peneo_pair_heads_fwd(const peneo_dims* dims, int prec, const void* pack, const void* ab, int32_t batch, int32_t n,
-                         float* const logits[PENEO_NUM_HEADS], void* stream);
+                         float* const logits[PENEO_NUM_HEADS], const peneo_dropout* dropout, void* stream);
 
 /* ------------------------------------------------------------------ loss */
 /* Class-weighted cross entropy of the five heads over the whole batch (OHEM off):
@@ -159,7 +168,7 @@ typedef struct peneo_grads {
 size_t peneo_heads_bwd_workspace_bytes(const peneo_dims* dims, int prec, int32_t batch, int32_t n);
 int peneo_heads_bwd(const peneo_dims* dims, int prec, const void* pack, const void* x, int x_dtype,
                     int64_t x_row_stride, int32_t batch, int32_t n, const float* const dlogits[PENEO_NUM_HEADS],
-                    const peneo_grads* grads, float* dx, void* workspace, void* stream);
+                    const peneo_grads* grads, float* dx, void* workspace, const peneo_dropout* dropout, void* stream);
 
 /* ------------------------------------------------------------------ tags */
 /* Dense tags from sparse spots: tags[b, p(i,j)] = tag for every (b, i, j, tag) quadruple

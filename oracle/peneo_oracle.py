@@ -66,15 +66,59 @@ def shaking_index(i: int, j: int, n: int) -> int:
 
 
 # --------------------------------------------------------------------------------------
+# dropout masks (training mode).  torch's RNG stream cannot be matched by a CUDA kernel, so the product
+# defines its own counter-based mask (peneo_b200/csrc/common.cuh); this is its restatement, so that the
+# training-mode forward / backward can be checked element for element with the SAME mask.
+# --------------------------------------------------------------------------------------
+SITE_TOK0, SITE_TOK1 = 0, 1
+
+
+def site_head(head: int, layer: int) -> int:
+    return 16 + 8 * head + layer
+
+
+def _mix32(x: np.ndarray) -> np.ndarray:
+    x = x.astype(np.uint64) & 0xFFFFFFFF
+    x ^= x >> 16
+    x = (x * 0x7FEB352D) & 0xFFFFFFFF
+    x ^= x >> 15
+    x = (x * 0x846CA68B) & 0xFFFFFFFF
+    x ^= x >> 16
+    return x
+
+
+def dropout_mask(dropout, site: int, rows: np.ndarray, ncols: int, dtype=torch.float64) -> torch.Tensor:
+    """[len(rows), ncols] tensor of 0 / (1 / (1 - p)) for the Dropout module `site`; `rows` are token indices
+    (per-token sites) or batch-flat pair indices (pair sites).  ``dropout = (p, seed)``."""
+    p, seed = dropout
+    p32 = np.float32(p)
+    thresh = min(int(float(p32) * 4294967296.0), 0xFFFFFFFF)
+    scale = float(np.float32(1.0) / (np.float32(1.0) - p32)) if p32 < 1 else 0.0
+    seed_lo, seed_hi = seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF
+    inner = _mix32(np.array([(seed_hi + 0x9E3779B9 * (site + 1)) & 0xFFFFFFFF], dtype=np.uint64))
+    key = _mix32(np.array([seed_lo], dtype=np.uint64) ^ inner)[0]
+    r = (np.asarray(rows, dtype=np.uint64)[:, None] * 0x9E3779B1 + np.arange(ncols, dtype=np.uint64)[None, :]) & 0xFFFFFFFF
+    keep = _mix32(r ^ key) >= thresh
+    return torch.from_numpy(keep.astype(np.float64) * scale).to(dtype)
+
+
+# --------------------------------------------------------------------------------------
 # heads
 # --------------------------------------------------------------------------------------
-def shrink_projection(p: dict, x: torch.Tensor) -> torch.Tensor:
-    """model/peneo_decoder.py:215-222 in eval mode (dropout = identity)."""
+def shrink_projection(p: dict, x: torch.Tensor, dropout=None) -> torch.Tensor:
+    """model/peneo_decoder.py:215-222; eval mode when ``dropout`` is None, else Dropout after each SiLU with the
+    product's mask (token index = position in the batch-flattened [B * N] token list)."""
     if p["shrink"] is None:
         return x
     w1, b1, w2, b2 = p["shrink"]
     y = silu(x @ w1.T + b1)
-    return silu(y @ w2.T + b2)
+    if dropout is not None:
+        rows = np.arange(x.shape[0] * x.shape[1])
+        y = y * dropout_mask(dropout, SITE_TOK0, rows, y.shape[-1], y.dtype).reshape(y.shape)
+    y = silu(y @ w2.T + b2)
+    if dropout is not None:
+        y = y * dropout_mask(dropout, SITE_TOK1, rows, y.shape[-1], y.dtype).reshape(y.shape)
+    return y
 
 
 def handshake_ref_style(p: dict, y: torch.Tensor) -> torch.Tensor:
@@ -89,22 +133,26 @@ def handshake_ref_style(p: dict, y: torch.Tensor) -> torch.Tensor:
     return silu(pairs @ p["combine_w"].T + p["combine_b"])
 
 
-def classifier(layers, s: torch.Tensor) -> torch.Tensor:
-    """model/peneo_decoder.py:253-271 in eval mode."""
+def classifier(layers, s: torch.Tensor, dropout=None, head: int = 0, rows=None) -> torch.Tensor:
+    """model/peneo_decoder.py:253-271; eval mode when ``dropout`` is None, else Dropout after every hidden SiLU
+    (``rows`` = batch-flat pair index of every row of ``s`` flattened to 2-D)."""
     h = s
     for li, (w, b) in enumerate(layers):
         h = h @ w.T + b
         if li + 1 < len(layers):
             h = silu(h)
+            if dropout is not None:
+                h = h * dropout_mask(dropout, site_head(head, li), rows, h.shape[-1], h.dtype).reshape(h.shape)
     return h
 
 
-def heads_ref_style(p: dict, x: torch.Tensor) -> List[torch.Tensor]:
+def heads_ref_style(p: dict, x: torch.Tensor, dropout=None) -> List[torch.Tensor]:
     """Full forward in the reference's own op order (model/peneo_decoder.py:349-363).
     Returns the 5 logits tensors in return order LE, EL-h2h, EL-t2t, LG-h2h, LG-t2t."""
-    y = shrink_projection(p, x)
+    y = shrink_projection(p, x, dropout)
     s = handshake_ref_style(p, y)
-    return [classifier(layers, s) for layers in p["heads"]]
+    rows = np.arange(s.shape[0] * s.shape[1]) if dropout is not None else None
+    return [classifier(layers, s, dropout, k, rows) for k, layers in enumerate(p["heads"])]
 
 
 def token_projections(p: dict, x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
@@ -213,8 +261,10 @@ def loss_and_grads(
     category_weights: Sequence[float],
     loss_ratio: Optional[Sequence[float]] = None,
     dtype=torch.float64,
+    dropout=None,
 ):
-    """Backward oracle: autograd through the restated forward (dropout off), fp64 by default.
+    """Backward oracle: autograd through the restated forward, fp64 by default (``dropout = (p, seed)`` applies
+    the product's training-mode masks; None = dropout off).
     Returns (loss, sub_losses, {param_key: grad}, d_sequence_output)."""
     sd = {}
     for k, v in state_dict.items():
@@ -224,7 +274,10 @@ def loss_and_grads(
         sd[k] = t
     p = _split_live(sd)
     xx = x.detach().to("cpu", dtype).requires_grad_(True)
-    logits = heads_chunked(p, xx, row_block=64) if xx.shape[1] > 64 else heads_ref_style(p, xx)
+    if dropout is not None:
+        logits = heads_ref_style(p, xx, dropout)
+    else:
+        logits = heads_chunked(p, xx, row_block=64) if xx.shape[1] > 64 else heads_ref_style(p, xx)
     total, subs = decoder_loss(logits, tags, category_weights, loss_ratio)
     total.backward()
     grads = {k: v.grad for k, v in sd.items() if v.requires_grad and v.grad is not None}

@@ -60,6 +60,12 @@ class Params(C.Structure):
     ]
 
 
+class Dropout(C.Structure):
+    """peneo_dropout: drop probability + per-step seed (NULL pointer = eval mode)."""
+
+    _fields_ = [("p", C.c_float), ("seed", C.c_uint64)]
+
+
 class Grads(C.Structure):
     _fields_ = Params._fields_
 
@@ -89,12 +95,12 @@ def load() -> C.CDLL:
     lib.peneo_pack_weights.argtypes = [C.POINTER(Dims), C.c_int, C.POINTER(Params), vp, vp]
     lib.peneo_token_proj_workspace_bytes.restype = sz
     lib.peneo_token_proj_workspace_bytes.argtypes = [C.POINTER(Dims), C.c_int, i64]
-    lib.peneo_token_proj_fwd.argtypes = [C.POINTER(Dims), C.c_int, vp, vp, C.c_int, i64, i64, vp, vp, vp]
-    lib.peneo_pair_heads_fwd.argtypes = [C.POINTER(Dims), C.c_int, vp, vp, i32, i32, PtrArray5, vp]
+    lib.peneo_token_proj_fwd.argtypes = [C.POINTER(Dims), C.c_int, vp, vp, C.c_int, i64, i64, vp, vp, C.POINTER(Dropout), vp]
+    lib.peneo_pair_heads_fwd.argtypes = [C.POINTER(Dims), C.c_int, vp, vp, i32, i32, PtrArray5, C.POINTER(Dropout), vp]
     lib.peneo_heads_bwd_workspace_bytes.restype = sz
     lib.peneo_heads_bwd_workspace_bytes.argtypes = [C.POINTER(Dims), C.c_int, i32, i32]
     lib.peneo_heads_bwd.argtypes = [C.POINTER(Dims), C.c_int, vp, vp, C.c_int, i64, i32, i32, PtrArray5,
-                                    C.POINTER(Grads), vp, vp, vp]
+                                    C.POINTER(Grads), vp, vp, C.POINTER(Dropout), vp]
     lib.peneo_pair_loss_workspace_bytes.restype = sz
     lib.peneo_pair_loss_workspace_bytes.argtypes = [i32, i32]
     lib.peneo_pair_loss_fwd.argtypes = [i32, i32, PtrArray5, PtrArray5, C.POINTER(C.c_float), C.POINTER(C.c_float), vp,
@@ -118,7 +124,7 @@ def load() -> C.CDLL:
     lib.peneo_decode_resolve.argtypes = [i32, i32, i32, vp, vp, vp, vp, C.c_int, C.c_float, vp, vp, vp]
     lib.peneo_selftest.argtypes = [C.POINTER(C.c_uint32), C.c_char_p, sz]
     lib.peneo_probe_rates.argtypes = [C.POINTER(C.c_double), C.c_int]
-    if lib.peneo_abi_version() != 1:
+    if lib.peneo_abi_version() != 2:
         raise RuntimeError("libpeneo_b200.so ABI version mismatch; rebuild with `python -m peneo_b200.build --force`")
     _lib = lib
     return lib
@@ -128,6 +134,13 @@ def check(rc: int, what: str) -> None:
     if rc != 0:
         msg = load().peneo_last_error().decode("utf-8", "replace")
         raise RuntimeError(f"{what} failed (status {rc}): {msg}")
+
+
+def dropout_arg(drop):
+    """(p, seed) tuple or None -> ctypes argument for a `const peneo_dropout*` parameter."""
+    if drop is None or drop[0] <= 0.0:
+        return None
+    return C.byref(Dropout(float(drop[0]), int(drop[1]) & 0xFFFFFFFFFFFFFFFF))
 
 
 def ptrs5(tensors: Sequence) -> PtrArray5:

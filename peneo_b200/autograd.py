@@ -37,7 +37,7 @@ def pair_loss_op(logits: Sequence[torch.Tensor], tags: Sequence[torch.Tensor], c
     return out6[5], [out6[h] for h in range(5)]
 
 
-def decoder_forward_with_grad(decoder, sequence_output: torch.Tensor) -> List[torch.Tensor]:
+def decoder_forward_with_grad(decoder, sequence_output: torch.Tensor, dropout=None) -> List[torch.Tensor]:
     from .train import heads_with_grad
 
-    return heads_with_grad(decoder, sequence_output)
+    return heads_with_grad(decoder, sequence_output, dropout)

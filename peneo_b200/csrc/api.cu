@@ -40,6 +40,36 @@ static int check_prec(const peneo_dims* dm, int prec) {
   return PENEO_OK;
 }
 
+// bf16 / tcgen05 per-token chain: x -> y1 -> y -> (0.5 A | 0.5 Bm), shared by the forward entry point and by the
+// backward pass (which needs the very same bf16 projections, dropout included).
+int token_proj_fwd_bf16(const peneo_dims& dm, const PackLayout& L, const char* pk, const void* x, int x_dtype,
+                        int64_t x_row_stride, int64_t tokens, void* ab, char* ws, cudaStream_t st, const DropSpec* dp) {
+  int rc;
+  __nv_bfloat16* xc = reinterpret_cast<__nv_bfloat16*>(ws);
+  __nv_bfloat16* y1 = reinterpret_cast<__nv_bfloat16*>(ws + align_up((size_t)tokens * dm.hin * 2, 1024));
+  __nv_bfloat16* y = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<char*>(y1) + align_up((size_t)tokens * dm.hid * 2, 1024));
+  const __nv_bfloat16* xin;
+  int64_t ldx;
+  if (x_dtype == PENEO_DT_BF16 && x_row_stride % 8 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+    xin = static_cast<const __nv_bfloat16*>(x), ldx = x_row_stride;
+  } else {
+    if ((rc = launch_cast_rows(x, x_dtype, x_row_stride, xc, PENEO_DT_BF16, tokens, dm.hin, st)) != PENEO_OK) return rc;
+    xin = xc, ldx = dm.hin;
+  }
+  // persistent tcgen05 GEMM chain (gemm_tc2): x -> y1 -> y -> (0.5 A | 0.5 Bm)
+  if ((rc = launch_gemm_tc2(xin, ldx, reinterpret_cast<const __nv_bfloat16*>(pk + L.w1_bf16), dm.hin,
+                            reinterpret_cast<const float*>(pk + L.b1), y1, dm.hid, tokens, dm.hid, dm.hin, 0, 1, st, 1, dp,
+                            kSiteTok0)) != PENEO_OK)
+    return rc;
+  if ((rc = launch_gemm_tc2(y1, dm.hid, reinterpret_cast<const __nv_bfloat16*>(pk + L.w2_bf16), dm.hid,
+                            reinterpret_cast<const float*>(pk + L.b2), y, dm.d, tokens, dm.d, dm.hid, 0, 1, st, 1, dp,
+                            kSiteTok1)) != PENEO_OK)
+    return rc;
+  return launch_gemm_tc2(y, dm.d, reinterpret_cast<const __nv_bfloat16*>(pk + L.wc_bf16), dm.d,
+                         reinterpret_cast<const float*>(pk + L.bc_half), static_cast<__nv_bfloat16*>(ab), 2 * dm.d, tokens,
+                         2 * dm.d, dm.d, 0, 1, st, 0);
+}
+
 }  // namespace peneo
 
 using namespace peneo;
@@ -88,7 +118,8 @@ size_t peneo_token_proj_workspace_bytes(const peneo_dims* dims, int prec, int64_
 }
 
 int peneo_token_proj_fwd(const peneo_dims* dims, int prec, const void* pack, const void* x, int x_dtype,
-                         int64_t x_row_stride, int64_t tokens, void* ab, void* workspace, void* stream) {
+                         int64_t x_row_stride, int64_t tokens, void* ab, void* workspace, const peneo_dropout* dropout,
+                         void* stream) {
   int rc;
   if ((rc = check_dims(dims)) != PENEO_OK || (rc = check_prec(dims, prec)) != PENEO_OK) return rc;
   PENEO_REQUIRE(pack && x && ab && workspace, "token_proj_fwd: NULL pointer");
@@ -101,7 +132,10 @@ int peneo_token_proj_fwd(const peneo_dims* dims, int prec, const void* pack, con
   const char* pk = static_cast<const char*>(pack);
   char* ws = static_cast<char*>(workspace);
   const int M = static_cast<int>(tokens);
-  if (prec == PENEO_PREC_FP32) {
+  const DropSpec drop = make_drop(dropout);
+  const DropSpec* dp = drop.thresh ? &drop : nullptr;
+  if (prec != PENEO_PREC_FP32) return token_proj_fwd_bf16(dm, L, pk, x, x_dtype, x_row_stride, tokens, ab, ws, st, dp);
+  {
     float* xc = reinterpret_cast<float*>(ws);
     float* y1 = reinterpret_cast<float*>(ws + align_up((size_t)tokens * dm.hin * 4, 1024));
     float* y = reinterpret_cast<float*>(reinterpret_cast<char*>(y1) + align_up((size_t)tokens * (dm.shrink ? dm.hid : 0) * 4, 1024));
@@ -117,10 +151,12 @@ int peneo_token_proj_fwd(const peneo_dims* dims, int prec, const void* pack, con
     int64_t ldy = ldx;
     if (dm.shrink) {
       if ((rc = launch_sgemm_nt(xin, ldx, reinterpret_cast<const float*>(pk + L.f_w1), dm.hin,
-                                reinterpret_cast<const float*>(pk + L.f_b1), y1, dm.hid, M, dm.hid, dm.hin, 1, 1.f, st)) != PENEO_OK)
+                                reinterpret_cast<const float*>(pk + L.f_b1), y1, dm.hid, M, dm.hid, dm.hin, 1, 1.f, st, dp,
+                                kSiteTok0)) != PENEO_OK)
         return rc;
       if ((rc = launch_sgemm_nt(y1, dm.hid, reinterpret_cast<const float*>(pk + L.f_w2), dm.hid,
-                                reinterpret_cast<const float*>(pk + L.f_b2), y, dm.d, M, dm.d, dm.hid, 1, 1.f, st)) != PENEO_OK)
+                                reinterpret_cast<const float*>(pk + L.f_b2), y, dm.d, M, dm.d, dm.hid, 1, 1.f, st, dp,
+                                kSiteTok1)) != PENEO_OK)
         return rc;
       yin = y, ldy = dm.d;
     }
@@ -131,32 +167,10 @@ int peneo_token_proj_fwd(const peneo_dims* dims, int prec, const void* pack, con
     return launch_sgemm_nt(yin, ldy, wc + dm.d, 2 * dm.d, reinterpret_cast<const float*>(pk + L.f_bc), abf + dm.d,
                            2 * dm.d, M, dm.d, dm.d, 0, 1.f, st);
   }
-  // bf16 / tcgen05
-  __nv_bfloat16* xc = reinterpret_cast<__nv_bfloat16*>(ws);
-  __nv_bfloat16* y1 = reinterpret_cast<__nv_bfloat16*>(ws + align_up((size_t)tokens * dm.hin * 2, 1024));
-  __nv_bfloat16* y = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<char*>(y1) + align_up((size_t)tokens * dm.hid * 2, 1024));
-  const __nv_bfloat16* xin;
-  int64_t ldx;
-  if (x_dtype == PENEO_DT_BF16 && x_row_stride % 8 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
-    xin = static_cast<const __nv_bfloat16*>(x), ldx = x_row_stride;
-  } else {
-    if ((rc = launch_cast_rows(x, x_dtype, x_row_stride, xc, PENEO_DT_BF16, tokens, dm.hin, st)) != PENEO_OK) return rc;
-    xin = xc, ldx = dm.hin;
-  }
-  // persistent tcgen05 GEMM chain (gemm_tc2): x -> y1 -> y -> (0.5 A | 0.5 Bm)
-  if ((rc = launch_gemm_tc2(xin, ldx, reinterpret_cast<const __nv_bfloat16*>(pk + L.w1_bf16), dm.hin,
-                            reinterpret_cast<const float*>(pk + L.b1), y1, dm.hid, tokens, dm.hid, dm.hin, 0, 1, st, 1)) != PENEO_OK)
-    return rc;
-  if ((rc = launch_gemm_tc2(y1, dm.hid, reinterpret_cast<const __nv_bfloat16*>(pk + L.w2_bf16), dm.hid,
-                            reinterpret_cast<const float*>(pk + L.b2), y, dm.d, tokens, dm.d, dm.hid, 0, 1, st, 1)) != PENEO_OK)
-    return rc;
-  return launch_gemm_tc2(y, dm.d, reinterpret_cast<const __nv_bfloat16*>(pk + L.wc_bf16), dm.d,
-                         reinterpret_cast<const float*>(pk + L.bc_half), static_cast<__nv_bfloat16*>(ab), 2 * dm.d, tokens,
-                         2 * dm.d, dm.d, 0, 1, st, 0);
 }
 
 int peneo_pair_heads_fwd(const peneo_dims* dims, int prec, const void* pack, const void* ab, int32_t batch, int32_t n,
-                         float* const logits[PENEO_NUM_HEADS], void* stream) {
+                         float* const logits[PENEO_NUM_HEADS], const peneo_dropout* dropout, void* stream) {
   int rc;
   if ((rc = check_dims(dims)) != PENEO_OK || (rc = check_prec(dims, prec)) != PENEO_OK) return rc;
   PENEO_REQUIRE(pack && ab && logits, "pair_heads_fwd: NULL pointer");
@@ -164,8 +178,11 @@ int peneo_pair_heads_fwd(const peneo_dims* dims, int prec, const void* pack, con
   if (batch == 0) return PENEO_OK;
   for (int h = 0; h < kNumHeads; ++h) PENEO_REQUIRE(logits[h], "pair_heads_fwd: logits[%d] is NULL", h);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (prec == PENEO_PREC_FP32) return launch_pair_heads_simt(*dims, pack, static_cast<const float*>(ab), batch, n, logits, st);
-  return launch_pair_heads_tc(pack, pack_layout(*dims, prec), static_cast<const __nv_bfloat16*>(ab), batch, n, logits, st);
+  const DropSpec drop = make_drop(dropout);
+  const DropSpec* dp = drop.thresh ? &drop : nullptr;
+  if (prec == PENEO_PREC_FP32)
+    return launch_pair_heads_simt(*dims, pack, static_cast<const float*>(ab), batch, n, logits, st, dp);
+  return launch_pair_heads_tc(pack, pack_layout(*dims, prec), static_cast<const __nv_bfloat16*>(ab), batch, n, logits, st, dp);
 }
 
 size_t peneo_heads_bwd_workspace_bytes(const peneo_dims* dims, int prec, int32_t batch, int32_t n) {
@@ -175,7 +192,7 @@ size_t peneo_heads_bwd_workspace_bytes(const peneo_dims* dims, int prec, int32_t
 
 int peneo_heads_bwd(const peneo_dims* dims, int prec, const void* pack, const void* x, int x_dtype, int64_t x_row_stride,
                     int32_t batch, int32_t n, const float* const dlogits[PENEO_NUM_HEADS], const peneo_grads* grads,
-                    float* dx, void* workspace, void* stream) {
+                    float* dx, void* workspace, const peneo_dropout* dropout, void* stream) {
   int rc;
   if ((rc = check_dims(dims)) != PENEO_OK || (rc = check_prec(dims, prec)) != PENEO_OK) return rc;
   PENEO_REQUIRE(pack && x && dlogits && grads && workspace, "heads_bwd: NULL pointer");
@@ -191,8 +208,9 @@ int peneo_heads_bwd(const peneo_dims* dims, int prec, const void* pack, const vo
     for (int l = 0; l + 1 < dims->num_layers; ++l)
       PENEO_REQUIRE(grads->mid_w[h * 8 + l] && grads->mid_b[h * 8 + l], "heads_bwd: head %d layer %d buffers missing", h, l);
   }
+  const DropSpec drop = make_drop(dropout);
   return launch_heads_bwd(*dims, prec, pack, x, x_dtype, x_row_stride, batch, n, dlogits, *grads, dx, workspace,
-                               static_cast<cudaStream_t>(stream));
+                          static_cast<cudaStream_t>(stream), drop.thresh ? &drop : nullptr);
 }
 
 size_t peneo_pair_loss_workspace_bytes(int32_t batch, int32_t n) { return pair_loss_workspace_bytes(batch, n); }

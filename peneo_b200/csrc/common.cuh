@@ -57,6 +57,44 @@ __device__ __forceinline__ void pair_from_flat(int32_t p, int32_t n, int32_t& i,
 
 __device__ __forceinline__ float silu_exact(float x) { return x / (1.0f + expf(-x)); }
 
+// ---- dropout ------------------------------------------------------------------------------------
+// The three dropout sites inside the decoder (model/peneo_decoder.py:218, 221, 261) use a counter-based mask so
+// that the backward pass can regenerate it instead of storing [P, D] masks: an element is kept iff
+//   mix32((row * 0x9E3779B1 + col) ^ key(seed, site)) >= p * 2^32 ,  kept values are scaled by 1 / (1 - p).
+// `row` is the token index (per-token sites) or the batch-flat pair index (pair sites); `site` numbers the
+// Dropout modules.  The RNG stream cannot match torch's; the mask is reproducible from (seed, site, row, col).
+__host__ __device__ __forceinline__ uint32_t mix32(uint32_t x) {
+  x ^= x >> 16;
+  x *= 0x7feb352du;
+  x ^= x >> 15;
+  x *= 0x846ca68bu;
+  x ^= x >> 16;
+  return x;
+}
+struct DropSpec {
+  uint32_t thresh;  // 0 = dropout disabled
+  float scale;      // 1 / (1 - p)
+  uint32_t seed_lo, seed_hi;
+};
+__host__ __device__ __forceinline__ uint32_t drop_key(const DropSpec& d, uint32_t site) {
+  return mix32(d.seed_lo ^ mix32(d.seed_hi + 0x9E3779B9u * (site + 1u)));
+}
+__host__ __device__ __forceinline__ bool drop_keep(uint32_t key, uint32_t thresh, uint32_t row, uint32_t col) {
+  return mix32((row * 0x9E3779B1u + col) ^ key) >= thresh;
+}
+constexpr uint32_t kSiteTok0 = 0, kSiteTok1 = 1;
+__host__ __device__ constexpr uint32_t site_head(int head, int layer) { return 16u + 8u * head + layer; }
+inline DropSpec make_drop(const peneo_dropout* d) {
+  DropSpec s{0u, 1.0f, 0u, 0u};
+  if (d && d->p > 0.0f) {
+    const double t = static_cast<double>(d->p) * 4294967296.0;
+    s.thresh = t >= 4294967295.0 ? 0xFFFFFFFFu : static_cast<uint32_t>(t);
+    s.scale = d->p < 1.0f ? 1.0f / (1.0f - d->p) : 0.0f;
+    s.seed_lo = static_cast<uint32_t>(d->seed), s.seed_hi = static_cast<uint32_t>(d->seed >> 32);
+  }
+  return s;
+}
+
 // ---- packed weights ---------------------------------------------------------------------------
 // One device buffer written by peneo_pack_weights; offsets in bytes from its start.
 constexpr int kMaxMidLayers = 7;  // num_layers <= 8

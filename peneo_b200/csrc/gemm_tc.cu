@@ -190,7 +190,8 @@ template <int OUT>
 __global__ void __launch_bounds__(192, 1)
     gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                     const float* __restrict__ bias, void* __restrict__ Cv, int64_t ldc, int64_t M, int N, int K,
-                    int kb_per_split, int splits, int n_blocks, int64_t num_items, int act) {
+                    int kb_per_split, int splits, int n_blocks, int64_t num_items, int act, uint32_t drop_thresh,
+                    float drop_scale, uint32_t drop_key) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kG2Stages * kGemmStageBytes);
@@ -304,7 +305,13 @@ __global__ void __launch_bounds__(192, 1)
             for (int x = 0; x < 32; x += 2) {
               float v0 = __uint_as_float(r[x]) + (bias ? bias[nb + x] : 0.f);
               float v1 = __uint_as_float(r[x + 1]) + (bias ? bias[nb + x + 1] : 0.f);
-              if (act) v0 = v0 / (1.f + __expf(-v0)), v1 = v1 / (1.f + __expf(-v1));
+              if (act) {
+                v0 = v0 / (1.f + __expf(-v0)), v1 = v1 / (1.f + __expf(-v1));
+                if (drop_thresh) {
+                  v0 = drop_keep(drop_key, drop_thresh, static_cast<uint32_t>(m), nb + x) ? v0 * drop_scale : 0.f;
+                  v1 = drop_keep(drop_key, drop_thresh, static_cast<uint32_t>(m), nb + x + 1) ? v1 * drop_scale : 0.f;
+                }
+              }
               packed[x / 2] = ptx::pack_bf16x2(v0, v1);
             }
             uint4* dst = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(Cv) + m * ldc + nb);
@@ -340,7 +347,8 @@ __global__ void __launch_bounds__(192, 1)
 }
 
 int launch_gemm_tc2(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* W, int64_t ldw, const float* bias, void* C,
-                    int64_t ldc, int64_t M, int N, int K, int out_mode, int splits, cudaStream_t st, int act) {
+                    int64_t ldc, int64_t M, int N, int K, int out_mode, int splits, cudaStream_t st, int act, const DropSpec* drop,
+                    uint32_t site) {
   PENEO_REQUIRE(N % 32 == 0 && K >= 1, "gemm_tc2: N %% 32 required (N=%d K=%d)", N, K);
   PENEO_REQUIRE(lda % 8 == 0 && ldw % 8 == 0 && ldc % (out_mode == 0 ? 8 : 4) == 0,
                 "gemm_tc2: leading dimensions not vector aligned (lda=%lld ldw=%lld ldc=%lld)", (long long)lda, (long long)ldw,
@@ -363,7 +371,9 @@ int launch_gemm_tc2(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* W,
     PENEO_CUDA_TRY(cudaGetDevice(&dev));
     PENEO_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   }
-  const int grid = static_cast<int>(std::min<int64_t>(items, sms));
+ const int grid = static_cast<int>(std::min<int64_t>(items, sms));
+  const uint32_t d_th = (drop && act) ? drop->thresh : 0u, d_key = drop ? drop_key(*drop, site) : 0u;
+  const float d_sc = drop ? drop->scale : 1.f;
 #define GO(OUT)                                                                                                      \
   {                                                                                                                  \
     static bool attr_set = false;                                                                                    \
@@ -372,7 +382,7 @@ int launch_gemm_tc2(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* W,
       attr_set = true;                                                                                               \
     }                                                                                                                \
     gemm_tc2_kernel<OUT><<<grid, 192, kG2Smem, st>>>(tmA, tmW, bias, C, ldc, M, N, K, kb_per_split, splits, n_blocks,  \
-                                                     items, act);                                                    \
+                                                     items, act, d_th, d_sc, d_key);                                 \
   }
   switch (out_mode) {
     case 0: GO(0) break;

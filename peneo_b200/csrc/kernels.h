@@ -6,12 +6,17 @@ namespace peneo {
 
 // simt_kernels.cu
 int launch_sgemm_nt(const float* A, int64_t lda, const float* W, int64_t ldw, const float* bias, float* C, int64_t ldc,
-                    int M, int N, int K, int act, float out_scale, cudaStream_t st);
+                    int M, int N, int K, int act, float out_scale, cudaStream_t st, const DropSpec* drop = nullptr,
+                    uint32_t site = 0);
 int launch_cast_rows(const void* src, int src_dtype, int64_t src_stride, void* dst, int dst_dtype, int64_t rows,
                      int cols, cudaStream_t st);
 int pack_weights_impl(const peneo_dims& dm, int prec, const peneo_params& P, void* pack, cudaStream_t st);
 int launch_pair_heads_simt(const peneo_dims& dm, const void* pack, const float* ab, int batch, int n,
-                           float* const logits[kNumHeads], cudaStream_t st);
+                           float* const logits[kNumHeads], cudaStream_t st, const DropSpec* drop = nullptr);
+
+// api.cu : bf16 per-token chain (x -> 0.5 A | 0.5 Bm), also used by the backward pass
+int token_proj_fwd_bf16(const peneo_dims& dm, const PackLayout& L, const char* pk, const void* x, int x_dtype,
+                        int64_t x_row_stride, int64_t tokens, void* ab, char* ws, cudaStream_t st, const DropSpec* dp);
 
 // gemm_tc.cu : C[M, N] = act(A[M, K] W[N, K]^T + bias) ; A, W bf16 K-contiguous; C bf16
 int launch_gemm_tc(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* W, int64_t ldw, const float* bias,
@@ -19,16 +24,17 @@ int launch_gemm_tc(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* W, 
 
 // C[M, N] (op)= A W^T ; out_mode 0 bf16 store (+bias, SiLU when act), 1 fp32 store, 2 fp32 +=, 3 fp32 atomicAdd with split-K
 int launch_gemm_tc2(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* W, int64_t ldw, const float* bias, void* C,
-                    int64_t ldc, int64_t M, int N, int K, int out_mode, int splits, cudaStream_t st, int act = 0);
+                    int64_t ldc, int64_t M, int N, int K, int out_mode, int splits, cudaStream_t st, int act = 0,
+                    const DropSpec* drop = nullptr, uint32_t site = 0);
 
 // pair_heads_tc.cu
 int launch_pair_heads_tc(const void* pack, const PackLayout& L, const __nv_bfloat16* ab, int batch, int n,
-                         float* const logits[kNumHeads], cudaStream_t st);
+                         float* const logits[kNumHeads], cudaStream_t st, const DropSpec* drop = nullptr);
 
 // pair_bwd_tc.cu : regenerated S, M = SiLU(u), G = (dz W_out) SiLU'(u) of a chunk of pairs (bf16 backward)
 int launch_pair_bwd_prep(const void* pack, const PackLayout& L, const __nv_bfloat16* ab, int n, int64_t g0, int rows,
                          const float* const dz[kNumHeads], __nv_bfloat16* S, __nv_bfloat16* G, __nv_bfloat16* M,
-                         cudaStream_t st);
+                         cudaStream_t st, const DropSpec* drop = nullptr);
 
 // gemm_bwd_tc.cu
 int launch_gemm_ds(const __nv_bfloat16* G, const __nv_bfloat16* wmid_full, float* dS, int rows, cudaStream_t st);
@@ -56,7 +62,7 @@ int launch_pair_loss_ohem_bwd(int batch, int n, const float* const logits[kNumHe
 size_t heads_bwd_workspace_bytes(const peneo_dims& dm, int prec, int batch, int n);
 int launch_heads_bwd(const peneo_dims& dm, int prec, const void* pack, const void* x, int x_dtype, int64_t x_row_stride,
                      int batch, int n, const float* const dlogits[kNumHeads], const peneo_grads& gr, float* dx,
-                     void* workspace, cudaStream_t st);
+                     void* workspace, cudaStream_t st, const DropSpec* drop = nullptr);
 
 // decode.cu
 size_t decode_spots_workspace_bytes(int batch, int n);

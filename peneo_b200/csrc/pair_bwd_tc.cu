@@ -59,6 +59,9 @@ struct Args {
   int32_t n, pairs_per_doc;
   int64_t g0;                // first flat pair of the chunk
   int32_t rows, num_tiles;
+  uint32_t drop_thresh;      // the forward pass's dropout after the hidden SiLU, regenerated (0 = none)
+  float drop_scale;
+  uint32_t drop_key[kNumHeads];
 };
 
 __global__ void __launch_bounds__(kThreads, 1) pair_bwd_prep_kernel(const __grid_constant__ CUtensorMap tmW, const Args a) {
@@ -193,8 +196,13 @@ __global__ void __launch_bounds__(kThreads, 1) pair_bwd_prep_kernel(const __grid
               const float u = h + h;
               mv[e] = u * sg;
               const uint2 wp = w4[col];  // (bf16 W_out[0][f], W_out[1][f]), (W_out[2][f], 0)
-              const float gm = fmaf(dz2, __uint_as_float(wp.y << 16),
-                                    fmaf(dz1, __uint_as_float(wp.x & 0xFFFF0000u), dz0 * __uint_as_float(wp.x << 16)));
+              float gm = fmaf(dz2, __uint_as_float(wp.y << 16),
+                              fmaf(dz1, __uint_as_float(wp.x & 0xFFFF0000u), dz0 * __uint_as_float(wp.x << 16)));
+              if (a.drop_thresh) {  // m_dropped = m * mask / (1 - p) feeds W_out; its gradient carries the same factor
+                const float ms = drop_keep(a.drop_key[k], a.drop_thresh, static_cast<uint32_t>(gp),
+                                           (c - 3 * k) * 128 + 64 * hsel + col) ? a.drop_scale : 0.f;
+                mv[e] *= ms, gm *= ms;
+              }
               gv[e] = gm * (sg * fmaf(u, 1.0f - sg, 1.0f));
             }
             mp[x / 2] = ptx::pack_bf16x2(mv[0], mv[1]);
@@ -330,7 +338,7 @@ __global__ void __launch_bounds__(kThreads, 1) pair_bwd_prep_kernel(const __grid
 
 int launch_pair_bwd_prep(const void* pack, const PackLayout& L, const __nv_bfloat16* ab, int n, int64_t g0, int rows,
                          const float* const dz[kNumHeads], __nv_bfloat16* S, __nv_bfloat16* G, __nv_bfloat16* M,
-                         cudaStream_t st) {
+                         cudaStream_t st, const DropSpec* drop) {
   using namespace t1;
   const char* base = static_cast<const char*>(pack);
   Args a{};
@@ -343,6 +351,10 @@ int launch_pair_bwd_prep(const void* pack, const PackLayout& L, const __nv_bfloa
   a.pairs_per_doc = static_cast<int32_t>(pair_count(n));
   a.g0 = g0, a.rows = rows;
   a.num_tiles = (rows + 127) / 128;
+  if (drop && drop->thresh) {
+    a.drop_thresh = drop->thresh, a.drop_scale = drop->scale;
+    for (int h = 0; h < kNumHeads; ++h) a.drop_key[h] = drop_key(*drop, site_head(h, 0));
+  }
   if (rows == 0) return PENEO_OK;
   alignas(64) CUtensorMap tmW;
   int rc;

@@ -14,7 +14,8 @@ template <int ACT>  // 0 none, 1 SiLU
 __global__ void __launch_bounds__(256) sgemm_nt_kernel(const float* __restrict__ A, int64_t lda,
                                                        const float* __restrict__ W, int64_t ldw,
                                                        const float* __restrict__ bias, float* __restrict__ C,
-                                                       int64_t ldc, int M, int N, int K, float out_scale) {
+                                                       int64_t ldc, int M, int N, int K, float out_scale,
+                                                       uint32_t drop_thresh, float drop_scale, uint32_t drop_key) {
   __shared__ __align__(16) float As[16][64 + 4];
   __shared__ __align__(16) float Bs[16][64 + 4];
   const int tid = threadIdx.x, tx = tid % 16, ty = tid / 16;
@@ -49,21 +50,27 @@ __global__ void __launch_bounds__(256) sgemm_nt_kernel(const float* __restrict__
       const int n = n0 + tx * 4 + c;
       if (n >= N) continue;
       float v = acc[r][c] + (bias ? bias[n] : 0.f);
-      if (ACT == 1) v = silu_exact(v);
+      if (ACT == 1) {
+        v = silu_exact(v);
+        if (drop_thresh) v = drop_keep(drop_key, drop_thresh, m, n) ? v * drop_scale : 0.f;
+      }
       C[(int64_t)m * ldc + n] = v * out_scale;
     }
   }
 }
 
 int launch_sgemm_nt(const float* A, int64_t lda, const float* W, int64_t ldw, const float* bias, float* C, int64_t ldc,
-                    int M, int N, int K, int act, float out_scale, cudaStream_t st) {
+                    int M, int N, int K, int act, float out_scale, cudaStream_t st, const DropSpec* drop, uint32_t site) {
   PENEO_REQUIRE(K % 4 == 0 && lda % 4 == 0 && ldw % 4 == 0, "sgemm_nt: K, lda, ldw must be multiples of 4");
   if (M == 0 || N == 0) return PENEO_OK;
   dim3 grid((N + 63) / 64, (M + 63) / 64);
+  const uint32_t th = (drop && act) ? drop->thresh : 0u;
+  const float sc = drop ? drop->scale : 1.f;
+  const uint32_t key = drop ? drop_key(*drop, site) : 0u;
   if (act)
-    sgemm_nt_kernel<1><<<grid, 256, 0, st>>>(A, lda, W, ldw, bias, C, ldc, M, N, K, out_scale);
+    sgemm_nt_kernel<1><<<grid, 256, 0, st>>>(A, lda, W, ldw, bias, C, ldc, M, N, K, out_scale, th, sc, key);
   else
-    sgemm_nt_kernel<0><<<grid, 256, 0, st>>>(A, lda, W, ldw, bias, C, ldc, M, N, K, out_scale);
+    sgemm_nt_kernel<0><<<grid, 256, 0, st>>>(A, lda, W, ldw, bias, C, ldc, M, N, K, out_scale, 0u, 1.f, 0u);
   PENEO_CUDA_TRY(cudaGetLastError());
   return PENEO_OK;
 }
@@ -253,6 +260,7 @@ struct PairSimtArgs {
   const float* out_w[kNumHeads];
   const float* out_b[kNumHeads];
   float* logits[kNumHeads];
+  DropSpec drop;
 };
 
 template <int TP>
@@ -345,7 +353,11 @@ __global__ void __launch_bounds__(256) pair_heads_simt_kernel(const PairSimtArgs
           const float bc = bias[col];
 #pragma unroll
           for (int r = 0; r < RM; ++r) {
-            const float m = silu_exact(acc[r][c] + bc);
+            float m = silu_exact(acc[r][c] + bc);
+            if (a.drop.thresh) {  // Dropout after every hidden SiLU (model/peneo_decoder.py:261)
+              const uint32_t g = static_cast<uint32_t>(g0 + ty * RM + r);
+              m = drop_keep(drop_key(a.drop, site_head(h, l)), a.drop.thresh, g, col) ? m * a.drop.scale : 0.f;
+            }
             if (last) {
               for (int cc = 0; cc < C; ++cc) z[r][cc] = fmaf(a.out_w[h][cc * d + col], m, z[r][cc]);
             } else {
@@ -381,13 +393,14 @@ __global__ void __launch_bounds__(256) pair_heads_simt_kernel(const PairSimtArgs
 }
 
 int launch_pair_heads_simt(const peneo_dims& dm, const void* pack, const float* ab, int batch, int n,
-                           float* const logits[kNumHeads], cudaStream_t st) {
+                           float* const logits[kNumHeads], cudaStream_t st, const DropSpec* drop) {
   const PackLayout L = pack_layout(dm, PENEO_PREC_FP32);
   const char* base = static_cast<const char*>(pack);
   PENEO_REQUIRE(dm.num_layers >= 1 && dm.num_layers <= kMaxMidLayers + 1, "num_layers %d out of range", dm.num_layers);
   PENEO_REQUIRE(dm.d % 4 == 0, "decoder hidden size must be a multiple of 4");
   PairSimtArgs a{};
   a.ab = ab, a.batch = batch, a.n = n, a.d = dm.d, a.num_layers = dm.num_layers;
+  a.drop = drop ? *drop : DropSpec{0u, 1.f, 0u, 0u};
   a.pairs_per_doc = static_cast<int32_t>(pair_count(n));
   a.total_pairs = (int64_t)batch * a.pairs_per_doc;
   for (int h = 0; h < kNumHeads; ++h) {

@@ -39,7 +39,8 @@ template <bool TA, bool TB>
 __global__ void __launch_bounds__(256) sgemm_kernel(const float* __restrict__ A, int64_t lda, const float* __restrict__ B,
                                                     int64_t ldb, float* __restrict__ C, int64_t ldc, int M, int N, int K,
                                                     int kslice, int mode, const float* __restrict__ bias,
-                                                    float* __restrict__ C2, int64_t ldc2) {
+                                                    float* __restrict__ C2, int64_t ldc2, uint32_t drop_thresh,
+                                                    float drop_scale, uint32_t drop_key_, uint32_t row0) {
   __shared__ __align__(16) float As[16][64 + 4];
   __shared__ __align__(16) float Bs[16][64 + 4];
   const int tid = threadIdx.x, tx = tid % 16, ty = tid / 16;
@@ -98,7 +99,11 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const float* __restrict__ A,
         if (bias) v += bias[n];
         if (mode == 1) v += *dst;
         *dst = v;
-        if (C2) C2[(int64_t)m * ldc2 + n] = v * sigmoid_exact(v);
+        if (C2) {
+          float h = v * sigmoid_exact(v);
+          if (drop_thresh) h = drop_keep(drop_key_, drop_thresh, row0 + m, n) ? h * drop_scale : 0.f;
+          C2[(int64_t)m * ldc2 + n] = h;
+        }
       }
     }
   }
@@ -115,8 +120,10 @@ struct Gemm {
   int M = 0, N = 0, K = 0;
   int mode = 0;  // 0 store, 1 add, 2 split-K atomic add
   const float* bias = nullptr;
-  float* C2 = nullptr;
+  float* C2 = nullptr;  // optional second output: Dropout(SiLU(C))
   int64_t ldc2 = 0;
+  uint32_t drop_thresh = 0, drop_key = 0, row0 = 0;  // dropout mask of C2: element (row0 + m, n)
+  float drop_scale = 1.f;
 };
 
 int run_gemm(const Gemm& g, cudaStream_t st) {
@@ -137,7 +144,7 @@ int run_gemm(const Gemm& g, cudaStream_t st) {
   dim3 grid((g.N + 63) / 64, (g.M + 63) / 64, splits);
 #define GO(TA, TB)                                                                                                   \
   sgemm_kernel<TA, TB><<<grid, 256, 0, st>>>(g.A, g.lda, g.B, g.ldb, g.C, g.ldc, g.M, g.N, g.K, kslice, g.mode, g.bias, \
-                                             g.C2, g.ldc2)
+                                             g.C2, g.ldc2, g.drop_thresh, g.drop_scale, g.drop_key, g.row0)
   if (g.ta && g.tb) GO(true, true);
   else if (g.ta) GO(true, false);
   else if (g.tb) GO(false, true);
@@ -166,7 +173,9 @@ template <int C>
 __global__ void __launch_bounds__(128) head_out_bwd_kernel(const float* __restrict__ U, const float* __restrict__ dz,
                                                            const float* __restrict__ Wout, int rows, int d,
                                                            float* __restrict__ G, float* __restrict__ dWout,
-                                                           float* __restrict__ dbout, float* __restrict__ dbmid) {
+                                                           float* __restrict__ dbout, float* __restrict__ dbmid,
+                                                           uint32_t drop_thresh, float drop_scale, uint32_t drop_key_,
+                                                           uint32_t row0) {
   __shared__ float sdz[128][C];
   const int r0 = blockIdx.x * 128, nr = min(128, rows - r0);
   for (int e = threadIdx.x; e < nr * C; e += 128) sdz[e / C][e % C] = dz[(int64_t)r0 * C + e];
@@ -183,14 +192,18 @@ __global__ void __launch_bounds__(128) head_out_bwd_kernel(const float* __restri
     for (int r = 0; r < nr; ++r) {
       const float u = U[(int64_t)(r0 + r) * d + f];
       const float s = sigmoid_exact(u);
-      const float m = u * s, ds = s * (1.0f + u * (1.0f - s));
+      float m = u * s;
+      const float ds = s * (1.0f + u * (1.0f - s));
+      // the forward pass fed Dropout(m) to W_out: same mask on m (for dW_out) and on the gradient through it
+      const float ms = drop_thresh ? (drop_keep(drop_key_, drop_thresh, row0 + r0 + r, f) ? drop_scale : 0.f) : 1.f;
+      m *= ms;
       float gm = 0.f;
 #pragma unroll
       for (int c = 0; c < C; ++c) {
         gm = fmaf(sdz[r][c], w[c], gm);
         aw[c] = fmaf(sdz[r][c], m, aw[c]);
       }
-      const float g = gm * ds;
+      const float g = gm * ms * ds;
       G[(int64_t)(r0 + r) * d + f] = g;
       ab_ += g;
     }
@@ -235,16 +248,20 @@ __global__ void __launch_bounds__(128) out_only_bwd_kernel(const float* __restri
   }
 }
 
-// G = dH * SiLU'(U) (in place over dH) ; db += column sums.  Grid: (row blocks of 32, column blocks of 128).
+// G = dH * mask / (1 - p) * SiLU'(U) (in place over dH; dH is the gradient w.r.t. Dropout(SiLU(U))) ;
+// db += column sums.  Grid: (row blocks of 32, column blocks of 128).
 __global__ void __launch_bounds__(128) act_bwd_kernel(float* __restrict__ dH, const float* __restrict__ U, int rows,
-                                                      int d, int64_t ld_dh, int64_t ld_u, float* __restrict__ db) {
+                                                      int d, int64_t ld_dh, int64_t ld_u, float* __restrict__ db,
+                                                      uint32_t drop_thresh, float drop_scale, uint32_t drop_key_,
+                                                      uint32_t row0) {
   const int r0 = blockIdx.x * 32, nr = min(32, rows - r0);
   const int f = blockIdx.y * 128 + threadIdx.x;
   if (f >= d) return;
   float acc = 0.f;
 #pragma unroll 8
   for (int r = 0; r < nr; ++r) {
-    const float g = dH[(int64_t)(r0 + r) * ld_dh + f] * dsilu_exact(U[(int64_t)(r0 + r) * ld_u + f]);
+    float g = dH[(int64_t)(r0 + r) * ld_dh + f] * dsilu_exact(U[(int64_t)(r0 + r) * ld_u + f]);
+    if (drop_thresh) g = drop_keep(drop_key_, drop_thresh, row0 + r0 + r, f) ? g * drop_scale : 0.f;
     dH[(int64_t)(r0 + r) * ld_dh + f] = g;
     acc += g;
   }
@@ -308,115 +325,7 @@ __global__ void __launch_bounds__(128) gv_reduce_kernel(const float* __restrict_
   }
 }
 
-// ------------------------------------------------------------------------------------------------
-// bf16 / tcgen05 pair part (PENEO_PREC_BF16: d == 384, num_layers == 2).  Same algorithm, but the three
-// [rows x 384] GEMMs of every head run on the tensor cores (gemm_tc2) with bf16 operands:
-//   U   = S W_mid^T + b            A = S   [rows, d]      W = W_mid   [d_out, d_in]      -> bf16
-//   dW += G^T S                    A = G^T [d, rows]      W = S^T     [d, rows]          -> fp32 atomic, split-K
-//   dS += G W_mid                  A = G   [rows, d]      W = W_mid^T [d_in, d_out]      -> fp32 (+)=
-// so the element-wise kernels emit every activation twice: row-major and transposed.
-// ------------------------------------------------------------------------------------------------
 constexpr int kD16 = 384;
-constexpr int kSubRows = 32;
-
-// S and S^T (ld = ldt) of the chunk; one CTA per 32 rows, 256 threads
-__global__ void __launch_bounds__(256) build_s_bf16_kernel(const float* __restrict__ ab, int b, int n, int p0, int rows,
-                                                           __nv_bfloat16* __restrict__ S, __nv_bfloat16* __restrict__ ST,
-                                                           int64_t ldt) {
-  __shared__ __nv_bfloat16 tile[kSubRows][kD16 + 8];
-  const int r0 = blockIdx.x * kSubRows, nr = min(kSubRows, rows - r0);
-  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
-  for (int r = warp; r < kSubRows; r += 8) {
-    if (r < nr) {
-      int i, j;
-      pair_from_flat(p0 + r0 + r, n, i, j);
-      const float* ai = ab + ((int64_t)b * n + i) * 2 * kD16;
-      const float* bj = ab + ((int64_t)b * n + j) * 2 * kD16 + kD16;
-      for (int f = 2 * lane; f < kD16; f += 64) {
-        const float2 a2 = *reinterpret_cast<const float2*>(ai + f), b2 = *reinterpret_cast<const float2*>(bj + f);
-        const __nv_bfloat162 v = __floats2bfloat162_rn(silu_exact(a2.x + b2.x), silu_exact(a2.y + b2.y));
-        *reinterpret_cast<__nv_bfloat162*>(&tile[r][f]) = v;
-        *reinterpret_cast<__nv_bfloat162*>(S + (int64_t)(r0 + r) * kD16 + f) = v;
-      }
-    } else {
-      for (int f = 2 * lane; f < kD16; f += 64) *reinterpret_cast<__nv_bfloat162*>(&tile[r][f]) = __floats2bfloat162_rn(0.f, 0.f);
-    }
-  }
-  __syncthreads();
-  // transposed store: 4 threads per feature row, 8 rows (16 B) each
-  for (int e = threadIdx.x; e < kD16 * 4; e += 256) {
-    const int f = e / 4, q = e % 4;
-    if (r0 + q * 8 >= rows) continue;
-    alignas(16) __nv_bfloat16 v[8];
-#pragma unroll
-    for (int x = 0; x < 8; ++x) v[x] = tile[q * 8 + x][f];
-    *reinterpret_cast<uint4*>(ST + (int64_t)f * ldt + r0 + q * 8) = *reinterpret_cast<const uint4*>(v);
-  }
-}
-
-// Last hidden layer + output layer of one head from bf16 pre-activations U:
-//   m = SiLU(U) ; G = (dz W_out) * SiLU'(U) -> G (row-major) and G^T ; dW_out += dz^T m ; db_out, db_mid
-// 192 threads, two adjacent features each (bf16x2 accesses); one CTA walks `sub_per_cta` consecutive
-// 32-row sub-tiles so that the fp32 atomics are amortised.
-template <int C>
-__global__ void __launch_bounds__(192) head_out_bwd_bf16_kernel(const __nv_bfloat16* __restrict__ U,
-                                                                const float* __restrict__ dz,
-                                                                const float* __restrict__ Wout, int rows, int sub_per_cta,
-                                                                __nv_bfloat16* __restrict__ G,
-                                                                __nv_bfloat16* __restrict__ GT, int64_t ldt,
-                                                                float* __restrict__ dWout, float* __restrict__ dbout,
-                                                                float* __restrict__ dbmid) {
-  __shared__ __nv_bfloat16 tile[kSubRows][kD16 + 8];
-  __shared__ float sdz[kSubRows][C];
-  const int f = 2 * threadIdx.x;
-  float w0[C], w1[C], aw0[C], aw1[C], ab0 = 0.f, ab1 = 0.f, dzsum = 0.f;
-#pragma unroll
-  for (int c = 0; c < C; ++c) w0[c] = Wout[c * kD16 + f], w1[c] = Wout[c * kD16 + f + 1], aw0[c] = 0.f, aw1[c] = 0.f;
-  for (int sub = 0; sub < sub_per_cta; ++sub) {
-    const int r0 = (blockIdx.x * sub_per_cta + sub) * kSubRows;
-    if (r0 >= rows) break;
-    const int nr = min(kSubRows, rows - r0);
-    __syncthreads();  // previous sub-tile's transposed store is done with `tile` / `sdz`
-    for (int e = threadIdx.x; e < kSubRows * C; e += 192) sdz[e / C][e % C] = e < nr * C ? dz[(int64_t)r0 * C + e] : 0.f;
-    __syncthreads();
-    if (threadIdx.x < C)
-      for (int r = 0; r < nr; ++r) dzsum += sdz[r][threadIdx.x];
-#pragma unroll 8
-    for (int r = 0; r < kSubRows; ++r) {
-      __nv_bfloat162 gb = __floats2bfloat162_rn(0.f, 0.f);
-      if (r < nr) {
-        const float2 u = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(U + (int64_t)(r0 + r) * kD16 + f));
-        const float s0 = sigmoid_exact(u.x), s1 = sigmoid_exact(u.y);
-        const float m0 = u.x * s0, m1 = u.y * s1;
-        float g0 = 0.f, g1 = 0.f;
-#pragma unroll
-        for (int c = 0; c < C; ++c) {
-          const float z = sdz[r][c];
-          g0 = fmaf(z, w0[c], g0), g1 = fmaf(z, w1[c], g1);
-          aw0[c] = fmaf(z, m0, aw0[c]), aw1[c] = fmaf(z, m1, aw1[c]);
-        }
-        gb = __floats2bfloat162_rn(g0 * (s0 * (1.0f + u.x * (1.0f - s0))), g1 * (s1 * (1.0f + u.y * (1.0f - s1))));
-        *reinterpret_cast<__nv_bfloat162*>(G + (int64_t)(r0 + r) * kD16 + f) = gb;
-        const float2 gf = __bfloat1622float2(gb);  // bias gradient of exactly what the GEMMs will see
-        ab0 += gf.x, ab1 += gf.y;
-      }
-      *reinterpret_cast<__nv_bfloat162*>(&tile[r][f]) = gb;
-    }
-    __syncthreads();
-    for (int e = threadIdx.x; e < kD16 * 4; e += 192) {
-      const int ff = e / 4, q = e % 4;
-      if (r0 + q * 8 >= rows) continue;
-      alignas(16) __nv_bfloat16 v[8];
-#pragma unroll
-      for (int x = 0; x < 8; ++x) v[x] = tile[q * 8 + x][ff];
-      *reinterpret_cast<uint4*>(GT + (int64_t)ff * ldt + r0 + q * 8) = *reinterpret_cast<const uint4*>(v);
-    }
-  }
-  if (threadIdx.x < C) atomicAdd(&dbout[threadIdx.x], dzsum);
-#pragma unroll
-  for (int c = 0; c < C; ++c) atomicAdd(&dWout[c * kD16 + f], aw0[c]), atomicAdd(&dWout[c * kD16 + f + 1], aw1[c]);
-  atomicAdd(&dbmid[f], ab0), atomicAdd(&dbmid[f + 1], ab1);
-}
 
 // dW_out, db_out, db_mid of all five heads from the bf16 matrices T1 wrote:
 //   dW_out[k][c][f] += sum_r dz_k[r][c] M[r][384 k + f] ; db_mid[k][f] += sum_r G[r][384 k + f] ; db_out[k][c] += sum_r dz_k[r][c]
@@ -465,11 +374,8 @@ struct Plan {
   int nU, nH;          // per-chunk [rows, d] buffers for pre-activations / hidden activations
   size_t off_x, off_u1, off_y1, off_u2, off_y, off_ab, off_dab, off_dy, off_dy1;
   size_t off_S, off_dS, off_G, off_U, off_H;
-  // bf16 pair part: row-major and transposed (ld = ldt) bf16 activations
-  size_t off_S16, off_ST16, off_U16, off_G16, off_GT16;
-  int64_t ldt;
-  // v2 (T1 + MN-major GEMMs): G / M [rows, 1920] bf16, bf16 per-token projections and their scratch
-  size_t off_Gc, off_Mc, off_ab16, off_tokws, tokws_bytes;
+  // bf16 pair part (T1 + MN-major GEMMs): S [rows, 384], G / M [rows, 1920] bf16, bf16 per-token projections
+  size_t off_S16, off_Gc, off_Mc, off_ab16, off_tokws, tokws_bytes;
   size_t total;
 };
 
@@ -502,12 +408,9 @@ Plan make_plan(const peneo_dims& dm, int prec, int batch, int n) {
   const size_t cb = fl((size_t)rows * d);
   p.off_dS = take(cb);
   if (tc) {
-    p.ldt = (rows + 63) / 64 * 64;
-    const size_t hb = align_up((size_t)p.ldt * d * 2, 1024);
-    const size_t gb = align_up((size_t)p.ldt * 5 * d * 2, 1024);
-    p.off_S16 = take(hb), p.off_Gc = take(gb), p.off_Mc = take(gb);
-    // the v1 path (PENEO_BWD_TC=1) carves its four [ldt, d] buffers out of the G / M regions
-    p.off_U16 = p.off_Gc, p.off_G16 = p.off_Gc + hb, p.off_GT16 = p.off_Mc, p.off_ST16 = p.off_Mc + hb;
+    const size_t rp = (rows + 127) / 128 * 128;
+    p.off_S16 = take(align_up(rp * d * 2, 1024));
+    p.off_Gc = take(align_up(rp * 5 * d * 2, 1024)), p.off_Mc = take(align_up(rp * 5 * d * 2, 1024));
     p.off_ab16 = take(align_up(T * 2 * d * 2, 1024));
     p.tokws_bytes = peneo_token_proj_workspace_bytes(&dm, PENEO_PREC_BF16, p.tokens);
     p.off_tokws = take(align_up(p.tokws_bytes, 1024));
@@ -527,8 +430,12 @@ size_t heads_bwd_workspace_bytes(const peneo_dims& dm, int prec, int batch, int 
 
 int launch_heads_bwd(const peneo_dims& dm, int prec, const void* pack, const void* x, int x_dtype, int64_t x_row_stride,
                      int batch, int n, const float* const dlogits[kNumHeads], const peneo_grads& gr, float* dx,
-                     void* workspace, cudaStream_t st) {
+                     void* workspace, cudaStream_t st, const DropSpec* drop_in) {
   const PackLayout L = pack_layout(dm, prec);
+  const DropSpec drop = drop_in ? *drop_in : DropSpec{0u, 1.f, 0u, 0u};
+  auto with_drop = [&](Gemm& gm, uint32_t site, uint32_t row0) {  // C2 = Dropout(SiLU(C)) of the forward pass
+    gm.drop_thresh = drop.thresh, gm.drop_scale = drop.scale, gm.drop_key = drop_key(drop, site), gm.row0 = row0;
+  };
   const bool tc = prec == PENEO_PREC_BF16;
   const char* pk = static_cast<const char*>(pack);
   const Plan pl = make_plan(dm, prec, batch, n);
@@ -580,9 +487,11 @@ int launch_heads_bwd(const peneo_dims& dm, int prec, const void* pack, const voi
   if (dm.shrink) {
     g = Gemm{}, g.tb = true, g.A = xin, g.lda = ldx, g.B = W(L.f_w1), g.ldb = hin, g.C = F(pl.off_u1), g.ldc = hid;
     g.M = T, g.N = hid, g.K = hin, g.bias = W(L.f_b1), g.C2 = F(pl.off_y1), g.ldc2 = hid;
+    with_drop(g, kSiteTok0, 0);
     TRY(run_gemm(g, st));
     g = Gemm{}, g.tb = true, g.A = F(pl.off_y1), g.lda = hid, g.B = W(L.f_w2), g.ldb = hid, g.C = F(pl.off_u2), g.ldc = d;
     g.M = T, g.N = d, g.K = hid, g.bias = W(L.f_b2), g.C2 = F(pl.off_y), g.ldc2 = d;
+    with_drop(g, kSiteTok1, 0);
     TRY(run_gemm(g, st));
     y = F(pl.off_y), ldy = d;
   }
@@ -596,13 +505,11 @@ int launch_heads_bwd(const peneo_dims& dm, int prec, const void* pack, const voi
   // ---- pair part, one chunk of whole pair-rows at a time
   float* dab = F(pl.off_dab);
   TRY(zero(dab, (size_t)T * 2 * d));
-  int tc_version = 2;
-  if (const char* e = getenv("PENEO_BWD_TC")) tc_version = atoi(e) == 1 ? 1 : 2;
   float **d_outw = nullptr, **d_outb = nullptr, **d_midb = nullptr;
-  if (tc && tc_version == 2) {
-    // bf16 per-token projections (0.5-scaled A | Bm) for T1, exactly what the forward pass used
-    rc = peneo_token_proj_fwd(&dm, PENEO_PREC_BF16, pack, x, x_dtype, x_row_stride, T, ws + pl.off_ab16, ws + pl.off_tokws, st);
-    if (rc != PENEO_OK) return rc;
+  if (tc) {
+    // bf16 per-token projections (0.5-scaled A | Bm) for T1, exactly what the forward pass used (same dropout)
+    TRY(token_proj_fwd_bf16(dm, L, pk, x, x_dtype, x_row_stride, T, ws + pl.off_ab16, ws + pl.off_tokws, st,
+                            drop.thresh ? &drop : nullptr));
     // device tables of the per-head gradient pointers (15 pointers at the start of the token scratch tail)
     float* h_tab[15];
     for (int h = 0; h < kNumHeads; ++h) h_tab[h] = gr.out_w[h], h_tab[5 + h] = gr.out_b[h], h_tab[10 + h] = gr.mid_b[h * 8];
@@ -620,13 +527,15 @@ int launch_heads_bwd(const peneo_dims& dm, int prec, const void* pack, const voi
       while (i1 < n && row_start(i1 + 1, n) - row_start(i0, n) <= pl.chunk_rows_max) ++i1;
       const int p0 = row_start(i0, n), rows = row_start(i1, n) - p0;  // row_start(n, n) == P
       const int rb = (rows + 127) / 128;
-      if (tc && tc_version == 2) {
+      const uint32_t row0 = static_cast<uint32_t>((int64_t)b * P + p0);  // batch-flat index of the chunk's first pair
+      if (tc) {
         __nv_bfloat16* S16 = reinterpret_cast<__nv_bfloat16*>(ws + pl.off_S16);
         __nv_bfloat16* Gc = reinterpret_cast<__nv_bfloat16*>(ws + pl.off_Gc);
         __nv_bfloat16* Mc = reinterpret_cast<__nv_bfloat16*>(ws + pl.off_Mc);
         const __nv_bfloat16* ab16 = reinterpret_cast<const __nv_bfloat16*>(ws + pl.off_ab16);
         // T1: regenerate S, M = SiLU(u), G = (dz W_out) SiLU'(u) for the five heads (tcgen05, K2's structure)
-        TRY(launch_pair_bwd_prep(pack, L, ab16, n, (int64_t)b * P + p0, rows, dlogits, S16, Gc, Mc, st));
+        TRY(launch_pair_bwd_prep(pack, L, ab16, n, (int64_t)b * P + p0, rows, dlogits, S16, Gc, Mc, st,
+                                 drop.thresh ? &drop : nullptr));
         // dS = G W_mid (all heads in one K = 1920 GEMM) ; dW_mid += G^T S
         TRY(launch_gemm_ds(Gc, reinterpret_cast<const __nv_bfloat16*>(pk + L.wmid_full_bf16), dS, rows, st));
         float* dwm[kNumHeads];
@@ -638,34 +547,6 @@ int launch_heads_bwd(const peneo_dims& dm, int prec, const void* pack, const voi
         TRY(launch_gemm_dw(Gc, S16, dwm, rows, st));
         dwout_bf16_kernel<<<dim3((rows + 255) / 256, 15), 128, 0, st>>>(Mc, Gc, dzp, rows, d_outw, d_outb, d_midb);
         PENEO_CUDA_TRY(cudaGetLastError());
-      } else if (tc) {
-        __nv_bfloat16* S16 = reinterpret_cast<__nv_bfloat16*>(ws + pl.off_S16);
-        __nv_bfloat16* ST16 = reinterpret_cast<__nv_bfloat16*>(ws + pl.off_ST16);
-        __nv_bfloat16* U16 = reinterpret_cast<__nv_bfloat16*>(ws + pl.off_U16);
-        __nv_bfloat16* G16 = reinterpret_cast<__nv_bfloat16*>(ws + pl.off_G16);
-        __nv_bfloat16* GT16 = reinterpret_cast<__nv_bfloat16*>(ws + pl.off_GT16);
-        const int nsub = (rows + kSubRows - 1) / kSubRows;
-        build_s_bf16_kernel<<<nsub, 256, 0, st>>>(ab, b, n, p0, rows, S16, ST16, pl.ldt);
-        PENEO_CUDA_TRY(cudaGetLastError());
-        const int sub_per_cta = std::max(1, (nsub + 1183) / 1184);
-        const int ctas = (nsub + sub_per_cta - 1) / sub_per_cta;
-        const int splits = std::max(1, std::min((rows + 63) / 64, 296 / 9));
-        for (int h = 0; h < kNumHeads; ++h) {
-          const int C = head_classes(h);
-          const float* dz = dlogits[h] + ((int64_t)b * P + p0) * C;
-          const __nv_bfloat16* Wm = reinterpret_cast<const __nv_bfloat16*>(pk + L.wmid_full_bf16) + (size_t)h * d * d;
-          const __nv_bfloat16* WmT = reinterpret_cast<const __nv_bfloat16*>(pk + L.wmidT_bf16) + (size_t)h * d * d;
-          TRY(launch_gemm_tc2(S16, d, Wm, d, W(L.bmid_full) + (size_t)h * d, U16, d, rows, d, d, 0, 1, st));
-          if (C == 2)
-            head_out_bwd_bf16_kernel<2><<<ctas, 192, 0, st>>>(U16, dz, W(L.f_out_w[h]), rows, sub_per_cta, G16, GT16, pl.ldt,
-                                                              gr.out_w[h], gr.out_b[h], gr.mid_b[h * 8]);
-          else
-            head_out_bwd_bf16_kernel<3><<<ctas, 192, 0, st>>>(U16, dz, W(L.f_out_w[h]), rows, sub_per_cta, G16, GT16, pl.ldt,
-                                                              gr.out_w[h], gr.out_b[h], gr.mid_b[h * 8]);
-          PENEO_CUDA_TRY(cudaGetLastError());
-          TRY(launch_gemm_tc2(GT16, pl.ldt, ST16, pl.ldt, nullptr, gr.mid_w[h * 8], d, d, d, rows, 3, splits, st));
-          TRY(launch_gemm_tc2(G16, d, WmT, d, nullptr, dS, d, rows, d, d, h > 0 ? 2 : 1, 1, st));
-        }
       } else {
       build_s_kernel<<<rows, 128, 0, st>>>(ab, b, n, d, p0, S);
       PENEO_CUDA_TRY(cudaGetLastError());
@@ -687,6 +568,7 @@ int launch_heads_bwd(const peneo_dims& dm, int prec, const void* pack, const voi
           float* Hn = (l + 2 < NL) ? F(pl.off_H) + (size_t)l * cstride : nullptr;
           g = Gemm{}, g.tb = true, g.A = in, g.lda = d, g.B = W(L.f_mid_w[h][l]), g.ldb = d, g.C = U, g.ldc = d;
           g.M = rows, g.N = d, g.K = d, g.bias = W(L.f_mid_b[h][l]), g.C2 = Hn, g.ldc2 = d;
+          with_drop(g, site_head(h, l), row0);
           TRY(run_gemm(g, st));
           in = Hn;
         }
@@ -694,10 +576,12 @@ int launch_heads_bwd(const peneo_dims& dm, int prec, const void* pack, const voi
           const float* U = F(pl.off_U) + (size_t)(NL - 2) * cstride;
           if (C == 2)
             head_out_bwd_kernel<2><<<rb, 128, 0, st>>>(U, dz, W(L.f_out_w[h]), rows, d, G, gr.out_w[h], gr.out_b[h],
-                                                       gr.mid_b[h * 8 + NL - 2]);
+                                                       gr.mid_b[h * 8 + NL - 2], drop.thresh, drop.scale,
+                                                       drop_key(drop, site_head(h, NL - 2)), row0);
           else
             head_out_bwd_kernel<3><<<rb, 128, 0, st>>>(U, dz, W(L.f_out_w[h]), rows, d, G, gr.out_w[h], gr.out_b[h],
-                                                       gr.mid_b[h * 8 + NL - 2]);
+                                                       gr.mid_b[h * 8 + NL - 2], drop.thresh, drop.scale,
+                                                       drop_key(drop, site_head(h, NL - 2)), row0);
           PENEO_CUDA_TRY(cudaGetLastError());
         }
         // G_l = gradient w.r.t. the pre-activation of hidden layer l.  Once G_l exists U_l is dead, so
@@ -718,8 +602,9 @@ int launch_heads_bwd(const peneo_dims& dm, int prec, const void* pack, const voi
             float* Ul = F(pl.off_U) + (size_t)l * cstride;
             g.C = Ul, g.ldc = d, g.mode = 0;
             TRY(run_gemm(g, st));
-            act_bwd_kernel<<<dim3((rows + 31) / 32, (d + 127) / 128), 128, 0, st>>>(Ul, F(pl.off_U) + (size_t)(l - 1) * cstride, rows, d, d, d,
-                                               gr.mid_b[h * 8 + l - 1]);
+            act_bwd_kernel<<<dim3((rows + 31) / 32, (d + 127) / 128), 128, 0, st>>>(
+                Ul, F(pl.off_U) + (size_t)(l - 1) * cstride, rows, d, d, d, gr.mid_b[h * 8 + l - 1], drop.thresh, drop.scale,
+                drop_key(drop, site_head(h, l - 1)), row0);
             PENEO_CUDA_TRY(cudaGetLastError());
             Gcur = Ul;
           }
@@ -752,7 +637,8 @@ int launch_heads_bwd(const peneo_dims& dm, int prec, const void* pack, const voi
   TRY(run_gemm(g, st));
   if (dm.shrink) {
     // G2 = dy * SiLU'(u2) ; db2 ; dW2 = G2^T y1 ; dy1 = G2 W2
-    act_bwd_kernel<<<dim3(tb, (d + 127) / 128), 128, 0, st>>>(dy, F(pl.off_u2), T, d, d, d, gr.shrink_b2);
+    act_bwd_kernel<<<dim3(tb, (d + 127) / 128), 128, 0, st>>>(dy, F(pl.off_u2), T, d, d, d, gr.shrink_b2, drop.thresh,
+                                                              drop.scale, drop_key(drop, kSiteTok1), 0u);
     PENEO_CUDA_TRY(cudaGetLastError());
     g = Gemm{}, g.ta = true, g.A = dy, g.lda = d, g.B = F(pl.off_y1), g.ldb = hid, g.C = gr.shrink_w2, g.ldc = hid;
     g.M = d, g.N = hid, g.K = T, g.mode = 2;
@@ -761,7 +647,8 @@ int launch_heads_bwd(const peneo_dims& dm, int prec, const void* pack, const voi
     g = Gemm{}, g.A = dy, g.lda = d, g.B = W(L.f_w2), g.ldb = hid, g.C = dy1, g.ldc = hid, g.M = T, g.N = hid, g.K = d;
     TRY(run_gemm(g, st));
     // G1 = dy1 * SiLU'(u1) ; db1 ; dW1 = G1^T x ; dx = G1 W1
-    act_bwd_kernel<<<dim3(tb, (hid + 127) / 128), 128, 0, st>>>(dy1, F(pl.off_u1), T, hid, hid, hid, gr.shrink_b1);
+    act_bwd_kernel<<<dim3(tb, (hid + 127) / 128), 128, 0, st>>>(dy1, F(pl.off_u1), T, hid, hid, hid, gr.shrink_b1,
+                                                                drop.thresh, drop.scale, drop_key(drop, kSiteTok0), 0u);
     PENEO_CUDA_TRY(cudaGetLastError());
     g = Gemm{}, g.ta = true, g.A = dy1, g.lda = hid, g.B = xin, g.ldb = ldx, g.C = gr.shrink_w1, g.ldc = hin;
     g.M = hid, g.N = hin, g.K = T, g.mode = 2;

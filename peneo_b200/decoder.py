@@ -181,13 +181,20 @@ class PEneoDecoderB200(nn.Module):
         needs_grad = torch.is_grad_enabled() and (
             sequence_output.requires_grad or any(p.requires_grad for p in self.parameters())
         )
+        # The decoder's own nn.Dropout modules (model/peneo_decoder.py:218, 221, 261) are active in train() mode
+        # only.  The per-step seed comes from torch's generator, so torch.manual_seed() makes a step reproducible;
+        # ``dropout_seed`` (attribute) pins it for tests.
+        drop = None
+        if self.training and self.dropout_prob > 0:
+            seed = getattr(self, "dropout_seed", None)
+            drop = (float(self.dropout_prob), int(torch.randint(0, 2**62, (1,)).item()) if seed is None else int(seed))
         if needs_grad and not self.inference_mode:
             from .autograd import decoder_forward_with_grad
 
-            logits = decoder_forward_with_grad(self, sequence_output)
+            logits = decoder_forward_with_grad(self, sequence_output, drop)
         else:
             pack = self._weight_pack(sequence_output.device)
-            logits = ops.heads_forward(pack, sequence_output.detach())
+            logits = ops.heads_forward(pack, sequence_output.detach(), drop)
         le, elh, elt, lgh, lgt = logits
         if self.inference_mode:
             return (le, elh, elt, lgh, lgt, orig_bbox)

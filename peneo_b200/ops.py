@@ -102,9 +102,9 @@ class WeightPack:
         del keep
 
 
-def token_projections(pack: WeightPack, x: torch.Tensor) -> torch.Tensor:
+def token_projections(pack: WeightPack, x: torch.Tensor, dropout=None) -> torch.Tensor:
     """x: [..., hin] (fp32 / bf16 / fp16, last dim contiguous) -> ab [tokens, 2d]
-    (fp32, or bf16 pre-multiplied by 1/2 in bf16 mode)."""
+    (fp32, or bf16 pre-multiplied by 1/2 in bf16 mode).  ``dropout``: None (eval) or ``(p, seed)``."""
     lib = _lib.load()
     _require_cuda(x, "sequence_output")
     dm = pack.dims
@@ -124,13 +124,13 @@ def token_projections(pack: WeightPack, x: torch.Tensor) -> torch.Tensor:
     _lib.check(
         lib.peneo_token_proj_fwd(dm.c(), pack.prec, pack.buf.data_ptr(), x2.data_ptr(), _TORCH_DT[x2.dtype],
                                  x2.stride(0) if tokens > 1 else dm.hin, tokens, ab.data_ptr(), ws.data_ptr(),
-                                 _stream(x.device)),
+                                 _lib.dropout_arg(dropout), _stream(x.device)),
         "peneo_token_proj_fwd",
     )
     return ab
 
 
-def pair_heads(pack: WeightPack, ab: torch.Tensor, batch: int, n: int) -> List[torch.Tensor]:
+def pair_heads(pack: WeightPack, ab: torch.Tensor, batch: int, n: int, dropout=None) -> List[torch.Tensor]:
     """ab from :func:`token_projections` -> five fp32 logits tensors [batch, P, C_h]."""
     lib = _lib.load()
     p = shaking_len(n)
@@ -138,18 +138,18 @@ def pair_heads(pack: WeightPack, ab: torch.Tensor, batch: int, n: int) -> List[t
     COUNTERS["kernels"] += 1
     _lib.check(
         lib.peneo_pair_heads_fwd(pack.dims.c(), pack.prec, pack.buf.data_ptr(), ab.data_ptr(), batch, n,
-                                 _lib.ptrs5(logits), _stream(ab.device)),
+                                 _lib.ptrs5(logits), _lib.dropout_arg(dropout), _stream(ab.device)),
         "peneo_pair_heads_fwd",
     )
     return logits
 
 
-def heads_forward(pack: WeightPack, x: torch.Tensor) -> List[torch.Tensor]:
+def heads_forward(pack: WeightPack, x: torch.Tensor, dropout=None) -> List[torch.Tensor]:
     """[B, N, hin] hidden states -> five logits tensors (return order LE, ELh, ELt, LGh, LGt)."""
     if x.dim() != 3:
         raise ValueError("sequence_output must be [batch, seq_len, hidden]")
     b, n, _ = x.shape
-    return pair_heads(pack, token_projections(pack, x), b, n)
+    return pair_heads(pack, token_projections(pack, x, dropout), b, n, dropout)
 
 
 def pair_loss(logits: Sequence[torch.Tensor], tags: Sequence[torch.Tensor], class_weights: Sequence[float],

@@ -39,8 +39,9 @@ def _grad_struct(dims, grads: Dict[str, torch.Tensor]) -> _lib.Grads:
     return g
 
 
-def heads_backward(decoder, x: torch.Tensor, dlogits: List[torch.Tensor], need_dx: bool):
-    """x: [B, N, hin] CUDA; dlogits: five fp32 [B, P, C_h].  Returns ({param_key: grad}, dx | None)."""
+def heads_backward(decoder, x: torch.Tensor, dlogits: List[torch.Tensor], need_dx: bool, dropout=None):
+    """x: [B, N, hin] CUDA; dlogits: five fp32 [B, P, C_h]; dropout: the forward pass's (p, seed) or None.
+    Returns ({param_key: grad}, dx | None)."""
     lib = _lib.load()
     dims = decoder.dims
     b, n, hin = x.shape
@@ -66,7 +67,8 @@ def heads_backward(decoder, x: torch.Tensor, dlogits: List[torch.Tensor], need_d
     _lib.check(
         lib.peneo_heads_bwd(dims.c(), prec, pack.buf.data_ptr(), x2.data_ptr(), ops._TORCH_DT[x2.dtype],
                             x2.stride(0) if b * n > 1 else hin, b, n, _lib.ptrs5(dl), gs,
-                            dx.data_ptr() if dx is not None else None, ws.data_ptr(), ops._stream(dev)),
+                            dx.data_ptr() if dx is not None else None, ws.data_ptr(), _lib.dropout_arg(dropout),
+                            ops._stream(dev)),
         "peneo_heads_bwd",
     )
     return grads, (dx.view(b, n, hin) if dx is not None else None)
@@ -74,9 +76,10 @@ def heads_backward(decoder, x: torch.Tensor, dlogits: List[torch.Tensor], need_d
 
 class _DecoderHeads(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, decoder, x, *params):
+    def forward(ctx, decoder, x, drop, *params):
         pack = decoder._weight_pack(x.device)
-        logits = ops.heads_forward(pack, x.detach())
+        ctx.dropout = drop  # (p, seed) of this step: the backward pass regenerates the same masks
+        logits = ops.heads_forward(pack, x.detach(), drop)
         ctx.decoder = decoder
         ctx.save_for_backward(x)
         ctx.need_dx = x.requires_grad
@@ -90,13 +93,13 @@ class _DecoderHeads(torch.autograd.Function):
         shapes = [(x.shape[0], ops.shaking_len(x.shape[1]), c) for c in ops.HEAD_CLASSES]
         dl = [g if g is not None else torch.zeros(s, dtype=torch.float32, device=x.device)
               for g, s in zip(glogits, shapes)]
-        grads, dx = heads_backward(dec, x, dl, ctx.need_dx)
-        out = [None, dx.to(x.dtype) if dx is not None else None]
+        grads, dx = heads_backward(dec, x, dl, ctx.need_dx, ctx.dropout)
+        out = [None, dx.to(x.dtype) if dx is not None else None, None]
         for k, p in _param_items(dec):
             out.append(grads[k].to(p.dtype) if p.requires_grad else None)
         return tuple(out)
 
 
-def heads_with_grad(decoder, sequence_output: torch.Tensor) -> List[torch.Tensor]:
+def heads_with_grad(decoder, sequence_output: torch.Tensor, dropout=None) -> List[torch.Tensor]:
     params = [p for _, p in _param_items(decoder)]
-    return list(_DecoderHeads.apply(decoder, sequence_output, *params))
+    return list(_DecoderHeads.apply(decoder, sequence_output, dropout, *params))

@@ -533,3 +533,76 @@ def test_strided_hidden_states_after_cls_strip():
         assert torch.equal(a[k], c[k])
         assert rel_err(a[k], ref[k]) <= FP32_TOL
         assert rel_err(h[k], ref[k]) <= 5e-3  # fp16 inputs: input rounding only
+
+
+# ------------------------------------------------------------------------------------------------
+# training-mode dropout (model/peneo_decoder.py:218, 221, 261): regenerable counter-based masks
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("hin,hidden,shrink,L,prec,tol", [
+    (64, 64, True, 2, "fp32", GRAD_TOL_FP32),
+    (64, 64, True, 3, "fp32", GRAD_TOL_FP32),   # two hidden layers per head: one Dropout after each
+    (48, 48, False, 1, "fp32", GRAD_TOL_FP32),  # no shrink, no hidden layer: nothing to drop
+    (768, 768, True, 2, "bf16", 3e-2),
+])
+def test_train_mode_dropout_forward_and_backward_match_oracle_with_same_mask(hin, hidden, shrink, L, prec, tol):
+    """train() mode: logits, loss and every gradient against the fp64 oracle applying the SAME masks (the oracle
+    restates the counter-based mask function); and the masks really drop ~p of the activations."""
+    n, b, p_drop, seed = 19, 2, 0.3, 0x1234567890ABCDEF
+    sd = synth.init_decoder_state(hin, hidden, shrink, L, seed=16, trained_like=True)
+    cfg = Cfg(hidden, shrink, L, inference_mode=False, precision=prec)
+    cfg.backbone_config["hidden_dropout_prob"] = p_drop
+    dec = PEneoDecoderB200(cfg, hin)
+    dec.load_state_dict(sd)
+    dec = dec.cuda().train()
+    dec.dropout_seed = seed
+    x = synth.hidden_states(b, n, hin, doc_id0=6)
+    docs = [synth.make_document(n, doc_id=800 + i) for i in range(b)]
+    tags = [torch.stack([d.tags()[k] for d in docs]) for k in range(5)]
+    out, dx, grads = _train_step(dec, x.cuda(), [t.cuda() for t in tags])
+    ref_loss, _subs, ref_grads, ref_dx = orc.loss_and_grads(sd, x, tags, [1.0, 10.0, 10.0], dropout=(p_drop, seed))
+    ref_logits = orc.heads_ref_style(orc.split_params(sd, torch.float64), x.double(), (p_drop, seed))
+    for k in range(5):
+        assert rel_err(out[f"{ops.HEAD_NAMES[k]}_shaking_outputs"], ref_logits[k]) <= (FP32_TOL if prec == "fp32" else BF16_TOL)
+    assert abs(out.loss.item() - ref_loss.item()) <= tol * max(1.0, abs(ref_loss.item()))
+    worst = {"dx": rel_err(dx, ref_dx)}
+    for key, g in ref_grads.items():
+        worst[key] = rel_err(grads[key], g)
+    bad = {k: v for k, v in worst.items() if v > tol}
+    assert not bad, bad
+    # the no-grad path in train() mode applies the same dropout; eval() does not
+    with torch.no_grad():
+        again = dec(x.cuda(), None, *[t.cuda() for t in tags])
+    assert torch.equal(again.line_extraction_shaking_outputs, out.line_extraction_shaking_outputs)
+    if L >= 2:
+        dec.eval()
+        with torch.no_grad():
+            ev = dec(x.cuda(), None, *[t.cuda() for t in tags])
+        assert not torch.equal(ev.line_extraction_shaking_outputs, out.line_extraction_shaking_outputs)
+        ref_eval = orc.heads_ref_style(orc.split_params(sd, torch.float64), x.double())
+        assert rel_err(ev.line_extraction_shaking_outputs, ref_eval[0]) <= (FP32_TOL if prec == "fp32" else BF16_TOL)
+
+
+def test_dropout_masks_are_statistically_sound_and_seeded():
+    import numpy as np
+
+    m = orc.dropout_mask((0.1, 99), orc.site_head(1, 0), np.arange(4000), 384)
+    keep = (m > 0).double().mean().item()
+    assert abs(keep - 0.9) < 0.003 and abs(m.max().item() - 1 / 0.9) < 1e-6
+    m2 = orc.dropout_mask((0.1, 100), orc.site_head(1, 0), np.arange(4000), 384)
+    m3 = orc.dropout_mask((0.1, 99), orc.site_head(2, 0), np.arange(4000), 384)
+    assert abs(((m > 0) == (m2 > 0)).double().mean().item() - 0.82) < 0.01  # independent masks agree 0.9^2 + 0.1^2
+    assert abs(((m > 0) == (m3 > 0)).double().mean().item() - 0.82) < 0.01
+    # different steps draw different seeds from torch's generator; manual_seed reproduces them
+    sd = synth.init_decoder_state(64, 64, True, 2, seed=16, trained_like=True)
+    cfg = Cfg(64, True, 2, inference_mode=True, precision="fp32")
+    dec = PEneoDecoderB200(cfg, 64)
+    dec.load_state_dict(sd)
+    dec = dec.cuda().train()
+    x = synth.hidden_states(1, 12, 64).cuda()
+    with torch.no_grad():
+        torch.manual_seed(5)
+        a = dec(x)[0]
+        b2 = dec(x)[0]
+        torch.manual_seed(5)
+        c = dec(x)[0]
+    assert torch.equal(a, c) and not torch.equal(a, b2)
