@@ -37,7 +37,8 @@ class HeadsDecodePipeline:
         b, n, _ = hidden.shape
         if hidden.is_cuda:
             x = hidden
-            ready = None
+            ready = torch.cuda.Event()  # whatever produced `hidden` on the caller's stream must be done first
+            ready.record(torch.cuda.current_stream(self.device))
         else:
             with torch.cuda.stream(self.copy):
                 x = hidden.to(self.device, non_blocking=True)

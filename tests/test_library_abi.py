@@ -88,3 +88,26 @@ def test_state_dict_keys_match_reference_checkpoint_interface():
         assert set(dec.state_dict().keys()) == set(sd.keys())
         for k, v in dec.state_dict().items():
             assert tuple(v.shape) == tuple(sd[k].shape), k
+
+
+@pytest.mark.skipif(not __import__("ref_shim").reference_available(), reason="reference tree not present")
+@pytest.mark.parametrize("hin,hidden,shrink,L", [(768, 768, True, 2), (960, 768, True, 2), (48, 48, False, 1), (64, 64, True, 3)])
+def test_module_is_checkpoint_compatible_with_the_live_reference(hin, hidden, shrink, L):
+    """Parameter / buffer names and shapes of PEneoDecoderB200 equal those of the real PEneoDecoder, both ways
+    (so `from_pretrained`, `save_model` and the trainer's "peneo_decoder" parameter grouping keep working)."""
+    import ref_shim
+    from peneo_b200 import PEneoDecoderB200
+
+    ns = ref_shim.load_reference()
+    cfg = ns.PEneoConfig(backbone_name="x", backbone_config={"hidden_size": hidden, "hidden_dropout_prob": 0.1},
+                         peneo_decoder_shrink=shrink, peneo_classifier_num_layers=L, peneo_category_weights=[1, 10, 10])
+    ref = ns.PEneoDecoder(cfg, hin)
+    mine = PEneoDecoderB200(cfg, hin)
+    a, b = ref.state_dict(), mine.state_dict()
+    assert list(a.keys()) == list(b.keys())
+    assert all(a[k].shape == b[k].shape and a[k].dtype == b[k].dtype for k in a)
+    assert [n for n, _ in ref.named_parameters()] == [n for n, _ in mine.named_parameters()]
+    missing = mine.load_state_dict(a)
+    assert not missing.missing_keys and not missing.unexpected_keys
+    missing = ref.load_state_dict(b)
+    assert not missing.missing_keys and not missing.unexpected_keys
