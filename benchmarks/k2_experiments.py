@@ -18,9 +18,9 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(10): ops.pair_heads(pack, ab, b, n)
+    for _ in range(int(os.environ.get("K2_ITERS", "10"))): ops.pair_heads(pack, ab, b, n)
     e1.record(); torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / 10
+    ms = e0.elapsed_time(e1) / int(os.environ.get("K2_ITERS", "10"))
     p = n * (n + 1) // 2
     fl = b * (10.0 * p * 384 * 384 + 28.0 * p * 384)
     print(json.dumps({"dbg": os.environ.get("PENEO_K2_DBG", "0"), "n": n, "b": b, "ms": ms, "tflops": fl / ms / 1e9}))

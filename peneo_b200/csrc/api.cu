@@ -1,5 +1,6 @@
 // extern "C" boundary (include/peneo_b200.h).  Argument validation, workspace carving and kernel
 // sequencing only; no allocation, no global mutable state beyond the thread-local error string.
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -182,6 +183,11 @@ int peneo_pair_heads_fwd(const peneo_dims* dims, int prec, const void* pack, con
   const DropSpec* dp = drop.thresh ? &drop : nullptr;
   if (prec == PENEO_PREC_FP32)
     return launch_pair_heads_simt(*dims, pack, static_cast<const float*>(ab), batch, n, logits, st, dp);
+  // Default: the CTA-pair (cta_group::2, M = 256) variant of K2 — same results, half the W_mid traffic per SM,
+  // ~3 % faster under the sustained power cap.  PENEO_K2_PAIR=0 selects the single-CTA kernel (A/B studies).
+  static const bool use_pair = [] { const char* e = getenv("PENEO_K2_PAIR"); return !e || atoi(e) != 0; }();
+  if (use_pair)
+    return launch_pair_heads_tc_pair(pack, pack_layout(*dims, prec), static_cast<const __nv_bfloat16*>(ab), batch, n, logits, st, dp);
   return launch_pair_heads_tc(pack, pack_layout(*dims, prec), static_cast<const __nv_bfloat16*>(ab), batch, n, logits, st, dp);
 }
 

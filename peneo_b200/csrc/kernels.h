@@ -31,6 +31,10 @@ int launch_gemm_tc2(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* W,
 int launch_pair_heads_tc(const void* pack, const PackLayout& L, const __nv_bfloat16* ab, int batch, int n,
                          float* const logits[kNumHeads], cudaStream_t st, const DropSpec* drop = nullptr);
 
+// pair_heads_tc2.cu : the same kernel on CTA pairs (cta_group::2, M = 256)
+int launch_pair_heads_tc_pair(const void* pack, const PackLayout& L, const __nv_bfloat16* ab, int batch, int n,
+                              float* const logits[kNumHeads], cudaStream_t st, const DropSpec* drop = nullptr);
+
 // pair_bwd_tc.cu : regenerated S, M = SiLU(u), G = (dz W_out) SiLU'(u) of a chunk of pairs (bf16 backward)
 int launch_pair_bwd_prep(const void* pack, const PackLayout& L, const __nv_bfloat16* ab, int n, int64_t g0, int rows,
                          const float* const dz[kNumHeads], __nv_bfloat16* S, __nv_bfloat16* G, __nv_bfloat16* M,

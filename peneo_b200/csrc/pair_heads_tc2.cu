@@ -1,0 +1,399 @@
+// K2 on CTA pairs (cta_group::2) — same algorithm, warp roles and TMEM layout as pair_heads_tc.cu, but two CTAs of
+// a cluster (one TPC) run every UMMA together with M = 256: each CTA owns one 128-pair tile (its S rows, accumulators
+// and epilogue) and supplies HALF of the B operand (64 of the 128 W_mid rows of a chunk, 8 of the 16 W_out rows)
+// from its shared memory.  Per SM this halves both the TMA writes of the W stream and the tensor core's B reads —
+// the two streams that saturate the 128 B/clk shared-memory port in the single-CTA kernel.
+//
+// Cross-CTA synchronisation (the protocol of CUTLASS / DeepGEMM 2-SM kernels):
+//   * only the leader (cluster rank 0) issues tcgen05.mma; it waits on ITS barriers for "W stage full" (both TMA
+//     warps arrive, transaction bytes of both halves are counted there), "S chunk full" (producer warps of both
+//     CTAs) and "m ready" (epilogue warps of both CTAs) — the peer arrives remotely (mapa + mbarrier.arrive);
+//   * everything the MMA releases ("W stage empty", "S chunk free", "u full", "z full", "W_out stage empty") is a
+//     tcgen05.commit multicast to the same barrier in both CTAs.
+#include <cuda.h>
+
+#include <cstdlib>
+
+#include "common.cuh"
+#include "kernels.h"
+#include "ptx.cuh"
+
+namespace peneo {
+namespace k2p {
+
+constexpr int D = 384;
+constexpr int kChunks = 15;       // 5 heads x 3 chunks of 128 mid features
+constexpr int kKChunks = 6;       // 384 / 64
+constexpr int kWStages = 8;
+constexpr int kWStageBytes = 64 * 64 * 2;  // 8 KB: this CTA's 64 of the chunk's 128 rows
+constexpr int kOStages = 3;
+constexpr int kOStageBytes = 2 * 8 * 64 * 2;  // 2 KB: two K-blocks of [8 rows x 64] (this CTA's half of 16)
+constexpr int kStageRowBytes = D * 2;          // staging: 128 rows x 768 B
+constexpr int kThreads = 512;
+
+constexpr uint32_t kColS = 0, kColU = 192, kColZ = 448;
+
+struct Smem {
+  static constexpr int w = 0;
+  static constexpr int o = w + kWStages * kWStageBytes;
+  static constexpr int stage = o + kOStages * kOStageBytes;
+  static constexpr int bmid = stage + 128 * kStageRowBytes;  // 1920 floats
+  static constexpr int bout = bmid + 5 * D * 4;              // 20 floats
+  static constexpr int bars = bout + 128;
+  static constexpr int total = bars + 512;
+};
+// barrier indices
+constexpr int bWFull = 0, bWEmpty = bWFull + kWStages, bOFull = bWEmpty + kWStages, bOEmpty = bOFull + kOStages,
+              bUFull = bOEmpty + kOStages, bMReady = bUFull + 2, bZFull = bMReady + 2, bSFull = bZFull + 2,
+              bSFree = bSFull + kKChunks, bCount = bSFree + kKChunks;
+static_assert(bCount * 8 + 16 <= 512, "barrier area too small");
+constexpr int kSmemBytes = Smem::total + 1024;
+
+struct Args {
+  const __nv_bfloat16* ab;  // [batch*n, 768] : 0.5*A | 0.5*Bm
+  const float* bmid_half;   // [1920]
+  const float* bout;        // [5][4]
+  float* logits[kNumHeads];
+  int32_t n, pairs_per_doc;
+  int64_t total_pairs;
+  int32_t num_tiles;
+  uint32_t drop_thresh;  // training-mode dropout after the hidden SiLU (DROP instantiation only)
+  float drop_scale;
+  uint32_t drop_key[kNumHeads];
+  uint32_t dbg;  // PENEO_K2_DBG experiment bits (timing studies only; results are wrong when set)
+};
+
+template <bool DROP>
+__global__ void __launch_bounds__(kThreads, 1)
+    pair_heads_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmO, const Args a) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Smem::bars);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + bCount);
+  float* s_bmid = reinterpret_cast<float*>(smem + Smem::bmid);
+  float* s_bout = reinterpret_cast<float*>(smem + Smem::bout);
+
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+
+  const uint32_t rank = ptx::cluster_ctarank();  // 0 = leader (issues every MMA of the pair)
+  const bool leader = rank == 0;
+  if (threadIdx.x == 0) {
+    ptx::prefetch_tmap(&tmW);
+    ptx::prefetch_tmap(&tmO);
+    for (int s = 0; s < kWStages; ++s) ptx::mbar_init(&bars[bWFull + s], 2), ptx::mbar_init(&bars[bWEmpty + s], 1);
+    for (int s = 0; s < kOStages; ++s) ptx::mbar_init(&bars[bOFull + s], 2), ptx::mbar_init(&bars[bOEmpty + s], 1);
+    for (int s = 0; s < 2; ++s) {
+      ptx::mbar_init(&bars[bUFull + s], 1);
+      ptx::mbar_init(&bars[bMReady + s], 16);  // 8 epilogue warps of each CTA
+      ptx::mbar_init(&bars[bZFull + s], 1);
+    }
+    for (int s = 0; s < kKChunks; ++s) ptx::mbar_init(&bars[bSFull + s], 8), ptx::mbar_init(&bars[bSFree + s], 1);
+    ptx::fence_barrier_init();
+  }
+  for (int e = threadIdx.x; e < 5 * D; e += kThreads) s_bmid[e] = a.bmid_half[e];
+  if (threadIdx.x < 20) s_bout[threadIdx.x] = a.bout[threadIdx.x];
+  ptx::cluster_sync_all();  // both CTAs' barriers exist before anyone (TMA of the peer, remote arrives) touches them
+  if (warp == 2) {
+    ptx::tmem_alloc_2sm(tmem_slot, 512);
+    ptx::tmem_relinquish_2sm();
+  }
+  ptx::tc_fence_before();
+  ptx::cluster_sync_all();
+  ptx::tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  // arrive on the LEADER's copy of a barrier (local for the leader, remote for the peer)
+  auto arrive_leader = [&](uint64_t* bar) {
+    if (leader) ptx::mbar_arrive(bar);
+    else ptx::mbar_arrive_remote(bar, 0);
+  };
+
+  // Tiles are handed out in pairs: cluster `cid` takes tile pairs cid, cid + nclusters, ...; this CTA owns tile
+  // 2 * pair + rank (the last pair may have a phantom second tile: all its rows are >= total_pairs).
+  const int cid = static_cast<int>(blockIdx.x >> 1), ncl = static_cast<int>(gridDim.x >> 1);
+  const int num_pairs = (a.num_tiles + 1) / 2;
+  const int my_tiles = (num_pairs > cid) ? (num_pairs - 1 - cid) / ncl + 1 : 0;
+  auto tile_of = [&](int it) { return 2 * (static_cast<int64_t>(cid) + static_cast<int64_t>(it) * ncl) + rank; };
+
+  if (warp == 0) {
+    // ============================== TMA producer ==============================
+    if (ptx::elect_one()) {
+      int ws = 0, os = 0;
+      uint32_t wph = 0, oph = 0;
+      for (int it = 0; it < my_tiles; ++it) {
+        for (int c = 0; c < kChunks; ++c) {
+          for (int kc = 0; kc < kKChunks; ++kc) {
+            ptx::mbar_wait(&bars[bWEmpty + ws], wph ^ 1);
+            // this CTA's 64 rows of the chunk; both halves complete on the leader's barrier
+            ptx::tma_load_2d_2sm(smem + Smem::w + ws * kWStageBytes, &tmW, &bars[bWFull + ws], kc * 64,
+                                 c * 128 + static_cast<int>(rank) * 64);
+            if (leader) ptx::mbar_arrive_expect_tx(&bars[bWFull + ws], 2 * kWStageBytes);
+            else ptx::mbar_arrive_remote(&bars[bWFull + ws], 0);
+            if (++ws == kWStages) ws = 0, wph ^= 1;
+          }
+          ptx::mbar_wait(&bars[bOEmpty + os], oph ^ 1);
+          unsigned char* od = smem + Smem::o + os * kOStageBytes;
+          ptx::tma_load_2d_2sm(od, &tmO, &bars[bOFull + os], 0, c * 16 + static_cast<int>(rank) * 8);
+          ptx::tma_load_2d_2sm(od + 1024, &tmO, &bars[bOFull + os], 64, c * 16 + static_cast<int>(rank) * 8);
+          if (leader) ptx::mbar_arrive_expect_tx(&bars[bOFull + os], 2 * kOStageBytes);
+          else ptx::mbar_arrive_remote(&bars[bOFull + os], 0);
+          if (++os == kOStages) os = 0, oph ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ============================== MMA issuer ==============================
+    // (elect_one, not lane == 0: ptxas then treats the region as uniform and keeps descriptors in
+    //  uniform registers instead of emitting a per-instruction R2UR waterfall loop)
+    if (leader && ptx::elect_one()) {
+      constexpr uint32_t idesc1 = ptx::umma_idesc_bf16(256, 128);  // M = 256 across the CTA pair
+      constexpr uint32_t idesc2 = ptx::umma_idesc_bf16(256, 16);
+      int ws = 0, os = 0;
+      uint32_t wph = 0, oph = 0;
+      const uint32_t w_base = ptx::smem_u32(smem + Smem::w), o_base = ptx::smem_u32(smem + Smem::o);
+      // second GEMM of global chunk gp: z[head] (+)= m(gp) * W_out chunk^T
+      auto mma2 = [&](int gp) {
+        const int buf = gp & 1, hg = gp / 3, cpos = gp - hg * 3;
+        ptx::mbar_wait(&bars[bMReady + buf], (gp >> 1) & 1);
+        ptx::mbar_wait(&bars[bOFull + os], oph);
+        ptx::tc_fence_after();
+        const uint32_t zt = tmem + kColZ + 16 * (hg & 1);
+        const uint32_t mt = tmem + kColU + 128 * buf;
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+          const uint32_t at = mt + (ks < 4 ? 8 * ks : 64 + 8 * (ks - 4));
+          const uint64_t bd = ptx::umma_desc_sw128(o_base + os * kOStageBytes + (ks / 4) * 1024 + (ks % 4) * 32);
+          ptx::umma_ts_2sm(zt, at, bd, idesc2, (cpos | ks) != 0);
+        }
+        ptx::tc_commit_2sm(&bars[bOEmpty + os], 3);
+        if (cpos == 2) ptx::tc_commit_2sm(&bars[bZFull + (hg & 1)], 3);
+        if (++os == kOStages) os = 0, oph ^= 1;
+      };
+      int g = 0;
+      for (int it = 0; it < my_tiles; ++it) {
+        for (int c = 0; c < kChunks; ++c, ++g) {
+          const uint32_t ut = tmem + kColU + 128 * (g & 1);
+          for (int kc = 0; kc < kKChunks; ++kc) {
+            if (c == 0) ptx::mbar_wait(&bars[bSFull + kc], it & 1);
+            ptx::mbar_wait(&bars[bWFull + ws], wph);
+            ptx::tc_fence_after();
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)
+              ptx::umma_ts_2sm(ut, tmem + kColS + 32 * kc + 8 * ks,
+                               ptx::umma_desc_sw128(w_base + ws * kWStageBytes + ks * 32), idesc1, (kc | ks) != 0);
+            ptx::tc_commit_2sm(&bars[bWEmpty + ws], 3);
+            if (c == kChunks - 1) ptx::tc_commit_2sm(&bars[bSFree + kc], 3);
+            if (++ws == kWStages) ws = 0, wph ^= 1;
+          }
+          ptx::tc_commit_2sm(&bars[bUFull + (g & 1)], 3);
+          if (g > 0) mma2(g - 1);
+        }
+      }
+      if (g > 0) mma2(g - 1);
+    }
+  } else if (warp >= 4 && warp < 12) {
+    // ============================== epilogue ==============================
+    const int q = warp % 4, hsel = (warp - 4) / 4;
+    const uint32_t lane_base = static_cast<uint32_t>(q * 32) << 16;
+    const int row = q * 32 + lane;
+    // logits of head-global index hg (tile = hg / 5, head = hg % 5)
+    auto emit_z = [&](int hg) {
+      ptx::mbar_wait(&bars[bZFull + (hg & 1)], (hg >> 1) & 1);
+      ptx::tc_fence_after();
+      uint32_t zr[4];
+      ptx::tmem_ld_x4(tmem + lane_base + kColZ + 16 * (hg & 1), zr);
+      ptx::tmem_ld_wait();
+      const int it = hg / 5, k = hg - it * 5;
+      const int64_t tile = tile_of(it);
+      const int64_t gp = tile * 128 + row;
+      if (gp < a.total_pairs) {
+        const int C = head_classes(k);
+        float* dst = a.logits[k] + gp * C;
+        for (int cc = 0; cc < C; ++cc) dst[cc] = __uint_as_float(zr[cc]) + s_bout[k * 4 + cc];
+      }
+    };
+    int g = 0;
+    for (int it = 0; it < my_tiles; ++it) {
+      const int64_t drop_row = tile_of(it) * 128 + row;
+      for (int c = 0; c < kChunks; ++c, ++g) {
+        const int buf = g & 1;
+        ptx::mbar_wait(&bars[bUFull + buf], (g >> 1) & 1);
+        ptx::tc_fence_after();
+        const uint32_t ut = tmem + lane_base + kColU + 128 * buf + 64 * hsel;
+        const float* hb = s_bmid + c * 128 + 64 * hsel;
+#pragma unroll
+        for (int piece = 0; piece < 2; ++piece) {
+          uint32_t r[32];
+          ptx::tmem_ld_x32(ut + 32 * piece, r);
+          ptx::tmem_ld_wait();
+          uint32_t packed[16];
+#pragma unroll
+          for (int x = 0; x < 32; x += 4) {
+            const float4 b4 = *reinterpret_cast<const float4*>(hb + 32 * piece + x);
+            float m0 = __uint_as_float(r[x + 0]) + b4.x, m1 = __uint_as_float(r[x + 1]) + b4.y;
+            float m2 = __uint_as_float(r[x + 2]) + b4.z, m3 = __uint_as_float(r[x + 3]) + b4.w;
+            if (!(a.dbg & 2u)) {  // (experiment bit 2: epilogue without the SiLU math)
+              m0 = ptx::silu_from_half(m0), m1 = ptx::silu_from_half(m1);
+              m2 = ptx::silu_from_half(m2), m3 = ptx::silu_from_half(m3);
+            }
+            if (DROP) {  // nn.Dropout after the hidden SiLU (model/peneo_decoder.py:261), regenerable mask
+              const uint32_t key = a.drop_key[c / 3], grow = static_cast<uint32_t>(drop_row);
+              const uint32_t col = (c % 3) * 128 + 64 * hsel + 32 * piece + x;
+              m0 = drop_keep(key, a.drop_thresh, grow, col) ? m0 * a.drop_scale : 0.f;
+              m1 = drop_keep(key, a.drop_thresh, grow, col + 1) ? m1 * a.drop_scale : 0.f;
+              m2 = drop_keep(key, a.drop_thresh, grow, col + 2) ? m2 * a.drop_scale : 0.f;
+              m3 = drop_keep(key, a.drop_thresh, grow, col + 3) ? m3 * a.drop_scale : 0.f;
+            }
+            packed[x / 2] = ptx::pack_bf16x2(m0, m1);
+            packed[x / 2 + 1] = ptx::pack_bf16x2(m2, m3);
+          }
+          // m overwrites the first half of the columns this warp has already consumed
+          ptx::tmem_st_x16(ut + 16 * piece, packed);
+        }
+        ptx::tmem_st_wait();
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) arrive_leader(&bars[bMReady + buf]);
+        if (hsel == 0 && g > 0 && g % 3 == 0) emit_z(g / 3 - 1);
+      }
+    }
+    if (hsel == 0 && g > 0) emit_z(g / 3 - 1);
+  } else if (warp >= 12) {
+    // ============================== pair producers ==============================
+    const int q = warp - 12;
+    const uint32_t lane_base = static_cast<uint32_t>(q * 32) << 16;
+    unsigned char* stg = smem + Smem::stage;
+    for (int it = 0; it < my_tiles; ++it) {
+      const int64_t tile = tile_of(it);
+      // (row offsets of a_i / b_j for the row this lane will later copy)
+      int64_t my_a = -1, my_b = -1;
+      {
+        const int64_t gp = tile * 128 + q * 32 + lane;
+        if (gp < a.total_pairs) {
+          const int64_t b = gp / a.pairs_per_doc;
+          const int p = static_cast<int>(gp - b * a.pairs_per_doc);
+          int i, j;
+          pair_from_flat(p, a.n, i, j);
+          my_a = (b * a.n + i) * (2 * D);
+          my_b = (b * a.n + j) * (2 * D) + D;
+        }
+      }
+      // ---- generate s rows [32q, 32q+32) into staging; lane = 4-column group (3 groups per lane)
+#pragma unroll 1
+      for (int rr = 0; rr < 32; rr += 4) {
+        uint2 av[4][3], bv[4][3];
+        int64_t offa[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          offa[u] = __shfl_sync(0xffffffffu, my_a, rr + u);
+          const int64_t offb = __shfl_sync(0xffffffffu, my_b, rr + u);
+#pragma unroll
+          for (int mth = 0; mth < 3; ++mth) {
+            const int col = 4 * (lane + 32 * mth);
+            if (offa[u] >= 0) {
+              av[u][mth] = __ldg(reinterpret_cast<const uint2*>(a.ab + offa[u] + col));
+              bv[u][mth] = __ldg(reinterpret_cast<const uint2*>(a.ab + offb + col));
+            } else {
+              av[u][mth] = make_uint2(0u, 0u), bv[u][mth] = make_uint2(0u, 0u);
+            }
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int r = q * 32 + rr + u;
+#pragma unroll
+          for (int mth = 0; mth < 3; ++mth) {
+            const int cg = lane + 32 * mth;  // 4-column group index, 0..95
+            // bf16 -> fp32 is a 16-bit shift
+            const float a0 = __uint_as_float(av[u][mth].x << 16), a1 = __uint_as_float(av[u][mth].x & 0xFFFF0000u);
+            const float a2 = __uint_as_float(av[u][mth].y << 16), a3 = __uint_as_float(av[u][mth].y & 0xFFFF0000u);
+            const float b0 = __uint_as_float(bv[u][mth].x << 16), b1 = __uint_as_float(bv[u][mth].x & 0xFFFF0000u);
+            const float b2 = __uint_as_float(bv[u][mth].y << 16), b3 = __uint_as_float(bv[u][mth].y & 0xFFFF0000u);
+            uint2 o;
+            o.x = ptx::pack_bf16x2(ptx::silu_from_half(a0 + b0), ptx::silu_from_half(a1 + b1));
+            o.y = ptx::pack_bf16x2(ptx::silu_from_half(a2 + b2), ptx::silu_from_half(a3 + b3));
+            const int chunk16 = (cg >> 1) ^ (r & 7);  // XOR swizzle keeps the row-wise reads below conflict-free
+            *reinterpret_cast<uint2*>(stg + r * kStageRowBytes + chunk16 * 16 + (cg & 1) * 8) = o;
+          }
+        }
+      }
+      __syncwarp();
+      // ---- copy into TMEM, one 64-feature K chunk at a time, as the MMA warp releases them
+      const int r = q * 32 + lane;
+#pragma unroll 1
+      for (int kc = 0; kc < kKChunks; ++kc) {
+        uint32_t v[32];
+#pragma unroll
+        for (int ch = 0; ch < 8; ++ch) {
+          const int chunk16 = (kc * 8 + ch) ^ (r & 7);
+          const uint4 t = *reinterpret_cast<const uint4*>(stg + r * kStageRowBytes + chunk16 * 16);
+          v[4 * ch] = t.x, v[4 * ch + 1] = t.y, v[4 * ch + 2] = t.z, v[4 * ch + 3] = t.w;
+        }
+        if (it > 0) ptx::mbar_wait(&bars[bSFree + kc], (it - 1) & 1);
+        ptx::tc_fence_after();
+        uint32_t lo[16], hi[16];
+#pragma unroll
+        for (int x = 0; x < 16; ++x) lo[x] = v[x], hi[x] = v[16 + x];
+        ptx::tmem_st_x16(tmem + lane_base + kColS + 32 * kc, lo);
+        ptx::tmem_st_x16(tmem + lane_base + kColS + 32 * kc + 16, hi);
+        ptx::tmem_st_wait();
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) arrive_leader(&bars[bSFull + kc]);
+      }
+      __syncwarp();
+    }
+  }
+
+  ptx::tc_fence_before();
+  ptx::cluster_sync_all();  // the peer's tensor-memory reads / remote arrives are finished as well
+  if (warp == 2) ptx::tmem_dealloc_2sm(tmem, 512);
+}
+
+}  // namespace k2p
+
+int launch_pair_heads_tc_pair(const void* pack, const PackLayout& L, const __nv_bfloat16* ab, int batch, int n,
+                              float* const logits[kNumHeads], cudaStream_t st, const DropSpec* drop) {
+  using namespace k2p;
+  const char* base = static_cast<const char*>(pack);
+  Args a{};
+  a.ab = ab;
+  a.bmid_half = reinterpret_cast<const float*>(base + L.bmid_half);
+  a.bout = reinterpret_cast<const float*>(base + L.bout);
+  for (int h = 0; h < kNumHeads; ++h) a.logits[h] = logits[h];
+  a.n = n;
+  a.pairs_per_doc = static_cast<int32_t>(pair_count(n));
+  a.total_pairs = (int64_t)batch * a.pairs_per_doc;
+  const int64_t tiles = (a.total_pairs + 127) / 128;
+  PENEO_REQUIRE(tiles < (1ll << 31), "pair_heads: too many pairs for one launch");
+  a.num_tiles = static_cast<int32_t>(tiles);
+  if (tiles == 0) return PENEO_OK;
+  alignas(64) CUtensorMap tmW, tmO;
+  int rc;
+  // boxes are the per-CTA halves: 64 of a chunk's 128 W_mid rows, 8 of its 16 (padded) W_out rows
+  if ((rc = make_tensor_map_bf16(&tmW, base + L.wmid_bf16, D, 5 * D, D * 2, 64, 64)) != PENEO_OK) return rc;
+  if ((rc = make_tensor_map_bf16(&tmO, base + L.wout_bf16, 128, 15 * 16, 128 * 2, 64, 8)) != PENEO_OK) return rc;
+  int dev = 0, sms = 148;
+  PENEO_CUDA_TRY(cudaGetDevice(&dev));
+  PENEO_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int64_t pairs = (tiles + 1) / 2;
+  const int grid = 2 * static_cast<int>(std::min<int64_t>(pairs, sms / 2));
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid), cfg.blockDim = dim3(kThreads), cfg.dynamicSmemBytes = kSmemBytes, cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr, cfg.numAttrs = 1;
+  if (drop && drop->thresh) {
+    a.drop_thresh = drop->thresh, a.drop_scale = drop->scale;
+    for (int h = 0; h < kNumHeads; ++h) a.drop_key[h] = drop_key(*drop, site_head(h, 0));
+    PENEO_CUDA_TRY(cudaFuncSetAttribute(pair_heads_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    PENEO_CUDA_TRY(cudaLaunchKernelEx(&cfg, pair_heads_tc_kernel<true>, tmW, tmO, a));
+  } else {
+    PENEO_CUDA_TRY(cudaFuncSetAttribute(pair_heads_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    PENEO_CUDA_TRY(cudaLaunchKernelEx(&cfg, pair_heads_tc_kernel<false>, tmW, tmO, a));
+  }
+  PENEO_CUDA_TRY(cudaGetLastError());
+  return PENEO_OK;
+}
+
+}  // namespace peneo
