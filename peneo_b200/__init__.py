@@ -4,9 +4,12 @@ Public surface mirrors the reference (ZeningLin/PEneo):
   PEneoDecoderB200 / PEneoOutput      <- model/peneo_decoder.py  PEneoDecoder / PEneoOutput
   HandshakingTaggingScheme            <- model/peneo_decoder.py  HandshakingTaggingScheme
   decode_peneo / sample_decode_peneo / parse_matrix_spots  <- pipeline/decode.py
+  CrossEntropyLossOHEM                <- model/custom_loss.py    CrossEntropyLossOHEM
+  evaluation.calculate_*_KVPE_metric  <- pipeline/evaluation.py
 """
 from .decode import decode_peneo, parse_matrix_spots, sample_decode_peneo  # noqa: F401
 from .decoder import PEneoDecoderB200, PEneoOutput  # noqa: F401
+from .loss import CrossEntropyLossOHEM  # noqa: F401
 from .pipeline import HeadsDecodePipeline  # noqa: F401
 from .tagging import HandshakingTaggingScheme  # noqa: F401
 
@@ -15,6 +18,7 @@ __all__ = [
     "PEneoOutput",
     "HandshakingTaggingScheme",
     "HeadsDecodePipeline",
+    "CrossEntropyLossOHEM",
     "decode_peneo",
     "sample_decode_peneo",
     "parse_matrix_spots",

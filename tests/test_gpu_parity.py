@@ -606,3 +606,22 @@ def test_dropout_masks_are_statistically_sound_and_seeded():
         torch.manual_seed(5)
         c = dec(x)[0]
     assert torch.equal(a, c) and not torch.equal(a, b2)
+
+
+def test_cross_entropy_loss_ohem_module_matches_reference_golden(golden):
+    """peneo_b200.CrossEntropyLossOHEM (model/custom_loss.py:104-288 drop-in) on every reference-generated loss
+    fixture: plain weighted CE and the OHEM variants, value and gradient."""
+    from peneo_b200 import CrossEntropyLossOHEM
+
+    for case in golden("loss.pt"):
+        crit = CrossEntropyLossOHEM(num_hard_positive=case["ohem"][0], num_hard_negative=case["ohem"][1],
+                                    weight=case["weight"]).cuda()
+        x = case["logits"].cuda().requires_grad_(True)
+        val = crit(x, case["target"].cuda())
+        assert abs(val.item() - case["loss"].item()) <= 2e-5 * max(1.0, abs(case["loss"].item())), case["name"]
+        val.backward()
+        xr = case["logits"].clone().requires_grad_(True)
+        orc.ce_loss(xr, case["target"], case["weight"], *case["ohem"]).backward()
+        assert rel_err(x.grad, xr.grad) <= 1e-4, case["name"]
+    with pytest.raises(NotImplementedError):
+        CrossEntropyLossOHEM(weight=torch.ones(3), random=True)
