@@ -14,6 +14,7 @@
 // chunk of whole pair-rows at a time (a chunk = rows i0..i1 of one document = a contiguous range
 // of flat pair indices), so the workspace is O(chunk * D * num_layers), not O(P * D).
 #include <cstdlib>
+#include <vector>
 
 #include "common.cuh"
 #include "kernels.h"
@@ -387,12 +388,14 @@ Plan make_plan(const peneo_dims& dm, int prec, int batch, int n) {
   p.nH = dm.num_layers >= 3 ? dm.num_layers - 2 : 0;
   const bool tc = prec == PENEO_PREC_BF16;
   const int nbuf = tc ? 7 : 3 + p.nU + p.nH;  // fp32: S, dS, G, U.., H.. ; bf16: dS (fp32) + S, G, M (bf16, 1 + 5 + 5 halves)
-  // ~512 MB of pair buffers, but never less than one full pair row (n pairs)
-  int64_t rows = (int64_t)(512ull << 20) / ((int64_t)nbuf * d * 4);
-  rows = std::min<int64_t>(rows, 65536);
+  // Pair buffers: up to 262 144 pairs per chunk within ~3 GB (measured: per-chunk launch / wave-quantisation overheads
+  // make 64 K-pair chunks 25 % slower end to end), never less than one full pair row (n pairs).  A chunk may span
+  // several documents.
+  int64_t rows = (int64_t)(3072ull << 20) / ((int64_t)nbuf * d * 4);
+  rows = std::min<int64_t>(rows, 262144);
   if (const char* e = getenv("PENEO_BWD_CHUNK_ROWS")) rows = std::max(1, atoi(e));  // test hook: force small chunks
   rows = std::max<int64_t>(n, rows);
-  rows = std::min<int64_t>(rows, pair_count(n));
+  rows = std::min<int64_t>(rows, (int64_t)batch * pair_count(n));
   p.chunk_rows_max = static_cast<int>(rows);
   size_t off = 0;
   auto take = [&](size_t bytes) {
@@ -520,21 +523,43 @@ int launch_heads_bwd(const peneo_dims& dm, int prec, const void* pack, const voi
   }
   float *S = F(pl.off_S), *dS = F(pl.off_dS), *G = F(pl.off_G);
   const size_t cstride = fl((size_t)pl.chunk_rows_max * d) / sizeof(float);
-  for (int b = 0; b < batch; ++b) {
-    int i0 = 0;
-    while (i0 < n) {
-      int i1 = i0 + 1;
-      while (i1 < n && row_start(i1 + 1, n) - row_start(i0, n) <= pl.chunk_rows_max) ++i1;
-      const int p0 = row_start(i0, n), rows = row_start(i1, n) - p0;  // row_start(n, n) == P
+  // A chunk is a contiguous range [g0, g0 + rows) of the batch-flat pair list made of whole pair-rows: segments
+  // (document b, rows i0..i1) that follow each other in memory.  Everything up to dS works on the flat range; only
+  // the dA / dBm reduction is per segment.
+  struct Seg {
+    int b, i0, i1, rows;
+    int64_t off;  // first row of the segment inside the chunk
+  };
+  std::vector<Seg> segs;
+  int cb = 0, ci0 = 0;  // next (document, pair-row) not yet assigned to a chunk
+  while (cb < batch) {
+    segs.clear();
+    const int64_t g0 = (int64_t)cb * P + row_start(ci0, n);
+    int rows = 0;
+    while (cb < batch) {
+      int i1 = ci0;
+      while (i1 < n && rows + (row_start(i1 + 1, n) - row_start(ci0, n)) <= pl.chunk_rows_max) ++i1;
+      if (i1 == ci0) {
+        if (rows > 0) break;  // chunk full
+        i1 = ci0 + 1;         // (cannot happen: chunk_rows_max >= n)
+      }
+      const int seg_rows = row_start(i1, n) - row_start(ci0, n);  // row_start(n, n) == P
+      segs.push_back(Seg{cb, ci0, i1, seg_rows, rows});
+      rows += seg_rows;
+      ci0 = i1;
+      if (ci0 == n) ci0 = 0, ++cb;
+      else break;  // the document did not fit completely: the chunk is full
+    }
+    {
       const int rb = (rows + 127) / 128;
-      const uint32_t row0 = static_cast<uint32_t>((int64_t)b * P + p0);  // batch-flat index of the chunk's first pair
+      const uint32_t row0 = static_cast<uint32_t>(g0);  // batch-flat index of the chunk's first pair
       if (tc) {
         __nv_bfloat16* S16 = reinterpret_cast<__nv_bfloat16*>(ws + pl.off_S16);
         __nv_bfloat16* Gc = reinterpret_cast<__nv_bfloat16*>(ws + pl.off_Gc);
         __nv_bfloat16* Mc = reinterpret_cast<__nv_bfloat16*>(ws + pl.off_Mc);
         const __nv_bfloat16* ab16 = reinterpret_cast<const __nv_bfloat16*>(ws + pl.off_ab16);
         // T1: regenerate S, M = SiLU(u), G = (dz W_out) SiLU'(u) for the five heads (tcgen05, K2's structure)
-        TRY(launch_pair_bwd_prep(pack, L, ab16, n, (int64_t)b * P + p0, rows, dlogits, S16, Gc, Mc, st,
+        TRY(launch_pair_bwd_prep(pack, L, ab16, n, g0, rows, dlogits, S16, Gc, Mc, st,
                                  drop.thresh ? &drop : nullptr));
         // dS = G W_mid (all heads in one K = 1920 GEMM) ; dW_mid += G^T S
         TRY(launch_gemm_ds(Gc, reinterpret_cast<const __nv_bfloat16*>(pk + L.wmid_full_bf16), dS, rows, st));
@@ -542,17 +567,19 @@ int launch_heads_bwd(const peneo_dims& dm, int prec, const void* pack, const voi
         DzPtrs dzp;
         for (int h = 0; h < kNumHeads; ++h) {
           dwm[h] = gr.mid_w[h * 8];
-          dzp.p[h] = dlogits[h] + ((int64_t)b * P + p0) * head_classes(h);
+          dzp.p[h] = dlogits[h] + g0 * head_classes(h);
         }
         TRY(launch_gemm_dw(Gc, S16, dwm, rows, st));
         dwout_bf16_kernel<<<dim3((rows + 255) / 256, 15), 128, 0, st>>>(Mc, Gc, dzp, rows, d_outw, d_outb, d_midb);
         PENEO_CUDA_TRY(cudaGetLastError());
       } else {
-      build_s_kernel<<<rows, 128, 0, st>>>(ab, b, n, d, p0, S);
-      PENEO_CUDA_TRY(cudaGetLastError());
+      for (const Seg& sg : segs) {
+        build_s_kernel<<<sg.rows, 128, 0, st>>>(ab, sg.b, n, d, row_start(sg.i0, n), S + sg.off * d);
+        PENEO_CUDA_TRY(cudaGetLastError());
+      }
       for (int h = 0; h < kNumHeads; ++h) {
         const int C = head_classes(h);
-        const float* dz = dlogits[h] + ((int64_t)b * P + p0) * C;
+        const float* dz = dlogits[h] + g0 * C;
         if (NL == 1) {
           if (C == 2)
             out_only_bwd_kernel<2><<<rb, 128, 0, st>>>(S, dz, W(L.f_out_w[h]), rows, d, dS, h > 0, gr.out_w[h], gr.out_b[h]);
@@ -611,9 +638,10 @@ int launch_heads_bwd(const peneo_dims& dm, int prec, const void* pack, const voi
         }
       }
       }  // fp32 pair part
-      gv_reduce_kernel<<<dim3(n, (d + 127) / 128), 128, 0, st>>>(dS, ab, b, n, d, i0, i1, dab);
-      PENEO_CUDA_TRY(cudaGetLastError());
-      i0 = i1;
+      for (const Seg& sg : segs) {
+        gv_reduce_kernel<<<dim3(n, (d + 127) / 128), 128, 0, st>>>(dS + sg.off * d, ab, sg.b, n, d, sg.i0, sg.i1, dab);
+        PENEO_CUDA_TRY(cudaGetLastError());
+      }
     }
   }
 
