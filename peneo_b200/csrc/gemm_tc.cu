@@ -31,8 +31,22 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
+static int make_tensor_map_any(void* tmap_out, CUtensorMapDataType dtype, const void* gptr, uint64_t inner, uint64_t outer,
+                               uint64_t row_stride_bytes, uint32_t box_inner, uint32_t box_outer);
+
 int make_tensor_map_bf16(void* tmap_out, const void* gptr, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes,
                          uint32_t box_inner, uint32_t box_outer) {
+  return make_tensor_map_any(tmap_out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, gptr, inner, outer, row_stride_bytes, box_inner,
+                             box_outer);
+}
+int make_tensor_map_f32(void* tmap_out, const void* gptr, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes,
+                        uint32_t box_inner, uint32_t box_outer) {
+  return make_tensor_map_any(tmap_out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, gptr, inner, outer, row_stride_bytes, box_inner,
+                             box_outer);
+}
+
+static int make_tensor_map_any(void* tmap_out, CUtensorMapDataType dtype, const void* gptr, uint64_t inner, uint64_t outer,
+                               uint64_t row_stride_bytes, uint32_t box_inner, uint32_t box_outer) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) {
     set_error("cuTensorMapEncodeTiled entry point unavailable");
@@ -42,7 +56,7 @@ int make_tensor_map_bf16(void* tmap_out, const void* gptr, uint64_t inner, uint6
   cuuint64_t strides[1] = {row_stride_bytes};
   cuuint32_t box[2] = {box_inner, box_outer};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(static_cast<CUtensorMap*>(tmap_out), CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(gptr),
+  CUresult r = fn(static_cast<CUtensorMap*>(tmap_out), dtype, 2, const_cast<void*>(gptr),
                   dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {

@@ -86,5 +86,27 @@ int run_probe_rates(double* out, int n_out);
 struct TensorMap2D;
 int make_tensor_map_bf16(void* tmap_out, const void* gptr, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes,
                          uint32_t box_inner, uint32_t box_outer);
+int make_tensor_map_f32(void* tmap_out, const void* gptr, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes,
+                        uint32_t box_inner, uint32_t box_outer);
+
+// gemm_tf32.cu : fp32 GEMM on tcgen05 kind::tf32.  C[M, N] (op)= op(A) op(B) (+ bias), optional C2 = Dropout(SiLU(C)).
+//   ta: A stored [K, M] (else [M, K]) ; tb: B stored [N, K] (else [K, N]) ; mode 0 store, 1 add, 2 split-K atomic add
+struct Tf32Gemm {
+  bool ta = false, tb = false;
+  const float* A = nullptr;
+  int64_t lda = 0;
+  const float* B = nullptr;
+  int64_t ldb = 0;
+  float* C = nullptr;
+  int64_t ldc = 0;
+  int M = 0, N = 0, K = 0, mode = 0;
+  const float* bias = nullptr;
+  float* C2 = nullptr;
+  int64_t ldc2 = 0;
+  uint32_t drop_thresh = 0, drop_key = 0, row0 = 0;
+  float drop_scale = 1.f;
+};
+bool gemm_tf32_supported(const Tf32Gemm& g);
+int launch_gemm_tf32(const Tf32Gemm& g, cudaStream_t st);
 
 }  // namespace peneo

@@ -240,6 +240,54 @@ static int check_mn(int N, int kblocks, int swap, double& max_err) {
   return PENEO_OK;
 }
 
+// TF32 GEMM (gemm_tf32.cu) in one of the four storage combinations, ragged M / N / K, against fp64 on TF32-rounded
+// inputs (error budget: accumulation only).
+static float tf32_round(float v) {
+  uint32_t u;
+  std::memcpy(&u, &v, 4);
+  u = (u + 0x1000u) & 0xFFFFE000u;  // round to 10 mantissa bits
+  std::memcpy(&v, &u, 4);
+  return v;
+}
+static int check_tf32(int combo, double& max_err) {
+  const bool ta = combo & 1, tb = combo & 2;
+  const int M = 200, N = 256, K = 100;
+  const int lda = ta ? 208 : 104, ldb = tb ? 104 : 256;  // multiples of 4 >= the contiguous extent
+  Lcg rng{9001ull + combo};
+  std::vector<float> A((size_t)(ta ? K : M) * lda, 0.f), B((size_t)(tb ? N : K) * ldb, 0.f);
+  auto a_at = [&](int m, int k) -> float& { return ta ? A[(size_t)k * lda + m] : A[(size_t)m * lda + k]; };
+  auto b_at = [&](int k, int n) -> float& { return tb ? B[(size_t)n * ldb + k] : B[(size_t)k * ldb + n]; };
+  for (int m = 0; m < M; ++m)
+    for (int k = 0; k < K; ++k) a_at(m, k) = tf32_round(rng.next());
+  for (int k = 0; k < K; ++k)
+    for (int n = 0; n < N; ++n) b_at(k, n) = tf32_round(rng.next());
+  float *dA, *dB, *dC;
+  PENEO_CUDA_TRY(cudaMalloc(&dA, A.size() * 4));
+  PENEO_CUDA_TRY(cudaMalloc(&dB, B.size() * 4));
+  PENEO_CUDA_TRY(cudaMalloc(&dC, (size_t)M * N * 4));
+  PENEO_CUDA_TRY(cudaMemcpy(dA, A.data(), A.size() * 4, cudaMemcpyHostToDevice));
+  PENEO_CUDA_TRY(cudaMemcpy(dB, B.data(), B.size() * 4, cudaMemcpyHostToDevice));
+  PENEO_CUDA_TRY(cudaMemset(dC, 0, (size_t)M * N * 4));
+  Tf32Gemm g;
+  g.ta = ta, g.tb = tb, g.A = dA, g.lda = lda, g.B = dB, g.ldb = ldb, g.C = dC, g.ldc = N, g.M = M, g.N = N, g.K = K;
+  g.mode = combo == 3 ? 2 : 0;  // exercise the split-K atomic path once
+  int rc = launch_gemm_tf32(g, 0);
+  if (rc != PENEO_OK) return rc;
+  PENEO_CUDA_TRY(cudaDeviceSynchronize());
+  std::vector<float> C((size_t)M * N);
+  PENEO_CUDA_TRY(cudaMemcpy(C.data(), dC, C.size() * 4, cudaMemcpyDeviceToHost));
+  cudaFree(dA), cudaFree(dB), cudaFree(dC);
+  max_err = 0.0;
+  for (int m = 0; m < M; ++m)
+    for (int n = 0; n < N; ++n) {
+      double ref = 0.0;
+      for (int k = 0; k < K; ++k) ref += static_cast<double>(a_at(m, k)) * b_at(k, n);
+      const double e = std::fabs(ref - C[(size_t)m * N + n]);
+      if (!(e <= max_err)) max_err = e;
+    }
+  return PENEO_OK;
+}
+
 static int check_ss(int M, int N, int K, double& max_err) {
   Lcg rng{777ull + M + N * 3 + K * 7};
   std::vector<float> A((size_t)M * K), W((size_t)N * K), bias(N);
@@ -291,6 +339,8 @@ int run_selftest(uint32_t* failed_mask, char* report, size_t report_bytes) {
       {"ts_mma_n128_k64", 1, 128, 1, 0, 1e-3},          {"ts_mma_n128_k384", 1, 128, 6, 0, 2e-3},
       {"ts_mma_n16_k128", 1, 16, 2, 0, 1e-3},
       {"mn_major_n128_k64", 2, 128, 1, 0, 1e-3},         {"mn_major_n256_k192", 2, 256, 3, 0, 2e-3},
+      {"tf32_gemm_nn", 3, 0, 0, 0, 1e-4},               {"tf32_gemm_tn", 3, 1, 0, 0, 1e-4},
+      {"tf32_gemm_nt", 3, 2, 0, 0, 1e-4},               {"tf32_gemm_tt_splitk", 3, 3, 0, 0, 1e-4},
   };
   int idx = 0;
   for (auto& cs : cases) {
@@ -298,7 +348,8 @@ int run_selftest(uint32_t* failed_mask, char* report, size_t report_bytes) {
     std::string note;
     int rc = cs.kind == 0 ? check_ss(cs.a, cs.b, cs.c, err)
              : cs.kind == 1 ? check_ts(cs.a, cs.b, err, note)
-                            : check_mn(cs.a, cs.b, cs.c, err);
+             : cs.kind == 2 ? check_mn(cs.a, cs.b, cs.c, err)
+                            : check_tf32(cs.a, err);
     if (cs.kind == 2 && rc == PENEO_OK && !(err <= cs.tol) && getenv("PENEO_SELFTEST_MN_SWAP")) {
       double err2 = 0.0;  // diagnostic: LBO / SBO exchanged
       if (check_mn(cs.a, cs.b, 1, err2) == PENEO_OK) note = " (swapped LBO/SBO: max_err=" + std::to_string(err2) + ")";

@@ -127,8 +127,17 @@ struct Gemm {
   float drop_scale = 1.f;
 };
 
-int run_gemm(const Gemm& g, cudaStream_t st) {
+// `tensor_cores`: bf16 mode — run on tcgen05 kind::tf32 (gemm_tf32.cu) when the shape qualifies; the fp32 mode
+// always uses the exact CUDA-core kernel below.
+int run_gemm(const Gemm& g, cudaStream_t st, bool tensor_cores = false) {
   if (g.M == 0 || g.N == 0) return PENEO_OK;
+  if (tensor_cores) {
+    Tf32Gemm t;
+    t.ta = g.ta, t.tb = g.tb, t.A = g.A, t.lda = g.lda, t.B = g.B, t.ldb = g.ldb, t.C = g.C, t.ldc = g.ldc;
+    t.M = g.M, t.N = g.N, t.K = g.K, t.mode = g.mode, t.bias = g.bias, t.C2 = g.C2, t.ldc2 = g.ldc2;
+    t.drop_thresh = g.drop_thresh, t.drop_key = g.drop_key, t.row0 = g.row0, t.drop_scale = g.drop_scale;
+    if (gemm_tf32_supported(t)) return launch_gemm_tf32(t, st);
+  }
   const bool ok = (g.ta ? (g.M % 4 == 0) : (g.K % 4 == 0)) && (g.tb ? (g.K % 4 == 0) : (g.N % 4 == 0)) &&
                   g.lda % 4 == 0 && g.ldb % 4 == 0 && (reinterpret_cast<uintptr_t>(g.A) & 15) == 0 &&
                   (reinterpret_cast<uintptr_t>(g.B) & 15) == 0;
@@ -491,19 +500,19 @@ int launch_heads_bwd(const peneo_dims& dm, int prec, const void* pack, const voi
     g = Gemm{}, g.tb = true, g.A = xin, g.lda = ldx, g.B = W(L.f_w1), g.ldb = hin, g.C = F(pl.off_u1), g.ldc = hid;
     g.M = T, g.N = hid, g.K = hin, g.bias = W(L.f_b1), g.C2 = F(pl.off_y1), g.ldc2 = hid;
     with_drop(g, kSiteTok0, 0);
-    TRY(run_gemm(g, st));
+    TRY(run_gemm(g, st, tc));
     g = Gemm{}, g.tb = true, g.A = F(pl.off_y1), g.lda = hid, g.B = W(L.f_w2), g.ldb = hid, g.C = F(pl.off_u2), g.ldc = d;
     g.M = T, g.N = d, g.K = hid, g.bias = W(L.f_b2), g.C2 = F(pl.off_y), g.ldc2 = d;
     with_drop(g, kSiteTok1, 0);
-    TRY(run_gemm(g, st));
+    TRY(run_gemm(g, st, tc));
     y = F(pl.off_y), ldy = d;
   }
   float* ab = F(pl.off_ab);
   g = Gemm{}, g.tb = true, g.A = y, g.lda = ldy, g.B = W(L.f_wc), g.ldb = 2 * d, g.C = ab, g.ldc = 2 * d;
   g.M = T, g.N = d, g.K = d;
-  TRY(run_gemm(g, st));
+  TRY(run_gemm(g, st, tc));
   g.B = W(L.f_wc) + d, g.C = ab + d, g.bias = W(L.f_bc);
-  TRY(run_gemm(g, st));
+  TRY(run_gemm(g, st, tc));
 
   // ---- pair part, one chunk of whole pair-rows at a time
   float* dab = F(pl.off_dab);
@@ -596,7 +605,7 @@ int launch_heads_bwd(const peneo_dims& dm, int prec, const void* pack, const voi
           g = Gemm{}, g.tb = true, g.A = in, g.lda = d, g.B = W(L.f_mid_w[h][l]), g.ldb = d, g.C = U, g.ldc = d;
           g.M = rows, g.N = d, g.K = d, g.bias = W(L.f_mid_b[h][l]), g.C2 = Hn, g.ldc2 = d;
           with_drop(g, site_head(h, l), row0);
-          TRY(run_gemm(g, st));
+          TRY(run_gemm(g, st, tc));
           in = Hn;
         }
         {
@@ -619,16 +628,16 @@ int launch_heads_bwd(const peneo_dims& dm, int prec, const void* pack, const voi
           // dW_l[out, in] += sum_r G_l[r, out] Hin[r, in]
           g = Gemm{}, g.ta = true, g.A = Gcur, g.lda = d, g.B = Hin, g.ldb = d, g.C = gr.mid_w[h * 8 + l], g.ldc = d;
           g.M = d, g.N = d, g.K = rows, g.mode = 2;
-          TRY(run_gemm(g, st));
+          TRY(run_gemm(g, st, tc));
           // dHin = G_l W_l
           g = Gemm{}, g.A = Gcur, g.lda = d, g.B = W(L.f_mid_w[h][l]), g.ldb = d, g.M = rows, g.N = d, g.K = d;
           if (l == 0) {
             g.C = dS, g.ldc = d, g.mode = h > 0 ? 1 : 0;
-            TRY(run_gemm(g, st));
+            TRY(run_gemm(g, st, tc));
           } else {
             float* Ul = F(pl.off_U) + (size_t)l * cstride;
             g.C = Ul, g.ldc = d, g.mode = 0;
-            TRY(run_gemm(g, st));
+            TRY(run_gemm(g, st, tc));
             act_bwd_kernel<<<dim3((rows + 31) / 32, (d + 127) / 128), 128, 0, st>>>(
                 Ul, F(pl.off_U) + (size_t)(l - 1) * cstride, rows, d, d, d, gr.mid_b[h * 8 + l - 1], drop.thresh, drop.scale,
                 drop_key(drop, site_head(h, l - 1)), row0);
@@ -653,16 +662,16 @@ int launch_heads_bwd(const peneo_dims& dm, int prec, const void* pack, const voi
   // dW_c[:, :d] = dA^T y ; dW_c[:, d:] = dBm^T y
   g = Gemm{}, g.ta = true, g.A = dab, g.lda = 2 * d, g.B = y, g.ldb = ldy, g.C = gr.combine_w, g.ldc = 2 * d;
   g.M = d, g.N = d, g.K = T, g.mode = 2;
-  TRY(run_gemm(g, st));
+  TRY(run_gemm(g, st, tc));
   g.A = dab + d, g.C = gr.combine_w + d;
-  TRY(run_gemm(g, st));
+  TRY(run_gemm(g, st, tc));
   // dy = dA W_c[:, :d] + dBm W_c[:, d:]
   float* dy = (dm.shrink || dx == nullptr) ? F(pl.off_dy) : dx;
   const int64_t lddy = (dm.shrink || dx == nullptr) ? d : hin;
   g = Gemm{}, g.A = dab, g.lda = 2 * d, g.B = W(L.f_wc), g.ldb = 2 * d, g.C = dy, g.ldc = lddy, g.M = T, g.N = d, g.K = d;
-  TRY(run_gemm(g, st));
+  TRY(run_gemm(g, st, tc));
   g.A = dab + d, g.B = W(L.f_wc) + d, g.mode = 1;
-  TRY(run_gemm(g, st));
+  TRY(run_gemm(g, st, tc));
   if (dm.shrink) {
     // G2 = dy * SiLU'(u2) ; db2 ; dW2 = G2^T y1 ; dy1 = G2 W2
     act_bwd_kernel<<<dim3(tb, (d + 127) / 128), 128, 0, st>>>(dy, F(pl.off_u2), T, d, d, d, gr.shrink_b2, drop.thresh,
@@ -670,20 +679,20 @@ int launch_heads_bwd(const peneo_dims& dm, int prec, const void* pack, const voi
     PENEO_CUDA_TRY(cudaGetLastError());
     g = Gemm{}, g.ta = true, g.A = dy, g.lda = d, g.B = F(pl.off_y1), g.ldb = hid, g.C = gr.shrink_w2, g.ldc = hid;
     g.M = d, g.N = hid, g.K = T, g.mode = 2;
-    TRY(run_gemm(g, st));
+    TRY(run_gemm(g, st, tc));
     float* dy1 = F(pl.off_dy1);
     g = Gemm{}, g.A = dy, g.lda = d, g.B = W(L.f_w2), g.ldb = hid, g.C = dy1, g.ldc = hid, g.M = T, g.N = hid, g.K = d;
-    TRY(run_gemm(g, st));
+    TRY(run_gemm(g, st, tc));
     // G1 = dy1 * SiLU'(u1) ; db1 ; dW1 = G1^T x ; dx = G1 W1
     act_bwd_kernel<<<dim3(tb, (hid + 127) / 128), 128, 0, st>>>(dy1, F(pl.off_u1), T, hid, hid, hid, gr.shrink_b1,
                                                                 drop.thresh, drop.scale, drop_key(drop, kSiteTok0), 0u);
     PENEO_CUDA_TRY(cudaGetLastError());
     g = Gemm{}, g.ta = true, g.A = dy1, g.lda = hid, g.B = xin, g.ldb = ldx, g.C = gr.shrink_w1, g.ldc = hin;
     g.M = hid, g.N = hin, g.K = T, g.mode = 2;
-    TRY(run_gemm(g, st));
+    TRY(run_gemm(g, st, tc));
     if (dx) {
       g = Gemm{}, g.A = dy1, g.lda = hid, g.B = W(L.f_w1), g.ldb = hin, g.C = dx, g.ldc = hin, g.M = T, g.N = hin, g.K = hid;
-      TRY(run_gemm(g, st));
+      TRY(run_gemm(g, st, tc));
     }
   }
 #undef TRY
