@@ -184,6 +184,10 @@ __global__ void __launch_bounds__(192, 1)
 bool gemm_tf32_supported(const Tf32Gemm& g) {
   // TMA: 16-byte aligned bases and row strides; the contiguous dimension must cover whole 16-byte groups
   auto ok_ptr = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  // Only the K-major x K-major combination (A [M, K], B [N, K]: every forward nn.Linear) is enabled: the selftest shows
+  // that MN-major operands of 4-byte elements need the 32-byte-base swizzle atom (SWIZZLE_128B_BASE32B), which the
+  // boxes loaded here do not have — those combinations fall back to the exact CUDA-core SGEMM.
+  if (g.ta || !g.tb) return false;
   return g.M > 0 && g.N > 0 && g.K > 0 && ok_ptr(g.A) && ok_ptr(g.B) && g.lda % 4 == 0 && g.ldb % 4 == 0 &&
          (int64_t)g.M * g.N >= 128 * 128;  // tiny outputs are not worth a tensor-core launch
 }
