@@ -625,3 +625,35 @@ def test_cross_entropy_loss_ohem_module_matches_reference_golden(golden):
         assert rel_err(x.grad, xr.grad) <= 1e-4, case["name"]
     with pytest.raises(NotImplementedError):
         CrossEntropyLossOHEM(weight=torch.ones(3), random=True)
+
+
+def test_c_abi_rejects_bad_arguments_with_status_codes():
+    """Error convention of the C ABI: negative PENEO_E_* status + peneo_last_error(), no crash, no fallback."""
+    from peneo_b200 import _lib
+
+    lib = _lib.load()
+    dims = _lib.Dims(768, 768, 384, 1, 2)
+    assert lib.peneo_device_supported(0) == 1
+    x = torch.zeros(4, 768, device="cuda")
+    ab = torch.zeros(4, 768, device="cuda")
+    # NULL pack pointer
+    rc = lib.peneo_token_proj_fwd(dims, _lib.PREC_FP32, None, x.data_ptr(), _lib.DT_F32, 768, 4, ab.data_ptr(), x.data_ptr(),
+                                  None, 0)
+    assert rc == -1 and b"NULL" in lib.peneo_last_error()
+    # row stride smaller than the row
+    rc = lib.peneo_token_proj_fwd(dims, _lib.PREC_FP32, x.data_ptr(), x.data_ptr(), _lib.DT_F32, 100, 4, ab.data_ptr(),
+                                  x.data_ptr(), None, 0)
+    assert rc == -1 and b"stride" in lib.peneo_last_error()
+    # bf16 tensor-core mode refused for a configuration it does not support (no silent downgrade)
+    odd = _lib.Dims(48, 0, 48, 0, 1)
+    logits = [torch.zeros(1, 3, c, device="cuda") for c in (2, 3, 3, 3, 3)]
+    rc = lib.peneo_pair_heads_fwd(odd, _lib.PREC_BF16, x.data_ptr(), ab.data_ptr(), 1, 2, _lib.ptrs5(logits), None, 0)
+    assert rc == -1 and b"PENEO_PREC_BF16" in lib.peneo_last_error()
+    # bad sizes
+    rc = lib.peneo_pair_heads_fwd(dims, _lib.PREC_FP32, x.data_ptr(), ab.data_ptr(), 1, 0, _lib.ptrs5(logits), None, 0)
+    assert rc == -1
+    with pytest.raises(RuntimeError, match="status -1"):
+        _lib.check(rc, "peneo_pair_heads_fwd")
+    # the Python layer refuses CPU tensors instead of falling back
+    with pytest.raises(RuntimeError, match="no CPU"):
+        ops.token_projections(ops.WeightPack(ops.DecoderDims(768, 768, 384, True, 2), _lib.PREC_FP32, "cuda"), torch.zeros(2, 768))
