@@ -10,7 +10,8 @@
 // (autograd of the five Linear(D, D) layers in model/peneo_decoder.py:258-269: grad_input = grad_output W,
 // grad_weight = grad_output^T input.)  Stage = one 64-deep K block: A 16 KB + B 6 x 8 KB = 64 KB, 3 stages.
 // Persistent CTAs: warp 0 TMA, warp 1 MMA (+ TMEM alloc), warps 2-5 epilogue.  The dW GEMM is split along K
-// (= pairs) across CTAs and accumulated with fp32 atomics.
+// (= pairs) across CTAs and accumulated with fp32 atomics.  It also produces db_mid = column sums of G for free: a
+// constant B box whose column 0 is all ones gives D[:, 384] = G^T 1 (one extra N = 16 MMA per K step).
 #include <cuda.h>
 
 #include "common.cuh"
@@ -24,7 +25,8 @@ constexpr int kN = 384;
 constexpr int kBlk = 64 * 128;              // one [64 rows x 64 cols] swizzled box = 8 KB
 constexpr int kStageBytes = 2 * kBlk + 6 * kBlk;  // 64 KB
 constexpr int kStages = 3;
-constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
+constexpr int kOnesOff = kStages * kStageBytes;  // dW only: constant [64 k x 64 n] box, column 0 = 1
+constexpr int kSmemBytes = kStages * kStageBytes + kBlk + 1024 + 256;
 
 struct Args {
   int64_t m_total;   // rows of the output (dS: pairs in the chunk; dW: 1920)
@@ -32,6 +34,7 @@ struct Args {
   int32_t kb_per_split, splits;
   int64_t num_items;  // m blocks * splits
   float* out[kNumHeads];  // dS: out[0] = dS (ld 384); dW: five [384, 384] matrices, m block -> head = mb / 3
+  float* colsum[kNumHeads];  // dW only: five [384] vectors += column sums of A (db_mid)
 };
 
 template <bool A_MN>
@@ -39,7 +42,7 @@ __global__ void __launch_bounds__(192, 1)
     gemm_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Args a) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes + kBlk);
   uint64_t* full = bars;
   uint64_t* empty = bars + kStages;
   uint64_t* acc_full = bars + 2 * kStages;
@@ -60,6 +63,15 @@ __global__ void __launch_bounds__(192, 1)
   if (warp == 1) {
     ptx::tmem_alloc(tmem_slot, 512);
     ptx::tmem_relinquish();
+  }
+  if (A_MN) {
+    // ones box in the MN-major SWIZZLE_128B layout: k-row r at r * 128 B, logical 16-byte chunk 0 at chunk (r & 7)
+    uint4* ones = reinterpret_cast<uint4*>(smem + kOnesOff);
+    for (int e = threadIdx.x; e < kBlk / 16; e += blockDim.x) {
+      const int r = e / 8, ch = e % 8;
+      ones[e] = make_uint4(ch == (r & 7) ? 0x00003F80u : 0u, 0u, 0u, 0u);  // bf16 1.0 in element 0
+    }
+    ptx::fence_proxy_async();
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -101,6 +113,8 @@ __global__ void __launch_bounds__(192, 1)
     if (ptx::elect_one()) {
       constexpr uint32_t idesc256 = ptx::umma_idesc_bf16_major(128, 256, A_MN, true);
       constexpr uint32_t idesc128 = ptx::umma_idesc_bf16_major(128, 128, A_MN, true);
+      constexpr uint32_t idesc16 = ptx::umma_idesc_bf16_major(128, 16, A_MN, true);
+      const uint32_t ones_addr = ptx::smem_u32(smem + kOnesOff);
       int s = 0;
       uint32_t ph = 0;
       int it = 0;
@@ -122,6 +136,8 @@ __global__ void __launch_bounds__(192, 1)
             ptx::umma_ss(tmem, ad, ptx::umma_desc_mn_sw128(b_addr + ks * 2048, kBlk, 1024), idesc256, (kb | ks) != 0);
             ptx::umma_ss(tmem + 256, ad, ptx::umma_desc_mn_sw128(b_addr + 4 * kBlk + ks * 2048, kBlk, 1024), idesc128,
                          (kb | ks) != 0);
+            if (A_MN)
+              ptx::umma_ss(tmem + kN, ad, ptx::umma_desc_mn_sw128(ones_addr + ks * 2048, kBlk, 1024), idesc16, (kb | ks) != 0);
           }
           ptx::tc_commit(&empty[s]);
           if (++s == kStages) s = 0, ph ^= 1;
@@ -144,6 +160,12 @@ __global__ void __launch_bounds__(192, 1)
         dst = a.out[static_cast<int>(m / kN)] + (m % kN) * kN;
       } else {
         dst = a.out[0] + m * kN;
+      }
+      if (A_MN) {
+        uint32_t c4[4];
+        ptx::tmem_ld_x4(tmem + (static_cast<uint32_t>(q * 32) << 16) + kN, c4);
+        ptx::tmem_ld_wait();
+        if (m < a.m_total) atomicAdd(a.colsum[static_cast<int>(m / kN)] + (m % kN), __uint_as_float(c4[0]));
       }
 #pragma unroll 1
       for (int piece = 0; piece < kN / 32; ++piece) {
@@ -210,7 +232,9 @@ int launch_gemm_ds(const __nv_bfloat16* G, const __nv_bfloat16* wmid_full, float
 }
 
 // dWmid[h][384, 384] += (G[:, 384 h : 384 (h + 1)])^T * S        (G [rows, 1920], S [rows, 384], bf16)
-int launch_gemm_dw(const __nv_bfloat16* G, const __nv_bfloat16* S, float* const dW[kNumHeads], int rows, cudaStream_t st) {
+// dbmid[h][384]     += column sums of G[:, 384 h : 384 (h + 1)]
+int launch_gemm_dw(const __nv_bfloat16* G, const __nv_bfloat16* S, float* const dW[kNumHeads], float* const db[kNumHeads],
+                   int rows, cudaStream_t st) {
   using namespace gb;
   if (rows == 0) return PENEO_OK;
   alignas(64) CUtensorMap tmA, tmB;
@@ -224,7 +248,7 @@ int launch_gemm_dw(const __nv_bfloat16* G, const __nv_bfloat16* S, float* const 
   a.kb_per_split = (num_kb + splits - 1) / splits;
   a.splits = (num_kb + a.kb_per_split - 1) / a.kb_per_split;
   a.num_items = (int64_t)m_blocks * a.splits;
-  for (int h = 0; h < kNumHeads; ++h) a.out[h] = dW[h];
+  for (int h = 0; h < kNumHeads; ++h) a.out[h] = dW[h], a.colsum[h] = db[h];
   const int grid = static_cast<int>(std::min<int64_t>(a.num_items, sm_count()));
   PENEO_CUDA_TRY(cudaFuncSetAttribute(gemm_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
   gemm_bwd_kernel<true><<<grid, 192, kSmemBytes, st>>>(tmA, tmB, a);

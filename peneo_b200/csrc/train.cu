@@ -343,9 +343,8 @@ constexpr int kD16 = 384;
 struct DzPtrs {
   const float* p[kNumHeads];
 };
-__global__ void __launch_bounds__(128) dwout_bf16_kernel(const __nv_bfloat16* __restrict__ M, const __nv_bfloat16* __restrict__ G,
-                                                         DzPtrs dz, int rows, float* const* __restrict__ dWout,
-                                                         float* const* __restrict__ dbout, float* const* __restrict__ dbmid) {
+__global__ void __launch_bounds__(128) dwout_bf16_kernel(const __nv_bfloat16* __restrict__ M, DzPtrs dz, int rows,
+                                                         float* const* __restrict__ dWout, float* const* __restrict__ dbout) {
   __shared__ float sdz[256][3];
   const int r0 = blockIdx.x * 256, nr = min(256, rows - r0);
   const int fs = blockIdx.y * 128 + threadIdx.x;  // stacked feature index in [0, 1920)
@@ -356,19 +355,16 @@ __global__ void __launch_bounds__(128) dwout_bf16_kernel(const __nv_bfloat16* __
     sdz[r][c] = (r < nr && c < C) ? dzk[(int64_t)(r0 + r) * C + c] : 0.f;
   }
   __syncthreads();
-  float a0 = 0.f, a1 = 0.f, a2 = 0.f, ab_ = 0.f;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f;
   const __nv_bfloat16* pm = M + (int64_t)r0 * (5 * kD16) + fs;
-  const __nv_bfloat16* pg = G + (int64_t)r0 * (5 * kD16) + fs;
 #pragma unroll 8
   for (int r = 0; r < nr; ++r) {
     const float m = __bfloat162float(pm[(int64_t)r * (5 * kD16)]);
-    ab_ += __bfloat162float(pg[(int64_t)r * (5 * kD16)]);
     a0 = fmaf(sdz[r][0], m, a0), a1 = fmaf(sdz[r][1], m, a1), a2 = fmaf(sdz[r][2], m, a2);
   }
   atomicAdd(&dWout[k][f], a0);
   atomicAdd(&dWout[k][kD16 + f], a1);
   if (C == 3) atomicAdd(&dWout[k][2 * kD16 + f], a2);
-  atomicAdd(&dbmid[k][f], ab_);
   if (blockIdx.y % 3 == 0 && threadIdx.x < C) {
     float s = 0.f;
     for (int r = 0; r < nr; ++r) s += sdz[r][threadIdx.x];
@@ -517,18 +513,18 @@ int launch_heads_bwd(const peneo_dims& dm, int prec, const void* pack, const voi
   // ---- pair part, one chunk of whole pair-rows at a time
   float* dab = F(pl.off_dab);
   TRY(zero(dab, (size_t)T * 2 * d));
-  float **d_outw = nullptr, **d_outb = nullptr, **d_midb = nullptr;
+  float **d_outw = nullptr, **d_outb = nullptr;
   if (tc) {
     // bf16 per-token projections (0.5-scaled A | Bm) for T1, exactly what the forward pass used (same dropout)
     TRY(token_proj_fwd_bf16(dm, L, pk, x, x_dtype, x_row_stride, T, ws + pl.off_ab16, ws + pl.off_tokws, st,
                             drop.thresh ? &drop : nullptr));
     // device tables of the per-head gradient pointers (15 pointers at the start of the token scratch tail)
-    float* h_tab[15];
-    for (int h = 0; h < kNumHeads; ++h) h_tab[h] = gr.out_w[h], h_tab[5 + h] = gr.out_b[h], h_tab[10 + h] = gr.mid_b[h * 8];
+    float* h_tab[10];
+    for (int h = 0; h < kNumHeads; ++h) h_tab[h] = gr.out_w[h], h_tab[5 + h] = gr.out_b[h];
     float** tab = reinterpret_cast<float**>(ws + pl.off_tokws + pl.tokws_bytes - 1024);
     PENEO_CUDA_TRY(cudaMemcpyAsync(tab, h_tab, sizeof h_tab, cudaMemcpyHostToDevice, st));
     PENEO_CUDA_TRY(cudaStreamSynchronize(st));  // h_tab lives on this stack frame
-    d_outw = tab, d_outb = tab + 5, d_midb = tab + 10;
+    d_outw = tab, d_outb = tab + 5;
   }
   float *S = F(pl.off_S), *dS = F(pl.off_dS), *G = F(pl.off_G);
   const size_t cstride = fl((size_t)pl.chunk_rows_max * d) / sizeof(float);
@@ -572,14 +568,14 @@ int launch_heads_bwd(const peneo_dims& dm, int prec, const void* pack, const voi
                                  drop.thresh ? &drop : nullptr));
         // dS = G W_mid (all heads in one K = 1920 GEMM) ; dW_mid += G^T S
         TRY(launch_gemm_ds(Gc, reinterpret_cast<const __nv_bfloat16*>(pk + L.wmid_full_bf16), dS, rows, st));
-        float* dwm[kNumHeads];
+        float *dwm[kNumHeads], *dbm[kNumHeads];
         DzPtrs dzp;
         for (int h = 0; h < kNumHeads; ++h) {
-          dwm[h] = gr.mid_w[h * 8];
+          dwm[h] = gr.mid_w[h * 8], dbm[h] = gr.mid_b[h * 8];
           dzp.p[h] = dlogits[h] + g0 * head_classes(h);
         }
-        TRY(launch_gemm_dw(Gc, S16, dwm, rows, st));
-        dwout_bf16_kernel<<<dim3((rows + 255) / 256, 15), 128, 0, st>>>(Mc, Gc, dzp, rows, d_outw, d_outb, d_midb);
+        TRY(launch_gemm_dw(Gc, S16, dwm, dbm, rows, st));  // + db_mid (column sums of G)
+        dwout_bf16_kernel<<<dim3((rows + 255) / 256, 15), 128, 0, st>>>(Mc, dzp, rows, d_outw, d_outb);
         PENEO_CUDA_TRY(cudaGetLastError());
       } else {
       for (const Seg& sg : segs) {
