@@ -64,9 +64,11 @@ struct Args {
   uint32_t drop_key[kNumHeads];
 };
 
+template <bool DROP>
 __global__ void __launch_bounds__(kThreads, 1) pair_bwd_prep_kernel(const __grid_constant__ CUtensorMap tmW, const Args a) {
   extern __shared__ unsigned char smem_raw[];
-  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment by offset (not by integer round trip): the compiler keeps the shared address space -> LDS / STS
+  unsigned char* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Smem::bars);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + bCount);
   float* s_bmid = reinterpret_cast<float*>(smem + Smem::bmid);
@@ -198,7 +200,7 @@ __global__ void __launch_bounds__(kThreads, 1) pair_bwd_prep_kernel(const __grid
               const uint2 wp = w4[col];  // (bf16 W_out[0][f], W_out[1][f]), (W_out[2][f], 0)
               float gm = fmaf(dz2, __uint_as_float(wp.y << 16),
                               fmaf(dz1, __uint_as_float(wp.x & 0xFFFF0000u), dz0 * __uint_as_float(wp.x << 16)));
-              if (a.drop_thresh) {  // m_dropped = m * mask / (1 - p) feeds W_out; its gradient carries the same factor
+              if (DROP) {  // m_dropped = m * mask / (1 - p) feeds W_out; its gradient carries the same factor
                 const float ms = drop_keep(a.drop_key[k], a.drop_thresh, static_cast<uint32_t>(gp),
                                            (c - 3 * k) * 128 + 64 * hsel + col) ? a.drop_scale : 0.f;
                 mv[e] *= ms, gm *= ms;
@@ -363,8 +365,9 @@ int launch_pair_bwd_prep(const void* pack, const PackLayout& L, const __nv_bfloa
   PENEO_CUDA_TRY(cudaGetDevice(&dev));
   PENEO_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const int grid = std::min(a.num_tiles, sms);
-  PENEO_CUDA_TRY(cudaFuncSetAttribute(pair_bwd_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-  pair_bwd_prep_kernel<<<grid, kThreads, kSmemBytes, st>>>(tmW, a);
+  auto kern = a.drop_thresh ? pair_bwd_prep_kernel<true> : pair_bwd_prep_kernel<false>;
+  PENEO_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+  kern<<<grid, kThreads, kSmemBytes, st>>>(tmW, a);
   PENEO_CUDA_TRY(cudaGetLastError());
   return PENEO_OK;
 }
