@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(192, 1)
                    const float* __restrict__ bias, __nv_bfloat16* __restrict__ C, int64_t ldc, int64_t M, int N,
                    int K) {
   extern __shared__ unsigned char smem_raw[];
-  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  unsigned char* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);  // by offset: keeps the shared address space
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kGemmStages * kGemmStageBytes);
   uint64_t* full = bars;                  // [stages]
   uint64_t* empty = bars + kGemmStages;   // [stages]
@@ -207,7 +207,7 @@ __global__ void __launch_bounds__(192, 1)
                     int kb_per_split, int splits, int n_blocks, int64_t num_items, int act, uint32_t drop_thresh,
                     float drop_scale, uint32_t drop_key) {
   extern __shared__ unsigned char smem_raw[];
-  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  unsigned char* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);  // by offset: keeps the shared address space
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kG2Stages * kGemmStageBytes);
   uint64_t* full = bars;
   uint64_t* empty = bars + kG2Stages;

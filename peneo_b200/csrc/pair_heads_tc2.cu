@@ -67,7 +67,7 @@ template <bool DROP>
 __global__ void __launch_bounds__(kThreads, 1)
     pair_heads_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmO, const Args a) {
   extern __shared__ unsigned char smem_raw[];
-  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  unsigned char* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);  // by offset: keeps the shared address space
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Smem::bars);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + bCount);
   float* s_bmid = reinterpret_cast<float*>(smem + Smem::bmid);

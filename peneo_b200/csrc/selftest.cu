@@ -19,7 +19,7 @@ __global__ void __launch_bounds__(128, 1)
     ts_mma_test_kernel(const __grid_constant__ CUtensorMap tmB, const uint32_t* __restrict__ a_packed,
                        float* __restrict__ d_out, int N, int kblocks) {
   extern __shared__ unsigned char smem_raw[];
-  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  unsigned char* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);  // by offset: keeps the shared address space
   __shared__ uint64_t bar_full, bar_done;
   __shared__ uint32_t tmem_slot;
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(128, 1)
     mn_mma_test_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                        float* __restrict__ d_out, int N, int kblocks, int swap) {
   extern __shared__ unsigned char smem_raw[];
-  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  unsigned char* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);  // by offset: keeps the shared address space
   __shared__ uint64_t bar_full, bar_done;
   __shared__ uint32_t tmem_slot;
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
