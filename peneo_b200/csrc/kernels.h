@@ -35,9 +35,10 @@ int launch_pair_heads_tc(const void* pack, const PackLayout& L, const __nv_bfloa
 int launch_pair_heads_tc_pair(const void* pack, const PackLayout& L, const __nv_bfloat16* ab, int batch, int n,
                               float* const logits[kNumHeads], cudaStream_t st, const DropSpec* drop = nullptr);
 
-// pair_bwd_tc.cu : regenerated S, M = SiLU(u), G = (dz W_out) SiLU'(u) of a chunk of pairs (bf16 backward)
+// pair_bwd_tc.cu : regenerated S and G = (dz W_out) SiLU'(u) of a chunk of pairs, plus per-CTA partial sums
+// [ctas][3][1920] of dz^T SiLU(u) (bf16 backward)
 int launch_pair_bwd_prep(const void* pack, const PackLayout& L, const __nv_bfloat16* ab, int n, int64_t g0, int rows,
-                         const float* const dz[kNumHeads], __nv_bfloat16* S, __nv_bfloat16* G, __nv_bfloat16* M,
+                         const float* const dz[kNumHeads], __nv_bfloat16* S, __nv_bfloat16* G, float* dwout_part,
                          cudaStream_t st, const DropSpec* drop = nullptr);
 
 // gemm_bwd_tc.cu

@@ -3,15 +3,20 @@
 // the batch-flattened pair list and every head k:
 //   s   = SiLU(a_i + b_j)                         regenerated (CUDA cores -> TMEM), also stored: S  [rows, 384]
 //   u_k = W_mid,k s + b_mid,k                     tcgen05, 15 chunks of 128 mid features
-//   m_k = SiLU(u_k)                               stored: M [rows, 1920]   (dW_out = dz^T M)
+//   m_k = SiLU(u_k)                               never leaves the SM: dW_out,k += dz_k^T m_k on the tensor cores
 //   g_k = (dz_k W_out,k) * SiLU'(u_k)             stored: G [rows, 1920]   (dW_mid = G^T S, dS = G W_mid)
-// dz_k = d loss / d logits of head k (fp32, from the loss backward).  Nothing is accumulated here; the three
-// bf16 matrices feed the GEMMs of train.cu.  What autograd keeps alive between forward and backward in the
-// reference ([P, D] activations of every layer) is recomputed instead.
+// dz_k = d loss / d logits of head k (fp32, from the loss backward).  S and G feed the GEMMs of train.cu.  What
+// autograd keeps alive between forward and backward in the reference ([P, D] activations of every layer) is
+// recomputed instead.
 //
-// Warp roles as in K2 minus the second MMA: warp 0 TMA (W_mid stream), warp 1 MMA issuer, warp 2 TMEM
-// allocator, warps 4-11 epilogue, warps 12-15 pair producers.
-// TMEM columns: [0,192) s | [192,320) u buffer 0 | [320,448) u buffer 1
+// dW_out: the epilogue writes the bf16 m tile of a chunk ([128 pairs x 128 features]) into shared memory in the
+// MN-major SWIZZLE_128B UMMA layout (A operand: M = feature, K = pair) and dz^T ([16 x 128 pairs], K-major, rows
+// 3..15 zero) as the B operand; eight N = 16 MMAs give D_w [128 features x 16] in TMEM, which four epilogue warps
+// add (RED, no contention) into this CTA's private [3][1920] partial sums; train.cu reduces the partials.
+//
+// Warp roles as in K2: warp 0 TMA (W_mid stream), warp 1 MMA issuer, warp 2 TMEM allocator, warps 4-11 epilogue,
+// warps 12-15 pair producers.
+// TMEM columns: [0,192) s | [192,320) u buffer 0 | [320,448) u buffer 1 | [448,464) D_w 0 | [464,480) D_w 1
 #include <cuda.h>
 
 #include "common.cuh"
@@ -24,27 +29,32 @@ namespace t1 {
 constexpr int D = 384;
 constexpr int kChunks = 15;       // 5 heads x 3 chunks of 128 mid features
 constexpr int kKChunks = 6;       // 384 / 64
-constexpr int kWStages = 5;
+constexpr int kWStages = 3;
 constexpr int kWStageBytes = 128 * 64 * 2;  // 16 KB
 constexpr int kStageRowBytes = D * 2;       // staging: 128 rows x 768 B
 constexpr int kThreads = 512;
 constexpr int kLdG = 5 * D;                 // row stride of G / M
 
-constexpr uint32_t kColS = 0, kColU = 192;
+constexpr uint32_t kColS = 0, kColU = 192, kColDw = 448;
 constexpr int kOutRowBytes = 64 + 16;            // 32 bf16 + pad (conflict-free 16-B accesses)
 constexpr int kOutWarpBytes = 32 * kOutRowBytes;  // 2560 B
 
 struct Smem {
   static constexpr int w = 0;
   static constexpr int stage = w + kWStages * kWStageBytes;
-  static constexpr int bmid = stage + 128 * kStageRowBytes;  // 1920 floats
+  static constexpr int mtile = stage + 128 * kStageRowBytes;  // m chunk, 2 x 2 boxes of [64 pairs x 64 features] bf16
+  static constexpr int dzt = mtile + 128 * 128 * 2;           // dz^T, 2 K blocks of [16 x 64 pairs] bf16
+  static constexpr int bmid = dzt + 2 * 16 * 128;             // 1920 floats
   static constexpr int out = bmid + 5 * D * 4;               // 8 epilogue warps x [32 rows][64 + 16 B]
   static constexpr int wout = out + 8 * kOutWarpBytes;       // [1920] x (bf16 W_out[0..2][f], 0) = 15 KB
   static constexpr int bars = wout + 5 * D * 8;
   static constexpr int total = bars + 512;
 };
 constexpr int bWFull = 0, bWEmpty = bWFull + kWStages, bUFull = bWEmpty + kWStages, bUFree = bUFull + 2,
-              bSFull = bUFree + 2, bSFree = bSFull + kKChunks, bCount = bSFree + kKChunks;
+              bSFull = bUFree + 2, bSFree = bSFull + kKChunks, bMFull = bSFree + kKChunks, bMFree = bMFull + 1,
+              bDwFull = bMFree + 1, bDwFree = bDwFull + 2, bCount = bDwFree + 2;
+static_assert(Smem::mtile % 1024 == 0 && Smem::dzt % 1024 == 0, "UMMA operand tiles need 1024-byte alignment");
+static_assert(Smem::total + 1024 <= 227 * 1024, "shared memory budget");
 static_assert(bCount * 8 + 16 <= 512, "barrier area too small");
 constexpr int kSmemBytes = Smem::total + 1024;
 
@@ -55,7 +65,7 @@ struct Args {
   const float* dz[kNumHeads];  // d loss / d logits, fp32 [batch*P, C_h]
   __nv_bfloat16* S;          // [rows, 384]
   __nv_bfloat16* G;          // [rows, 1920]
-  __nv_bfloat16* M;          // [rows, 1920]
+  float* dwout_part;         // [gridDim.x][3][1920] per-CTA partial sums of dz^T M (accumulated)
   int32_t n, pairs_per_doc;
   int64_t g0;                // first flat pair of the chunk
   int32_t rows, num_tiles;
@@ -80,6 +90,8 @@ __global__ void __launch_bounds__(kThreads, 1) pair_bwd_prep_kernel(const __grid
     for (int s = 0; s < kWStages; ++s) ptx::mbar_init(&bars[bWFull + s], 1), ptx::mbar_init(&bars[bWEmpty + s], 1);
     for (int s = 0; s < 2; ++s) ptx::mbar_init(&bars[bUFull + s], 1), ptx::mbar_init(&bars[bUFree + s], 8);
     for (int s = 0; s < kKChunks; ++s) ptx::mbar_init(&bars[bSFull + s], 4), ptx::mbar_init(&bars[bSFree + s], 1);
+    ptx::mbar_init(&bars[bMFull], 8), ptx::mbar_init(&bars[bMFree], 1);
+    for (int s = 0; s < 2; ++s) ptx::mbar_init(&bars[bDwFull + s], 1), ptx::mbar_init(&bars[bDwFree + s], 4);
     ptx::fence_barrier_init();
   }
   if (warp == 2) {
@@ -92,6 +104,8 @@ __global__ void __launch_bounds__(kThreads, 1) pair_bwd_prep_kernel(const __grid
     const float4 w = a.wout4[e];
     s_wout[e] = make_uint2(ptx::pack_bf16x2(w.x, w.y), ptx::pack_bf16x2(w.z, 0.f));
   }
+  for (int e = threadIdx.x; e < 2 * 16 * 128 / 16; e += kThreads)  // dz^T rows 3..15 stay zero for the whole kernel
+    reinterpret_cast<uint4*>(smem + Smem::dzt)[e] = make_uint4(0u, 0u, 0u, 0u);
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
@@ -122,6 +136,22 @@ __global__ void __launch_bounds__(kThreads, 1) pair_bwd_prep_kernel(const __grid
       int ws = 0;
       uint32_t wph = 0;
       const uint32_t w_base = ptx::smem_u32(smem + Smem::w);
+      constexpr uint32_t idesc_w = ptx::umma_idesc_bf16_major(128, 16, true, false);
+      const uint32_t m_base = ptx::smem_u32(smem + Smem::mtile), dz_base = ptx::smem_u32(smem + Smem::dzt);
+      // D_w[g & 1] = m(g)^T-tile x dz^T : 8 K steps of 16 pairs
+      auto issue_dw = [&](int gw) {
+        const int wb = gw & 1;
+        ptx::mbar_wait(&bars[bMFull], gw & 1);
+        ptx::mbar_wait(&bars[bDwFree + wb], ((gw >> 1) & 1) ^ 1);
+        ptx::tc_fence_after();
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks)
+          ptx::umma_ss(tmem + kColDw + 16 * wb,
+                       ptx::umma_desc_mn_sw128(m_base + (ks >> 2) * 16384 + (ks & 3) * 2048, 8192, 1024),
+                       ptx::umma_desc_sw128(dz_base + (ks >> 2) * 2048 + (ks & 3) * 32), idesc_w, ks != 0);
+        ptx::tc_commit(&bars[bMFree]);
+        ptx::tc_commit(&bars[bDwFull + wb]);
+      };
       int g = 0;
       for (int it = 0; it < my_tiles; ++it) {
         for (int c = 0; c < kChunks; ++c, ++g) {
@@ -143,14 +173,36 @@ __global__ void __launch_bounds__(kThreads, 1) pair_bwd_prep_kernel(const __grid
             if (++ws == kWStages) ws = 0, wph ^= 1;
           }
           ptx::tc_commit(&bars[bUFull + buf]);
+          if (g > 0) issue_dw(g - 1);  // queued behind u(g): the tensor pipe never waits for the epilogue
         }
       }
+      if (g > 0) issue_dw(g - 1);
     }
   } else if (warp >= 4 && warp < 12) {
     // ============================== epilogue ==============================
     const int q = warp % 4, hsel = (warp - 4) / 4;
     const uint32_t lane_base = static_cast<uint32_t>(q * 32) << 16;
     const int row = q * 32 + lane;
+    unsigned char* mt = smem + Smem::mtile + ((q >> 1) * 2 + hsel) * 8192 + (row & 63) * 128;  // this lane's m row
+    unsigned char* dzt = smem + Smem::dzt + (q >> 1) * 2048 + (row & 7) * 2;  // K block of this pair, byte inside a chunk
+    const int dz_ch = (row & 63) >> 3;                                         // logical 16-byte chunk of this pair
+    float* part = a.dwout_part + static_cast<size_t>(blockIdx.x) * (3 * kLdG) + q * 32 + lane;
+    // D_w of chunk gw (TMEM lanes = features): add into this CTA's partial sums (hsel == 1 warps, one lane quarter each)
+    auto flush_dw = [&](int gw) {
+      const int wb = gw & 1;
+      ptx::mbar_wait(&bars[bDwFull + wb], (gw >> 1) & 1);
+      ptx::tc_fence_after();
+      uint32_t d4[4];
+      ptx::tmem_ld_x4(tmem + lane_base + kColDw + 16 * wb, d4);
+      ptx::tmem_ld_wait();
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&bars[bDwFree + wb]);
+      float* dst = part + (gw % kChunks) * 128;
+      atomicAdd(dst, __uint_as_float(d4[0]));
+      atomicAdd(dst + kLdG, __uint_as_float(d4[1]));
+      atomicAdd(dst + 2 * kLdG, __uint_as_float(d4[2]));
+    };
     int g = 0;
     for (int it = 0; it < my_tiles; ++it) {
       const int64_t tile = static_cast<int64_t>(blockIdx.x) + static_cast<int64_t>(it) * gridDim.x;
@@ -168,6 +220,16 @@ __global__ void __launch_bounds__(kThreads, 1) pair_bwd_prep_kernel(const __grid
             dz0 = p[0], dz1 = p[1];
             if (C == 3) dz2 = p[2];
           }
+        }
+        if (hsel == 1 && g >= 2) flush_dw(g - 2);
+        if (hsel == 0 && c - 3 * k == 0) {
+          // new head: dz^T (B operand of the dW_out MMA), once the MMA of the previous chunk has read the old one
+          if (g > 0) ptx::mbar_wait(&bars[bMFree], (g - 1) & 1);
+          const uint32_t d01 = ptx::pack_bf16x2(dz0, dz1), d2 = ptx::pack_bf16x2(dz2, 0.f);
+          // row c of the K-major tile: 128 B per row, 16-byte chunk index XOR (c & 7)
+          *reinterpret_cast<uint16_t*>(dzt + 0 * 128 + ((dz_ch ^ 0) * 16)) = static_cast<uint16_t>(d01);
+          *reinterpret_cast<uint16_t*>(dzt + 1 * 128 + ((dz_ch ^ 1) * 16)) = static_cast<uint16_t>(d01 >> 16);
+          *reinterpret_cast<uint16_t*>(dzt + 2 * 128 + ((dz_ch ^ 2) * 16)) = static_cast<uint16_t>(d2);
         }
         ptx::mbar_wait(&bars[bUFull + buf], (g >> 1) & 1);
         ptx::tc_fence_after();
@@ -215,10 +277,9 @@ __global__ void __launch_bounds__(kThreads, 1) pair_bwd_prep_kernel(const __grid
           // 32 rows x 16 B (one LSU transaction per lane).
           unsigned char* ob = smem + Smem::out + (warp - 4) * kOutWarpBytes;
           const int64_t row0 = tile * 128 + q * 32;  // first chunk-row of this warp
-#pragma unroll
-          for (int arr = 0; arr < 2; ++arr) {
-            const uint32_t* src = arr == 0 ? mp : gpk;
-            __nv_bfloat16* dstm = (arr == 0 ? a.M : a.G) + f0 + 32 * piece;
+          {
+            const uint32_t* src = gpk;
+            __nv_bfloat16* dstm = a.G + f0 + 32 * piece;
             __syncwarp();
 #pragma unroll
             for (int v = 0; v < 4; ++v)
@@ -232,8 +293,24 @@ __global__ void __launch_bounds__(kThreads, 1) pair_bwd_prep_kernel(const __grid
               if (row0 + rr < a.rows) *reinterpret_cast<uint4*>(dstm + (row0 + rr) * kLdG + c16 * 8) = val;
             }
           }
+          // m into the MN-major operand tile (rows past the chunk end are zero: dz is zero there anyway, but keep NaNs out)
+          if (piece == 0 && g > 0) {
+            ptx::mbar_wait(&bars[bMFree], (g - 1) & 1);  // the dW_out MMA of the previous chunk has read the tile
+            ptx::tc_fence_after();
+          }
+#pragma unroll
+          for (int v = 0; v < 4; ++v)
+            *reinterpret_cast<uint4*>(mt + (((4 * piece + v) ^ (row & 7)) * 16)) =
+                live ? make_uint4(mp[4 * v], mp[4 * v + 1], mp[4 * v + 2], mp[4 * v + 3]) : make_uint4(0u, 0u, 0u, 0u);
         }
+        ptx::fence_proxy_async();  // generic-proxy writes (m tile, dz^T) -> visible to the tensor core's async proxy
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&bars[bMFull]);
       }
+    }
+    if (hsel == 1) {
+      if (g >= 2) flush_dw(g - 2);
+      if (g >= 1) flush_dw(g - 1);
     }
   } else if (warp >= 12) {
     // ============================== pair producers ==============================
@@ -339,7 +416,7 @@ __global__ void __launch_bounds__(kThreads, 1) pair_bwd_prep_kernel(const __grid
 }  // namespace t1
 
 int launch_pair_bwd_prep(const void* pack, const PackLayout& L, const __nv_bfloat16* ab, int n, int64_t g0, int rows,
-                         const float* const dz[kNumHeads], __nv_bfloat16* S, __nv_bfloat16* G, __nv_bfloat16* M,
+                         const float* const dz[kNumHeads], __nv_bfloat16* S, __nv_bfloat16* G, float* dwout_part,
                          cudaStream_t st, const DropSpec* drop) {
   using namespace t1;
   const char* base = static_cast<const char*>(pack);
@@ -348,7 +425,7 @@ int launch_pair_bwd_prep(const void* pack, const PackLayout& L, const __nv_bfloa
   a.bmid_half = reinterpret_cast<const float*>(base + L.bmid_half);
   a.wout4 = reinterpret_cast<const float4*>(base + L.wout_f32x4);
   for (int h = 0; h < kNumHeads; ++h) a.dz[h] = dz[h];
-  a.S = S, a.G = G, a.M = M;
+  a.S = S, a.G = G, a.dwout_part = dwout_part;
   a.n = n;
   a.pairs_per_doc = static_cast<int32_t>(pair_count(n));
   a.g0 = g0, a.rows = rows;

@@ -337,38 +337,38 @@ __global__ void __launch_bounds__(128) gv_reduce_kernel(const float* __restrict_
 
 constexpr int kD16 = 384;
 
-// dW_out, db_out, db_mid of all five heads from the bf16 matrices T1 wrote:
-//   dW_out[k][c][f] += sum_r dz_k[r][c] M[r][384 k + f] ; db_mid[k][f] += sum_r G[r][384 k + f] ; db_out[k][c] += sum_r dz_k[r][c]
-// Grid: (blocks of 256 rows, 15 blocks of 128 stacked mid features); one thread per feature.
+// bf16 backward, output layer: T1 leaves per-CTA partial sums of dz^T M ([ctas][3][1920] fp32); db_out is the column
+// sum of dz.
+//   dW_out[k][c][f] += sum_cta part[cta][c][384 k + f] ;  db_out[k][c] += sum_r dz_k[r][c]
 struct DzPtrs {
   const float* p[kNumHeads];
 };
-__global__ void __launch_bounds__(128) dwout_bf16_kernel(const __nv_bfloat16* __restrict__ M, DzPtrs dz, int rows,
-                                                         float* const* __restrict__ dWout, float* const* __restrict__ dbout) {
-  __shared__ float sdz[256][3];
-  const int r0 = blockIdx.x * 256, nr = min(256, rows - r0);
-  const int fs = blockIdx.y * 128 + threadIdx.x;  // stacked feature index in [0, 1920)
-  const int k = fs / kD16, f = fs - k * kD16, C = head_classes(k);
-  const float* dzk = dz.p[k];
-  for (int e = threadIdx.x; e < 256 * 3; e += 128) {
-    const int r = e / 3, c = e - 3 * r;
-    sdz[r][c] = (r < nr && c < C) ? dzk[(int64_t)(r0 + r) * C + c] : 0.f;
-  }
-  __syncthreads();
+constexpr int kDwPartCtas = 256;  // upper bound of T1's grid (one CTA per SM)
+__global__ void __launch_bounds__(128) dwout_finish_kernel(const float* __restrict__ part, int ctas,
+                                                           float* const* __restrict__ dWout) {
+  const int fs = blockIdx.x * 128 + threadIdx.x;  // stacked feature index in [0, 1920)
+  const int c = blockIdx.y;
+  const int k = fs / kD16, f = fs - k * kD16;
+  if (c >= head_classes(k)) return;
+  float acc = 0.f;
+  for (int b = 0; b < ctas; ++b) acc += part[((size_t)b * 3 + c) * (5 * kD16) + fs];
+  atomicAdd(&dWout[k][c * kD16 + f], acc);
+}
+__global__ void __launch_bounds__(256) dbout_kernel(DzPtrs dz, int rows, float* const* __restrict__ dbout) {
+  const int k = blockIdx.y, C = head_classes(k);
+  const float* p = dz.p[k];
   float a0 = 0.f, a1 = 0.f, a2 = 0.f;
-  const __nv_bfloat16* pm = M + (int64_t)r0 * (5 * kD16) + fs;
-#pragma unroll 8
-  for (int r = 0; r < nr; ++r) {
-    const float m = __bfloat162float(pm[(int64_t)r * (5 * kD16)]);
-    a0 = fmaf(sdz[r][0], m, a0), a1 = fmaf(sdz[r][1], m, a1), a2 = fmaf(sdz[r][2], m, a2);
+  for (int64_t r = (int64_t)blockIdx.x * 256 + threadIdx.x; r < rows; r += (int64_t)gridDim.x * 256) {
+    a0 += p[r * C], a1 += p[r * C + 1];
+    if (C == 3) a2 += p[r * C + 2];
   }
-  atomicAdd(&dWout[k][f], a0);
-  atomicAdd(&dWout[k][kD16 + f], a1);
-  if (C == 3) atomicAdd(&dWout[k][2 * kD16 + f], a2);
-  if (blockIdx.y % 3 == 0 && threadIdx.x < C) {
-    float s = 0.f;
-    for (int r = 0; r < nr; ++r) s += sdz[r][threadIdx.x];
-    atomicAdd(&dbout[k][threadIdx.x], s);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a0 += __shfl_xor_sync(0xffffffffu, a0, o), a1 += __shfl_xor_sync(0xffffffffu, a1, o), a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+  }
+  if (threadIdx.x % 32 == 0) {
+    atomicAdd(&dbout[k][0], a0), atomicAdd(&dbout[k][1], a1);
+    if (C == 3) atomicAdd(&dbout[k][2], a2);
   }
 }
 
@@ -381,7 +381,7 @@ struct Plan {
   size_t off_x, off_u1, off_y1, off_u2, off_y, off_ab, off_dab, off_dy, off_dy1;
   size_t off_S, off_dS, off_G, off_U, off_H;
   // bf16 pair part (T1 + MN-major GEMMs): S [rows, 384], G / M [rows, 1920] bf16, bf16 per-token projections
-  size_t off_S16, off_Gc, off_Mc, off_ab16, off_tokws, tokws_bytes;
+  size_t off_S16, off_Gc, off_dwpart, off_ab16, off_tokws, tokws_bytes;
   size_t total;
 };
 
@@ -392,7 +392,7 @@ Plan make_plan(const peneo_dims& dm, int prec, int batch, int n) {
   p.nU = dm.num_layers - 1;
   p.nH = dm.num_layers >= 3 ? dm.num_layers - 2 : 0;
   const bool tc = prec == PENEO_PREC_BF16;
-  const int nbuf = tc ? 7 : 3 + p.nU + p.nH;  // fp32: S, dS, G, U.., H.. ; bf16: dS (fp32) + S, G, M (bf16, 1 + 5 + 5 halves)
+  const int nbuf = tc ? 4 : 3 + p.nU + p.nH;  // fp32: S, dS, G, U.., H.. ; bf16: dS (fp32) + S, G (bf16, 1 + 5 halves)
   // Pair buffers: up to 262 144 pairs per chunk within ~3 GB (measured: per-chunk launch / wave-quantisation overheads
   // make 64 K-pair chunks 25 % slower end to end), never less than one full pair row (n pairs).  A chunk may span
   // several documents.
@@ -418,7 +418,8 @@ Plan make_plan(const peneo_dims& dm, int prec, int batch, int n) {
   if (tc) {
     const size_t rp = (rows + 127) / 128 * 128;
     p.off_S16 = take(align_up(rp * d * 2, 1024));
-    p.off_Gc = take(align_up(rp * 5 * d * 2, 1024)), p.off_Mc = take(align_up(rp * 5 * d * 2, 1024));
+    p.off_Gc = take(align_up(rp * 5 * d * 2, 1024));
+    p.off_dwpart = take(fl((size_t)kDwPartCtas * 3 * 5 * d));
     p.off_ab16 = take(align_up(T * 2 * d * 2, 1024));
     p.tokws_bytes = peneo_token_proj_workspace_bytes(&dm, PENEO_PREC_BF16, p.tokens);
     p.off_tokws = take(align_up(p.tokws_bytes, 1024));
@@ -514,7 +515,13 @@ int launch_heads_bwd(const peneo_dims& dm, int prec, const void* pack, const voi
   float* dab = F(pl.off_dab);
   TRY(zero(dab, (size_t)T * 2 * d));
   float **d_outw = nullptr, **d_outb = nullptr;
+  int dw_ctas = 0;
   if (tc) {
+    int dev = 0;
+    PENEO_CUDA_TRY(cudaGetDevice(&dev));
+    PENEO_CUDA_TRY(cudaDeviceGetAttribute(&dw_ctas, cudaDevAttrMultiProcessorCount, dev));  // T1's grid never exceeds it
+    PENEO_REQUIRE(dw_ctas <= kDwPartCtas, "device has %d SMs, dW_out partial buffer holds %d", dw_ctas, kDwPartCtas);
+    TRY(zero(F(pl.off_dwpart), (size_t)dw_ctas * 3 * 5 * d));
     // bf16 per-token projections (0.5-scaled A | Bm) for T1, exactly what the forward pass used (same dropout)
     TRY(token_proj_fwd_bf16(dm, L, pk, x, x_dtype, x_row_stride, T, ws + pl.off_ab16, ws + pl.off_tokws, st,
                             drop.thresh ? &drop : nullptr));
@@ -561,10 +568,9 @@ int launch_heads_bwd(const peneo_dims& dm, int prec, const void* pack, const voi
       if (tc) {
         __nv_bfloat16* S16 = reinterpret_cast<__nv_bfloat16*>(ws + pl.off_S16);
         __nv_bfloat16* Gc = reinterpret_cast<__nv_bfloat16*>(ws + pl.off_Gc);
-        __nv_bfloat16* Mc = reinterpret_cast<__nv_bfloat16*>(ws + pl.off_Mc);
         const __nv_bfloat16* ab16 = reinterpret_cast<const __nv_bfloat16*>(ws + pl.off_ab16);
         // T1: regenerate S, M = SiLU(u), G = (dz W_out) SiLU'(u) for the five heads (tcgen05, K2's structure)
-        TRY(launch_pair_bwd_prep(pack, L, ab16, n, g0, rows, dlogits, S16, Gc, Mc, st,
+        TRY(launch_pair_bwd_prep(pack, L, ab16, n, g0, rows, dlogits, S16, Gc, F(pl.off_dwpart), st,
                                  drop.thresh ? &drop : nullptr));
         // dS = G W_mid (all heads in one K = 1920 GEMM) ; dW_mid += G^T S
         TRY(launch_gemm_ds(Gc, reinterpret_cast<const __nv_bfloat16*>(pk + L.wmid_full_bf16), dS, rows, st));
@@ -575,7 +581,7 @@ int launch_heads_bwd(const peneo_dims& dm, int prec, const void* pack, const voi
           dzp.p[h] = dlogits[h] + g0 * head_classes(h);
         }
         TRY(launch_gemm_dw(Gc, S16, dwm, dbm, rows, st));  // + db_mid (column sums of G)
-        dwout_bf16_kernel<<<dim3((rows + 255) / 256, 15), 128, 0, st>>>(Mc, dzp, rows, d_outw, d_outb);
+        dbout_kernel<<<dim3(std::min((rows + 1023) / 1024, 296), kNumHeads), 256, 0, st>>>(dzp, rows, d_outb);
         PENEO_CUDA_TRY(cudaGetLastError());
       } else {
       for (const Seg& sg : segs) {
@@ -648,6 +654,11 @@ int launch_heads_bwd(const peneo_dims& dm, int prec, const void* pack, const voi
         PENEO_CUDA_TRY(cudaGetLastError());
       }
     }
+  }
+
+  if (tc) {
+    dwout_finish_kernel<<<dim3(15, 3), 128, 0, st>>>(F(pl.off_dwpart), dw_ctas, d_outw);
+    PENEO_CUDA_TRY(cudaGetLastError());
   }
 
   // ---- per-token chain backward
