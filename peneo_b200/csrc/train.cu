@@ -335,6 +335,48 @@ __global__ void __launch_bounds__(128) gv_reduce_kernel(const float* __restrict_
   }
 }
 
+// Single-pass variant for the bf16 mode (whose weight gradients already use fp32 atomics): a block walks 128
+// consecutive pairs of the batch-flat chunk for 128 feature columns, reads dS once, keeps the running row sum (dA)
+// in a register and adds g_v into dBm[j] with RED.  No per-document launches, no strided second pass over dS.
+constexpr int kGvRows = 128;
+__global__ void __launch_bounds__(128) gv_reduce_flat_kernel(const float* __restrict__ dS, const float* __restrict__ ab,
+                                                             int64_t g0, int rows, int n, int pairs_per_doc, int d,
+                                                             float* __restrict__ dab) {
+  const int f = blockIdx.y * 128 + threadIdx.x;
+  if (f >= d) return;
+  const int r0 = blockIdx.x * kGvRows, nr = min(kGvRows, rows - r0);
+  const int64_t gp = g0 + r0;
+  int64_t b = gp / pairs_per_doc;
+  int i, j;
+  pair_from_flat(static_cast<int>(gp - b * pairs_per_doc), n, i, j);
+  const float* src = dS + (int64_t)r0 * d + f;
+  const int64_t ld = 2 * (int64_t)d;
+  float at = ab[(b * n + i) * ld + f];
+  float acc = 0.f;
+  bool pending = false;
+  for (int rb = 0; rb < nr; rb += 8) {
+    float sv[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) sv[u] = (rb + u < nr) ? src[(int64_t)(rb + u) * d] : 0.f;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      if (rb + u >= nr) break;
+      const int64_t tj = (b * n + j) * ld + d + f;
+      const float gv = sv[u] * dsilu_exact(at + ab[tj]);
+      acc += gv, pending = true;
+      atomicAdd(&dab[tj], gv);
+      if (++j == n) {  // end of pair-row i
+        atomicAdd(&dab[(b * n + i) * ld + f], acc);
+        acc = 0.f, pending = false;
+        if (++i == n) i = 0, ++b;
+        j = i;
+        if (rb + u + 1 < nr) at = ab[(b * n + i) * ld + f];
+      }
+    }
+  }
+  if (pending) atomicAdd(&dab[(b * n + i) * ld + f], acc);
+}
+
 constexpr int kD16 = 384;
 
 // bf16 backward, output layer: T1 leaves per-CTA partial sums of dz^T M ([ctas][3][1920] fp32); db_out is the column
@@ -649,7 +691,11 @@ int launch_heads_bwd(const peneo_dims& dm, int prec, const void* pack, const voi
         }
       }
       }  // fp32 pair part
-      for (const Seg& sg : segs) {
+      if (tc) {
+        gv_reduce_flat_kernel<<<dim3((rows + kGvRows - 1) / kGvRows, (d + 127) / 128), 128, 0, st>>>(
+            dS, ab, g0, rows, n, static_cast<int>(P), d, dab);
+        PENEO_CUDA_TRY(cudaGetLastError());
+      } else for (const Seg& sg : segs) {
         gv_reduce_kernel<<<dim3(n, (d + 127) / 128), 128, 0, st>>>(dS + sg.off * d, ab, sg.b, n, d, sg.i0, sg.i1, dab);
         PENEO_CUDA_TRY(cudaGetLastError());
       }
