@@ -36,8 +36,7 @@ constexpr int kThreads = 512;
 constexpr int kLdG = 5 * D;                 // row stride of G / M
 
 constexpr uint32_t kColS = 0, kColU = 192, kColDw = 448;
-constexpr int kOutRowBytes = 64 + 16;            // 32 bf16 + pad (conflict-free 16-B accesses)
-constexpr int kOutWarpBytes = 32 * kOutRowBytes;  // 2560 B
+constexpr int kOutWarpBytes = 32 * 64;  // per epilogue warp: 32 rows x 32 bf16, XOR-swizzled 16-byte chunks
 
 struct Smem {
   static constexpr int w = 0;
@@ -45,9 +44,9 @@ struct Smem {
   static constexpr int mtile = stage + 128 * kStageRowBytes;  // m chunk, 2 x 2 boxes of [64 pairs x 64 features] bf16
   static constexpr int dzt = mtile + 128 * 128 * 2;           // dz^T, 2 K blocks of [16 x 64 pairs] bf16
   static constexpr int bmid = dzt + 2 * 16 * 128;             // 1920 floats
-  static constexpr int out = bmid + 5 * D * 4;               // 8 epilogue warps x [32 rows][64 + 16 B]
-  static constexpr int wout = out + 8 * kOutWarpBytes;       // [1920] x (bf16 W_out[0..2][f], 0) = 15 KB
-  static constexpr int bars = wout + 5 * D * 8;
+  static constexpr int out = bmid + 5 * D * 4;               // 8 epilogue warps x [32 rows][64 B]
+  static constexpr int wout = out + 8 * kOutWarpBytes;       // [3][960] bf16x2: W_out[c] of feature pairs (2f, 2f+1)
+  static constexpr int bars = wout + 3 * (5 * D / 2) * 4;
   static constexpr int total = bars + 512;
 };
 constexpr int bWFull = 0, bWEmpty = bWFull + kWStages, bUFull = bWEmpty + kWStages, bUFree = bUFull + 2,
@@ -99,10 +98,12 @@ __global__ void __launch_bounds__(kThreads, 1) pair_bwd_prep_kernel(const __grid
     ptx::tmem_relinquish();
   }
   for (int e = threadIdx.x; e < 5 * D; e += kThreads) s_bmid[e] = a.bmid_half[e];
-  uint2* s_wout = reinterpret_cast<uint2*>(smem + Smem::wout);
-  for (int e = threadIdx.x; e < 5 * D; e += kThreads) {
-    const float4 w = a.wout4[e];
-    s_wout[e] = make_uint2(ptx::pack_bf16x2(w.x, w.y), ptx::pack_bf16x2(w.z, 0.f));
+  uint32_t* s_wout = reinterpret_cast<uint32_t*>(smem + Smem::wout);
+  for (int e = threadIdx.x; e < 5 * D / 2; e += kThreads) {
+    const float4 w0 = a.wout4[2 * e], w1 = a.wout4[2 * e + 1];
+    s_wout[e] = ptx::pack_bf16x2(w0.x, w1.x);
+    s_wout[5 * D / 2 + e] = ptx::pack_bf16x2(w0.y, w1.y);
+    s_wout[5 * D + e] = ptx::pack_bf16x2(w0.z, w1.z);
   }
   for (int e = threadIdx.x; e < 2 * 16 * 128 / 16; e += kThreads)  // dz^T rows 3..15 stay zero for the whole kernel
     reinterpret_cast<uint4*>(smem + Smem::dzt)[e] = make_uint4(0u, 0u, 0u, 0u);
@@ -236,7 +237,9 @@ __global__ void __launch_bounds__(kThreads, 1) pair_bwd_prep_kernel(const __grid
         const uint32_t ut = tmem + lane_base + kColU + 128 * buf + 64 * hsel;
         const int f0 = c * 128 + 64 * hsel;  // column in the stacked [0, 1920) feature space
         const float* hb = s_bmid + f0;
-        const uint2* w4 = s_wout + f0;       // indexed by the stacked feature index k * 384 + f
+        const uint32_t* wp = s_wout + f0 / 2;  // feature pairs, indexed by the stacked feature index k * 384 + f
+        // dz of this pair as bf16x2 broadcasts: g_m = dz W_out runs on packed bf16 FMAs, two features at a time
+        const uint32_t dzb0 = ptx::pack_bf16x2(dz0, dz0), dzb1 = ptx::pack_bf16x2(dz1, dz1), dzb2 = ptx::pack_bf16x2(dz2, dz2);
 #pragma unroll
         for (int piece = 0; piece < 2; ++piece) {
           uint32_t r[32];
@@ -247,49 +250,50 @@ __global__ void __launch_bounds__(kThreads, 1) pair_bwd_prep_kernel(const __grid
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(&bars[bUFree + buf]);
           }
-          uint32_t mp[16], gpk[16];
-#pragma unroll
-          for (int x = 0; x < 32; x += 2) {
-            float mv[2], gv[2];
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-              const int col = 32 * piece + x + e;
-              const float h = __uint_as_float(r[x + e]) + hb[col];  // u / 2
-              const float t = ptx::tanh_approx(h);
-              const float sg = fmaf(0.5f, t, 0.5f);                 // sigmoid(u)
-              const float u = h + h;
-              mv[e] = u * sg;
-              const uint2 wp = w4[col];  // (bf16 W_out[0][f], W_out[1][f]), (W_out[2][f], 0)
-              float gm = fmaf(dz2, __uint_as_float(wp.y << 16),
-                              fmaf(dz1, __uint_as_float(wp.x & 0xFFFF0000u), dz0 * __uint_as_float(wp.x << 16)));
-              if (DROP) {  // m_dropped = m * mask / (1 - p) feeds W_out; its gradient carries the same factor
-                const float ms = drop_keep(a.drop_key[k], a.drop_thresh, static_cast<uint32_t>(gp),
-                                           (c - 3 * k) * 128 + 64 * hsel + col) ? a.drop_scale : 0.f;
-                mv[e] *= ms, gm *= ms;
-              }
-              gv[e] = gm * (sg * fmaf(u, 1.0f - sg, 1.0f));
-            }
-            mp[x / 2] = ptx::pack_bf16x2(mv[0], mv[1]);
-            gpk[x / 2] = ptx::pack_bf16x2(gv[0], gv[1]);
-          }
-          // Coalesced stores: lane = row in TMEM, so each lane holds 64 B of its own row; going through a
-          // per-warp smem tile lets one store instruction write 8 rows x 64 B (full sectors) instead of
-          // 32 rows x 16 B (one LSU transaction per lane).
+          // G goes to global memory through a per-warp smem tile (lane = row in TMEM, so each lane holds 64 B of
+          // its own row; the tile lets one store instruction write 8 rows x 64 B, full sectors).  The tile is
+          // filled 16 B at a time as the values are produced, which keeps few of them live in registers.
           unsigned char* ob = smem + Smem::out + (warp - 4) * kOutWarpBytes;
-          const int64_t row0 = tile * 128 + q * 32;  // first chunk-row of this warp
-          {
-            const uint32_t* src = gpk;
-            __nv_bfloat16* dstm = a.G + f0 + 32 * piece;
-            __syncwarp();
+          uint32_t mp[16];
+          __syncwarp();  // the read-back of the previous piece is complete
 #pragma unroll
-            for (int v = 0; v < 4; ++v)
-              *reinterpret_cast<uint4*>(ob + lane * kOutRowBytes + v * 16) =
-                  make_uint4(src[4 * v], src[4 * v + 1], src[4 * v + 2], src[4 * v + 3]);
-            __syncwarp();
+          for (int v = 0; v < 4; ++v) {
+            uint32_t gq[4];
+#pragma unroll
+            for (int y = 0; y < 4; ++y) {
+              const int x = 8 * v + 2 * y;
+              float mv[2], dv[2];
+#pragma unroll
+              for (int e = 0; e < 2; ++e) {
+                const int col = 32 * piece + x + e;
+                const float h = __uint_as_float(r[x + e]) + hb[col];  // u / 2
+                const float t = ptx::tanh_approx(h);
+                mv[e] = fmaf(h, t, h);                                  // SiLU(u) = u sigmoid(u) = h (1 + tanh h)
+                const float sg = fmaf(0.5f, t, 0.5f), oms = fmaf(-0.5f, t, 0.5f);
+                dv[e] = fmaf(mv[e], oms, sg);                           // SiLU'(u) = sg + m (1 - sg)
+                if (DROP) {  // m_dropped = m * mask / (1 - p) feeds W_out; its gradient carries the same factor
+                  const float ms = drop_keep(a.drop_key[k], a.drop_thresh, static_cast<uint32_t>(gp),
+                                             (c - 3 * k) * 128 + 64 * hsel + col) ? a.drop_scale : 0.f;
+                  mv[e] *= ms, dv[e] *= ms;
+                }
+              }
+              mp[x / 2] = ptx::pack_bf16x2(mv[0], mv[1]);
+              const int pi = 16 * piece + x / 2;
+              const uint32_t gm = ptx::hfma2_bf16(dzb2, wp[5 * D + pi],
+                                                  ptx::hfma2_bf16(dzb1, wp[5 * D / 2 + pi], ptx::hmul2_bf16(dzb0, wp[pi])));
+              gq[y] = ptx::hmul2_bf16(gm, ptx::pack_bf16x2(dv[0], dv[1]));
+            }
+            // row pitch 64 B, 16-byte chunk index XOR ((row >> 1) & 3): conflict-free for these writes and the reads below
+            *reinterpret_cast<uint4*>(ob + lane * 64 + ((v ^ ((lane >> 1) & 3)) * 16)) = make_uint4(gq[0], gq[1], gq[2], gq[3]);
+          }
+          __syncwarp();
+          {
+            __nv_bfloat16* dstm = a.G + f0 + 32 * piece;
+            const int64_t row0 = tile * 128 + q * 32;  // first chunk-row of this warp
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               const int rr = 8 * i + (lane >> 2), c16 = lane & 3;
-              const uint4 val = *reinterpret_cast<const uint4*>(ob + rr * kOutRowBytes + c16 * 16);
+              const uint4 val = *reinterpret_cast<const uint4*>(ob + rr * 64 + ((c16 ^ ((rr >> 1) & 3)) * 16));
               if (row0 + rr < a.rows) *reinterpret_cast<uint4*>(dstm + (row0 + rr) * kLdG + c16 * 8) = val;
             }
           }

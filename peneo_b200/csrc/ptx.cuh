@@ -275,6 +275,17 @@ __device__ __forceinline__ float tanh_approx(float x) {
 }
 // SiLU(2h) / 1 = h + h * tanh(h)  where h = x / 2  (one MUFU op)
 __device__ __forceinline__ float silu_from_half(float h) { return fmaf(h, tanh_approx(h), h); }
+// packed bf16 arithmetic on raw 32-bit registers
+__device__ __forceinline__ uint32_t hmul2_bf16(uint32_t a, uint32_t b) {
+  uint32_t r;
+  asm("mul.rn.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  return r;
+}
+__device__ __forceinline__ uint32_t hfma2_bf16(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t r;
+  asm("fma.rn.bf16x2 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+  return r;
+}
 // pack two floats to bf16x2: `lo` in bits [0,16), `hi` in bits [16,32)
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   uint32_t r;
