@@ -22,8 +22,8 @@ def main():
     ap.add_argument("--seq-len", type=int, default=1024)
     ap.add_argument("--batch", type=int, default=4)
     ap.add_argument("--precision", default="bf16")
-    ap.add_argument("--steps", type=int, default=5)
-    ap.add_argument("--warmup", type=int, default=2)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
     args = ap.parse_args()
 
     class Cfg:

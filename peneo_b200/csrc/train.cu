@@ -18,6 +18,7 @@
 
 #include "common.cuh"
 #include "kernels.h"
+#include "ptx.cuh"
 
 namespace peneo {
 
@@ -335,46 +336,58 @@ __global__ void __launch_bounds__(128) gv_reduce_kernel(const float* __restrict_
   }
 }
 
-// Single-pass variant for the bf16 mode (whose weight gradients already use fp32 atomics): a block walks 128
-// consecutive pairs of the batch-flat chunk for 128 feature columns, reads dS once, keeps the running row sum (dA)
-// in a register and adds g_v into dBm[j] with RED.  No per-document launches, no strided second pass over dS.
-constexpr int kGvRows = 128;
-__global__ void __launch_bounds__(128) gv_reduce_flat_kernel(const float* __restrict__ dS, const float* __restrict__ ab,
-                                                             int64_t g0, int rows, int n, int pairs_per_doc, int d,
+// Single-pass variant for the bf16 mode (whose weight gradients already use fp32 atomics): a block owns the tile
+// rows [it, it + 8) x columns [jt, jt + 8) of one document's pair matrix, one thread per 4 features (float4 loads:
+// every pair is one contiguous 4 d-byte read, 8 of them in flight per thread).  b_j and the 8 column sums stay in
+// registers; 8 + 8 vector REDs per 64 pairs.  Tiles below the diagonal exit.
+constexpr int kGvR = 8, kGvC = 8;
+// SiLU'(x) with one MUFU (tanh.approx), the same approximation the bf16 forward pass uses for SiLU itself
+__device__ __forceinline__ float dsilu_tanh(float x) {
+  const float t = ptx::tanh_approx(0.5f * x);
+  const float sg = fmaf(0.5f, t, 0.5f), oms = fmaf(-0.5f, t, 0.5f);
+  return fmaf(x * sg, oms, sg);
+}
+__global__ void __launch_bounds__(128) gv_reduce_tile_kernel(const float* __restrict__ dS, const float* __restrict__ ab,
+                                                             int b, int n, int d, int i0, int i1,
                                                              float* __restrict__ dab) {
-  const int f = blockIdx.y * 128 + threadIdx.x;
-  if (f >= d) return;
-  const int r0 = blockIdx.x * kGvRows, nr = min(kGvRows, rows - r0);
-  const int64_t gp = g0 + r0;
-  int64_t b = gp / pairs_per_doc;
-  int i, j;
-  pair_from_flat(static_cast<int>(gp - b * pairs_per_doc), n, i, j);
-  const float* src = dS + (int64_t)r0 * d + f;
+  const int f = 4 * threadIdx.x;  // blockDim.x = d / 4
+  const int it = i0 + blockIdx.y * kGvR, jt = blockIdx.x * kGvC;
+  const int ie = min(it + kGvR, i1), je = min(jt + kGvC, n);
+  if (je <= it) return;  // every pair of the tile has j < i
   const int64_t ld = 2 * (int64_t)d;
-  float at = ab[(b * n + i) * ld + f];
-  float acc = 0.f;
-  bool pending = false;
-  for (int rb = 0; rb < nr; rb += 8) {
-    float sv[8];
+  const float* abd = ab + (int64_t)b * n * ld + f;
+  float* out = dab + (int64_t)b * n * ld + f;
+  const int p0 = row_start(i0, n);
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 bj[kGvC], cs[kGvC];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) sv[u] = (rb + u < nr) ? src[(int64_t)(rb + u) * d] : 0.f;
-#pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      if (rb + u >= nr) break;
-      const int64_t tj = (b * n + j) * ld + d + f;
-      const float gv = sv[u] * dsilu_exact(at + ab[tj]);
-      acc += gv, pending = true;
-      atomicAdd(&dab[tj], gv);
-      if (++j == n) {  // end of pair-row i
-        atomicAdd(&dab[(b * n + i) * ld + f], acc);
-        acc = 0.f, pending = false;
-        if (++i == n) i = 0, ++b;
-        j = i;
-        if (rb + u + 1 < nr) at = ab[(b * n + i) * ld + f];
-      }
-    }
+  for (int c = 0; c < kGvC; ++c) {
+    bj[c] = (jt + c < je) ? *reinterpret_cast<const float4*>(abd + (int64_t)(jt + c) * ld + d) : zero4;
+    cs[c] = zero4;
   }
-  if (pending) atomicAdd(&dab[(b * n + i) * ld + f], acc);
+  for (int i = it; i < ie; ++i) {
+    const float4 ai = *reinterpret_cast<const float4*>(abd + (int64_t)i * ld);
+    // pair (i, j) lives at flat row row_start(i) + (j - i)
+    const float* src = dS + ((int64_t)(row_start(i, n) - p0) + (jt - i)) * d + f;
+    float4 v[kGvC];
+#pragma unroll
+    for (int c = 0; c < kGvC; ++c) {
+      const int j = jt + c;
+      v[c] = (j >= i && j < je) ? *reinterpret_cast<const float4*>(src + (int64_t)c * d) : zero4;
+    }
+    float4 rs = zero4;
+#pragma unroll
+    for (int c = 0; c < kGvC; ++c) {  // v = 0 outside the triangle
+      const float gx = v[c].x * dsilu_tanh(ai.x + bj[c].x), gy = v[c].y * dsilu_tanh(ai.y + bj[c].y);
+      const float gz = v[c].z * dsilu_tanh(ai.z + bj[c].z), gw = v[c].w * dsilu_tanh(ai.w + bj[c].w);
+      rs.x += gx, rs.y += gy, rs.z += gz, rs.w += gw;
+      cs[c].x += gx, cs[c].y += gy, cs[c].z += gz, cs[c].w += gw;
+    }
+    atomicAdd(reinterpret_cast<float4*>(out + (int64_t)i * ld), rs);
+  }
+#pragma unroll
+  for (int c = 0; c < kGvC; ++c)
+    if (jt + c < je && jt + c >= it) atomicAdd(reinterpret_cast<float4*>(out + (int64_t)(jt + c) * ld + d), cs[c]);
 }
 
 constexpr int kD16 = 384;
@@ -692,9 +705,11 @@ int launch_heads_bwd(const peneo_dims& dm, int prec, const void* pack, const voi
       }
       }  // fp32 pair part
       if (tc) {
-        gv_reduce_flat_kernel<<<dim3((rows + kGvRows - 1) / kGvRows, (d + 127) / 128), 128, 0, st>>>(
-            dS, ab, g0, rows, n, static_cast<int>(P), d, dab);
-        PENEO_CUDA_TRY(cudaGetLastError());
+        for (const Seg& sg : segs) {
+          gv_reduce_tile_kernel<<<dim3((n + kGvC - 1) / kGvC, (sg.i1 - sg.i0 + kGvR - 1) / kGvR), d / 4, 0, st>>>(
+              dS + sg.off * d, ab, sg.b, n, d, sg.i0, sg.i1, dab);
+          PENEO_CUDA_TRY(cudaGetLastError());
+        }
       } else for (const Seg& sg : segs) {
         gv_reduce_kernel<<<dim3(n, (d + 127) / 128), 128, 0, st>>>(dS + sg.off * d, ab, sg.b, n, d, sg.i0, sg.i1, dab);
         PENEO_CUDA_TRY(cudaGetLastError());
