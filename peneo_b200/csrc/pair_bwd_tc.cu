@@ -297,7 +297,7 @@ __global__ void __launch_bounds__(kThreads, 1) pair_bwd_prep_kernel(const __grid
               if (row0 + rr < a.rows) *reinterpret_cast<uint4*>(dstm + (row0 + rr) * kLdG + c16 * 8) = val;
             }
           }
-          // m into the MN-major operand tile (rows past the chunk end are zero: dz is zero there anyway, but keep NaNs out)
+          // m into the MN-major operand tile (rows past the chunk end: s = 0, so m = SiLU(b_mid) is finite, and dz = 0)
           if (piece == 0 && g > 0) {
             ptx::mbar_wait(&bars[bMFree], (g - 1) & 1);  // the dW_out MMA of the previous chunk has read the tile
             ptx::tc_fence_after();
@@ -305,7 +305,7 @@ __global__ void __launch_bounds__(kThreads, 1) pair_bwd_prep_kernel(const __grid
 #pragma unroll
           for (int v = 0; v < 4; ++v)
             *reinterpret_cast<uint4*>(mt + (((4 * piece + v) ^ (row & 7)) * 16)) =
-                live ? make_uint4(mp[4 * v], mp[4 * v + 1], mp[4 * v + 2], mp[4 * v + 3]) : make_uint4(0u, 0u, 0u, 0u);
+                make_uint4(mp[4 * v], mp[4 * v + 1], mp[4 * v + 2], mp[4 * v + 3]);
         }
         ptx::fence_proxy_async();  // generic-proxy writes (m tile, dz^T) -> visible to the tensor core's async proxy
         __syncwarp();

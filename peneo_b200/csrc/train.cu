@@ -126,7 +126,20 @@ struct Gemm {
   int64_t ldc2 = 0;
   uint32_t drop_thresh = 0, drop_key = 0, row0 = 0;  // dropout mask of C2: element (row0 + m, n)
   float drop_scale = 1.f;
+  float* scratch = nullptr;  // bf16 mode: room for transposed copies of A ([M, K]) and B ([N, K]) -> K-major TF32 GEMM
 };
+
+// out[c, r] = in[r, c]   (in: [R, C] with row stride ld_in ; out: [C, R] with row stride ld_out)
+__global__ void __launch_bounds__(256) transpose_kernel(const float* __restrict__ in, int64_t ld_in, int R, int C,
+                                                        float* __restrict__ out, int64_t ld_out) {
+  __shared__ float tile[32][33];
+  const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32, tx = threadIdx.x % 32, ty = threadIdx.x / 32;
+  for (int y = ty; y < 32; y += 8)
+    if (r0 + y < R && c0 + tx < C) tile[y][tx] = in[(int64_t)(r0 + y) * ld_in + c0 + tx];
+  __syncthreads();
+  for (int y = ty; y < 32; y += 8)
+    if (c0 + y < C && r0 + tx < R) out[(int64_t)(c0 + y) * ld_out + r0 + tx] = tile[tx][y];
+}
 
 // `tensor_cores`: bf16 mode — run on tcgen05 kind::tf32 (gemm_tf32.cu) when the shape qualifies; the fp32 mode
 // always uses the exact CUDA-core kernel below.
@@ -137,6 +150,22 @@ int run_gemm(const Gemm& g, cudaStream_t st, bool tensor_cores = false) {
     t.ta = g.ta, t.tb = g.tb, t.A = g.A, t.lda = g.lda, t.B = g.B, t.ldb = g.ldb, t.C = g.C, t.ldc = g.ldc;
     t.M = g.M, t.N = g.N, t.K = g.K, t.mode = g.mode, t.bias = g.bias, t.C2 = g.C2, t.ldc2 = g.ldc2;
     t.drop_thresh = g.drop_thresh, t.drop_key = g.drop_key, t.row0 = g.row0, t.drop_scale = g.drop_scale;
+    if (g.scratch && (g.ta || !g.tb)) {
+      // kind::tf32 only takes K-major operands here: transpose what is stored the other way round (a few MB, a
+      // few microseconds) instead of falling back to the CUDA-core SGEMM
+      float* sc = g.scratch;
+      const int64_t kp = (g.K + 3) / 4 * 4;
+      if (g.ta) {
+        transpose_kernel<<<dim3((g.M + 31) / 32, (g.K + 31) / 32), 256, 0, st>>>(g.A, g.lda, g.K, g.M, sc, kp);
+        PENEO_CUDA_TRY(cudaGetLastError());
+        t.A = sc, t.lda = kp, t.ta = false, sc += (int64_t)g.M * kp;
+      }
+      if (!g.tb) {
+        transpose_kernel<<<dim3((g.N + 31) / 32, (g.K + 31) / 32), 256, 0, st>>>(g.B, g.ldb, g.K, g.N, sc, kp);
+        PENEO_CUDA_TRY(cudaGetLastError());
+        t.B = sc, t.ldb = kp, t.tb = true;
+      }
+    }
     if (gemm_tf32_supported(t)) return launch_gemm_tf32(t, st);
   }
   const bool ok = (g.ta ? (g.M % 4 == 0) : (g.K % 4 == 0)) && (g.tb ? (g.K % 4 == 0) : (g.N % 4 == 0)) &&
@@ -436,7 +465,7 @@ struct Plan {
   size_t off_x, off_u1, off_y1, off_u2, off_y, off_ab, off_dab, off_dy, off_dy1;
   size_t off_S, off_dS, off_G, off_U, off_H;
   // bf16 pair part (T1 + MN-major GEMMs): S [rows, 384], G / M [rows, 1920] bf16, bf16 per-token projections
-  size_t off_S16, off_Gc, off_dwpart, off_ab16, off_tokws, tokws_bytes;
+  size_t off_S16, off_Gc, off_dwpart, off_ab16, off_tokws, tokws_bytes, off_tr;
   size_t total;
 };
 
@@ -478,6 +507,10 @@ Plan make_plan(const peneo_dims& dm, int prec, int batch, int n) {
     p.off_ab16 = take(align_up(T * 2 * d * 2, 1024));
     p.tokws_bytes = peneo_token_proj_workspace_bytes(&dm, PENEO_PREC_BF16, p.tokens);
     p.off_tokws = take(align_up(p.tokws_bytes, 1024));
+    {
+      const size_t wmax = std::max(std::max(hin, hid), 2 * d), tp = (T + 3) / 4 * 4;
+      p.off_tr = take(fl(std::max(2 * tp * wmax, wmax * wmax)));  // transposed GEMM operands (activations or a weight)
+    }
   } else {
     p.off_S = take(cb), p.off_G = take(cb);
     p.off_U = take(cb * p.nU), p.off_H = take(cb * p.nH);
@@ -724,11 +757,12 @@ int launch_heads_bwd(const peneo_dims& dm, int prec, const void* pack, const voi
 
   // ---- per-token chain backward
   const int tb = (T + 31) / 32;
+  float* tr = tc ? F(pl.off_tr) : nullptr;
   // db_c = column sums of dBm
   colsum_kernel<<<dim3(tb, (d + 127) / 128), 128, 0, st>>>(dab + d, T, d, 2 * d, gr.combine_b);
   PENEO_CUDA_TRY(cudaGetLastError());
   // dW_c[:, :d] = dA^T y ; dW_c[:, d:] = dBm^T y
-  g = Gemm{}, g.ta = true, g.A = dab, g.lda = 2 * d, g.B = y, g.ldb = ldy, g.C = gr.combine_w, g.ldc = 2 * d;
+  g = Gemm{}, g.scratch = tr, g.ta = true, g.A = dab, g.lda = 2 * d, g.B = y, g.ldb = ldy, g.C = gr.combine_w, g.ldc = 2 * d;
   g.M = d, g.N = d, g.K = T, g.mode = 2;
   TRY(run_gemm(g, st, tc));
   g.A = dab + d, g.C = gr.combine_w + d;
@@ -736,7 +770,7 @@ int launch_heads_bwd(const peneo_dims& dm, int prec, const void* pack, const voi
   // dy = dA W_c[:, :d] + dBm W_c[:, d:]
   float* dy = (dm.shrink || dx == nullptr) ? F(pl.off_dy) : dx;
   const int64_t lddy = (dm.shrink || dx == nullptr) ? d : hin;
-  g = Gemm{}, g.A = dab, g.lda = 2 * d, g.B = W(L.f_wc), g.ldb = 2 * d, g.C = dy, g.ldc = lddy, g.M = T, g.N = d, g.K = d;
+  g = Gemm{}, g.scratch = tr, g.A = dab, g.lda = 2 * d, g.B = W(L.f_wc), g.ldb = 2 * d, g.C = dy, g.ldc = lddy, g.M = T, g.N = d, g.K = d;
   TRY(run_gemm(g, st, tc));
   g.A = dab + d, g.B = W(L.f_wc) + d, g.mode = 1;
   TRY(run_gemm(g, st, tc));
@@ -745,21 +779,21 @@ int launch_heads_bwd(const peneo_dims& dm, int prec, const void* pack, const voi
     act_bwd_kernel<<<dim3(tb, (d + 127) / 128), 128, 0, st>>>(dy, F(pl.off_u2), T, d, d, d, gr.shrink_b2, drop.thresh,
                                                               drop.scale, drop_key(drop, kSiteTok1), 0u);
     PENEO_CUDA_TRY(cudaGetLastError());
-    g = Gemm{}, g.ta = true, g.A = dy, g.lda = d, g.B = F(pl.off_y1), g.ldb = hid, g.C = gr.shrink_w2, g.ldc = hid;
+    g = Gemm{}, g.scratch = tr, g.ta = true, g.A = dy, g.lda = d, g.B = F(pl.off_y1), g.ldb = hid, g.C = gr.shrink_w2, g.ldc = hid;
     g.M = d, g.N = hid, g.K = T, g.mode = 2;
     TRY(run_gemm(g, st, tc));
     float* dy1 = F(pl.off_dy1);
-    g = Gemm{}, g.A = dy, g.lda = d, g.B = W(L.f_w2), g.ldb = hid, g.C = dy1, g.ldc = hid, g.M = T, g.N = hid, g.K = d;
+    g = Gemm{}, g.scratch = tr, g.A = dy, g.lda = d, g.B = W(L.f_w2), g.ldb = hid, g.C = dy1, g.ldc = hid, g.M = T, g.N = hid, g.K = d;
     TRY(run_gemm(g, st, tc));
     // G1 = dy1 * SiLU'(u1) ; db1 ; dW1 = G1^T x ; dx = G1 W1
     act_bwd_kernel<<<dim3(tb, (hid + 127) / 128), 128, 0, st>>>(dy1, F(pl.off_u1), T, hid, hid, hid, gr.shrink_b1,
                                                                 drop.thresh, drop.scale, drop_key(drop, kSiteTok0), 0u);
     PENEO_CUDA_TRY(cudaGetLastError());
-    g = Gemm{}, g.ta = true, g.A = dy1, g.lda = hid, g.B = xin, g.ldb = ldx, g.C = gr.shrink_w1, g.ldc = hin;
+    g = Gemm{}, g.scratch = tr, g.ta = true, g.A = dy1, g.lda = hid, g.B = xin, g.ldb = ldx, g.C = gr.shrink_w1, g.ldc = hin;
     g.M = hid, g.N = hin, g.K = T, g.mode = 2;
     TRY(run_gemm(g, st, tc));
     if (dx) {
-      g = Gemm{}, g.A = dy1, g.lda = hid, g.B = W(L.f_w1), g.ldb = hin, g.C = dx, g.ldc = hin, g.M = T, g.N = hin, g.K = hid;
+      g = Gemm{}, g.scratch = tr, g.A = dy1, g.lda = hid, g.B = W(L.f_w1), g.ldb = hin, g.C = dx, g.ldc = hin, g.M = T, g.N = hin, g.K = hid;
       TRY(run_gemm(g, st, tc));
     }
   }
