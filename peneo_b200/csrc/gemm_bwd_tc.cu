@@ -3,6 +3,7 @@
 // by using MN-major shared-memory descriptors where the contraction index is the ROW index in memory:
 //
 //   dS  [rows, 384]  = G [rows, 1920] * W_mid [1920, 384]        A K-major (row = m, contiguous = k = mid feature)
+//       (stored as bf16: its only consumer is the dA / dBm reduction, a sum over up to N terms)
 //                                                                B MN-major (row = k = mid feature, contiguous = n)
 //   dWm [1920, 384] += G^T [1920, rows] * S [rows, 384]          A MN-major (row = k = pair, contiguous = m)
 //                                                                B MN-major (row = k = pair, contiguous = n)
@@ -25,7 +26,7 @@ constexpr int kN = 384;
 constexpr int kBlk = 64 * 128;              // one [64 rows x 64 cols] swizzled box = 8 KB
 constexpr int kStageBytes = 2 * kBlk + 6 * kBlk;  // 64 KB
 constexpr int kStages = 3;
-constexpr int kOnesOff = kStages * kStageBytes;  // dW only: constant [64 k x 64 n] box, column 0 = 1
+constexpr int kOnesOff = kStages * kStageBytes;  // dW: constant [64 k x 64 n] box, column 0 = 1 ; dS: store staging
 constexpr int kSmemBytes = kStages * kStageBytes + kBlk + 1024 + 256;
 
 struct Args {
@@ -33,7 +34,7 @@ struct Args {
   int32_t k_total;   // contraction length (dS: 1920; dW: pairs in the chunk)
   int32_t kb_per_split, splits;
   int64_t num_items;  // m blocks * splits
-  float* out[kNumHeads];  // dS: out[0] = dS (ld 384); dW: five [384, 384] matrices, m block -> head = mb / 3
+  float* out[kNumHeads];  // dS: out[0] = dS (bf16, ld 384); dW: five [384, 384] matrices, m block -> head = mb / 3
   float* colsum[kNumHeads];  // dW only: five [384] vectors += column sums of A (db_mid)
 };
 
@@ -155,12 +156,13 @@ __global__ void __launch_bounds__(192, 1)
       ptx::mbar_wait(acc_full, it & 1);
       ptx::tc_fence_after();
       const int64_t m = mb * 128 + q * 32 + lane;
-      float* dst;
-      if (A_MN) {  // dW: row m of the stacked [1920, 384] gradient = row (m % 384) of head m / 384
-        dst = a.out[static_cast<int>(m / kN)] + (m % kN) * kN;
-      } else {
-        dst = a.out[0] + m * kN;
-      }
+      float* dst = nullptr;
+      if (A_MN) dst = a.out[static_cast<int>(m / kN)] + (m % kN) * kN;  // row m of the stacked [1920, 384] gradient
+      // dS: bf16 rows through a per-warp smem tile ([32 rows][64 B], 16-byte chunks XOR-swizzled by (row >> 1) & 3) so
+      // that one store instruction covers 8 rows x 64 B instead of 32 rows x 16 B
+      unsigned char* ob = smem + kOnesOff + q * 2048;
+      __nv_bfloat16* ds16 = reinterpret_cast<__nv_bfloat16*>(a.out[0]);
+      const int64_t wrow0 = mb * 128 + q * 32;
       if (A_MN) {
         uint32_t c4[4];
         ptx::tmem_ld_x4(tmem + (static_cast<uint32_t>(q * 32) << 16) + kN, c4);
@@ -184,11 +186,23 @@ __global__ void __launch_bounds__(192, 1)
               atomicAdd(reinterpret_cast<float4*>(dst + piece * 32 + x),
                         make_float4(__uint_as_float(r[x]), __uint_as_float(r[x + 1]), __uint_as_float(r[x + 2]),
                                     __uint_as_float(r[x + 3])));
-          } else {
+          }
+        }
+        if (!A_MN) {
+          __syncwarp();  // the read-back of the previous piece is complete
 #pragma unroll
-            for (int x = 0; x < 32; x += 4)
-              *reinterpret_cast<float4*>(dst + piece * 32 + x) = make_float4(
-                  __uint_as_float(r[x]), __uint_as_float(r[x + 1]), __uint_as_float(r[x + 2]), __uint_as_float(r[x + 3]));
+          for (int v = 0; v < 4; ++v)
+            *reinterpret_cast<uint4*>(ob + lane * 64 + ((v ^ ((lane >> 1) & 3)) * 16)) = make_uint4(
+                ptx::pack_bf16x2(__uint_as_float(r[8 * v]), __uint_as_float(r[8 * v + 1])),
+                ptx::pack_bf16x2(__uint_as_float(r[8 * v + 2]), __uint_as_float(r[8 * v + 3])),
+                ptx::pack_bf16x2(__uint_as_float(r[8 * v + 4]), __uint_as_float(r[8 * v + 5])),
+                ptx::pack_bf16x2(__uint_as_float(r[8 * v + 6]), __uint_as_float(r[8 * v + 7])));
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int rr = 8 * i + (lane >> 2), c16 = lane & 3;
+            const uint4 val = *reinterpret_cast<const uint4*>(ob + rr * 64 + ((c16 ^ ((rr >> 1) & 3)) * 16));
+            if (wrow0 + rr < a.m_total) *reinterpret_cast<uint4*>(ds16 + (wrow0 + rr) * kN + piece * 32 + c16 * 8) = val;
           }
         }
       }
@@ -211,8 +225,8 @@ static int sm_count() {
 
 }  // namespace gb
 
-// dS[rows, 384] = G[rows, 1920] * Wmid[1920, 384]   (Wmid: the five [d_out, d_in] matrices stacked, bf16, unscaled)
-int launch_gemm_ds(const __nv_bfloat16* G, const __nv_bfloat16* wmid_full, float* dS, int rows, cudaStream_t st) {
+// dS[rows, 384] (bf16) = G[rows, 1920] * Wmid[1920, 384]   (Wmid: the five [d_out, d_in] matrices stacked, bf16, unscaled)
+int launch_gemm_ds(const __nv_bfloat16* G, const __nv_bfloat16* wmid_full, __nv_bfloat16* dS, int rows, cudaStream_t st) {
   using namespace gb;
   if (rows == 0) return PENEO_OK;
   alignas(64) CUtensorMap tmA, tmB;
@@ -223,7 +237,7 @@ int launch_gemm_ds(const __nv_bfloat16* G, const __nv_bfloat16* wmid_full, float
   a.m_total = rows, a.k_total = 5 * kN;
   a.splits = 1, a.kb_per_split = (a.k_total + 63) / 64;
   a.num_items = (rows + 127) / 128;
-  a.out[0] = dS;
+  a.out[0] = reinterpret_cast<float*>(dS);
   const int grid = static_cast<int>(std::min<int64_t>(a.num_items, sm_count()));
   PENEO_CUDA_TRY(cudaFuncSetAttribute(gemm_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
   gemm_bwd_kernel<false><<<grid, 192, kSmemBytes, st>>>(tmA, tmB, a);

@@ -42,7 +42,7 @@ int launch_pair_bwd_prep(const void* pack, const PackLayout& L, const __nv_bfloa
                          cudaStream_t st, const DropSpec* drop = nullptr);
 
 // gemm_bwd_tc.cu
-int launch_gemm_ds(const __nv_bfloat16* G, const __nv_bfloat16* wmid_full, float* dS, int rows, cudaStream_t st);
+int launch_gemm_ds(const __nv_bfloat16* G, const __nv_bfloat16* wmid_full, __nv_bfloat16* dS, int rows, cudaStream_t st);
 int launch_gemm_dw(const __nv_bfloat16* G, const __nv_bfloat16* S, float* const dW[kNumHeads], float* const db[kNumHeads],
                    int rows, cudaStream_t st);
 

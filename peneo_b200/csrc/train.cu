@@ -376,9 +376,9 @@ __device__ __forceinline__ float dsilu_tanh(float x) {
   const float sg = fmaf(0.5f, t, 0.5f), oms = fmaf(-0.5f, t, 0.5f);
   return fmaf(x * sg, oms, sg);
 }
-__global__ void __launch_bounds__(128) gv_reduce_tile_kernel(const float* __restrict__ dS, const float* __restrict__ ab,
-                                                             int b, int n, int d, int i0, int i1,
-                                                             float* __restrict__ dab) {
+__global__ void __launch_bounds__(128) gv_reduce_tile_kernel(const __nv_bfloat16* __restrict__ dS,
+                                                             const float* __restrict__ ab, int b, int n, int d, int i0,
+                                                             int i1, float* __restrict__ dab) {
   const int f = 4 * threadIdx.x;  // blockDim.x = d / 4
   const int it = i0 + blockIdx.y * kGvR, jt = blockIdx.x * kGvC;
   const int ie = min(it + kGvR, i1), je = min(jt + kGvC, n);
@@ -388,31 +388,43 @@ __global__ void __launch_bounds__(128) gv_reduce_tile_kernel(const float* __rest
   float* out = dab + (int64_t)b * n * ld + f;
   const int p0 = row_start(i0, n);
   const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  // the 8 pairs (i, jt .. jt + 7) of row i: 8-byte loads, zero outside the triangle / the document
+  auto load_row = [&](int i, uint2 (&v)[kGvC]) {
+    // pair (i, j) lives at flat row row_start(i) + (j - i)
+    const __nv_bfloat16* src = dS + ((int64_t)(row_start(i, n) - p0) + (jt - i)) * d + f;
+#pragma unroll
+    for (int c = 0; c < kGvC; ++c) {
+      const int j = jt + c;
+      v[c] = (i < ie && j >= i && j < je) ? *reinterpret_cast<const uint2*>(src + (int64_t)c * d) : make_uint2(0u, 0u);
+    }
+  };
+  uint2 v[2][kGvC];
+  load_row(it, v[0]);
   float4 bj[kGvC], cs[kGvC];
 #pragma unroll
   for (int c = 0; c < kGvC; ++c) {
     bj[c] = (jt + c < je) ? *reinterpret_cast<const float4*>(abd + (int64_t)(jt + c) * ld + d) : zero4;
     cs[c] = zero4;
   }
-  for (int i = it; i < ie; ++i) {
-    const float4 ai = *reinterpret_cast<const float4*>(abd + (int64_t)i * ld);
-    // pair (i, j) lives at flat row row_start(i) + (j - i)
-    const float* src = dS + ((int64_t)(row_start(i, n) - p0) + (jt - i)) * d + f;
-    float4 v[kGvC];
 #pragma unroll
-    for (int c = 0; c < kGvC; ++c) {
-      const int j = jt + c;
-      v[c] = (j >= i && j < je) ? *reinterpret_cast<const float4*>(src + (int64_t)c * d) : zero4;
-    }
-    float4 rs = zero4;
+  for (int r = 0; r < kGvR; ++r) {
+    const int i = it + r;
+    if (r + 1 < kGvR) load_row(i + 1, v[(r + 1) & 1]);  // next row in flight while this one is reduced
+    if (i < ie) {
+      const float4 ai = *reinterpret_cast<const float4*>(abd + (int64_t)i * ld);
+      float4 rs = zero4;
 #pragma unroll
-    for (int c = 0; c < kGvC; ++c) {  // v = 0 outside the triangle
-      const float gx = v[c].x * dsilu_tanh(ai.x + bj[c].x), gy = v[c].y * dsilu_tanh(ai.y + bj[c].y);
-      const float gz = v[c].z * dsilu_tanh(ai.z + bj[c].z), gw = v[c].w * dsilu_tanh(ai.w + bj[c].w);
-      rs.x += gx, rs.y += gy, rs.z += gz, rs.w += gw;
-      cs[c].x += gx, cs[c].y += gy, cs[c].z += gz, cs[c].w += gw;
+      for (int c = 0; c < kGvC; ++c) {
+        const uint2 w = v[r & 1][c];
+        const float gx = __uint_as_float(w.x << 16) * dsilu_tanh(ai.x + bj[c].x);
+        const float gy = __uint_as_float(w.x & 0xFFFF0000u) * dsilu_tanh(ai.y + bj[c].y);
+        const float gz = __uint_as_float(w.y << 16) * dsilu_tanh(ai.z + bj[c].z);
+        const float gw = __uint_as_float(w.y & 0xFFFF0000u) * dsilu_tanh(ai.w + bj[c].w);
+        rs.x += gx, rs.y += gy, rs.z += gz, rs.w += gw;
+        cs[c].x += gx, cs[c].y += gy, cs[c].z += gz, cs[c].w += gw;
+      }
+      atomicAdd(reinterpret_cast<float4*>(out + (int64_t)i * ld), rs);
     }
-    atomicAdd(reinterpret_cast<float4*>(out + (int64_t)i * ld), rs);
   }
 #pragma unroll
   for (int c = 0; c < kGvC; ++c)
@@ -661,7 +673,7 @@ int launch_heads_bwd(const peneo_dims& dm, int prec, const void* pack, const voi
         TRY(launch_pair_bwd_prep(pack, L, ab16, n, g0, rows, dlogits, S16, Gc, F(pl.off_dwpart), st,
                                  drop.thresh ? &drop : nullptr));
         // dS = G W_mid (all heads in one K = 1920 GEMM) ; dW_mid += G^T S
-        TRY(launch_gemm_ds(Gc, reinterpret_cast<const __nv_bfloat16*>(pk + L.wmid_full_bf16), dS, rows, st));
+        TRY(launch_gemm_ds(Gc, reinterpret_cast<const __nv_bfloat16*>(pk + L.wmid_full_bf16), reinterpret_cast<__nv_bfloat16*>(dS), rows, st));
         float *dwm[kNumHeads], *dbm[kNumHeads];
         DzPtrs dzp;
         for (int h = 0; h < kNumHeads; ++h) {
@@ -740,7 +752,7 @@ int launch_heads_bwd(const peneo_dims& dm, int prec, const void* pack, const voi
       if (tc) {
         for (const Seg& sg : segs) {
           gv_reduce_tile_kernel<<<dim3((n + kGvC - 1) / kGvC, (sg.i1 - sg.i0 + kGvR - 1) / kGvR), d / 4, 0, st>>>(
-              dS + sg.off * d, ab, sg.b, n, d, sg.i0, sg.i1, dab);
+              reinterpret_cast<const __nv_bfloat16*>(dS) + sg.off * d, ab, sg.b, n, d, sg.i0, sg.i1, dab);
           PENEO_CUDA_TRY(cudaGetLastError());
         }
       } else for (const Seg& sg : segs) {
