@@ -204,23 +204,31 @@ __global__ void __launch_bounds__(kThreads, 1) pair_bwd_prep_kernel(const __grid
       atomicAdd(dst + kLdG, __uint_as_float(d4[1]));
       atomicAdd(dst + 2 * kLdG, __uint_as_float(d4[2]));
     };
+    // dz of (tile, head) for this lane's pair; loaded one chunk ahead of its first use so the latency is hidden
+    auto load_dz = [&](int64_t tile_, int k_, float& z0, float& z1, float& z2) {
+      z0 = z1 = z2 = 0.f;
+      const int64_t lr_ = tile_ * 128 + row;
+      if (lr_ < a.rows) {
+        const int C = head_classes(k_);
+        const float* p = a.dz[k_] + (a.g0 + lr_) * C;
+        z0 = p[0], z1 = p[1];
+        if (C == 3) z2 = p[2];
+      }
+    };
     int g = 0;
+    float nz0 = 0.f, nz1 = 0.f, nz2 = 0.f;
+    if (my_tiles > 0) load_dz(blockIdx.x, 0, nz0, nz1, nz2);
     for (int it = 0; it < my_tiles; ++it) {
       const int64_t tile = static_cast<int64_t>(blockIdx.x) + static_cast<int64_t>(it) * gridDim.x;
       const int64_t lr = tile * 128 + row;          // row inside the chunk
-      const bool live = lr < a.rows;
       const int64_t gp = a.g0 + lr;                 // flat pair index in the batch
       float dz0 = 0.f, dz1 = 0.f, dz2 = 0.f;
       for (int c = 0; c < kChunks; ++c, ++g) {
         const int buf = g & 1, k = c / 3;
-        if (c - 3 * k == 0) {
-          dz0 = dz1 = dz2 = 0.f;
-          if (live) {
-            const int C = head_classes(k);
-            const float* p = a.dz[k] + gp * C;
-            dz0 = p[0], dz1 = p[1];
-            if (C == 3) dz2 = p[2];
-          }
+        if (c - 3 * k == 0) dz0 = nz0, dz1 = nz1, dz2 = nz2;
+        if (c - 3 * k == 2) {  // prefetch for the next head (or head 0 of this CTA's next tile)
+          if (k + 1 < kNumHeads) load_dz(tile, k + 1, nz0, nz1, nz2);
+          else if (it + 1 < my_tiles) load_dz(tile + gridDim.x, 0, nz0, nz1, nz2);
         }
         if (hsel == 1 && g >= 2) flush_dw(g - 2);
         if (hsel == 0 && c - 3 * k == 0) {
@@ -244,6 +252,9 @@ __global__ void __launch_bounds__(kThreads, 1) pair_bwd_prep_kernel(const __grid
         for (int piece = 0; piece < 2; ++piece) {
           uint32_t r[32];
           ptx::tmem_ld_x32(ut + 32 * piece, r);
+          float4 hb4[8];  // this piece's biases, fetched while the TMEM load is in flight
+#pragma unroll
+          for (int v = 0; v < 8; ++v) hb4[v] = *reinterpret_cast<const float4*>(hb + 32 * piece + 4 * v);
           ptx::tmem_ld_wait();
           if (piece == 1) {  // accumulator drained: release it to the MMA warp before the math / stores
             ptx::tc_fence_before();
@@ -266,7 +277,9 @@ __global__ void __launch_bounds__(kThreads, 1) pair_bwd_prep_kernel(const __grid
 #pragma unroll
               for (int e = 0; e < 2; ++e) {
                 const int col = 32 * piece + x + e;
-                const float h = __uint_as_float(r[x + e]) + hb[col];  // u / 2
+                const float4 hq = hb4[(x + e) / 4];
+                const float hbv = ((x + e) % 4 == 0) ? hq.x : ((x + e) % 4 == 1) ? hq.y : ((x + e) % 4 == 2) ? hq.z : hq.w;
+                const float h = __uint_as_float(r[x + e]) + hbv;  // u / 2
                 const float t = ptx::tanh_approx(h);
                 mv[e] = fmaf(h, t, h);                                  // SiLU(u) = u sigmoid(u) = h (1 + tanh h)
                 const float sg = fmaf(0.5f, t, 0.5f), oms = fmaf(-0.5f, t, 0.5f);
