@@ -439,18 +439,21 @@ constexpr int kD16 = 384;
 struct DzPtrs {
   const float* p[kNumHeads];
 };
+struct HeadPtrs {  // per-head gradient destinations, passed by value (no device-side pointer table, no sync)
+  float* p[kNumHeads];
+};
 constexpr int kDwPartCtas = 256;  // upper bound of T1's grid (one CTA per SM)
 __global__ void __launch_bounds__(128) dwout_finish_kernel(const float* __restrict__ part, int ctas,
-                                                           float* const* __restrict__ dWout) {
+                                                           HeadPtrs dWout) {
   const int fs = blockIdx.x * 128 + threadIdx.x;  // stacked feature index in [0, 1920)
   const int c = blockIdx.y;
   const int k = fs / kD16, f = fs - k * kD16;
   if (c >= head_classes(k)) return;
   float acc = 0.f;
   for (int b = 0; b < ctas; ++b) acc += part[((size_t)b * 3 + c) * (5 * kD16) + fs];
-  atomicAdd(&dWout[k][c * kD16 + f], acc);
+  atomicAdd(&dWout.p[k][c * kD16 + f], acc);
 }
-__global__ void __launch_bounds__(256) dbout_kernel(DzPtrs dz, int rows, float* const* __restrict__ dbout) {
+__global__ void __launch_bounds__(256) dbout_kernel(DzPtrs dz, int rows, HeadPtrs dbout) {
   const int k = blockIdx.y, C = head_classes(k);
   const float* p = dz.p[k];
   float a0 = 0.f, a1 = 0.f, a2 = 0.f;
@@ -463,8 +466,8 @@ __global__ void __launch_bounds__(256) dbout_kernel(DzPtrs dz, int rows, float* 
     a0 += __shfl_xor_sync(0xffffffffu, a0, o), a1 += __shfl_xor_sync(0xffffffffu, a1, o), a2 += __shfl_xor_sync(0xffffffffu, a2, o);
   }
   if (threadIdx.x % 32 == 0) {
-    atomicAdd(&dbout[k][0], a0), atomicAdd(&dbout[k][1], a1);
-    if (C == 3) atomicAdd(&dbout[k][2], a2);
+    atomicAdd(&dbout.p[k][0], a0), atomicAdd(&dbout.p[k][1], a1);
+    if (C == 3) atomicAdd(&dbout.p[k][2], a2);
   }
 }
 
@@ -614,7 +617,7 @@ int launch_heads_bwd(const peneo_dims& dm, int prec, const void* pack, const voi
   // ---- pair part, one chunk of whole pair-rows at a time
   float* dab = F(pl.off_dab);
   TRY(zero(dab, (size_t)T * 2 * d));
-  float **d_outw = nullptr, **d_outb = nullptr;
+  HeadPtrs d_outw{}, d_outb{};
   int dw_ctas = 0;
   if (tc) {
     int dev = 0;
@@ -625,13 +628,7 @@ int launch_heads_bwd(const peneo_dims& dm, int prec, const void* pack, const voi
     // bf16 per-token projections (0.5-scaled A | Bm) for T1, exactly what the forward pass used (same dropout)
     TRY(token_proj_fwd_bf16(dm, L, pk, x, x_dtype, x_row_stride, T, ws + pl.off_ab16, ws + pl.off_tokws, st,
                             drop.thresh ? &drop : nullptr));
-    // device tables of the per-head gradient pointers (15 pointers at the start of the token scratch tail)
-    float* h_tab[10];
-    for (int h = 0; h < kNumHeads; ++h) h_tab[h] = gr.out_w[h], h_tab[5 + h] = gr.out_b[h];
-    float** tab = reinterpret_cast<float**>(ws + pl.off_tokws + pl.tokws_bytes - 1024);
-    PENEO_CUDA_TRY(cudaMemcpyAsync(tab, h_tab, sizeof h_tab, cudaMemcpyHostToDevice, st));
-    PENEO_CUDA_TRY(cudaStreamSynchronize(st));  // h_tab lives on this stack frame
-    d_outw = tab, d_outb = tab + 5;
+    for (int h = 0; h < kNumHeads; ++h) d_outw.p[h] = gr.out_w[h], d_outb.p[h] = gr.out_b[h];
   }
   float *S = F(pl.off_S), *dS = F(pl.off_dS), *G = F(pl.off_G);
   const size_t cstride = fl((size_t)pl.chunk_rows_max * d) / sizeof(float);
