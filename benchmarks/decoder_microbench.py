@@ -43,7 +43,7 @@ def main():
             xs = [synth.hidden_states(b, n, 768, doc_id0=100 * r).to(dev, torch.bfloat16) for r in range(2)]
             texts = [[f"w{t} " for t in range(n)] for _ in range(b)]
             pipe = HeadsDecodePipeline(dec, dev)
-            steps = max(4, min(50, int(2e7 / (b * pairs)) + 1))
+            steps = max(8, min(50, int(2e7 / (b * pairs)) + 1))
 
             def run(k):
                 for s in range(k):
