@@ -245,6 +245,7 @@ def run_ours(args):
     run_steps(xs_host, 2, True)
     barrier()
     pipe.h2d_bytes = pipe.d2h_bytes = 0
+    pipe.wait_s = pipe.assemble_s = 0.0
     wall0 = time.perf_counter()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(pipe.compute)
@@ -291,6 +292,8 @@ def run_ours(args):
         "dtype": "bf16", "data": "synthetic", "config": workload_config(args, world),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": e2e_ms / args.steps,
+                "host_assemble_ms_per_step": pipe.assemble_s * 1e3 / args.steps,
+                "host_wait_gpu_ms_per_step": pipe.wait_s * 1e3 / args.steps,
                 "api": "peneo_b200.HeadsDecodePipeline.submit()/result(): pinned host hidden states in, reference 7-tuples out, 2 batches in flight"},
         "gpu_launches": int(launches),
         "clocks": clocks,

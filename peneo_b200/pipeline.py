@@ -9,6 +9,7 @@ unit that is sharded across GPUs (one pipeline per process / GPU, no collective)
 """
 from __future__ import annotations
 
+import time
 from collections import deque
 from typing import List, Optional, Sequence
 
@@ -29,6 +30,8 @@ class HeadsDecodePipeline:
         self.score_thresh = score_thresh
         self._queue = deque()
         self.h2d_bytes = 0
+        self.wait_s = 0.0      # result(): time blocked on the GPU
+        self.assemble_s = 0.0  # result(): time building the Python result objects
         self.d2h_bytes = 0
         self.k2_events = None  # set to a list to collect (start, stop) CUDA events around K2
 
@@ -67,11 +70,16 @@ class HeadsDecodePipeline:
         """Python results (one reference 7-tuple per document) of the oldest submitted batch.
         ``assemble=False`` returns the raw :class:`decode.DeviceDecode` (records on the host)."""
         pending, texts, bboxes = self._queue.popleft()
+        t0 = time.perf_counter()
         with torch.cuda.stream(self.compute):
             dd = pending.finish()
+        t1 = time.perf_counter()
+        self.wait_s += t1 - t0  # host blocked on the GPU (0 when the host is the slower side)
         if not assemble:
             return dd
-        return decode.assemble_many(dd, range(dd.batch), texts, bboxes)
+        out = decode.assemble_many(dd, range(dd.batch), texts, bboxes)
+        self.assemble_s += time.perf_counter() - t1
+        return out
 
     def __len__(self):
         return len(self._queue)
