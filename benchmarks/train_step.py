@@ -3,6 +3,7 @@ SIBR-shaped documents, timed with CUDA events.  Reports ms / step and the fracti
 against 3 x F_heads (what autograd would execute with stored activations).
 
     python benchmarks/train_step.py --seq-len 1024 --batch 4 --precision bf16
+    torchrun --nproc-per-node 2 --master-addr 127.0.0.1 benchmarks/train_step.py     # DDP: NCCL gradient all-reduce
 """
 import argparse
 import json
@@ -38,15 +39,23 @@ def main():
         peneo_b200_precision = args.precision
 
     n = args.seq_len - 1
+    world, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
     dec = PEneoDecoderB200(Cfg, 768)
     dec.load_state_dict(synth.init_decoder_state(seed=0))
     dec = dec.cuda().eval()
-    x = synth.hidden_states(args.batch, n, 768).cuda().requires_grad_(True)
-    docs = [synth.make_document(n, doc_id=i, style="sibr") for i in range(args.batch)]
+    module = dec
+    if world > 1:  # what HF Trainer does for the reference: DDP, one process per GPU, gradients averaged over NCCL
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dec = torch.nn.parallel.DistributedDataParallel(dec, device_ids=[local_rank])
+    x = synth.hidden_states(args.batch, n, 768, doc_id0=1000 * rank).cuda().requires_grad_(True)
+    docs = [synth.make_document(n, doc_id=1000 * rank + i, style="sibr") for i in range(args.batch)]
     tags = [torch.stack([d.tags()[k] for d in docs]).cuda() for k in range(5)]
 
     def step():
-        dec.zero_grad(set_to_none=True)
+        module.zero_grad(set_to_none=True)
         x.grad = None
         out = dec(x, None, *tags)
         out.loss.backward()
@@ -56,13 +65,16 @@ def main():
         step()
     torch.cuda.synchronize()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
-    fwd_ms = 0.0
     ev[0].record()
     for _ in range(args.steps):
         loss = step()
     ev[1].record()
     torch.cuda.synchronize()
     ms = ev[0].elapsed_time(ev[1]) / args.steps
+    if world > 1:
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
     p = n * (n + 1) // 2
     f_heads = 2.0 * n * (768 * 768 + 768 * 384 + 2 * 384 * 384) + 10.0 * p * 384 * 384 + 28.0 * p * 384
     peak = 1427.8
@@ -70,11 +82,15 @@ def main():
         peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops_sustained"]
     except Exception:
         pass
-    tf = 3.0 * f_heads * args.batch / (ms * 1e-3) / 1e12
-    print(json.dumps({"what": "decoder fine-tuning step (fwd + loss + bwd)", "precision": args.precision, "seq_len": args.seq_len,
-                      "batch": args.batch, "ms_per_step": ms, "docs_per_s": args.batch / (ms * 1e-3), "loss": float(loss),
+    tf = 3.0 * f_heads * args.batch / (ms * 1e-3) / 1e12  # per GPU
+    if rank == 0:
+        print(json.dumps({"what": "decoder fine-tuning step (fwd + loss + bwd" + (", DDP all-reduce)" if world > 1 else ")"),
+                      "precision": args.precision, "seq_len": args.seq_len, "n_gpus": world,
+                      "batch": args.batch, "ms_per_step": ms, "docs_per_s": world * args.batch / (ms * 1e-3), "loss": float(loss),
                       "tflops_vs_3F": tf, "frac_of_sustained_bf16_peak": tf / peak,
                       "peak_mem_gb": torch.cuda.max_memory_allocated() / 2**30}))
+    if world > 1:
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":
