@@ -200,7 +200,9 @@ int launch_gemm_tc(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* W, 
 constexpr int kG2Stages = 5;
 constexpr int kG2Smem = kG2Stages * kGemmStageBytes + 1024 + 256;
 
-template <int OUT>
+// ACT: 0 = linear, 1 = SiLU, 2 = SiLU + dropout (bf16 output only).  Compile-time so that the unrolled epilogue has no
+// per-element branches; SiLU is h + h tanh(h), h = v / 2 (one MUFU), as in K2.
+template <int OUT, int ACT>
 __global__ void __launch_bounds__(192, 1)
     gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                     const float* __restrict__ bias, void* __restrict__ Cv, int64_t ldc, int64_t M, int N, int K,
@@ -315,18 +317,30 @@ __global__ void __launch_bounds__(192, 1)
         if (m < M && nb < N) {
           if (OUT == 0) {
             uint32_t packed[16];
+            float bv[32];
+            if (bias) {  // 16-byte aligned (checked by the launcher), nb is a multiple of 32
+#pragma unroll
+              for (int x = 0; x < 32; x += 4) {
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + nb + x));
+                bv[x] = b4.x, bv[x + 1] = b4.y, bv[x + 2] = b4.z, bv[x + 3] = b4.w;
+              }
+            } else {
+#pragma unroll
+              for (int x = 0; x < 32; ++x) bv[x] = 0.f;
+            }
 #pragma unroll
             for (int x = 0; x < 32; x += 2) {
-              float v0 = __uint_as_float(r[x]) + (bias ? bias[nb + x] : 0.f);
-              float v1 = __uint_as_float(r[x + 1]) + (bias ? bias[nb + x + 1] : 0.f);
-              if (act) {
-                v0 = v0 / (1.f + __expf(-v0)), v1 = v1 / (1.f + __expf(-v1));
-                if (drop_thresh) {
-                  v0 = drop_keep(drop_key, drop_thresh, static_cast<uint32_t>(m), nb + x) ? v0 * drop_scale : 0.f;
-                  v1 = drop_keep(drop_key, drop_thresh, static_cast<uint32_t>(m), nb + x + 1) ? v1 * drop_scale : 0.f;
+              float v[2];
+#pragma unroll
+              for (int e = 0; e < 2; ++e) {
+                v[e] = __uint_as_float(r[x + e]) + bv[x + e];
+                if (ACT >= 1) {
+                  const float h = 0.5f * v[e];
+                  v[e] = fmaf(h, ptx::tanh_approx(h), h);
                 }
+                if (ACT == 2) v[e] = drop_keep(drop_key, drop_thresh, static_cast<uint32_t>(m), nb + x + e) ? v[e] * drop_scale : 0.f;
               }
-              packed[x / 2] = ptx::pack_bf16x2(v0, v1);
+              packed[x / 2] = ptx::pack_bf16x2(v[0], v[1]);
             }
             uint4* dst = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(Cv) + m * ldc + nb);
 #pragma unroll
@@ -388,21 +402,26 @@ int launch_gemm_tc2(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* W,
  const int grid = static_cast<int>(std::min<int64_t>(items, sms));
   const uint32_t d_th = (drop && act) ? drop->thresh : 0u, d_key = drop ? drop_key(*drop, site) : 0u;
   const float d_sc = drop ? drop->scale : 1.f;
-#define GO(OUT)                                                                                                      \
+#define GO(OUT, ACT)                                                                                                 \
   {                                                                                                                  \
     static bool attr_set = false;                                                                                    \
     if (!attr_set) {                                                                                                 \
-      PENEO_CUDA_TRY(cudaFuncSetAttribute(gemm_tc2_kernel<OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kG2Smem)); \
+      PENEO_CUDA_TRY(                                                                                                \
+          cudaFuncSetAttribute(gemm_tc2_kernel<OUT, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kG2Smem));    \
       attr_set = true;                                                                                               \
     }                                                                                                                \
-    gemm_tc2_kernel<OUT><<<grid, 192, kG2Smem, st>>>(tmA, tmW, bias, C, ldc, M, N, K, kb_per_split, splits, n_blocks,  \
-                                                     items, act, d_th, d_sc, d_key);                                 \
+    gemm_tc2_kernel<OUT, ACT><<<grid, 192, kG2Smem, st>>>(tmA, tmW, bias, C, ldc, M, N, K, kb_per_split, splits,      \
+                                                          n_blocks, items, act, d_th, d_sc, d_key);                  \
   }
+  PENEO_REQUIRE(out_mode == 0 || !act, "gemm_tc2: the activation is fused for the bf16 output only");
+  PENEO_REQUIRE((reinterpret_cast<uintptr_t>(bias) & 15) == 0, "gemm_tc2: bias not 16-byte aligned");
   switch (out_mode) {
-    case 0: GO(0) break;
-    case 1: GO(1) break;
-    case 2: GO(2) break;
-    default: GO(3) break;
+    case 0:
+      if (!act) GO(0, 0) else if (!d_th) GO(0, 1) else GO(0, 2)
+      break;
+    case 1: GO(1, 0) break;
+    case 2: GO(2, 0) break;
+    default: GO(3, 0) break;
   }
 #undef GO
   PENEO_CUDA_TRY(cudaGetLastError());
