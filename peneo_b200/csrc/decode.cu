@@ -32,10 +32,16 @@ __device__ __forceinline__ float round_like(float v) {
 // softmax over C classes the way ATen does it (exp(x - max) / sum in fp32, result rounded to the
 // tensor dtype), then argmax of the *probabilities* (first maximum) and its value.
 template <int DT, int C>
+__device__ __forceinline__ void classify_vals(const float* x, int& pred, float& score);
+template <int DT, int C>
 __device__ __forceinline__ void classify(const void* base, int64_t row, int& pred, float& score) {
   float x[C];
 #pragma unroll
   for (int c = 0; c < C; ++c) x[c] = load_as_float<DT>(base, row * C + c);
+  classify_vals<DT, C>(x, pred, score);
+}
+template <int DT, int C>
+__device__ __forceinline__ void classify_vals(const float* x, int& pred, float& score) {
   float m = x[0];
 #pragma unroll
   for (int c = 1; c < C; ++c) m = fmaxf(m, x[c]);
@@ -65,6 +71,50 @@ struct SpotArgs {
   int32_t* status;  // [batch*5*chunks] : inclusive prefix + 1, 0 = not ready
 };
 
+// fp32 logits, 16-byte aligned document: one warp iteration scans 128 pairs, 4 consecutive pairs per lane, read as
+// C float4 (every byte of the logits crosses the LSU once, in full 16-byte requests).  Same fast reject, same
+// ordered compaction (order inside the iteration = lane major, then the lane's 4 pairs).
+template <int C>
+__device__ __forceinline__ int scan_pairs_vec4(const float* __restrict__ doc, int pairs, int p0, int lane, int32_t* bp,
+                                               float* bs, uint8_t* bt) {
+  int cnt = 0;
+#pragma unroll 2
+  for (int it = 0; it < kSpotWarpPairs / 128; ++it) {
+    const int pl = p0 + it * 128 + lane * 4;
+    float x[4 * C];
+    if (pl + 3 < pairs) {
+      const float4* src = reinterpret_cast<const float4*>(doc + (int64_t)pl * C);
+#pragma unroll
+      for (int v = 0; v < C; ++v) {
+        const float4 t = __ldg(src + v);
+        x[4 * v] = t.x, x[4 * v + 1] = t.y, x[4 * v + 2] = t.z, x[4 * v + 3] = t.w;
+      }
+    } else {
+#pragma unroll
+      for (int e = 0; e < 4 * C; ++e) x[e] = (pl + e / C < pairs) ? doc[(int64_t)pl * C + e] : 0.f;
+    }
+    int pred[4];
+    float score[4];
+    unsigned mask[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      pred[k] = 0, score[k] = 1.f;
+      const float x0 = x[k * C];
+      float xo = x[k * C + 1];
+      if (C == 3) xo = fmaxf(xo, x[k * C + 2]);
+      if (pl + k < pairs && !(x0 >= xo)) classify_vals<PENEO_DT_F32, C>(x + k * C, pred[k], score[k]);
+      mask[k] = __ballot_sync(0xffffffffu, pred[k] != 0);
+    }
+    const unsigned lt = (1u << lane) - 1u;
+    int pos = cnt + __popc(mask[0] & lt) + __popc(mask[1] & lt) + __popc(mask[2] & lt) + __popc(mask[3] & lt);
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (pred[k] != 0) bp[pos] = pl + k, bs[pos] = score[k], bt[pos] = static_cast<uint8_t>(pred[k]), ++pos;
+    cnt += __popc(mask[0]) + __popc(mask[1]) + __popc(mask[2]) + __popc(mask[3]);
+  }
+  return cnt;
+}
+
 template <int DT>
 __global__ void __launch_bounds__(256) decode_spots_kernel(const SpotArgs a) {
   __shared__ int32_t buf_p[8][kSpotWarpPairs];
@@ -84,8 +134,17 @@ __global__ void __launch_bounds__(256) decode_spots_kernel(const SpotArgs a) {
   const int64_t doc_row0 = (int64_t)b * a.pairs;
   int cnt = 0;
   const int p0 = chunk * kSpotChunk + warp * kSpotWarpPairs;
+  bool scanned = false;
+  if constexpr (DT == PENEO_DT_F32) {
+    const float* doc = reinterpret_cast<const float*>(base) + doc_row0 * C;
+    if ((reinterpret_cast<uintptr_t>(doc) & 15) == 0) {
+      cnt = C == 2 ? scan_pairs_vec4<2>(doc, a.pairs, p0, lane, buf_p[warp], buf_s[warp], buf_t[warp])
+                   : scan_pairs_vec4<3>(doc, a.pairs, p0, lane, buf_p[warp], buf_s[warp], buf_t[warp]);
+      scanned = true;
+    }
+  }
 #pragma unroll 4
-  for (int it = 0; it < kSpotWarpPairs / 32; ++it) {
+  for (int it = 0; !scanned && it < kSpotWarpPairs / 32; ++it) {
     const int p = p0 + it * 32 + lane;
     int pred = 0;
     float score = 1.f;
