@@ -60,7 +60,6 @@ struct Args {
   uint32_t drop_thresh;  // training-mode dropout after the hidden SiLU (DROP instantiation only)
   float drop_scale;
   uint32_t drop_key[kNumHeads];
-  uint32_t dbg;  // PENEO_K2_DBG experiment bits (timing studies only; results are wrong when set)
 };
 
 template <bool DROP>
@@ -231,10 +230,8 @@ __global__ void __launch_bounds__(kThreads, 1)
             const float4 b4 = *reinterpret_cast<const float4*>(hb + 32 * piece + x);
             float m0 = __uint_as_float(r[x + 0]) + b4.x, m1 = __uint_as_float(r[x + 1]) + b4.y;
             float m2 = __uint_as_float(r[x + 2]) + b4.z, m3 = __uint_as_float(r[x + 3]) + b4.w;
-            if (!(a.dbg & 2u)) {  // (experiment bit 2: epilogue without the SiLU math)
-              m0 = ptx::silu_from_half(m0), m1 = ptx::silu_from_half(m1);
-              m2 = ptx::silu_from_half(m2), m3 = ptx::silu_from_half(m3);
-            }
+            m0 = ptx::silu_from_half(m0), m1 = ptx::silu_from_half(m1);
+            m2 = ptx::silu_from_half(m2), m3 = ptx::silu_from_half(m3);
             if (DROP) {  // nn.Dropout after the hidden SiLU (model/peneo_decoder.py:261), regenerable mask
               const uint32_t key = a.drop_key[c / 3], grow = static_cast<uint32_t>(drop_row);
               const uint32_t col = (c % 3) * 128 + 64 * hsel + 32 * piece + x;
