@@ -256,7 +256,7 @@ int launch_decode_spots(int batch, int n, const void* const in[kNumHeads], int i
 }
 
 // ------------------------------------------------------------------------------------------------
-// K4 : one CTA per document
+// K4 : K4a one CTA per (document, 1-1 map), K4b one CTA per document
 // ------------------------------------------------------------------------------------------------
 struct ResolveArgs {
   int32_t batch, n, cap, npow2, decode_gt;
@@ -431,18 +431,39 @@ __device__ __forceinline__ void chain_walk(int hd, int tl, const int32_t* le, co
   last_tail = cur_t;
 }
 
-__global__ void __launch_bounds__(256) decode_resolve_kernel(const ResolveArgs a) {
+// K4a: the three 1-1 maps of a document are independent -> one CTA per (document, map).
+//   y = 0: line extraction (head 0) ; y = 1: line grouping tail-to-tail (head 4) ; y = 2: line grouping head-to-head (head 3)
+__global__ void __launch_bounds__(256) decode_maps_kernel(const ResolveArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int n = a.n, np2 = a.npow2, b = blockIdx.x;
+  const int n = a.n, np2 = a.npow2, b = blockIdx.x, which = blockIdx.y;
   unsigned long long* best1 = reinterpret_cast<unsigned long long*>(smem_raw);
   unsigned long long* best2 = best1 + n;
   unsigned long long* sortbuf = best2 + n;
   uint32_t* first = reinterpret_cast<uint32_t*>(sortbuf + np2);
   uint32_t* ord2 = first + n;
-  int32_t* le = reinterpret_cast<int32_t*>(ord2 + n);
+  int32_t* map = reinterpret_cast<int32_t*>(ord2 + n);
+  __shared__ int32_t s_count;
+
+  int32_t* out = a.out + (int64_t)b * a.doc_ints;
+  const int h = which == 0 ? 0 : (which == 1 ? 4 : 3);
+  int32_t* o_pairs = out + 16 + (which == 0 ? 0 : (which == 1 ? 4 * n : 2 * n));  // o_le | o_lgh | o_lgt order in the record
+  SpotList L;
+  const int64_t off = ((int64_t)b * kNumHeads + h) * a.cap;
+  L.p = a.spot_p + off, L.tag = a.spot_tag + off, L.score = a.spot_score + off;
+  L.cnt = min(a.counts[b * kNumHeads + h], a.cap);
+  const int cnt = resolve_map(L, n, np2, which != 0, a.decode_gt == 0, a.thresh, best1, best2, first, ord2, sortbuf, map,
+                              o_pairs, &s_count);
+  if (threadIdx.x == 0) out[which == 0 ? 0 : (which == 1 ? 2 : 1)] = cnt;  // n_le | n_lgt | n_lgh
+}
+
+// K4b: one CTA per document: entity-linking edge lists and the key/value chain walk over the maps of K4a
+__global__ void __launch_bounds__(256) decode_links_kernel(const ResolveArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int n = a.n, b = blockIdx.x;
+  int32_t* le = reinterpret_cast<int32_t*>(smem_raw);
   int32_t* lgh = le + n;
   int32_t* lgt = lgh + n;
-  __shared__ int32_t s_count, s_run, s_warp[8];
+  __shared__ int32_t s_run, s_warp[8];
 
   int32_t* out = a.out + (int64_t)b * a.doc_ints;
   int32_t* o_le = out + 16;
@@ -459,10 +480,14 @@ __global__ void __launch_bounds__(256) decode_resolve_kernel(const ResolveArgs a
     L.cnt = min(a.counts[b * kNumHeads + h], a.cap);
     return L;
   };
-  const bool top = a.decode_gt == 0;
-  const int n_le = resolve_map(list(0), n, np2, false, top, a.thresh, best1, best2, first, ord2, sortbuf, le, o_le, &s_count);
-  const int n_lgt = resolve_map(list(4), n, np2, true, top, a.thresh, best1, best2, first, ord2, sortbuf, lgt, o_lgt, &s_count);
-  const int n_lgh = resolve_map(list(3), n, np2, true, top, a.thresh, best1, best2, first, ord2, sortbuf, lgh, o_lgh, &s_count);
+  // dense maps back from the (head, tail) lists K4a wrote (heads are unique within a map)
+  const int n_le = out[0], n_lgh = out[1], n_lgt = out[2];
+  for (int t = threadIdx.x; t < 3 * n; t += blockDim.x) le[t] = -1;
+  __syncthreads();
+  for (int r = threadIdx.x; r < n_le; r += blockDim.x) le[o_le[2 * r]] = o_le[2 * r + 1];
+  for (int r = threadIdx.x; r < n_lgh; r += blockDim.x) lgh[o_lgh[2 * r]] = o_lgh[2 * r + 1];
+  for (int r = threadIdx.x; r < n_lgt; r += blockDim.x) lgt[o_lgt[2 * r]] = o_lgt[2 * r + 1];
+  __syncthreads();
 
   uint32_t* bitmap = a.bitmap + (int64_t)b * a.bitmap_words;
   const int n_elt = emit_edges(list(2), n, a.thresh, o_elt, bitmap, s_warp, &s_run);
@@ -508,7 +533,7 @@ __global__ void __launch_bounds__(256) decode_resolve_kernel(const ResolveArgs a
     __syncthreads();
   }
   if (tid == 0) {
-    out[0] = n_le, out[1] = n_lgh, out[2] = n_lgt, out[3] = n_elh, out[4] = n_elt, out[5] = s_run;
+    out[3] = n_elh, out[4] = n_elt, out[5] = s_run;
     for (int q = 6; q < 16; ++q) out[q] = 0;
   }
 }
@@ -535,10 +560,12 @@ int launch_decode_resolve(int batch, int n, int cap, const int32_t* spot_p, cons
   a.bitmap = static_cast<uint32_t*>(ws);
   a.bitmap_words = ((int64_t)n * n + 31) / 32;
   PENEO_CUDA_TRY(cudaMemsetAsync(ws, 0, decode_resolve_workspace_bytes(batch, n), st));
-  const size_t smem = (size_t)(2 * n + np2) * 8 + (size_t)5 * n * 4;
-  PENEO_CUDA_TRY(cudaFuncSetAttribute(decode_resolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      static_cast<int>(smem)));
-  decode_resolve_kernel<<<batch, 256, smem, st>>>(a);
+  const size_t smem_a = (size_t)(2 * n + np2) * 8 + (size_t)3 * n * 4, smem_b = (size_t)3 * n * 4;
+  PENEO_CUDA_TRY(cudaFuncSetAttribute(decode_maps_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_a)));
+  PENEO_CUDA_TRY(cudaFuncSetAttribute(decode_links_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_b)));
+  decode_maps_kernel<<<dim3(batch, 3), 256, smem_a, st>>>(a);
+  PENEO_CUDA_TRY(cudaGetLastError());
+  decode_links_kernel<<<batch, 256, smem_b, st>>>(a);
   PENEO_CUDA_TRY(cudaGetLastError());
   return PENEO_OK;
 }

@@ -117,7 +117,7 @@ class PendingDecode:
                                      _thresh_f32(self.score_thresh), rec.data_ptr(), ws2.data_ptr(), _stream(dev)),
             "peneo_decode_resolve",
         )
-        COUNTERS["kernels"] += 2
+        COUNTERS["kernels"] += 3  # K3 spots, K4a maps, K4b links
         self.counts_h = torch.empty(counts.shape, dtype=torch.int32, pin_memory=True)
         self.rec_h = torch.empty(rec.shape, dtype=torch.int32, pin_memory=True)
         cur = torch.cuda.current_stream(dev)
