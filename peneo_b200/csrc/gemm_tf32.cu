@@ -132,6 +132,9 @@ __global__ void __launch_bounds__(192, 1)
     }
   } else {
     const int q = warp % 4;
+    const bool vec_ok = a.ldc % 4 == 0 && (reinterpret_cast<uintptr_t>(a.C) & 15) == 0 &&
+                        (reinterpret_cast<uintptr_t>(a.bias) & 15) == 0 &&
+                        (a.C2 == nullptr || (a.ldc2 % 4 == 0 && (reinterpret_cast<uintptr_t>(a.C2) & 15) == 0));
     int it = 0;
     for (int64_t item = blockIdx.x; item < a.num_items; item += gridDim.x, ++it) {
       int m0, n0, kb0, nk;
@@ -153,6 +156,57 @@ __global__ void __launch_bounds__(192, 1)
         const int nb = n0 + piece * 32;
         if (m >= a.M) continue;
         float* dst = a.C + (int64_t)m * a.ldc + nb;
+        if (vec_ok && nb + 32 <= a.N) {
+          // fast path (every GEMM of the decoder: N % 32 == 0, 16-byte aligned rows): straight-line float4 code, the
+          // mode / bias / C2 decisions are made once per 32 columns instead of once per element
+          if (a.mode == 2) {
+#pragma unroll
+            for (int x = 0; x < 32; x += 4)
+              atomicAdd(reinterpret_cast<float4*>(dst + x),
+                        make_float4(__uint_as_float(r[x]), __uint_as_float(r[x + 1]), __uint_as_float(r[x + 2]),
+                                    __uint_as_float(r[x + 3])));
+            continue;
+          }
+          float v[32];
+#pragma unroll
+          for (int x = 0; x < 32; ++x) v[x] = __uint_as_float(r[x]);
+          if (a.bias) {
+#pragma unroll
+            for (int x = 0; x < 32; x += 4) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(a.bias + nb + x));
+              v[x] += b4.x, v[x + 1] += b4.y, v[x + 2] += b4.z, v[x + 3] += b4.w;
+            }
+          }
+          if (a.mode == 1) {
+#pragma unroll
+            for (int x = 0; x < 32; x += 4) {
+              const float4 o = *reinterpret_cast<const float4*>(dst + x);
+              v[x] += o.x, v[x + 1] += o.y, v[x + 2] += o.z, v[x + 3] += o.w;
+            }
+          }
+#pragma unroll
+          for (int x = 0; x < 32; x += 4) *reinterpret_cast<float4*>(dst + x) = make_float4(v[x], v[x + 1], v[x + 2], v[x + 3]);
+          if (a.C2) {
+            float* dst2 = a.C2 + (int64_t)m * a.ldc2 + nb;
+            const bool drop = a.drop_thresh != 0;
+#pragma unroll
+            for (int x = 0; x < 32; x += 4) {
+              float h[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float hh = 0.5f * v[x + e];
+                h[e] = fmaf(hh, ptx::tanh_approx(hh), hh);  // SiLU with one MUFU, as everywhere in the bf16 mode
+              }
+              if (drop) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                  h[e] = drop_keep(a.drop_key, a.drop_thresh, a.row0 + m, nb + x + e) ? h[e] * a.drop_scale : 0.f;
+              }
+              *reinterpret_cast<float4*>(dst2 + x) = make_float4(h[0], h[1], h[2], h[3]);
+            }
+          }
+          continue;
+        }
 #pragma unroll
         for (int x = 0; x < 32; ++x) {
           const int n = nb + x;
