@@ -68,21 +68,33 @@ __global__ void __launch_bounds__(256) pair_loss_partial_kernel(const LossArgs a
   }
 }
 
-__global__ void pair_loss_final_kernel(const LossArgs a, int nblocks) {
-  if (threadIdx.x != 0) return;
-  double total = 0.0;
-  for (int h = 0; h < kNumHeads; ++h) {
-    double tl = 0.0, tw = 0.0;
-    for (int b = 0; b < nblocks; ++b) {
-      tl += a.partial[((int64_t)h * nblocks + b) * 2 + 0];
-      tw += a.partial[((int64_t)h * nblocks + b) * 2 + 1];
-    }
+// One warp per head: lane l adds the partials of blocks l, l + 32, ... in order, then a fixed shuffle tree —
+// deterministic, and 32 loads in flight instead of one thread walking 2 * 5 * nblocks doubles.
+__global__ void __launch_bounds__(32 * kNumHeads) pair_loss_final_kernel(const LossArgs a, int nblocks) {
+  __shared__ double s_loss[kNumHeads];
+  const int h = threadIdx.x / 32, lane = threadIdx.x % 32;
+  double tl = 0.0, tw = 0.0;
+  for (int b = lane; b < nblocks; b += 32) {
+    tl += a.partial[((int64_t)h * nblocks + b) * 2 + 0];
+    tw += a.partial[((int64_t)h * nblocks + b) * 2 + 1];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    tl += __shfl_xor_sync(0xffffffffu, tl, o);
+    tw += __shfl_xor_sync(0xffffffffu, tw, o);
+  }
+  if (lane == 0) {
     a.final_[h * 2 + 0] = tl, a.final_[h * 2 + 1] = tw;
     const double lh = tl / tw;
     a.out6[h] = static_cast<float>(lh);
-    total += static_cast<double>(a.ratio[h]) * lh;
+    s_loss[h] = static_cast<double>(a.ratio[h]) * lh;
   }
-  a.out6[5] = static_cast<float>(total);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double total = 0.0;
+    for (int k = 0; k < kNumHeads; ++k) total += s_loss[k];
+    a.out6[5] = static_cast<float>(total);
+  }
 }
 
 __global__ void __launch_bounds__(256) pair_loss_bwd_kernel(const LossArgs a) {
@@ -125,7 +137,7 @@ int launch_pair_loss_fwd(int batch, int n, const float* const logits[kNumHeads],
   a.out6 = out6;
   pair_loss_partial_kernel<<<dim3(kLossBlocks, kNumHeads), 256, 0, st>>>(a);
   PENEO_CUDA_TRY(cudaGetLastError());
-  pair_loss_final_kernel<<<1, 32, 0, st>>>(a, kLossBlocks);
+  pair_loss_final_kernel<<<1, 32 * kNumHeads, 0, st>>>(a, kLossBlocks);
   PENEO_CUDA_TRY(cudaGetLastError());
   return PENEO_OK;
 }
