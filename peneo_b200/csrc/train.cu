@@ -1,6 +1,7 @@
-// Backward of the decoder heads, PENEO_PREC_FP32 (CUDA-core fp32, every configuration the reference
-// accepts).  What autograd does for model/peneo_decoder.py:349-363 in the reference, restated as
-// explicit kernels:
+// Backward of the decoder heads: the driver (peneo_heads_bwd) for both precisions, the CUDA-core fp32 kernels
+// (PENEO_PREC_FP32: every configuration the reference accepts) and the element-wise / reduction kernels of the bf16
+// mode (whose tensor-core kernels live in pair_bwd_tc.cu, gemm_bwd_tc.cu, gemm_tf32.cu).  What autograd does for
+// model/peneo_decoder.py:349-363 in the reference, restated as explicit kernels:
 //
 //   g_z   = dlogits                                  (from peneo_pair_loss_bwd / peneo_pair_loss_ohem)
 //   dW_out += g_z^T m ,  db_out += sum g_z           m = SiLU(u_last)
@@ -666,7 +667,8 @@ int launch_heads_bwd(const peneo_dims& dm, int prec, const void* pack, const voi
         __nv_bfloat16* S16 = reinterpret_cast<__nv_bfloat16*>(ws + pl.off_S16);
         __nv_bfloat16* Gc = reinterpret_cast<__nv_bfloat16*>(ws + pl.off_Gc);
         const __nv_bfloat16* ab16 = reinterpret_cast<const __nv_bfloat16*>(ws + pl.off_ab16);
-        // T1: regenerate S, M = SiLU(u), G = (dz W_out) SiLU'(u) for the five heads (tcgen05, K2's structure)
+        // T1: regenerate S and u, store S and G = (dz W_out) SiLU'(u), reduce dW_out += dz^T SiLU(u) into the per-CTA
+        // partial sums (tcgen05, K2's structure)
         TRY(launch_pair_bwd_prep(pack, L, ab16, n, g0, rows, dlogits, S16, Gc, F(pl.off_dwpart), st,
                                  drop.thresh ? &drop : nullptr));
         // dS = G W_mid (all heads in one K = 1920 GEMM) ; dW_mid += G^T S
