@@ -62,7 +62,7 @@ def main():
             yield x, [[f"w{t} " for t in range(n)]] * len(g)
 
     # warm-up on a few small groups, then the timed pass over everything
-    for i, _ in enumerate(pipe.run((b for j, b in enumerate(feed()) if j < 3), depth=2)):
+    for i, _ in enumerate(pipe.run((b for j, b in enumerate(feed()) if j < 3), depth=3)):
         pass
     if world > 1:
         dist.barrier()
@@ -71,7 +71,7 @@ def main():
     t0 = time.perf_counter()
     e0.record(pipe.compute)
     ndocs = npairs = 0
-    for g, res in zip(groups, pipe.run(feed(), depth=2)):
+    for g, res in zip(groups, pipe.run(feed(), depth=3)):
         ndocs += len(res)
         npairs += len(g) * shard.pair_cost(lens[g[0]])
     e1.record(pipe.compute)
