@@ -64,6 +64,7 @@ def main():
     # warm-up on a few small groups, then the timed pass over everything
     for i, _ in enumerate(pipe.run((b for j, b in enumerate(feed()) if j < 3), depth=3)):
         pass
+    pipe.freeze_host_gc()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
