@@ -32,3 +32,22 @@ def test_reference_arm_non_zero_rank_is_silent():
     out = _run({"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"}, "--impl", "reference", "--steps", "1", "--warmup", "0",
                "--seq-len", "64", "--gpus", "2")
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def test_benchmark_scripts_parse_and_pipeline_defaults():
+    """Every script under benchmarks/ is valid Python; the serving loop keeps three batches in flight and offers the
+    GC freeze the end-to-end leg of bench.py relies on."""
+    import ast
+    import glob
+    import inspect
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    scripts = sorted(glob.glob(os.path.join(root, "benchmarks", "*.py")))
+    assert scripts, "benchmarks/ is empty"
+    for path in scripts:
+        with open(path) as f:
+            ast.parse(f.read(), filename=path)
+    from peneo_b200 import HeadsDecodePipeline
+
+    assert inspect.signature(HeadsDecodePipeline.run).parameters["depth"].default == 3
+    assert callable(HeadsDecodePipeline.freeze_host_gc)
