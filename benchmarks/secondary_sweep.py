@@ -1,11 +1,11 @@
 """SURVEY.md §8(d) secondary sweeps: the configurations next to the shipped one (hidden 768 -> d 384, L = 2), each
-through the same plugin call (HeadsDecodePipeline: heads + decode, device-resident inputs):
+through the same plugin call (PEneoDecoderB200.forward in inference mode: the five logits tensors, device-resident inputs):
 
-    Hin = 960 (LiLT width), shrink on, L = 2     -> bf16 tensor-core path (K1 takes any Hin)
-    L = 1 (no hidden layer in the heads)         -> fp32 CUDA-core path, SiLU / MUFU regime
-    shrink off (D = Hin = 768)                   -> fp32 CUDA-core path, 4x the pair flops of D = 384
+    Hin = 960 (LiLT width), shrink on, L = 2     -> fused tcgen05 path (K1 takes any Hin)
+    L = 1 / L = 3, shrink off (D = Hin = 768)    -> unfused tensor-core forward (pair_heads_generic.cu) and, for
+                                                    comparison, the exact fp32 CUDA-core path
 
-One JSON line per configuration.  trained_like weights (logits O(1), class 0 favoured) keep the decode sparse.
+One JSON line per configuration.
 
     python benchmarks/secondary_sweep.py [--seq-len 512] [--batch 8]
 """
@@ -19,7 +19,7 @@ sys.path.insert(0, ROOT)
 
 import torch  # noqa: E402
 
-from peneo_b200 import HeadsDecodePipeline, PEneoDecoderB200, synth  # noqa: E402
+from peneo_b200 import PEneoDecoderB200, synth  # noqa: E402
 
 
 def make_cfg(shrink, layers, precision):
@@ -49,8 +49,11 @@ def main():
     cases = [
         ("shipped: Hin 768, shrink, L=2", 768, True, 2, "bf16"),
         ("Hin 960 (LiLT), shrink, L=2", 960, True, 2, "bf16"),
-        ("L=1", 768, True, 1, "fp32"),
-        ("shrink off (D = 768), L=2", 768, False, 2, "fp32"),
+        ("L=1, unfused tensor-core forward", 768, True, 1, "bf16"),
+        ("L=1, fp32 CUDA-core path", 768, True, 1, "fp32"),
+        ("shrink off (D = 768), L=2, unfused tensor-core forward", 768, False, 2, "bf16"),
+        ("shrink off (D = 768), L=2, fp32 CUDA-core path", 768, False, 2, "fp32"),
+        ("L=3, unfused tensor-core forward", 768, True, 3, "bf16"),
         ("shipped configuration on the fp32 CUDA-core path", 768, True, 2, "fp32"),
     ]
     for name, hin, shrink, layers, prec in cases:
@@ -61,31 +64,27 @@ def main():
         dec = dec.to(dev).eval()
         dt = torch.bfloat16 if prec == "bf16" else torch.float32
         xs = [synth.hidden_states(args.batch, n, hin, doc_id0=100 * r).to(dev, dt) for r in range(2)]
-        texts = [[f"w{t} " for t in range(n)] for _ in range(args.batch)]
-        pipe = HeadsDecodePipeline(dec, dev)
-
+        # heads only (token projections + pair heads through PEneoDecoderB200.forward): with uncalibrated weights these
+        # configurations emit dense "spots", and the decode of dense garbage would dominate a heads + decode number
         def run(k):
-            for s in range(k):
-                pipe.submit(xs[s % 2], texts)
-                if len(pipe) >= 2:
-                    pipe.result(assemble=False)
-            while len(pipe):
-                pipe.result(assemble=False)
+            with torch.no_grad():
+                for s in range(k):
+                    dec(xs[s % 2])
 
         run(3)
         torch.cuda.synchronize()
         t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        t0.record(pipe.compute)
+        t0.record()
         run(args.steps)
-        t1.record(pipe.compute)
+        t1.record()
         torch.cuda.synchronize()
         ms = t0.elapsed_time(t1) / args.steps
         per_token = 2.0 * n * ((hin * 768 + 768 * d) if shrink else 0) + 2.0 * n * 2 * d * d
-        f_heads = per_token + (10.0 * pairs * d * d if layers == 2 else 0.0) + 28.0 * pairs * d
+        f_heads = per_token + 10.0 * pairs * d * d * (layers - 1) + 28.0 * pairs * d
         print(json.dumps({"config": name, "hin": hin, "d": d, "layers": layers, "precision": prec, "seq_len": args.seq_len,
                           "batch": args.batch, "ms_per_step": round(ms, 3), "docs_per_s": round(args.batch / (ms * 1e-3), 1),
                           "tflops": round(args.batch * f_heads / (ms * 1e-3) / 1e12, 1)}), flush=True)
-        del pipe, xs, dec
+        del xs, dec
         torch.cuda.empty_cache()
 
 

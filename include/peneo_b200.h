@@ -45,7 +45,7 @@ extern "C" {
 
 /* arithmetic modes of the heads */
 #define PENEO_PREC_FP32 0 /* CUDA-core fp32, exact SiLU: meets the 1e-3 logit tolerance */
-#define PENEO_PREC_BF16 1 /* tcgen05 bf16 x bf16 -> fp32: meets the 2e-2 logit tolerance */
+#define PENEO_PREC_BF16 1 /* tcgen05 bf16 x bf16 -> fp32: meets the 2e-2 logit tolerance (see peneo_pack_bytes) */
 
 /* element types of caller tensors */
 #define PENEO_DT_F32 0
@@ -92,8 +92,11 @@ typedef struct peneo_dropout {
   uint64_t seed; /* fresh per training step */
 } peneo_dropout;
 
-/* Bytes of the packed-weight buffer for (dims, prec).  0 if the combination is unsupported
- * (PENEO_PREC_BF16 needs shrink-style d == 384 and num_layers == 2). */
+/* Bytes of the packed-weight buffer for (dims, prec).  0 if the combination is unsupported.
+ * PENEO_PREC_BF16: hin, hid and d in multiples of 64.  shrink = 1, hid = 768 (d = 384), num_layers = 2 runs the fused
+ * tcgen05 kernels, forward and backward; every other configuration runs an unfused tensor-core FORWARD
+ * (peneo_token_proj_fwd / peneo_pair_heads_fwd without dropout) and has to be trained with PENEO_PREC_FP32:
+ * peneo_heads_bwd returns PENEO_E_INVALID for it. */
 size_t peneo_pack_bytes(const peneo_dims* dims, int prec);
 /* Convert the fp32 parameters into the kernel layouts (bf16 copies, concatenated and pre-scaled
  * matrices).  Call again whenever a parameter changed. */

@@ -33,8 +33,9 @@ static int check_dims(const peneo_dims* dm) {
 
 static int check_prec(const peneo_dims* dm, int prec) {
   PENEO_REQUIRE(prec == PENEO_PREC_FP32 || prec == PENEO_PREC_BF16, "unknown precision mode %d", prec);
-  if (prec == PENEO_PREC_BF16 && !bf16_supported(*dm)) {
-    set_error("PENEO_PREC_BF16 needs shrink=1, hid=768, d=384, num_layers=2, hin %% 64 == 0 (got shrink=%d hid=%d d=%d L=%d hin=%d)",
+  if (prec == PENEO_PREC_BF16 && !bf16_supported(*dm) && !bf16_generic_supported(*dm)) {
+    set_error("PENEO_PREC_BF16 needs hin, hid and d in multiples of 64 (fused path: shrink=1, hid=768, d=384, num_layers=2); "
+              "got shrink=%d hid=%d d=%d L=%d hin=%d",
               dm->shrink, dm->hid, dm->d, dm->num_layers, dm->hin);
     return PENEO_E_INVALID;
   }
@@ -57,6 +58,10 @@ int token_proj_fwd_bf16(const peneo_dims& dm, const PackLayout& L, const char* p
     if ((rc = launch_cast_rows(x, x_dtype, x_row_stride, xc, PENEO_DT_BF16, tokens, dm.hin, st)) != PENEO_OK) return rc;
     xin = xc, ldx = dm.hin;
   }
+  if (!dm.shrink)  // combine_fc reads the backbone output directly
+    return launch_gemm_tc2(xin, ldx, reinterpret_cast<const __nv_bfloat16*>(pk + L.wc_bf16), dm.d,
+                           reinterpret_cast<const float*>(pk + L.bc_half), static_cast<__nv_bfloat16*>(ab), 2 * dm.d, tokens,
+                           2 * dm.d, dm.d, 0, 1, st, 0);
   // persistent tcgen05 GEMM chain (gemm_tc2): x -> y1 -> y -> (0.5 A | 0.5 Bm)
   if ((rc = launch_gemm_tc2(xin, ldx, reinterpret_cast<const __nv_bfloat16*>(pk + L.w1_bf16), dm.hin,
                             reinterpret_cast<const float*>(pk + L.b1), y1, dm.hid, tokens, dm.hid, dm.hin, 0, 1, st, 1, dp,
@@ -183,6 +188,10 @@ int peneo_pair_heads_fwd(const peneo_dims* dims, int prec, const void* pack, con
   const DropSpec* dp = drop.thresh ? &drop : nullptr;
   if (prec == PENEO_PREC_FP32)
     return launch_pair_heads_simt(*dims, pack, static_cast<const float*>(ab), batch, n, logits, st, dp);
+  if (!bf16_supported(*dims)) {  // unfused tensor-core forward (inference: the decoder's dropout is not available here)
+    PENEO_REQUIRE(dp == nullptr, "pair_heads_fwd: training-mode dropout needs PENEO_PREC_FP32 for this configuration");
+    return launch_pair_heads_generic(*dims, pack, pack_layout(*dims, prec), static_cast<const __nv_bfloat16*>(ab), batch, n, logits, st);
+  }
   // Default: the CTA-pair (cta_group::2, M = 256) variant of K2 — same results, half the W_mid traffic per SM,
   // ~3 % faster under the sustained power cap.  PENEO_K2_PAIR=0 selects the single-CTA kernel (A/B studies).
   static const bool use_pair = [] { const char* e = getenv("PENEO_K2_PAIR"); return !e || atoi(e) != 0; }();
@@ -193,6 +202,7 @@ int peneo_pair_heads_fwd(const peneo_dims* dims, int prec, const void* pack, con
 
 size_t peneo_heads_bwd_workspace_bytes(const peneo_dims* dims, int prec, int32_t batch, int32_t n) {
   if (check_dims(dims) != PENEO_OK || check_prec(dims, prec) != PENEO_OK || batch < 0 || n < 1) return 0;
+  if (prec == PENEO_PREC_BF16 && !bf16_supported(*dims)) return 0;  // forward only: train this configuration in fp32
   return heads_bwd_workspace_bytes(*dims, prec, batch, n);
 }
 
@@ -201,6 +211,8 @@ int peneo_heads_bwd(const peneo_dims* dims, int prec, const void* pack, const vo
                     float* dx, void* workspace, const peneo_dropout* dropout, void* stream) {
   int rc;
   if ((rc = check_dims(dims)) != PENEO_OK || (rc = check_prec(dims, prec)) != PENEO_OK) return rc;
+  PENEO_REQUIRE(prec == PENEO_PREC_FP32 || bf16_supported(*dims),
+                "heads_bwd: PENEO_PREC_BF16 is forward-only for this configuration, train it with PENEO_PREC_FP32");
   PENEO_REQUIRE(pack && x && dlogits && grads && workspace, "heads_bwd: NULL pointer");
   PENEO_REQUIRE(batch >= 1 && n >= 1 && n <= 46340, "heads_bwd: bad sizes batch=%d n=%d", batch, n);
   PENEO_REQUIRE((int64_t)batch * n < (1ll << 31), "heads_bwd: too many tokens");

@@ -120,11 +120,17 @@ struct PackLayout {
   // f_out_w, f_out_b), which the bf16 pack also carries.
   size_t wmid_full_bf16, wmidT_bf16, bmid_full;
   size_t wout_f32x4;  // [5d] float4: (W_out[0][f], W_out[1][f], W_out[2][f] or 0, 0) per stacked mid feature
+  // PENEO_PREC_BF16 for every other configuration (unfused tensor-core forward, pair_heads_generic.cu): w1 / w2 / wc
+  // as above (w1 / w2 only with shrink), plus per head and layer the bf16 [d, d] hidden weights (unscaled), fp32
+  // biases, and the output layer zero-padded to 32 rows ([32, d] bf16, bias fp32 [32]).
+  size_t g_mid_w[kNumHeads][kMaxMidLayers], g_mid_b[kNumHeads][kMaxMidLayers];
+  size_t g_out_w[kNumHeads], g_out_b[kNumHeads];
   size_t total;
 };
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+inline bool bf16_supported(const peneo_dims& dm);
 inline PackLayout pack_layout(const peneo_dims& dm, int prec) {
   PackLayout L{};
   size_t off = 0;
@@ -144,6 +150,16 @@ inline PackLayout pack_layout(const peneo_dims& dm, int prec) {
       for (int l = 0; l + 1 < dm.num_layers; ++l) L.f_mid_w[h][l] = take(d * d * 4), L.f_mid_b[h][l] = take(d * 4);
       L.f_out_w[h] = take(head_classes(h) * d * 4), L.f_out_b[h] = take(16);
     }
+  } else if (!bf16_supported(dm)) {
+    if (dm.shrink) {
+      L.w1_bf16 = take(hid * hin * 2), L.b1 = take(hid * 4);
+      L.w2_bf16 = take(d * hid * 2), L.b2 = take(d * 4);
+    }
+    L.wc_bf16 = take(2 * d * d * 2), L.bc_half = take(2 * d * 4);
+    for (int h = 0; h < kNumHeads; ++h) {
+      for (int l = 0; l + 1 < dm.num_layers; ++l) L.g_mid_w[h][l] = take(d * d * 2), L.g_mid_b[h][l] = take(d * 4);
+      L.g_out_w[h] = take(32 * d * 2), L.g_out_b[h] = take(32 * 4);
+    }
   } else {
     L.w1_bf16 = take(hid * hin * 2), L.b1 = take(hid * 4);
     L.w2_bf16 = take(d * hid * 2), L.b2 = take(d * 4);
@@ -161,8 +177,14 @@ inline PackLayout pack_layout(const peneo_dims& dm, int prec) {
   return L;
 }
 
+// fused tcgen05 path (K2 / T1): the shipped configuration
 inline bool bf16_supported(const peneo_dims& dm) {
   return dm.shrink == 1 && dm.d == 384 && dm.hid == 768 && dm.num_layers == 2 && dm.hin % 64 == 0;
+}
+// unfused tensor-core forward for the other configurations (inference only): widths in whole 64-element K blocks
+inline bool bf16_generic_supported(const peneo_dims& dm) {
+  return !bf16_supported(dm) && dm.d % 64 == 0 && dm.hin % 64 == 0 && (!dm.shrink || dm.hid % 64 == 0) &&
+         dm.num_layers >= 1 && dm.num_layers <= kMaxMidLayers + 1;
 }
 
 }  // namespace peneo

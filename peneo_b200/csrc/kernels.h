@@ -35,6 +35,12 @@ int launch_pair_heads_tc(const void* pack, const PackLayout& L, const __nv_bfloa
 int launch_pair_heads_tc_pair(const void* pack, const PackLayout& L, const __nv_bfloat16* ab, int batch, int n,
                               float* const logits[kNumHeads], cudaStream_t st, const DropSpec* drop = nullptr);
 
+// pair_heads_generic.cu : unfused tensor-core forward for the configurations K2 does not cover (any d % 64 == 0, any
+// num_layers): S = SiLU(a_i + b_j) per chunk of pairs, one gemm_tc2 per hidden layer and head, output layer as an
+// N = 32 GEMM
+int launch_pair_heads_generic(const peneo_dims& dm, const void* pack, const PackLayout& L, const __nv_bfloat16* ab, int batch,
+                              int n, float* const logits[kNumHeads], cudaStream_t st);
+
 // pair_bwd_tc.cu : regenerated S and G = (dz W_out) SiLU'(u) of a chunk of pairs, plus per-CTA partial sums
 // [ctas][3][1920] of dz^T SiLU(u) (bf16 backward)
 int launch_pair_bwd_prep(const void* pack, const PackLayout& L, const __nv_bfloat16* ab, int n, int64_t g0, int rows,

@@ -203,6 +203,29 @@ int pack_weights_impl(const peneo_dims& dm, int prec, const peneo_params& P, voi
       TRY(f32(P.out_w[h], L.f_out_w[h], (int64_t)head_classes(h) * d, 1.f));
       TRY(f32(P.out_b[h], L.f_out_b[h], head_classes(h), 1.f));
     }
+  } else if (!bf16_supported(dm)) {
+    // unfused tensor-core forward (pair_heads_generic.cu)
+    if (dm.shrink) {
+      TRY(bf(P.shrink_w1, hin, 0, L.w1_bf16, hid, hin, 1.f));
+      TRY(f32(P.shrink_b1, L.b1, hid, 1.f));
+      TRY(bf(P.shrink_w2, hid, 0, L.w2_bf16, d, hid, 1.f));
+      TRY(f32(P.shrink_b2, L.b2, d, 1.f));
+    }
+    TRY(bf(P.combine_w, 2 * d, 0, L.wc_bf16, d, d, 0.5f));
+    TRY(bf(P.combine_w, 2 * d, d, L.wc_bf16 + (size_t)d * d * 2, d, d, 0.5f));
+    TRY(f32(nullptr, L.bc_half, d, 0.f));
+    TRY(f32(P.combine_b, L.bc_half + (size_t)d * 4, d, 0.5f));
+    for (int h = 0; h < kNumHeads; ++h) {
+      for (int l = 0; l + 1 < dm.num_layers; ++l) {
+        TRY(bf(P.mid_w[h * 8 + l], d, 0, L.g_mid_w[h][l], d, d, 1.f));
+        TRY(f32(P.mid_b[h * 8 + l], L.g_mid_b[h][l], d, 1.f));
+      }
+      const int C = head_classes(h);
+      PENEO_CUDA_TRY(cudaMemsetAsync(base + L.g_out_w[h], 0, (size_t)32 * d * 2, st));
+      PENEO_CUDA_TRY(cudaMemsetAsync(base + L.g_out_b[h], 0, 32 * 4, st));
+      TRY(bf(P.out_w[h], d, 0, L.g_out_w[h], C, d, 1.f));
+      TRY(f32(P.out_b[h], L.g_out_b[h], C, 1.f));
+    }
   } else {
     TRY(bf(P.shrink_w1, hin, 0, L.w1_bf16, hid, hin, 1.f));
     TRY(f32(P.shrink_b1, L.b1, hid, 1.f));

@@ -116,7 +116,9 @@ class PEneoDecoderB200(nn.Module):
         self.dims = DecoderDims(input_size, hidden if self.decoder_shrink else 0, d, self.decoder_shrink, self.num_layers)
         prec = _cfg(config, "peneo_b200_precision", None)
         if prec is None:
-            prec = "bf16" if self.dims.bf16_capable() else "fp32"
+            # fused tcgen05 path where it exists; the unfused tensor-core forward only for inference-mode models
+            # (it has no backward: such configurations train on the fp32 path)
+            prec = "bf16" if self.dims.bf16_capable() or (self.inference_mode and self.dims.bf16_forward_capable()) else "fp32"
         self.set_precision(prec)
         self._pack: Optional[WeightPack] = None
         self._pack_key = None
@@ -133,8 +135,8 @@ class PEneoDecoderB200(nn.Module):
     def set_precision(self, prec: str) -> None:
         if prec not in ("bf16", "fp32"):
             raise ValueError("precision must be 'bf16' or 'fp32'")
-        if prec == "bf16" and not self.dims.bf16_capable():
-            raise ValueError("the bf16 tcgen05 path needs shrink=True, hidden 768 (d=384) and 2 classifier layers; "
+        if prec == "bf16" and not self.dims.bf16_forward_capable():
+            raise ValueError("the bf16 tensor-core paths need input / hidden / pair widths in multiples of 64; "
                              "use precision='fp32' for this configuration")
         self.precision = prec
         self._pack = None
@@ -188,6 +190,10 @@ class PEneoDecoderB200(nn.Module):
         if self.training and self.dropout_prob > 0:
             seed = getattr(self, "dropout_seed", None)
             drop = (float(self.dropout_prob), int(torch.randint(0, 2**62, (1,)).item()) if seed is None else int(seed))
+        unfused = self.precision == "bf16" and not self.dims.bf16_capable()
+        if unfused and ((needs_grad and not self.inference_mode) or drop is not None):
+            raise RuntimeError("precision='bf16' is forward-only (no dropout, no backward) for this decoder "
+                               "configuration; train it with precision='fp32'")
         if needs_grad and not self.inference_mode:
             from .autograd import decoder_forward_with_grad
 

@@ -56,7 +56,16 @@ class DecoderDims:
         return _lib.Dims(self.hin, self.hid, self.d, int(self.shrink), self.num_layers)
 
     def bf16_capable(self) -> bool:
+        """The fused tcgen05 path (K2 / T1, forward and backward): the shipped configuration."""
         return self.shrink and self.hid == 768 and self.d == 384 and self.num_layers == 2 and self.hin % 64 == 0
+
+    def bf16_forward_capable(self) -> bool:
+        """PREC_BF16 is accepted for the forward pass: the fused path, or the unfused tensor-core forward
+        (csrc/pair_heads_generic.cu) for any widths in multiples of 64 and up to 8 classifier layers."""
+        if self.bf16_capable():
+            return True
+        return (self.d % 64 == 0 and self.hin % 64 == 0 and (not self.shrink or self.hid % 64 == 0)
+                and 1 <= self.num_layers <= 8)
 
 
 class WeightPack:

@@ -657,3 +657,34 @@ def test_c_abi_rejects_bad_arguments_with_status_codes():
     # the Python layer refuses CPU tensors instead of falling back
     with pytest.raises(RuntimeError, match="no CPU"):
         ops.token_projections(ops.WeightPack(ops.DecoderDims(768, 768, 384, True, 2), _lib.PREC_FP32, "cuda"), torch.zeros(2, 768))
+
+
+@pytest.mark.parametrize("hin,hidden,shrink,L,n,b", [
+    (64, 64, False, 2, 37, 2),      # shrink off, D = 64
+    (128, 128, True, 3, 41, 2),     # shrink on, d = 64, three classifier layers
+    (768, 768, True, 1, 50, 2),     # no hidden layer in the heads
+    (768, 768, False, 2, 60, 1),    # shrink off at the backbone width (D = 768)
+    (960, 768, True, 3, 33, 1),     # LiLT input width, deeper heads
+])
+def test_unfused_bf16_forward_matches_oracle(hin, hidden, shrink, L, n, b):
+    """Configurations the fused K2 does not cover run PENEO_PREC_BF16 through the unfused tensor-core forward
+    (csrc/pair_heads_generic.cu): logits within the bf16 tolerance of the fp64 oracle, decode identical in shape,
+    and the mode refuses to train."""
+    sd = synth.init_decoder_state(hin, hidden, shrink, L, seed=21, trained_like=True)
+    x = synth.hidden_states(b, n, hin, doc_id0=5)
+    ref = orc.heads_chunked(orc.split_params(sd, torch.float64), x.double())
+    dec = build(sd, hin, hidden, shrink, L, "bf16")
+    assert dec.precision == "bf16" and not dec.dims.bf16_capable()
+    with torch.no_grad():
+        out = dec(x.cuda())
+    for k in range(5):
+        assert tuple(out[k].shape) == tuple(ref[k].shape)
+        e = rel_err(out[k], ref[k])
+        print((hin, hidden, shrink, L), k, f"{e:.3e}")
+        assert e <= BF16_TOL, (k, e)
+    # default precision of an inference-mode model with these widths is the tensor-core forward; a trainable one is fp32
+    assert PEneoDecoderB200(Cfg(hidden, shrink, L, inference_mode=True), hin).precision == "bf16"
+    assert PEneoDecoderB200(Cfg(hidden, shrink, L, inference_mode=False), hin).precision == "fp32"
+    trainable = build(sd, hin, hidden, shrink, L, "bf16", inference_mode=False)
+    with pytest.raises(RuntimeError, match="forward-only"):
+        trainable(x.cuda().requires_grad_(True))
