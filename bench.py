@@ -84,14 +84,15 @@ def calibrate_bias(sd, n_eff, device):
 
 
 class ClockSampler:
-    """SM clock / throttle-reason samples DURING the timed region: NVML polled from a thread every few
-    milliseconds (nvidia-smi -lms cannot sample a sub-second region densely enough); falls back to
-    nvidia-smi when pynvml is unavailable."""
+    """SM clock / throttle-reason samples DURING the timed region: NVML polled from a thread every 20 ms
+    (nvidia-smi -lms cannot sample a sub-second region densely enough; polling every 4 ms made the NVML calls
+    contend with kernel launches and showed up as 50-100 ms stalls of the device-resident leg in one run out of
+    four); falls back to nvidia-smi when pynvml is unavailable."""
 
     REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20),
                ("sw_power_cap", 0x4))
 
-    def __init__(self, gpu_index: int, period_s: float = 0.004):
+    def __init__(self, gpu_index: int, period_s: float = 0.02):
         self.gpu, self.period = gpu_index, period_s
         self.sm, self.reasons, self.power = [], set(), []
         self.sm_max, self.stop_flag, self.thread, self.mode = None, False, None, None
@@ -224,6 +225,9 @@ def run_ours(args):
 
     # ---- device-resident leg: inputs already in HBM, records copied back, no Python objects
     run_steps(xs_dev, args.warmup, False)
+    # a full CPython GC pass (~45 ms with torch loaded) inside a timed region would drain the GPU queue: freeze what the
+    # set-up created (covers both legs; the end-to-end leg creates tens of thousands of containers per step)
+    pipe.freeze_host_gc()
     sampler = ClockSampler(local_rank)
     sampler.start()
     barrier()
@@ -243,7 +247,6 @@ def run_ours(args):
 
     # ---- end-to-end leg: pinned host hidden states -> H2D -> heads -> decode -> D2H -> Python objects
     run_steps(xs_host, 2, True)
-    pipe.freeze_host_gc()  # a full CPython GC pass (~45 ms with torch loaded) would drain the GPU queue once per ~60 steps
     barrier()
     pipe.h2d_bytes = pipe.d2h_bytes = 0
     pipe.wait_s = pipe.assemble_s = 0.0
