@@ -212,13 +212,16 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def run_steps(inputs, steps, assemble, depth=3):
-        """`steps` passes of the hot path with `depth` batches in flight; returns the last result."""
+    def run_steps(inputs, steps, assemble, depth=3, stamps=None):
+        """`steps` passes of the hot path with `depth` batches in flight; returns the last result.
+        `stamps` (optional list) receives the host time after every loop iteration."""
         last = None
         for s in range(steps):
             pipe.submit(inputs[s % args.rotate], texts)
             if len(pipe) >= depth:
                 last = pipe.result(assemble=assemble)
+            if stamps is not None:
+                stamps.append(time.perf_counter())
         while len(pipe):
             last = pipe.result(assemble=assemble)
         return last
@@ -253,7 +256,8 @@ def run_ours(args):
     wall0 = time.perf_counter()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(pipe.compute)
-    res = run_steps(xs_host, args.steps, True)
+    stamps = [wall0]
+    res = run_steps(xs_host, args.steps, True, stamps=stamps)
     e1.record(pipe.compute)
     barrier()
     ms_e2e = e0.elapsed_time(e1)
@@ -298,6 +302,9 @@ def run_ours(args):
                 "ms_per_step": e2e_ms / args.steps,
                 "host_assemble_ms_per_step": pipe.assemble_s * 1e3 / args.steps,
                 "host_wait_gpu_ms_per_step": pipe.wait_s * 1e3 / args.steps,
+                # longest single loop iteration on the host: an outlier here (GC, scheduler, allocator) explains an
+                # end-to-end value below the device-resident one
+                "host_slowest_iteration_ms": max(b - a for a, b in zip(stamps, stamps[1:])) * 1e3,
                 "api": "peneo_b200.HeadsDecodePipeline.submit()/result(): pinned host hidden states in, reference 7-tuples out, 3 batches in flight"},
         "gpu_launches": int(launches),
         "clocks": clocks,
