@@ -38,6 +38,14 @@ def test_abi_version_and_sizes(lib):
     assert lib.peneo_pack_bytes(_lib.Dims(48, 0, 48, 0, 1), _lib.PREC_BF16) == 0
     assert b"PENEO_PREC_BF16" in lib.peneo_last_error()
     assert lib.peneo_decode_resolve_doc_ints(512, 1024) == 16 + 6 * 512 + 8 * 1024
+    # widths in multiples of 64 outside the fused configuration: bf16 packs exist (unfused tensor-core forward) but the
+    # mode has no backward, which the workspace query reports as 0
+    for dims in (_lib.Dims(768, 0, 768, 0, 2), _lib.Dims(768, 768, 384, 1, 1), _lib.Dims(128, 128, 64, 1, 3)):
+        nb = lib.peneo_pack_bytes(dims, _lib.PREC_BF16)
+        assert nb > 5 * dims.d * 32 * 2, (dims.hin, dims.d, dims.num_layers, nb)
+        assert lib.peneo_heads_bwd_workspace_bytes(dims, _lib.PREC_BF16, 2, 37) == 0
+        assert lib.peneo_heads_bwd_workspace_bytes(dims, _lib.PREC_FP32, 2, 37) > 0
+    assert lib.peneo_heads_bwd_workspace_bytes(_lib.Dims(768, 768, 384, 1, 2), _lib.PREC_BF16, 2, 37) > 0
 
 
 def test_product_path_never_imports_the_oracle():
