@@ -73,14 +73,7 @@ def calibrate_bias(sd, n_eff, device):
     x = synth.hidden_states(1, n_eff, 768, doc_id0=999).to(device=device, dtype=torch.bfloat16)
     with torch.no_grad():
         logits = dec(x)[:5]
-    names = ("line_extraction", "ent_linking_h2h", "ent_linking_t2t", "line_grouping_h2h", "line_grouping_t2t")
-    q = 1.0 - 1.0 / n_eff * 2.0
-    for name, lg in zip(names, logits):
-        lg = lg[0].float()
-        margin = lg[:, 1:].max(dim=1)[0] - lg[:, 0]
-        shift = torch.quantile(margin[:: max(1, margin.numel() // 100000)], q).item()
-        sd[f"{name}_fc.3.bias"][0] += shift
-    return sd
+    return synth.calibrate_class0_bias(sd, [l.cpu() for l in logits], n_eff)
 
 
 class ClockSampler:
@@ -176,10 +169,178 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
+def load_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return {}
+
+
+def tensor_fracs(achieved_tf, peaks, clocks):
+    """Fractions of both measured cuBLAS bf16 peaks and the one that fits the run: a region whose SM clock sat at
+    >= 95 % of the maximum without `sw_power_cap` is a burst (compare with the best-of-10 `bf16_tflops`); a region
+    that ran into the power cap compares with the 4-second back-to-back `bf16_tflops_sustained`."""
+    burst, sust = peaks.get("bf16_tflops", 1687.9), peaks.get("bf16_tflops_sustained", 1427.8)
+    src = "MEASURED_PEAKS.json" if "bf16_tflops" in peaks else "fallback (B200_PROFILING.md)"
+    sm, smax = (clocks or {}).get("sm_mhz"), (clocks or {}).get("sm_max_mhz")
+    capped = "sw_power_cap" in ((clocks or {}).get("reasons") or [])
+    is_burst = bool(sm and smax and sm >= 0.95 * smax and not capped)
+    peak = burst if is_burst else sust
+    return {"peak": peak, "frac": achieved_tf / peak, "frac_burst": achieved_tf / burst, "frac_sustained": achieved_tf / sust,
+            "peak_burst": burst, "peak_sustained": sust,
+            "peak_source": f"{src} {'bf16_tflops (burst' if is_burst else 'bf16_tflops_sustained (sustained'}: "
+                           f"median SM clock {sm} of {smax} MHz{', sw_power_cap' if capped else ''})"}
+
+
+def heads_flops_pairs(pairs, d=384):
+    """Algorithmic flops of the pair part (K2) per document: five Linear(D, D) + five output layers."""
+    return 10.0 * pairs * d * d + 28.0 * pairs * d
+
+
+def heads_flops_doc(n, hin=768, hid=768, d=384):
+    """F_heads of SURVEY.md §8d: per-token chain + pair part."""
+    return 2.0 * n * (hin * hid + hid * d + 2 * d * d) + heads_flops_pairs(n * (n + 1) // 2, d)
+
+
+def make_decoder(n_eff, dev, hin=768, inference=True):
+    """Random-init decoder of the shipped configuration with the class-0 biases calibrated for N = n_eff."""
+    from peneo_b200 import PEneoDecoderB200, synth
+
+    class C(Cfg):
+        inference_mode = inference
+
+    sd = synth.init_decoder_state(hin=hin, seed=0)
+    probe = PEneoDecoderB200(Cfg, hin)
+    probe.load_state_dict(sd)
+    probe = probe.to(dev).eval()
+    x = synth.hidden_states(1, n_eff, hin, doc_id0=999).to(device=dev, dtype=torch.bfloat16)
+    with torch.no_grad():
+        logits = probe(x)[:5]
+    sd = synth.calibrate_class0_bias(sd, [l.cpu() for l in logits], n_eff)
+    dec = PEneoDecoderB200(C, hin)
+    dec.load_state_dict(sd)
+    return dec.to(dev).eval(), sd
+
+
+def sweep_leg(dev, rank, world, dist, peaks, clocks, steps=10, warmup=3):
+    """Device-resident heads + decode at the other two sizes BASELINE.json's metric is quoted on (seq 1024 / 2048),
+    same pairs per step as the headline (8 x 523 776 and 2 x 2 096 128 vs 32 x 130 816)."""
+    from peneo_b200 import HeadsDecodePipeline, synth
+
+    out = []
+    for seq_len, batch in ((1024, 8), (2048, 2)):
+        n_eff = seq_len - 1
+        pairs = n_eff * (n_eff + 1) // 2
+        dec, _ = make_decoder(n_eff, dev)
+        xs = [synth.hidden_states(batch, n_eff, 768, doc_id0=10000 * rank + 50 * r).to(device=dev, dtype=torch.bfloat16)
+              for r in range(4)]
+        texts = [[f"w{t} " for t in range(n_eff)] for _ in range(batch)]
+        pipe = HeadsDecodePipeline(dec, dev)
+
+        def run(k):
+            last = None
+            for s in range(k):
+                pipe.submit(xs[s % len(xs)], texts)
+                if len(pipe) >= 3:
+                    last = pipe.result(assemble=False)
+            while len(pipe):
+                last = pipe.result(assemble=False)
+            return last
+
+        run(warmup)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        pipe.k2_events, pipe.k3_events = [], []
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record(pipe.compute)
+        dd = run(steps)
+        t1.record(pipe.compute)
+        torch.cuda.synchronize()
+        ms = t0.elapsed_time(t1)
+        k2_ms = sum(a.elapsed_time(b) for a, b in pipe.k2_events) / len(pipe.k2_events)
+        k3_ms = sum(a.elapsed_time(b) for a, b in pipe.k3_events) / len(pipe.k3_events)
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        tf = batch * heads_flops_pairs(pairs) / (k2_ms * 1e-3) / 1e12
+        fr = tensor_fracs(tf, peaks, clocks)
+        out.append({"seq_len": seq_len, "pair_dim": n_eff, "batch_per_gpu": batch, "steps": steps,
+                    "docs_per_s": batch * steps * world / (ms * 1e-3), "ms_per_step": ms / steps,
+                    "k2_ms": k2_ms, "k2_tflops": tf, "frac_burst": fr["frac_burst"], "frac_sustained": fr["frac_sustained"],
+                    "k3_ms": k3_ms, "k3_gbs": batch * pairs * 56 / (k3_ms * 1e-3) / 1e9,
+                    "spots_per_head_per_doc": float(dd.counts.mean())})
+        del pipe, dec, xs
+        torch.cuda.empty_cache()
+    return out
+
+
+def train_leg(dev, rank, local_rank, world, dist, peaks, steps=10, warmup=3):
+    """Fine-tuning step of the decoder: forward + fused loss + backward (+ NCCL gradient all-reduce under torchrun, DDP
+    semantics as in the reference's HF Trainer: per-rank batch-global weighted-mean loss, averaged gradients).  Two
+    shapes: the headline shape (seq 512, batch 32 per GPU, hidden 768) and BASELINE configs[2] (LiLT: hidden states of
+    width 960, seq 1024, batch 4 per GPU, SIBR-shaped documents).  Per GPU, against 3 x F_heads."""
+    from peneo_b200 import PEneoDecoderB200, synth
+
+    out = []
+    for name, hin, seq_len, batch, style in (("seq512_b32_h768", 768, 512, 32, "rfund"),
+                                             ("configs[2]: LiLT hin 960, seq 1024, b4", 960, 1024, 4, "sibr")):
+        n = seq_len - 1
+
+        class C(Cfg):
+            inference_mode = False
+
+        dec = PEneoDecoderB200(C, hin)
+        dec.load_state_dict(synth.init_decoder_state(hin=hin, seed=0))
+        dec = dec.to(dev).eval()  # eval(): the decoder's dropout off, like every parity test of the gradients
+        module = dec
+        if world > 1:
+            dec = torch.nn.parallel.DistributedDataParallel(dec, device_ids=[local_rank])
+        x = synth.hidden_states(batch, n, hin, doc_id0=1000 * rank).to(dev).requires_grad_(True)
+        docs = [synth.make_document(n, doc_id=1000 * rank + i, style=style) for i in range(batch)]
+        tags = [torch.stack([d.tags()[k] for d in docs]).to(dev) for k in range(5)]
+
+        def step():
+            module.zero_grad(set_to_none=True)
+            x.grad = None
+            o = dec(x, None, *tags)
+            o.loss.backward()
+            return o.loss
+
+        for _ in range(warmup):
+            step()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            loss = step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        tf = 3.0 * heads_flops_doc(n, hin) * batch / (ms * 1e-3) / 1e12
+        sust = peaks.get("bf16_tflops_sustained", 1427.8)
+        out.append({"shape": name, "seq_len": seq_len, "hin": hin, "batch_per_gpu": batch, "steps": steps,
+                    "ms_per_step": ms, "docs_per_s": world * batch / (ms * 1e-3), "loss": float(loss),
+                    "tflops_vs_3F_per_gpu": tf, "frac_sustained": tf / sust, "frac_burst": tf / peaks.get("bf16_tflops", 1687.9),
+                    "collective": f"NCCL all-reduce of {sum(p.numel() for p in module.parameters())} decoder gradients (DDP)"
+                                  if world > 1 else "none (1 GPU)",
+                    "peak_mem_gb": torch.cuda.max_memory_allocated(dev) / 2**30})
+        del dec, module, x, tags
+        torch.cuda.empty_cache()
+    return out
+
+
 def run_ours(args):
     import torch.distributed as dist
 
-    from peneo_b200 import PEneoDecoderB200, decode, ops, synth
+    from peneo_b200 import HeadsDecodePipeline, ops, synth
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -191,19 +352,13 @@ def run_ours(args):
     n_eff = args.seq_len - 1
     pairs = n_eff * (n_eff + 1) // 2
 
-    sd = synth.init_decoder_state(seed=0)
-    sd = calibrate_bias(sd, n_eff, dev)
-    dec = PEneoDecoderB200(Cfg, 768)
-    dec.load_state_dict(sd)
-    dec = dec.to(dev).eval()
+    dec, sd = make_decoder(n_eff, dev)
 
     # rotating input set, resident in HBM (and its pinned-host twin for the end-to-end leg)
     xs_host = [synth.hidden_states(args.batch, n_eff, 768, doc_id0=10000 * rank + 100 * r).to(torch.bfloat16).pin_memory()
                for r in range(args.rotate)]
     xs_dev = [x.to(dev) for x in xs_host]
     texts = [[f"w{t} " for t in range(n_eff)] for _ in range(args.batch)]
-
-    from peneo_b200 import HeadsDecodePipeline
 
     pipe = HeadsDecodePipeline(dec, dev)
 
@@ -234,7 +389,7 @@ def run_ours(args):
     sampler = ClockSampler(local_rank)
     sampler.start()
     barrier()
-    pipe.k2_events = []
+    pipe.k2_events, pipe.k3_events = [], []
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches0 = ops.COUNTERS["kernels"]
     t0.record(pipe.compute)
@@ -245,7 +400,8 @@ def run_ours(args):
     ms_dev = t0.elapsed_time(t1)
     clocks = sampler.stop()
     k2_ms = sum(a.elapsed_time(b) for a, b in pipe.k2_events) / len(pipe.k2_events)
-    pipe.k2_events = None
+    k3_ms = sum(a.elapsed_time(b) for a, b in pipe.k3_events) / len(pipe.k3_events)
+    pipe.k2_events = pipe.k3_events = None
     spots_per_head = float(dd.counts.mean())
 
     # ---- end-to-end leg: pinned host hidden states -> H2D -> heads -> decode -> D2H -> Python objects
@@ -274,15 +430,10 @@ def run_ours(args):
     e2e_ms = max(ms_e2e, wall_e2e)
     e2e_value = docs / (e2e_ms * 1e-3)
 
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
-    peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained" if "bf16_tflops_sustained" in peaks else "fallback 1.4 PF sustained"
-    k2_flops = args.batch * (10.0 * pairs * 384 * 384 + 28.0 * pairs * 384)
+    peaks = load_peaks()
+    k2_flops = args.batch * heads_flops_pairs(pairs)
     achieved = k2_flops / (k2_ms * 1e-3) / 1e12
+    fr = tensor_fracs(achieved, peaks, clocks)
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "k2_traffic.json")
     if os.path.exists(tpath):
@@ -293,26 +444,43 @@ def run_ours(args):
                 traffic = prof.get("dram_bytes_per_launch")
         except Exception:
             traffic = None
+    hbm = peaks.get("hbm_gbs", 6457.4)
+    k3_bytes = args.batch * pairs * 56  # P * 14 logits * 4 B read once (SURVEY.md §8d Bytes_decode)
+    k3_gbs = k3_bytes / (k3_ms * 1e-3) / 1e9
+
+    assemble_ms, wait_ms = pipe.assemble_s * 1e3 / args.steps, pipe.wait_s * 1e3 / args.steps
+    del pipe, xs_dev
+    torch.cuda.empty_cache()
+    sweep = None if args.no_sweep else sweep_leg(dev, rank, world, dist, peaks, clocks)
+    train = None if args.no_train else train_leg(dev, rank, local_rank, world, dist, peaks)
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic", "config": workload_config(args, world),
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                "ms_per_step": e2e_ms / args.steps,
-                "host_assemble_ms_per_step": pipe.assemble_s * 1e3 / args.steps,
-                "host_wait_gpu_ms_per_step": pipe.wait_s * 1e3 / args.steps,
-                # longest single loop iteration on the host: an outlier here (GC, scheduler, allocator) explains an
-                # end-to-end value below the device-resident one
-                "host_slowest_iteration_ms": max(b - a for a, b in zip(stamps, stamps[1:])) * 1e3,
-                "api": "peneo_b200.HeadsDecodePipeline.submit()/result(): pinned host hidden states in, reference 7-tuples out, 3 batches in flight"},
+    }
+    line["e2e"] = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                   "ms_per_step": e2e_ms / args.steps,
+                   "host_assemble_ms_per_step": assemble_ms, "host_wait_gpu_ms_per_step": wait_ms,
+                   # longest single loop iteration on the host: an outlier here (GC, scheduler, allocator) explains an
+                   # end-to-end value below the device-resident one
+                   "host_slowest_iteration_ms": max(b - a for a, b in zip(stamps, stamps[1:])) * 1e3,
+                   "api": "peneo_b200.HeadsDecodePipeline.submit()/result(): pinned host hidden states in, reference 7-tuples out, 3 batches in flight"}
+    line.update({
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"bound": "tensor", "kernel": "pair_heads_tc_kernel", "achieved": achieved, "peak": peak_tf,
-                     "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": traffic, "peak_source": peak_src,
+        "roofline": {"bound": "tensor", "kernel": "pair_heads_tc_kernel", "achieved": achieved, "peak": fr["peak"],
+                     "unit": "TFLOP/s", "frac": fr["frac"], "traffic": traffic, "peak_source": fr["peak_source"],
+                     "frac_burst": fr["frac_burst"], "frac_sustained": fr["frac_sustained"],
+                     "peak_burst": fr["peak_burst"], "peak_sustained": fr["peak_sustained"],
                      "kernel_ms": k2_ms, "flops_per_launch": k2_flops},
+        "roofline_decode": {"bound": "hbm", "kernel": "decode_spots_kernel", "achieved": k3_gbs, "peak": hbm, "unit": "GB/s",
+                            "frac": k3_gbs / hbm, "kernel_ms": k3_ms, "bytes_per_launch": k3_bytes,
+                            "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback"},
         "spots_per_head_per_doc": spots_per_head,
-    }
+        "sweep": sweep,
+        "train": train,
+    })
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args, sd, docs_target=args.cpu_docs)
@@ -322,32 +490,57 @@ def run_ours(args):
 
 
 # ------------------------------------------------------------------------------------------------
-def cpu_reference_step(p32, x_doc, text, n_eff):
-    """One document through the reference algorithm on the host (oracle port, torch CPU fp32)."""
-    import peneo_oracle as orc
+class ReferencePath:
+    """The reference's hot path on the host cores.  `kind == "reference"`: the reference's own PEneoDecoder.forward
+    (inference_mode) + sample_decode_peneo, imported through oracle/ref_shim.py (source tree in the build container,
+    byte code from oracle/_ref on the GPU box).  `kind == "port"`: the oracle's restatement of the same op sequence,
+    only when neither is present."""
 
-    with torch.no_grad():
-        logits = orc.heads_ref_style(p32, x_doc)
-    return orc.sample_decode(text, [l[0] for l in logits], n_eff)
+    def __init__(self, sd, n_eff):
+        import peneo_oracle as orc
+        import ref_shim
+
+        self.n, self.orc = n_eff, orc
+        self.text = [f"w{t} " for t in range(n_eff)]
+        if ref_shim.reference_available():
+            ns = ref_shim.load_reference()
+            cfg = ns.PEneoConfig(backbone_name="bench", backbone_config={"hidden_size": 768, "hidden_dropout_prob": 0.1},
+                                 peneo_category_weights=[1, 10, 10], inference_mode=True)
+            self.dec = ns.PEneoDecoder(cfg, 768).eval()
+            self.dec.load_state_dict(sd)
+            self.ns, self.kind = ns, "reference"
+            self.how = (f"ZeningLin/PEneo's own PEneoDecoder.forward + sample_decode_peneo ({ref_shim.reference_kind()} "
+                        "modules via oracle/ref_shim.py), torch CPU fp32")
+        else:
+            self.p32 = orc.split_params(sd, torch.float32)
+            self.kind = "port"
+            self.how = "oracle.heads_ref_style + oracle.sample_decode (the reference's op sequence restated), torch CPU fp32"
+
+    def step(self, x_doc):
+        """One document: hidden states [1, N, 768] -> the reference's 7-tuple."""
+        with torch.no_grad():
+            if self.kind == "reference":
+                out = self.dec(x_doc)
+                return self.ns.sample_decode_peneo(self.ns.HandshakingTaggingScheme(), self.text, *[o[0] for o in out[:5]],
+                                                   seq_len=self.n)
+            logits = self.orc.heads_ref_style(self.p32, x_doc)
+            return self.orc.sample_decode(self.text, [l[0] for l in logits], self.n)
 
 
 def cpu_baseline(args, sd, docs_target=3):
-    import peneo_oracle as orc
     from peneo_b200 import synth
 
     n_eff = args.seq_len - 1
     torch.set_num_threads(os.cpu_count() or 1)
-    p32 = orc.split_params(sd, torch.float32)
-    text = [f"w{t} " for t in range(n_eff)]
-    x = synth.hidden_states(1, n_eff, 768, doc_id0=7)
-    cpu_reference_step(p32, x, text, n_eff)  # warm-up
+    ref = ReferencePath(sd, n_eff)
+    ref.step(synth.hidden_states(1, n_eff, 768, doc_id0=7))  # warm-up
     t0 = time.perf_counter()
     for d in range(docs_target):
-        cpu_reference_step(p32, synth.hidden_states(1, n_eff, 768, doc_id0=8 + d), text, n_eff)
+        ref.step(synth.hidden_states(1, n_eff, 768, doc_id0=8 + d))
     dt = time.perf_counter() - t0
-    return {"value": docs_target / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-            "sample": f"{docs_target} documents of the same workload (seq {args.seq_len}, batch 1 each) through "
-                      "oracle.heads_ref_style + oracle.sample_decode (the reference's op sequence, torch CPU fp32)",
+    return {"value": docs_target / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": ref.kind,
+            "sample": f"{docs_target} documents of the same workload (seq {args.seq_len}, batch 1 each, same calibrated "
+                      f"weights) through {ref.how}",
             "seconds": dt}
 
 
@@ -367,29 +560,25 @@ def run_reference(args):
     x = synth.hidden_states(1, n_eff, 768, doc_id0=999)
     with torch.no_grad():
         logits = orc.heads_ref_style(p32, x)
-    names = ("line_extraction", "ent_linking_h2h", "ent_linking_t2t", "line_grouping_h2h", "line_grouping_t2t")
-    for name, lg in zip(names, logits):
-        margin = lg[0][:, 1:].max(dim=1)[0] - lg[0][:, 0]
-        sd[f"{name}_fc.3.bias"][0] += torch.quantile(margin[:: max(1, margin.numel() // 100000)], 1.0 - 2.0 / n_eff).item()
-    p32 = orc.split_params(sd, torch.float32)
-    text = [f"w{t} " for t in range(n_eff)]
+    sd = synth.calibrate_class0_bias(sd, logits, n_eff)
+    ref = ReferencePath(sd, n_eff)
     docs_per_step = args.ref_docs_per_step
     for w in range(args.warmup):
-        cpu_reference_step(p32, synth.hidden_states(1, n_eff, 768, doc_id0=w), text, n_eff)
+        ref.step(synth.hidden_states(1, n_eff, 768, doc_id0=w))
     t0 = time.perf_counter()
     for s in range(args.steps):
         for d in range(docs_per_step):
-            cpu_reference_step(p32, synth.hidden_states(1, n_eff, 768, doc_id0=100 + s * docs_per_step + d), text, n_eff)
+            ref.step(synth.hidden_states(1, n_eff, 768, doc_id0=100 + s * docs_per_step + d))
     dt = time.perf_counter() - t0
     value = args.steps * docs_per_step / dt
     cfg = workload_config(args, world)
-    sample = (f"each step = {docs_per_step} document(s) of the workload (seq {args.seq_len}), one at a time, through the "
-              "reference's op sequence restated in oracle/ (torch CPU fp32, all host threads)")
+    sample = (f"each step = {docs_per_step} document(s) of the workload (seq {args.seq_len}), one at a time, through "
+              f"{ref.how}, all host threads")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt * 1e3 / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": ref.kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -408,6 +597,8 @@ def main():
     ap.add_argument("--cpu-docs", type=int, default=3)
     ap.add_argument("--ref-docs-per-step", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the seq 1024 / 2048 legs")
+    ap.add_argument("--no-train", action="store_true", help="skip the fine-tuning step legs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define PENEO_ABI_VERSION 2
+#define PENEO_ABI_VERSION 3
 
 #define PENEO_OK 0
 #define PENEO_E_INVALID -1     /* bad argument / unsupported configuration */
@@ -127,10 +127,11 @@ size_t peneo_pair_loss_workspace_bytes(int32_t batch, int32_t n);
 int peneo_pair_loss_fwd(int32_t batch, int32_t n, const float* const logits[PENEO_NUM_HEADS],
                         const int64_t* const tags[PENEO_NUM_HEADS], const float* class_w_host,
                         const float* ratio_host, float* out6, void* workspace, void* stream);
-/* d loss / d logits for the same definition, scaled by grad_out (a device scalar, fp32). */
+/* d L / d logits for the same definition.  grad_out6: six device floats, d L / d out[0..5] of the forward call
+ * (the five sub-losses, then their ratio-weighted sum), so head h is scaled by grad_out6[5] * ratio_h + grad_out6[h]. */
 int peneo_pair_loss_bwd(int32_t batch, int32_t n, const float* const logits[PENEO_NUM_HEADS],
                         const int64_t* const tags[PENEO_NUM_HEADS], const float* class_w_host,
-                        const float* ratio_host, const float* grad_out, const void* workspace,
+                        const float* ratio_host, const float* grad_out6, const void* workspace,
                         float* const dlogits[PENEO_NUM_HEADS], void* stream);
 
 /* Same five sub-losses with online hard-example mining (num_hard_positive / num_hard_negative as in
@@ -145,7 +146,7 @@ int peneo_pair_loss_ohem_fwd(int32_t batch, int32_t n, const float* const logits
                              void* workspace, void* stream);
 int peneo_pair_loss_ohem_bwd(int32_t batch, int32_t n, const float* const logits[PENEO_NUM_HEADS],
                              const int64_t* const tags[PENEO_NUM_HEADS], const float* class_w_host,
-                             const float* ratio_host, const float* grad_out, const void* workspace,
+                             const float* ratio_host, const float* grad_out6, const void* workspace,
                              float* const dlogits[PENEO_NUM_HEADS], void* stream);
 
 /* ------------------------------------------------------------------ heads, backward */

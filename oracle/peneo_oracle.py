@@ -317,7 +317,13 @@ def spots_to_tags(batch_spots: Sequence[Sequence[Tuple[int, int, int]]], seq_len
     out = torch.zeros(len(batch_spots), shaking_len(seq_len), dtype=torch.int64)
     for b, spots in enumerate(batch_spots):
         for sp in spots:
-            out[b, shaking_index(sp[0], sp[1], seq_len)] = sp[2]
+            # the reference looks (i, j) up in an N x N list-of-lists that is 0 below the diagonal (lines 55-59, 70):
+            # Python indexing, so indices in [-N, N) are legal and anything else raises IndexError
+            i, j = sp[0], sp[1]
+            if not (-seq_len <= i < seq_len and -seq_len <= j < seq_len):
+                raise IndexError("list index out of range")
+            i, j = i % seq_len, j % seq_len
+            out[b, shaking_index(i, j, seq_len) if i <= j else 0] = sp[2]
     return out
 
 

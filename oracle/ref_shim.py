@@ -2,9 +2,11 @@
 
 Imports ZeningLin/PEneo's decoder / loss / decode modules from ``/root/reference`` without
 triggering the package ``__init__`` files (which pull in timm / detectron2 / an old
-transformers API).  Only usable in the build container: the GPU box has
-no ``/root/reference``.  Used by ``oracle/make_golden.py`` (fixture generation) and by the
-``not gpu`` tests that pin the oracle against the reference when the reference is present.
+transformers API).  In the build container the modules come from the reference's
+source tree; on the GPU box (no ``/root/reference``) from the byte code ``oracle/build_ref.py`` compiled
+from that tree into the git-ignored ``oracle/_ref/``.  Used by ``oracle/make_golden.py`` (fixture
+generation), by the tests that pin the oracle against the reference, and by ``bench.py``'s reference arm /
+``cpu_baseline`` leg (which time the reference itself on the host cores).
 
 Nothing under ``peneo_b200/`` may import this module.
 """
@@ -13,21 +15,41 @@ import sys
 import types
 
 REFERENCE_ROOT = os.environ.get("PENEO_REFERENCE_ROOT", "/root/reference")
+# byte code of the same modules, written by oracle/build_ref.py (git-ignored; travels to the GPU box)
+COMPILED_ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+
+
+def source_available() -> bool:
+    return os.path.isfile(os.path.join(REFERENCE_ROOT, "model", "peneo_decoder.py"))
+
+
+def compiled_available() -> bool:
+    ver = os.path.join(COMPILED_ROOT, "PYTHON_VERSION")
+    if not os.path.isfile(os.path.join(COMPILED_ROOT, "model", "peneo_decoder.pyc")) or not os.path.isfile(ver):
+        return False
+    with open(ver) as f:
+        return f.read().strip() == "%d.%d" % sys.version_info[:2]
 
 
 def reference_available() -> bool:
-    return os.path.isfile(os.path.join(REFERENCE_ROOT, "model", "peneo_decoder.py"))
+    return source_available() or compiled_available()
+
+
+def reference_kind() -> str:
+    """Where load_reference() takes the reference from: its source tree, or the byte code compiled from it."""
+    return "source" if source_available() else "compiled" if compiled_available() else "none"
 
 
 def load_reference():
     """Return a namespace with the reference's hot-path symbols."""
     if not reference_available():
-        raise RuntimeError(f"reference not found under {REFERENCE_ROOT}")
+        raise RuntimeError(f"reference not found under {REFERENCE_ROOT} nor compiled under {COMPILED_ROOT}")
+    root = REFERENCE_ROOT if source_available() else COMPILED_ROOT
     sys.dont_write_bytecode = True  # /root/reference is read-only
     for pkg in ("model", "data", "pipeline"):
         if pkg not in sys.modules or not hasattr(sys.modules[pkg], "__path__"):
             m = types.ModuleType(pkg)
-            m.__path__ = [os.path.join(REFERENCE_ROOT, pkg)]
+            m.__path__ = [os.path.join(root, pkg)]
             sys.modules[pkg] = m
     from model.configuration_peneo import PEneoConfig
     from model.peneo_decoder import (

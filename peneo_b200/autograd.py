@@ -21,13 +21,9 @@ class _PairLoss(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g6):
-        ws, lg, tg, w3, r5, b, n = ctx.saved
-        g6 = g6.detach().float()
-        # d(sum_h g6[h] * loss_h + g6[5] * sum_h ratio_h loss_h) / d logits_h : per-head scale
-        eff = [(g6[5] * r5[h] + g6[h]) for h in range(5)]
-        one = torch.ones(1, device=g6.device)
-        dl = ops.pair_loss_backward((ws, lg, tg, w3, [1.0] * 5, b, n), one)
-        dl = [d * e for d, e in zip(dl, eff)]
+        # d(sum_h g6[h] * loss_h + g6[5] * sum_h ratio_h loss_h) / d logits_h: the per-head scale is applied inside
+        # the kernel (no elementwise passes over the [B, P, C] gradients on the torch side)
+        dl = ops.pair_loss_backward(ctx.saved, g6)
         return (None, None, None, None, None, None, None, *dl)
 
 

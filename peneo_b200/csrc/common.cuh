@@ -57,6 +57,15 @@ __device__ __forceinline__ void pair_from_flat(int32_t p, int32_t n, int32_t& i,
 
 __device__ __forceinline__ float silu_exact(float x) { return x / (1.0f + expf(-x)); }
 
+// Class index of a target for a C-class head.  The reference raises on a target outside [0, C)
+// (F.cross_entropy, model/custom_loss.py:196-210); a kernel cannot raise, so an out-of-range target is clamped to
+// class 0 for every memory access and `bad` tells the caller to poison its result with NaN — the loss (and every
+// gradient derived from it) then reads NaN instead of silently touching memory outside w[] / the logits row.
+__device__ __forceinline__ int checked_tag(long long t, int C, bool& bad) {
+  bad = t < 0 || t >= C;
+  return bad ? 0 : static_cast<int>(t);
+}
+
 // ---- dropout ------------------------------------------------------------------------------------
 // The three dropout sites inside the decoder (model/peneo_decoder.py:218, 221, 261) use a counter-based mask so
 // that the backward pass can regenerate it instead of storing [P, D] masks: an element is kept iff

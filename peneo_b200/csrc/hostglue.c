@@ -36,7 +36,7 @@ static PyObject* cached_int(IntCache* c, long v) {
 
 /* {head: tail} in record order */
 static PyObject* build_map(IntCache* c, const int32_t* pairs, int cnt) {
-  PyObject* d = _PyDict_NewPresized(cnt);
+  PyObject* d = PyDict_New();
   if (!d) return NULL;
   for (int r = 0; r < cnt; ++r) {
     PyObject* k = cached_int(c, pairs[2 * r]);
@@ -64,7 +64,7 @@ static PyObject* build_multimap(IntCache* c, const int32_t* pairs, int cnt, int 
     }
     if (slot[h]++ == 0) ++distinct;
   }
-  PyObject* d = _PyDict_NewPresized(distinct);
+  PyObject* d = PyDict_New();
   if (!d) return NULL;
   PyObject** lists = (PyObject**)calloc((size_t)n, sizeof(PyObject*)); /* borrowed (the dict owns them) */
   if (!lists) {

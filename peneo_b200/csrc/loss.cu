@@ -47,9 +47,10 @@ __global__ void __launch_bounds__(256) pair_loss_partial_kernel(const LossArgs a
       row_lse<2>(x, lse, e, m);
     else
       row_lse<3>(x, lse, e, m);
-    const int t = static_cast<int>(a.tags[h][r]);
+    bool bad;
+    const int t = checked_tag(a.tags[h][r], C, bad);
     const float w = a.w[t];
-    sl += static_cast<double>(w * (lse - x[t]));
+    sl += bad ? static_cast<double>(NAN) : static_cast<double>(w * (lse - x[t]));
     sw += static_cast<double>(w);
   }
   __shared__ double red[2][8];
@@ -99,7 +100,8 @@ __global__ void __launch_bounds__(32 * kNumHeads) pair_loss_final_kernel(const L
 
 __global__ void __launch_bounds__(256) pair_loss_bwd_kernel(const LossArgs a) {
   const int h = blockIdx.y, C = head_classes(h);
-  const float scale = a.grad_out[0] * a.ratio[h] / static_cast<float>(a.final_[h * 2 + 1]);
+  // grad_out = d L / d (loss_0 .. loss_4, total): the total is sum_h ratio_h loss_h (model/peneo_decoder.py:399-420)
+  const float scale = (a.grad_out[5] * a.ratio[h] + a.grad_out[h]) / static_cast<float>(a.final_[h * 2 + 1]);
   for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < a.rows; r += (int64_t)gridDim.x * blockDim.x) {
     float x[3] = {0.f, 0.f, 0.f}, e[3], lse, m;
     for (int c = 0; c < C; ++c) x[c] = a.logits[h][r * C + c];
@@ -109,8 +111,9 @@ __global__ void __launch_bounds__(256) pair_loss_bwd_kernel(const LossArgs a) {
       row_lse<3>(x, lse, e, m);
     float s = 0.f;
     for (int c = 0; c < C; ++c) s += e[c];
-    const int t = static_cast<int>(a.tags[h][r]);
-    const float g = scale * a.w[t];
+    bool bad;
+    const int t = checked_tag(a.tags[h][r], C, bad);
+    const float g = bad ? NAN : scale * a.w[t];
     for (int c = 0; c < C; ++c) a.dlogits[h][r * C + c] = g * (e[c] / s - (c == t ? 1.f : 0.f));
   }
 }
@@ -158,20 +161,28 @@ int launch_pair_loss_bwd(int batch, int n, const float* const logits[kNumHeads],
 // ------------------------------------------------------------------------------------------------
 // tags[b, p(i, j)] = tag, last spot wins (model/peneo_decoder.py:68-72)
 // ------------------------------------------------------------------------------------------------
-__global__ void scatter_claim_kernel(const int32_t* __restrict__ spots, int64_t num, int n, int64_t pairs,
-                                     long long* tags) {
-  const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= num) return;
+// Cell of spot (b, i, j), or -1 when it lies outside the batch / the document (the host wrapper validates and
+// raises like the reference's list indexing would; the kernel itself never writes out of bounds).  A spot below
+// the diagonal (i > j) lands in cell 0 of its document: the reference looks it up in an N x N table that is zero
+// everywhere below the diagonal (model/peneo_decoder.py:55-59, 70).
+__device__ __forceinline__ int64_t scatter_cell(const int32_t* spots, int64_t s, int batch, int n, int64_t pairs) {
   const int b = spots[4 * s], i = spots[4 * s + 1], j = spots[4 * s + 2];
-  atomicMin(&tags[b * pairs + row_start(i, n) + (j - i)], -(s + 1));
+  if (b < 0 || b >= batch || i < 0 || i >= n || j < 0 || j >= n) return -1;
+  return b * pairs + (j < i ? 0 : row_start(i, n) + (j - i));
 }
-__global__ void scatter_write_kernel(const int32_t* __restrict__ spots, int64_t num, int n, int64_t pairs,
+__global__ void scatter_claim_kernel(const int32_t* __restrict__ spots, int64_t num, int batch, int n, int64_t pairs,
                                      long long* tags) {
   const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= num) return;
-  const int b = spots[4 * s], i = spots[4 * s + 1], j = spots[4 * s + 2];
-  long long* cell = &tags[b * pairs + row_start(i, n) + (j - i)];
-  if (*cell == -(s + 1)) *cell = spots[4 * s + 3];
+  const int64_t cell = scatter_cell(spots, s, batch, n, pairs);
+  if (cell >= 0) atomicMin(&tags[cell], -(s + 1));
+}
+__global__ void scatter_write_kernel(const int32_t* __restrict__ spots, int64_t num, int batch, int n, int64_t pairs,
+                                     long long* tags) {
+  const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= num) return;
+  const int64_t cell = scatter_cell(spots, s, batch, n, pairs);
+  if (cell >= 0 && tags[cell] == -(s + 1)) tags[cell] = spots[4 * s + 3];
 }
 
 int launch_scatter_tags(const int32_t* spots, int64_t num_spots, int batch, int n, int64_t* tags, cudaStream_t st) {
@@ -179,9 +190,9 @@ int launch_scatter_tags(const int32_t* spots, int64_t num_spots, int batch, int 
   PENEO_CUDA_TRY(cudaMemsetAsync(tags, 0, (size_t)batch * pairs * sizeof(int64_t), st));
   if (num_spots == 0) return PENEO_OK;
   const unsigned blocks = static_cast<unsigned>((num_spots + 255) / 256);
-  scatter_claim_kernel<<<blocks, 256, 0, st>>>(spots, num_spots, n, pairs, reinterpret_cast<long long*>(tags));
+  scatter_claim_kernel<<<blocks, 256, 0, st>>>(spots, num_spots, batch, n, pairs, reinterpret_cast<long long*>(tags));
   PENEO_CUDA_TRY(cudaGetLastError());
-  scatter_write_kernel<<<blocks, 256, 0, st>>>(spots, num_spots, n, pairs, reinterpret_cast<long long*>(tags));
+  scatter_write_kernel<<<blocks, 256, 0, st>>>(spots, num_spots, batch, n, pairs, reinterpret_cast<long long*>(tags));
   PENEO_CUDA_TRY(cudaGetLastError());
   return PENEO_OK;
 }

@@ -40,11 +40,12 @@ __global__ void __launch_bounds__(256) ohem_ce_kernel(const float* __restrict__ 
                                                       float* __restrict__ ce, int32_t* __restrict__ is_pos) {
   const float w[3] = {w0, w1, w2};
   for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += (int64_t)gridDim.x * blockDim.x) {
-    const int t = static_cast<int>(tags[r]);
+    bool bad;  // target outside [0, C): NaN loss instead of an out-of-bounds read (common.cuh: checked_tag)
+    const int t = checked_tag(tags[r], C, bad);
     float x[3] = {0.f, 0.f, 0.f};
     for (int c = 0; c < C; ++c) x[c] = logits[r * C + c];
-    ce[r] = C == 2 ? weighted_nll<2>(x, t, w) : weighted_nll<3>(x, t, w);
-    is_pos[r] = t != 0;
+    ce[r] = bad ? NAN : (C == 2 ? weighted_nll<2>(x, t, w) : weighted_nll<3>(x, t, w));
+    is_pos[r] = bad || t != 0;
   }
 }
 
@@ -106,10 +107,10 @@ __global__ void ohem_final_kernel(const double* __restrict__ sums, const double*
 // dlogits = scale_h * keep * w[t] * (softmax - onehot)
 __global__ void __launch_bounds__(256) ohem_bwd_kernel(const float* __restrict__ logits, const int64_t* __restrict__ tags,
                                                        const uint8_t* __restrict__ keep, int C, int64_t rows, float w0,
-                                                       float w1, float w2, const float* __restrict__ grad_out,
-                                                       float coef, float* __restrict__ dlogits) {
+                                                       float w1, float w2, const float* __restrict__ grad_out6, int h,
+                                                       float ratio, float inv_denom, float* __restrict__ dlogits) {
   const float w[3] = {w0, w1, w2};
-  const float scale = grad_out[0] * coef;
+  const float scale = (grad_out6[5] * ratio + grad_out6[h]) * inv_denom;
   for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += (int64_t)gridDim.x * blockDim.x) {
     float x[3] = {0.f, 0.f, 0.f}, e[3];
     for (int c = 0; c < C; ++c) x[c] = logits[r * C + c];
@@ -117,8 +118,9 @@ __global__ void __launch_bounds__(256) ohem_bwd_kernel(const float* __restrict__
     for (int c = 1; c < C; ++c) m = fmaxf(m, x[c]);
     float s = 0.f;
     for (int c = 0; c < C; ++c) e[c] = expf(x[c] - m), s += e[c];
-    const int t = static_cast<int>(tags[r]);
-    const float g = keep[r] ? scale * w[t] : 0.f;
+    bool bad;
+    const int t = checked_tag(tags[r], C, bad);
+    const float g = bad ? NAN : (keep[r] ? scale * w[t] : 0.f);
     for (int c = 0; c < C; ++c) dlogits[r * C + c] = g * (e[c] / s - (c == t ? 1.f : 0.f));
   }
 }
@@ -250,9 +252,9 @@ int launch_pair_loss_ohem_bwd(int batch, int n, const float* const logits[kNumHe
   PENEO_CUDA_TRY(cudaMemcpyAsync(h_denom, ws + L.off_denom, sizeof h_denom, cudaMemcpyDeviceToHost, st));
   PENEO_CUDA_TRY(cudaStreamSynchronize(st));
   for (int h = 0; h < kNumHeads; ++h) {
-    const float coef = static_cast<float>((ratio ? ratio[h] : 1.f) / h_denom[h]);
     ohem_bwd_kernel<<<kBlocks, 256, 0, st>>>(logits[h], tags[h], keep + (size_t)h * M, head_classes(h), M, class_w[0],
-                                             class_w[1], class_w[2], grad_out, coef, dlogits[h]);
+                                             class_w[1], class_w[2], grad_out, h, ratio ? ratio[h] : 1.f,
+                                             static_cast<float>(1.0 / h_denom[h]), dlogits[h]);
     PENEO_CUDA_TRY(cudaGetLastError());
   }
   return PENEO_OK;

@@ -17,6 +17,9 @@ from . import _lib
 from .ops import COUNTERS, _TORCH_DT, _require_cuda, _stream, seq_len_from_pairs, shaking_len
 
 NUM_HEADS = 5
+# upper bound on the pairs decoded by one kernel batch of decode_peneo (8 M pairs = 64 documents of seq 512:
+# ~0.5 GB of stacked fp32 logits, ~0.5 GB of int64 tags)
+DECODE_GROUP_PAIRS = 8 << 20
 
 
 def merge_bbox(bbox_list):
@@ -41,8 +44,14 @@ class DeviceDecode:
                  spots: Optional[Tuple[np.ndarray, np.ndarray, np.ndarray]]):
         self.n, self.cap, self.batch = n, cap, batch
         self.records, self.counts, self.spots = records, counts, spots
+        # documents whose spot lists overflowed `cap` were decoded again with a larger capacity: their records live
+        # in `redo` (a DeviceDecode of just those documents), `redo_rows[b]` is document b's row there
+        self.redo: Optional["DeviceDecode"] = None
+        self.redo_rows: Dict[int, int] = {}
 
     def doc(self, b: int):
+        if b in self.redo_rows:
+            return self.redo.doc(self.redo_rows[b])
         n, cap = self.n, self.cap
         rec = self.records[b]
         hdr = rec[:16]
@@ -83,13 +92,14 @@ def _as_batched_inputs(shakings: Sequence[torch.Tensor]):
 
 class PendingDecode:
     """K3 + K4 enqueued for a batch; the compact result is on its way to pinned host memory.
-    ``finish()`` waits for it (and transparently re-runs with the worst-case capacity in the rare
-    case a spot list overflowed)."""
+    ``finish()`` waits for it; documents whose spot lists overflowed the capacity (dense predictions of an
+    untrained model) are decoded again, alone, with exactly the capacity their longest list needs."""
 
-    def __init__(self, ins, n, cap, decode_gt, score_thresh, want_spots, d2h_stream=None):
+    def __init__(self, ins, n, cap, decode_gt, score_thresh, want_spots, d2h_stream=None, k3_events=None):
         self.ins, self.n, self.cap = ins, n, cap
         self.decode_gt, self.score_thresh, self.want_spots = decode_gt, score_thresh, want_spots
         self.d2h_stream = d2h_stream  # optional side stream so the record copy does not stall the next batch
+        self.k3_events = k3_events    # optional list: receives (start, stop) CUDA events around the spot-extraction kernel
         self._launch()
 
     def _launch(self):
@@ -103,11 +113,17 @@ class PendingDecode:
         self.spot_score = torch.empty(b * NUM_HEADS * cap, dtype=torch.float32, device=dev)
         counts = torch.empty(b * NUM_HEADS, dtype=torch.int32, device=dev)
         ws = torch.empty(max(16, lib.peneo_decode_spots_workspace_bytes(b, n)), dtype=torch.uint8, device=dev)
+        if self.k3_events is not None:
+            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            ev[0].record(torch.cuda.current_stream(dev))
         _lib.check(
             lib.peneo_decode_spots(b, n, _lib.ptrs5(ins), dt, cap, self.spot_p.data_ptr(), self.spot_tag.data_ptr(),
                                    self.spot_score.data_ptr(), counts.data_ptr(), ws.data_ptr(), _stream(dev)),
             "peneo_decode_spots",
         )
+        if self.k3_events is not None:
+            ev[1].record(torch.cuda.current_stream(dev))
+            self.k3_events.append(ev)
         doc_ints = lib.peneo_decode_resolve_doc_ints(n, cap)
         rec = torch.empty(b, doc_ints, dtype=torch.int32, device=dev)
         ws2 = torch.empty(max(16, lib.peneo_decode_resolve_workspace_bytes(b, n)), dtype=torch.uint8, device=dev)
@@ -144,21 +160,30 @@ class PendingDecode:
         self.event.synchronize()
         b = self.ins[0].shape[0]
         p = shaking_len(self.n)
-        if int(self.counts_h.max()) > self.cap and self.cap < p:
-            self.cap = p  # a list overflowed: redo with the worst-case capacity
-            self._launch()
-            self.event.synchronize()
+        redo, redo_rows = None, {}
+        worst = self.counts_h.numpy().reshape(b, NUM_HEADS).max(axis=1)
+        if self.cap < p and int(worst.max()) > self.cap:
+            # some lists overflowed: decode those documents again (only those) with the capacity they need
+            over = np.nonzero(worst > self.cap)[0]
+            idx = torch.as_tensor(over, device=self.ins[0].device)
+            sub = PendingDecode([t.index_select(0, idx) for t in self.ins], self.n, min(p, int(worst.max())),
+                                self.decode_gt, self.score_thresh, self.want_spots, None)
+            self.d2h_bytes += sub.d2h_bytes
+            redo, redo_rows = sub.finish(), {int(d): r for r, d in enumerate(over)}
         spots = None
         if self.want_spots:
             cap = self.cap
             spots = (self.spot_p.cpu().numpy().reshape(b, NUM_HEADS, cap), self.spot_tag.cpu().numpy().reshape(b, NUM_HEADS, cap),
                      self.spot_score.cpu().numpy().reshape(b, NUM_HEADS, cap))
         self._keep = None
-        return DeviceDecode(self.n, self.cap, b, self.rec_h.numpy(), self.counts_h.numpy().reshape(b, NUM_HEADS), spots)
+        dd = DeviceDecode(self.n, self.cap, b, self.rec_h.numpy(), self.counts_h.numpy().reshape(b, NUM_HEADS), spots)
+        dd.redo, dd.redo_rows = redo, redo_rows
+        return dd
 
 
 def device_decode_async(shakings: Sequence[torch.Tensor], n: int, decode_gt: bool = False, score_thresh: float = 0,
-                        cap: Optional[int] = None, want_spots: bool = False, d2h_stream=None) -> PendingDecode:
+                        cap: Optional[int] = None, want_spots: bool = False, d2h_stream=None,
+                        k3_events=None) -> PendingDecode:
     """Enqueue K3 (spots) + K4 (resolve) + the D2H copy of the compact records on the current stream."""
     ins, _tag_mode = _as_batched_inputs(shakings)
     p = shaking_len(n)
@@ -167,7 +192,7 @@ def device_decode_async(shakings: Sequence[torch.Tensor], n: int, decode_gt: boo
             raise ValueError(f"shaking tensor {k} has {t.shape[1]} rows, expected {p} for seq_len {n}")
     if cap is None:
         cap = min(p, max(8 * n, 1024))
-    return PendingDecode(ins, n, cap, decode_gt, score_thresh, want_spots, d2h_stream)
+    return PendingDecode(ins, n, cap, decode_gt, score_thresh, want_spots, d2h_stream, k3_events)
 
 
 def device_decode(shakings: Sequence[torch.Tensor], n: int, decode_gt: bool = False, score_thresh: float = 0,
@@ -188,6 +213,8 @@ def _unflatten(p: np.ndarray, n: int):
 
 def spots_from_device(dd: DeviceDecode, b: int, head: int) -> List[Tuple[int, int, int, float]]:
     """The reference's spot list [(i, j, tag, score)] for one document / head."""
+    if b in dd.redo_rows:
+        return spots_from_device(dd.redo, dd.redo_rows[b], head)
     cnt = int(dd.counts[b, head])
     sp, st, ss = dd.spots
     ii, jj = _unflatten(sp[b, head, :cnt], dd.n)
@@ -218,8 +245,27 @@ def assemble_many(dd: DeviceDecode, docs: Sequence[int], texts: Sequence[List[st
         bboxes = [_plain_bbox(bx) for bx in bboxes]
         if all(bx is None for bx in bboxes):
             bboxes = None
+    docs = list(docs)
+    if dd.redo_rows and any(d in dd.redo_rows for d in docs):
+        # documents decoded a second time (capacity overflow) come from dd.redo; keep the caller's order
+        out = [None] * len(docs)
+        for src, rows in ((dd.redo, dd.redo_rows), (dd, None)):
+            pos = [k for k, d in enumerate(docs) if (d in dd.redo_rows) == (rows is not None)]
+            if not pos:
+                continue
+            part = assemble_many(src if rows is not None else _without_redo(dd),
+                                 [rows[docs[k]] if rows is not None else docs[k] for k in pos],
+                                 [texts[k] for k in pos], None if bboxes is None else [bboxes[k] for k in pos])
+            for k, r in zip(pos, part):
+                out[k] = r
+        return out
     rec = dd.records
-    return _glue().assemble(memoryview(rec).cast("B"), rec.shape[1], dd.n, dd.cap, list(docs), texts, bboxes)
+    return _glue().assemble(memoryview(rec).cast("B"), rec.shape[1], dd.n, dd.cap, docs, texts, bboxes)
+
+
+def _without_redo(dd: DeviceDecode) -> DeviceDecode:
+    plain = DeviceDecode(dd.n, dd.cap, dd.batch, dd.records, dd.counts, dd.spots)
+    return plain
 
 
 def _assemble(dd: DeviceDecode, b: int, text: List[str], bbox):
@@ -317,14 +363,23 @@ def decode_peneo(
     for s in range(count):
         by_len.setdefault(len(orig_bboxes[s]), []).append(s)
     device = next((o[0].device for o in outs if len(o) and torch.is_tensor(o[0]) and o[0].is_cuda), torch.device("cuda"))
-    for n, idxs in by_len.items():
-        pred_in = [torch.stack([_to_device(o[s], device) for s in idxs]) for o in outs]
-        gt_in = [torch.stack([_to_device(t[s], device) for s in idxs]) for t in tags]
-        dp = device_decode(pred_in, n, decode_gt=False)
-        dg = device_decode(gt_in, n, decode_gt=True)
-        rows = list(range(len(idxs)))
-        tx = [texts[s] for s in idxs]
-        for s, pr, gt in zip(idxs, assemble_many(dp, rows, tx), assemble_many(dg, rows, tx)):
-            all_pred[s], all_gt[s] = pr, gt
+    for n, group in by_len.items():
+        # Bounded kernel batches: stacking copies every logit / tag tensor of the group once more on the device, and
+        # the compact buffers scale with batch * capacity, so a group is decoded in slices of at most
+        # DECODE_GROUP_PAIRS pairs (the reference decodes sample by sample; the kernels' grid also caps a batch
+        # at 65 535 documents).
+        step = max(1, min(65535, DECODE_GROUP_PAIRS // max(1, shaking_len(n))))
+        for lo in range(0, len(group), step):
+            idxs = group[lo : lo + step]
+            pred_in = [torch.stack([_to_device(o[s], device) for s in idxs]) for o in outs]
+            dp = device_decode(pred_in, n, decode_gt=False)
+            del pred_in
+            gt_in = [torch.stack([_to_device(t[s], device) for s in idxs]) for t in tags]
+            dg = device_decode(gt_in, n, decode_gt=True)
+            del gt_in
+            rows = list(range(len(idxs)))
+            tx = [texts[s] for s in idxs]
+            for s, pr, gt in zip(idxs, assemble_many(dp, rows, tx), assemble_many(dg, rows, tx)):
+                all_pred[s], all_gt[s] = pr, gt
     all_ids = [file_ids[s] for s in range(count)]
     return all_pred, all_gt, all_ids

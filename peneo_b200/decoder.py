@@ -76,6 +76,8 @@ class PEneoDecoderB200(nn.Module):
       shrink, hidden 768 -> d 384, 2 classifier layers) or ``"fp32"`` (CUDA-core fp32).
     """
 
+    _warned_bf16_training = False
+
     def __init__(self, config, input_size: int) -> None:
         super().__init__()
         self.decoder_shrink = bool(_cfg(config, "peneo_decoder_shrink", True))
@@ -122,6 +124,8 @@ class PEneoDecoderB200(nn.Module):
         self.set_precision(prec)
         self._pack: Optional[WeightPack] = None
         self._pack_key = None
+        self._pack_readers = {}
+        self._explicit_precision = _cfg(config, "peneo_b200_precision", None) is not None
 
     # ------------------------------------------------------------------ construction helpers
     @classmethod
@@ -143,15 +147,45 @@ class PEneoDecoderB200(nn.Module):
 
     # ------------------------------------------------------------------ weights
     def _weight_pack(self, device) -> WeightPack:
+        """Kernel-layout weights, re-packed when a parameter changed.  The pack is shared by every CUDA stream that
+        runs the decoder (the caller's stream, HeadsDecodePipeline's compute stream): a stream other than the one
+        that packed waits for the pack kernels, and a re-pack waits for the readers other streams registered with
+        :meth:`_pack_read_done`."""
         state = {k: v for k, v in self.named_parameters()}
         key = (self.precision, str(device), tuple((p.data_ptr(), p._version) for p in state.values()))
+        cur = torch.cuda.current_stream(device)
         if self._pack is None or self._pack_key != key:
             prec = PREC_BF16 if self.precision == "bf16" else PREC_FP32
             if self._pack is None or self._pack.prec != prec or self._pack.buf.device != device:
                 self._pack = WeightPack(self.dims, prec, device)
+                self._pack_readers = {}
+            for ev in self._pack_readers.values():  # kernels of other streams still reading the old contents
+                cur.wait_event(ev)
+            self._pack_readers = {}
             self._pack.update({k: v.detach() for k, v in state.items()})
             self._pack_key = key
+            self._pack_ready = torch.cuda.Event()
+            self._pack_ready.record(cur)
+            self._pack_stream = cur
+        elif cur != self._pack_stream:
+            cur.wait_event(self._pack_ready)
         return self._pack
+
+    def _pack_read_done(self, device) -> None:
+        """Called by multi-stream users after enqueueing kernels that read the pack on a side stream."""
+        cur = torch.cuda.current_stream(device)
+        if self._pack is not None and cur != getattr(self, "_pack_stream", cur):
+            ev = torch.cuda.Event()
+            ev.record(cur)
+            self._pack_readers[cur.cuda_stream] = ev
+
+    def _class_weights_host(self):
+        """The three class weights as Python floats, cached (``.tolist()`` is a device sync)."""
+        w = self.link_loss.weight
+        key = (w.data_ptr(), w._version)
+        if getattr(self, "_cw_key", None) != key:
+            self._cw_host, self._cw_key = [float(v) for v in w.tolist()], key
+        return self._cw_host
 
     def _fp32_pack(self, device) -> WeightPack:
         """fp32 kernel-layout weights (the backward pass always runs in fp32)."""
@@ -195,6 +229,15 @@ class PEneoDecoderB200(nn.Module):
             raise RuntimeError("precision='bf16' is forward-only (no dropout, no backward) for this decoder "
                                "configuration; train it with precision='fp32'")
         if needs_grad and not self.inference_mode:
+            if self.precision == "bf16" and not self._explicit_precision and not PEneoDecoderB200._warned_bf16_training:
+                PEneoDecoderB200._warned_bf16_training = True
+                import warnings
+
+                warnings.warn(
+                    "PEneoDecoderB200 trains in its bf16 tensor-core mode by default (bf16 operands, fp32 accumulation, "
+                    "tanh.approx SiLU): parameter gradients agree with the fp32 reference to ~1e-2 relative per tensor, "
+                    "like the reference's own --fp16 AMP recipe.  Set config.peneo_b200_precision = 'fp32' for "
+                    "fp32-exact (1e-6) training numerics.", stacklevel=2)
             from .autograd import decoder_forward_with_grad
 
             logits = decoder_forward_with_grad(self, sequence_output, drop)
@@ -220,7 +263,7 @@ class PEneoDecoderB200(nn.Module):
         else:
             from .autograd import pair_loss_op
 
-            total, subs = pair_loss_op(logits, tags, self.link_loss.weight.tolist(), self.loss_ratio)
+            total, subs = pair_loss_op(logits, tags, self._class_weights_host(), self.loss_ratio)
         return PEneoOutput(
             loss=total,
             line_extraction_loss=subs[0],

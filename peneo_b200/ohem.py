@@ -47,15 +47,14 @@ class _OhemLoss(torch.autograd.Function):
         lib = _lib.load()
         ws, lg, tg, w3, b, n = ctx.saved
         dev = lg[0].device
-        one = torch.ones(1, dtype=torch.float32, device=dev)
+        g6 = torch.zeros(6, dtype=torch.float32, device=dev)  # d L / d (five sub-losses, unused total)
+        g6[:5] = g5.detach().float()
         dl = [torch.empty_like(l) for l in lg]
         _lib.check(
             lib.peneo_pair_loss_ohem_bwd(b, n, _lib.ptrs5(lg), _lib.ptrs5(tg), _lib.floats(w3), _lib.floats([1.0] * 5),
-                                         one.data_ptr(), ws.data_ptr(), _lib.ptrs5(dl), _stream(dev)),
+                                         g6.data_ptr(), ws.data_ptr(), _lib.ptrs5(dl), _stream(dev)),
             "peneo_pair_loss_ohem_bwd",
         )
-        g5 = g5.detach().float()
-        dl = [d * g5[h] for h, d in enumerate(dl)]
         return (None, None, None, None, None, None, None, *dl)
 
 

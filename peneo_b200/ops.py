@@ -189,11 +189,12 @@ def pair_loss(logits: Sequence[torch.Tensor], tags: Sequence[torch.Tensor], clas
     return out6, (ws, lg, tg, w3, r5, b, n)
 
 
-def pair_loss_backward(ctx, grad_out: torch.Tensor) -> List[torch.Tensor]:
+def pair_loss_backward(ctx, grad_out6: torch.Tensor) -> List[torch.Tensor]:
+    """grad_out6: d L / d out6 of :func:`pair_loss` (six values) -> d L / d logits of the five heads."""
     lib = _lib.load()
     ws, lg, tg, w3, r5, b, n = ctx
     dev = lg[0].device
-    g = grad_out.detach().to(device=dev, dtype=torch.float32).reshape(1).contiguous()
+    g = grad_out6.detach().to(device=dev, dtype=torch.float32).reshape(6).contiguous()
     dl = [torch.empty_like(l) for l in lg]
     _lib.check(
         lib.peneo_pair_loss_bwd(b, n, _lib.ptrs5(lg), _lib.ptrs5(tg), _lib.floats(w3), _lib.floats(r5), g.data_ptr(),

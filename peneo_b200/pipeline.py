@@ -34,6 +34,7 @@ class HeadsDecodePipeline:
         self.assemble_s = 0.0  # result(): time building the Python result objects
         self.d2h_bytes = 0
         self.k2_events = None  # set to a list to collect (start, stop) CUDA events around K2
+        self.k3_events = None  # same for the spot-extraction kernel K3
 
     def submit(self, hidden: torch.Tensor, texts: Sequence[List[str]], bboxes=None):
         """hidden: [B, N, Hin] on the host (pinned for a truly asynchronous copy) or on the device."""
@@ -60,7 +61,9 @@ class HeadsDecodePipeline:
             if self.k2_events is not None:
                 e1.record(self.compute)
                 self.k2_events.append((e0, e1))
-            pending = decode.device_decode_async(logits, n, score_thresh=self.score_thresh, d2h_stream=self.d2h)
+            self.decoder._pack_read_done(self.device)  # a later re-pack on another stream waits for these kernels
+            pending = decode.device_decode_async(logits, n, score_thresh=self.score_thresh, d2h_stream=self.d2h,
+                                                 k3_events=self.k3_events)
             x.record_stream(self.compute)
         self.d2h_bytes += pending.d2h_bytes
         self._queue.append((pending, list(texts), bboxes))

@@ -179,3 +179,22 @@ def init_decoder_state(
     sd["link_loss.weight"] = w.clone()
     sd["le_loss.weight"] = w[:-1].clone()
     return sd
+
+
+HEAD_NAMES = ("line_extraction", "ent_linking_h2h", "ent_linking_t2t", "line_grouping_h2h", "line_grouping_t2t")
+
+
+def calibrate_class0_bias(sd: dict, logits: List[torch.Tensor], n: int, spots_per_head: float = 2.0) -> dict:
+    """Decode regime (ii) of SURVEY.md §8d ("calibrated random-init"): random-init logits are ~0, so argmax is
+    ~uniform and 1/2 - 2/3 of all pairs come out positive — a regime no trained model produces.  Shift the class-0
+    output bias of every head to the ``1 - spots_per_head / n`` quantile of ``max_{c>0} l_c - l_0`` of a probe
+    document's logits, so that about ``spots_per_head * (n + 1) / 2`` spots per head survive.  ``logits``: the five
+    ``[1, P, C]`` tensors the *uncalibrated* weights give for the probe document (any device).  Returns ``sd``
+    (modified in place; shipped configuration: the output layer is ``<head>_fc.3``)."""
+    q = 1.0 - spots_per_head / n
+    for name, lg in zip(HEAD_NAMES, logits):
+        lg = lg[0].float()
+        margin = lg[:, 1:].max(dim=1)[0] - lg[:, 0]
+        shift = torch.quantile(margin[:: max(1, margin.numel() // 100000)], q).item()
+        sd[f"{name}_fc.3.bias"][0] += shift
+    return sd

@@ -24,7 +24,16 @@ class HandshakingTaggingScheme:
                 "If shaking_ind2matrix_ind and matrix_ind2shaking_ind are not provided,seq_len must be given"
             )
         quads = [(b, sp[0], sp[1], sp[2]) for b, spots in enumerate(batch_spots) for sp in spots]
-        q = torch.tensor(quads, dtype=torch.int32).reshape(-1, 4).cuda()
+        q = torch.tensor(quads, dtype=torch.int64).reshape(-1, 4)
+        if q.numel():
+            # the reference indexes an N x N Python table with the spot: indices in [-N, N) are legal (negative ones
+            # count from the end), anything else raises IndexError (model/peneo_decoder.py:70).  Same here, on the
+            # host, before the kernel sees the list; spots below the diagonal go to cell 0 inside the kernel.
+            ij = q[:, 1:3]
+            if bool(((ij < -seq_len) | (ij >= seq_len)).any()):
+                raise IndexError("list index out of range")
+            q[:, 1:3] = torch.where(ij < 0, ij + seq_len, ij)
+        q = q.to(torch.int32).cuda()
         tags = ops.scatter_tags(q, len(batch_spots), seq_len)
         return tags.cpu() if device is None else tags.to(device)
 

@@ -66,6 +66,29 @@ def main():
         mean = sum(g[k] for g in gathered) / world
         err = (p.grad.cpu() - mean).abs().max().item() / max(mean.abs().max().item(), 1e-30)
         assert err <= 1e-5, (k, err)
+    # ---- evaluation metrics ("next" row N2): the fixed-width int64 all_gather under NCCL gives every rank the
+    #      numbers the reference computes in one process over all files (pipeline/evaluation.py:150-183, 416-513),
+    #      including the de-duplication of files the distributed sampler put on two ranks
+    from peneo_b200 import evaluation as ev
+
+    g = torch.load(os.path.join(ROOT, "tests", "golden", "eval.pt"), weights_only=False)
+    nfiles = len(g["names"])
+    idx = [i for i in range(nfiles) if i % world == rank] + ([0] if rank == world - 1 else [])  # file 0 twice
+    sub = lambda xs: [xs[i] for i in idx]  # noqa: E731
+    kv = ev.calculate_KVPE_metric(sub(g["preds"]), sub(g["gts"]), sub(g["names"]))
+    det = ev.calculate_detail_KVPE_metric(sub(g["preds"]), sub(g["gts"]), sub(g["names"]))
+    assert kv[0] == g["kvpe"][0], (kv[0], g["kvpe"][0])
+    assert det[0] == g["detail"][0]
+    assert kv[1]["num_sample_processed"] == g["kvpe"][1]["num_sample_processed"]
+
+    # ---- DDP (what HF Trainer wraps the reference's model in): same averaged gradients as the flat bucket above
+    ddp = torch.nn.parallel.DistributedDataParallel(dec, device_ids=[local])
+    dec.zero_grad(set_to_none=True)
+    ddp(x, None, *tags).loss.backward()
+    for k, p in dec.named_parameters():
+        mean = sum(gr[k] for gr in gathered) / world
+        err = (p.grad.cpu() - mean).abs().max().item() / max(mean.abs().max().item(), 1e-30)
+        assert err <= 1e-5, ("ddp", k, err)
     dist.barrier()
     if rank == 0:
         print(f"sharded ok world={world}")

@@ -1,6 +1,7 @@
-"""Multi-GPU check (needs >= 2 GPUs: run with `gpurun --gpus 2 -- python -m pytest tests -m gpu`): one process
-per GPU under torchrun, NCCL; document-sharded inference equals the single-GPU result and the gradient
-all-reduce equals the mean of the per-rank gradients."""
+"""Multi-GPU check (needs >= 2 GPUs: run with `gpurun --gpus N -- python -m pytest tests -m gpu`): one process per
+VISIBLE GPU under torchrun, NCCL; document-sharded inference equals the single-GPU result, the gradient all-reduce
+(flat bucket and DDP) equals the mean of the per-rank gradients, and the evaluation-metric all_gather gives every
+rank the single-process numbers."""
 import os
 import subprocess
 import sys
@@ -15,7 +16,7 @@ def test_sharded_inference_and_gradient_allreduce_nccl():
     n = torch.cuda.device_count()
     if n < 2:
         pytest.skip("needs at least 2 GPUs")
-    world = 2
+    world = n  # every visible GPU
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr",
            "127.0.0.1", "--master-port", "29631", os.path.join(root, "tests", "helpers", "sharded_worker.py")]

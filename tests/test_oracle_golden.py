@@ -136,3 +136,51 @@ def test_oracle_against_live_reference_larger_case():
     got = orc.heads_chunked(orc.split_params(sd, torch.float64), x.double())
     for k in range(5):
         assert _close(got[k].float(), ref[k], 2e-5)
+
+
+@pytest.mark.skipif(not __import__("ref_shim").reference_available(), reason="reference tree not present")
+def test_tag_codec_edge_cases_against_live_reference():
+    """Python-indexing semantics of the reference's N x N lookup table (model/peneo_decoder.py:55-59, 70): spots
+    below the diagonal hit cell 0, negative indices count from the end, out-of-range indices raise IndexError."""
+    import ref_shim
+
+    ns = ref_shim.load_reference()
+    edge = [[(3, 1, 2), (-1, -1, 1), (1, 2, 1)], [(0, -2, 2), (4, 0, 1)]]
+    ref = ns.HandshakingTaggingScheme.spots2shaking_tag4batch(edge, seq_len=5)
+    assert torch.equal(orc.spots_to_tags(edge, 5), ref)
+    for bad in ([[(0, 5, 1)]], [[(-6, 0, 1)]]):
+        with pytest.raises(IndexError):
+            ns.HandshakingTaggingScheme.spots2shaking_tag4batch(bad, seq_len=5)
+        with pytest.raises(IndexError):
+            orc.spots_to_tags(bad, 5)
+
+
+def test_compiled_reference_recipe_round_trips(tmp_path, monkeypatch):
+    """oracle/build_ref.py: byte code compiled from the reference tree imports without its sources and computes the
+    same logits as the source tree (skipped where /root/reference does not exist, e.g. on the GPU box)."""
+    import importlib
+    import subprocess
+    import sys
+
+    import build_ref
+    import ref_shim
+
+    if not ref_shim.source_available():
+        pytest.skip("reference source tree not present")
+    assert build_ref.build(quiet=True)
+    code = (
+        "import sys, torch; sys.path.insert(0, %r); import ref_shim; "
+        "assert ref_shim.reference_kind() == 'compiled', ref_shim.reference_kind(); ns = ref_shim.load_reference(); "
+        "cfg = ns.PEneoConfig(backbone_name='x', backbone_config={'hidden_size': 64, 'hidden_dropout_prob': 0.1}, "
+        "peneo_category_weights=[1, 10, 10], inference_mode=True); torch.manual_seed(0); "
+        "d = ns.PEneoDecoder(cfg, 64).eval(); print(float(d(torch.ones(1, 5, 64))[1].sum()))"
+    ) % build_ref.HERE
+    env = dict(__import__("os").environ, PENEO_REFERENCE_ROOT="/nonexistent")
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    ns = ref_shim.load_reference()
+    cfg = ns.PEneoConfig(backbone_name="x", backbone_config={"hidden_size": 64, "hidden_dropout_prob": 0.1},
+                         peneo_category_weights=[1, 10, 10], inference_mode=True)
+    torch.manual_seed(0)
+    d = ns.PEneoDecoder(cfg, 64).eval()
+    assert abs(float(d(torch.ones(1, 5, 64))[1].sum()) - float(out.stdout.strip())) < 1e-6
