@@ -2,10 +2,11 @@
 
 The reference is pure Python, so "compiling the reference from its own sources" means byte-compiling: the six
 modules of ZeningLin/PEneo that make up the hot path (and nothing else of it) are compiled with ``py_compile``
-from where they lie under ``/root/reference`` into ``oracle/_ref/<package>/<module>.pyc``.  ``oracle/_ref/`` is
+from where they lie under ``/root/reference`` into ``oracle/_ref/<package>/<module>.refbc`` (a regular ``.pyc`` image under a
+neutral extension: the gpurun snapshot drops ``*.pyc`` files).  ``oracle/_ref/`` is
 git-ignored (no reference source or binary ever enters the history) but not gpurun-ignored, so the byte code
 travels with the repository snapshot like our own built ``.so``; ``ref_shim.load_reference()`` imports it through
-Python's sourceless-module loader on a box that has no ``/root/reference``.  No reference source text is copied.
+a sourceless loader on a box that has no ``/root/reference``.  No reference source text is copied.
 
     python oracle/build_ref.py            # called by __graft_entry__.build() when /root/reference exists
 
@@ -38,7 +39,7 @@ def build(quiet: bool = False) -> bool:
         return False
     for pkg, mod in MODULES:
         src = os.path.join(REFERENCE_ROOT, pkg, mod + ".py")
-        dst = os.path.join(OUT, pkg, mod + ".pyc")
+        dst = os.path.join(OUT, pkg, mod + ".refbc")
         os.makedirs(os.path.dirname(dst), exist_ok=True)
         # dfile: the path recorded in tracebacks points at the reference tree, not at a file of this repository
         py_compile.compile(src, cfile=dst, dfile=f"<reference>/{pkg}/{mod}.py", doraise=True,

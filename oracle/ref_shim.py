@@ -10,6 +10,9 @@ generation), by the tests that pin the oracle against the reference, and by ``be
 
 Nothing under ``peneo_b200/`` may import this module.
 """
+import importlib.abc
+import importlib.util
+import marshal
 import os
 import sys
 import types
@@ -25,7 +28,7 @@ def source_available() -> bool:
 
 def compiled_available() -> bool:
     ver = os.path.join(COMPILED_ROOT, "PYTHON_VERSION")
-    if not os.path.isfile(os.path.join(COMPILED_ROOT, "model", "peneo_decoder.pyc")) or not os.path.isfile(ver):
+    if not os.path.isfile(os.path.join(COMPILED_ROOT, "model", "peneo_decoder.refbc")) or not os.path.isfile(ver):
         return False
     with open(ver) as f:
         return f.read().strip() == "%d.%d" % sys.version_info[:2]
@@ -40,12 +43,37 @@ def reference_kind() -> str:
     return "source" if source_available() else "compiled" if compiled_available() else "none"
 
 
+class _CompiledFinder(importlib.abc.MetaPathFinder, importlib.abc.Loader):
+    """Imports ``<pkg>.<mod>`` from ``oracle/_ref/<pkg>/<mod>.refbc`` (a .pyc image written by build_ref.py)."""
+
+    def find_spec(self, fullname, path=None, target=None):
+        parts = fullname.split(".")
+        if len(parts) != 2 or parts[0] not in ("model", "data", "pipeline"):
+            return None
+        fn = os.path.join(COMPILED_ROOT, parts[0], parts[1] + ".refbc")
+        if not os.path.isfile(fn):
+            return None
+        return importlib.util.spec_from_loader(fullname, self, origin=fn)
+
+    def create_module(self, spec):
+        return None
+
+    def exec_module(self, module):
+        with open(module.__spec__.origin, "rb") as f:
+            data = f.read()
+        module.__file__ = module.__spec__.origin
+        exec(marshal.loads(data[16:]), module.__dict__)  # 16-byte .pyc header, then the marshalled code object
+
+
 def load_reference():
     """Return a namespace with the reference's hot-path symbols."""
     if not reference_available():
         raise RuntimeError(f"reference not found under {REFERENCE_ROOT} nor compiled under {COMPILED_ROOT}")
-    root = REFERENCE_ROOT if source_available() else COMPILED_ROOT
+    compiled = not source_available()
+    root = COMPILED_ROOT if compiled else REFERENCE_ROOT
     sys.dont_write_bytecode = True  # /root/reference is read-only
+    if compiled and not any(isinstance(f, _CompiledFinder) for f in sys.meta_path):
+        sys.meta_path.insert(0, _CompiledFinder())
     for pkg in ("model", "data", "pipeline"):
         if pkg not in sys.modules or not hasattr(sys.modules[pkg], "__path__"):
             m = types.ModuleType(pkg)
