@@ -47,10 +47,29 @@ int launch_pair_bwd_prep(const void* pack, const PackLayout& L, const __nv_bfloa
                          const float* const dz[kNumHeads], __nv_bfloat16* S, __nv_bfloat16* G, float* dwout_part,
                          cudaStream_t st, const DropSpec* drop = nullptr);
 
+// pair_bwd_tc2.cu : T1 on CTA pairs.  With `fused` != NULL the loss backward happens inside the kernel: dz is computed
+// in registers from the stored logits + tags (no d loss / d logits tensor in HBM) and db_out is reduced there too.
+struct FusedLossBwd {
+  const float* logits[kNumHeads];   // fp32 [batch*P, C_h]
+  const int64_t* tags[kNumHeads];   // int64 [batch*P]
+  const float* grad_out6;           // device: d L / d (loss_0 .. loss_4, total)
+  const double* loss_final;         // device: [5][2] = (sum w nll, sum w) of the forward loss (workspace of pair_loss_fwd)
+  float ratio[kNumHeads], class_w[3];
+  float* dbout[kNumHeads];          // db_out gradient buffers (accumulated into)
+};
+int launch_pair_bwd_prep_pair(const void* pack, const PackLayout& L, const __nv_bfloat16* ab, int n, int64_t g0, int rows,
+                              const float* const dz[kNumHeads], const FusedLossBwd* fused, __nv_bfloat16* S,
+                              __nv_bfloat16* G, float* dwout_part, cudaStream_t st, const DropSpec* drop = nullptr);
+
 // gemm_bwd_tc.cu
 int launch_gemm_ds(const __nv_bfloat16* G, const __nv_bfloat16* wmid_full, __nv_bfloat16* dS, int rows, cudaStream_t st);
 int launch_gemm_dw(const __nv_bfloat16* G, const __nv_bfloat16* S, float* const dW[kNumHeads], float* const db[kNumHeads],
                    int rows, cudaStream_t st);
+
+// gemm_bwd_tc2.cu : the same two GEMMs on CTA pairs (cta_group::2): half the B-operand traffic per SM
+int launch_gemm_ds_pair(const __nv_bfloat16* G, const __nv_bfloat16* wmid_full, __nv_bfloat16* dS, int rows, cudaStream_t st);
+int launch_gemm_dw_pair(const __nv_bfloat16* G, const __nv_bfloat16* S, float* const dW[kNumHeads], float* const db[kNumHeads],
+                        int rows, cudaStream_t st);
 
 // loss.cu
 size_t pair_loss_workspace_bytes(int batch, int n);
@@ -72,9 +91,11 @@ int launch_pair_loss_ohem_bwd(int batch, int n, const float* const logits[kNumHe
 
 // train.cu
 size_t heads_bwd_workspace_bytes(const peneo_dims& dm, int prec, int batch, int n);
+struct FusedLossBwd;
 int launch_heads_bwd(const peneo_dims& dm, int prec, const void* pack, const void* x, int x_dtype, int64_t x_row_stride,
                      int batch, int n, const float* const dlogits[kNumHeads], const peneo_grads& gr, float* dx,
-                     void* workspace, cudaStream_t st, const DropSpec* drop = nullptr);
+                     void* workspace, cudaStream_t st, const DropSpec* drop = nullptr,
+                     const FusedLossBwd* fused = nullptr);
 
 // decode.cu
 size_t decode_spots_workspace_bytes(int batch, int n);

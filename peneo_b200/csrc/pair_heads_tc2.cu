@@ -29,7 +29,10 @@ constexpr int kWStageBytes = 64 * 64 * 2;  // 8 KB: this CTA's 64 of the chunk's
 constexpr int kOStages = 3;
 constexpr int kOStageBytes = 2 * 8 * 64 * 2;  // 2 KB: two K-blocks of [8 rows x 64] (this CTA's half of 16)
 constexpr int kStageRowBytes = D * 2;          // staging: 128 rows x 768 B
-constexpr int kThreads = 512;
+constexpr int kEpiWarps = 16;      // 4 per scheduler: each takes 32 of a chunk's 128 columns
+constexpr int kProdWarp0 = 4 + kEpiWarps;
+constexpr int kProdRows = 2;        // pair rows a producer warp has in flight (register budget: 80 / thread)
+constexpr int kThreads = 32 * (kProdWarp0 + 4);
 
 constexpr uint32_t kColS = 0, kColU = 192, kColZ = 448;
 
@@ -83,7 +86,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     for (int s = 0; s < kOStages; ++s) ptx::mbar_init(&bars[bOFull + s], 2), ptx::mbar_init(&bars[bOEmpty + s], 1);
     for (int s = 0; s < 2; ++s) {
       ptx::mbar_init(&bars[bUFull + s], 1);
-      ptx::mbar_init(&bars[bMReady + s], 16);  // 8 epilogue warps of each CTA
+      ptx::mbar_init(&bars[bMReady + s], 2 * kEpiWarps);  // the epilogue warps of both CTAs
       ptx::mbar_init(&bars[bZFull + s], 1);
     }
     for (int s = 0; s < kKChunks; ++s) ptx::mbar_init(&bars[bSFull + s], 8), ptx::mbar_init(&bars[bSFree + s], 1);
@@ -159,7 +162,7 @@ __global__ void __launch_bounds__(kThreads, 1)
         const uint32_t mt = tmem + kColU + 128 * buf;
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks) {
-          const uint32_t at = mt + (ks < 4 ? 8 * ks : 64 + 8 * (ks - 4));
+          const uint32_t at = mt + 32 * (ks >> 1) + 8 * (ks & 1);  // m of columns [32 j, 32 j + 32) sits in TMEM columns [32 j, 32 j + 16)
           const uint64_t bd = ptx::umma_desc_sw128(o_base + os * kOStageBytes + (ks / 4) * 1024 + (ks % 4) * 32);
           ptx::umma_ts_2sm(zt, at, bd, idesc2, (cpos | ks) != 0);
         }
@@ -189,9 +192,11 @@ __global__ void __launch_bounds__(kThreads, 1)
       }
       if (g > 0) mma2(g - 1);
     }
-  } else if (warp >= 4 && warp < 12) {
+  } else if (warp >= 4 && warp < kProdWarp0) {
     // ============================== epilogue ==============================
-    const int q = warp % 4, hsel = (warp - 4) / 4;
+    // 16 warps: quadrant q = warp % 4 (TMEM lanes 32 q ..), column slice csel = (warp - 4) / 4 of the chunk's 128 columns.
+    // Four warps per scheduler hide the TMEM-load / MUFU / barrier latencies of one another.
+    const int q = warp % 4, csel = (warp - 4) / 4;
     const uint32_t lane_base = static_cast<uint32_t>(q * 32) << 16;
     const int row = q * 32 + lane;
     // logits of head-global index hg (tile = hg / 5, head = hg % 5)
@@ -217,46 +222,43 @@ __global__ void __launch_bounds__(kThreads, 1)
         const int buf = g & 1;
         ptx::mbar_wait(&bars[bUFull + buf], (g >> 1) & 1);
         ptx::tc_fence_after();
-        const uint32_t ut = tmem + lane_base + kColU + 128 * buf + 64 * hsel;
-        const float* hb = s_bmid + c * 128 + 64 * hsel;
+        const uint32_t ut = tmem + lane_base + kColU + 128 * buf + 32 * csel;
+        const float* hb = s_bmid + c * 128 + 32 * csel;
+        uint32_t r[32];
+        ptx::tmem_ld_x32(ut, r);
+        ptx::tmem_ld_wait();
+        uint32_t packed[16];
 #pragma unroll
-        for (int piece = 0; piece < 2; ++piece) {
-          uint32_t r[32];
-          ptx::tmem_ld_x32(ut + 32 * piece, r);
-          ptx::tmem_ld_wait();
-          uint32_t packed[16];
-#pragma unroll
-          for (int x = 0; x < 32; x += 4) {
-            const float4 b4 = *reinterpret_cast<const float4*>(hb + 32 * piece + x);
-            float m0 = __uint_as_float(r[x + 0]) + b4.x, m1 = __uint_as_float(r[x + 1]) + b4.y;
-            float m2 = __uint_as_float(r[x + 2]) + b4.z, m3 = __uint_as_float(r[x + 3]) + b4.w;
-            m0 = ptx::silu_from_half(m0), m1 = ptx::silu_from_half(m1);
-            m2 = ptx::silu_from_half(m2), m3 = ptx::silu_from_half(m3);
-            if (DROP) {  // nn.Dropout after the hidden SiLU (model/peneo_decoder.py:261), regenerable mask
-              const uint32_t key = a.drop_key[c / 3], grow = static_cast<uint32_t>(drop_row);
-              const uint32_t col = (c % 3) * 128 + 64 * hsel + 32 * piece + x;
-              m0 = drop_keep(key, a.drop_thresh, grow, col) ? m0 * a.drop_scale : 0.f;
-              m1 = drop_keep(key, a.drop_thresh, grow, col + 1) ? m1 * a.drop_scale : 0.f;
-              m2 = drop_keep(key, a.drop_thresh, grow, col + 2) ? m2 * a.drop_scale : 0.f;
-              m3 = drop_keep(key, a.drop_thresh, grow, col + 3) ? m3 * a.drop_scale : 0.f;
-            }
-            packed[x / 2] = ptx::pack_bf16x2(m0, m1);
-            packed[x / 2 + 1] = ptx::pack_bf16x2(m2, m3);
+        for (int x = 0; x < 32; x += 4) {
+          const float4 b4 = *reinterpret_cast<const float4*>(hb + x);
+          float m0 = __uint_as_float(r[x + 0]) + b4.x, m1 = __uint_as_float(r[x + 1]) + b4.y;
+          float m2 = __uint_as_float(r[x + 2]) + b4.z, m3 = __uint_as_float(r[x + 3]) + b4.w;
+          m0 = ptx::silu_from_half(m0), m1 = ptx::silu_from_half(m1);
+          m2 = ptx::silu_from_half(m2), m3 = ptx::silu_from_half(m3);
+          if (DROP) {  // nn.Dropout after the hidden SiLU (model/peneo_decoder.py:261), regenerable mask
+            const uint32_t key = a.drop_key[c / 3], grow = static_cast<uint32_t>(drop_row);
+            const uint32_t col = (c % 3) * 128 + 32 * csel + x;
+            m0 = drop_keep(key, a.drop_thresh, grow, col) ? m0 * a.drop_scale : 0.f;
+            m1 = drop_keep(key, a.drop_thresh, grow, col + 1) ? m1 * a.drop_scale : 0.f;
+            m2 = drop_keep(key, a.drop_thresh, grow, col + 2) ? m2 * a.drop_scale : 0.f;
+            m3 = drop_keep(key, a.drop_thresh, grow, col + 3) ? m3 * a.drop_scale : 0.f;
           }
-          // m overwrites the first half of the columns this warp has already consumed
-          ptx::tmem_st_x16(ut + 16 * piece, packed);
+          packed[x / 2] = ptx::pack_bf16x2(m0, m1);
+          packed[x / 2 + 1] = ptx::pack_bf16x2(m2, m3);
         }
+        // m overwrites the first half of the 32 columns this warp has consumed
+        ptx::tmem_st_x16(ut, packed);
         ptx::tmem_st_wait();
         ptx::tc_fence_before();
         __syncwarp();
         if (lane == 0) arrive_leader(&bars[bMReady + buf]);
-        if (hsel == 0 && g > 0 && g % 3 == 0) emit_z(g / 3 - 1);
+        if (csel == 0 && g > 0 && g % 3 == 0) emit_z(g / 3 - 1);
       }
     }
-    if (hsel == 0 && g > 0) emit_z(g / 3 - 1);
-  } else if (warp >= 12) {
+    if (csel == 0 && g > 0) emit_z(g / 3 - 1);
+  } else if (warp >= kProdWarp0) {
     // ============================== pair producers ==============================
-    const int q = warp - 12;
+    const int q = warp - kProdWarp0;
     const uint32_t lane_base = static_cast<uint32_t>(q * 32) << 16;
     unsigned char* stg = smem + Smem::stage;
     for (int it = 0; it < my_tiles; ++it) {
@@ -276,11 +278,11 @@ __global__ void __launch_bounds__(kThreads, 1)
       }
       // ---- generate s rows [32q, 32q+32) into staging; lane = 4-column group (3 groups per lane)
 #pragma unroll 1
-      for (int rr = 0; rr < 32; rr += 4) {
-        uint2 av[4][3], bv[4][3];
-        int64_t offa[4];
+      for (int rr = 0; rr < 32; rr += kProdRows) {
+        uint2 av[kProdRows][3], bv[kProdRows][3];
+        int64_t offa[kProdRows];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < kProdRows; ++u) {
           offa[u] = __shfl_sync(0xffffffffu, my_a, rr + u);
           const int64_t offb = __shfl_sync(0xffffffffu, my_b, rr + u);
 #pragma unroll
@@ -295,7 +297,7 @@ __global__ void __launch_bounds__(kThreads, 1)
           }
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < kProdRows; ++u) {
           const int r = q * 32 + rr + u;
 #pragma unroll
           for (int mth = 0; mth < 3; ++mth) {

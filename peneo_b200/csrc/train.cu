@@ -543,7 +543,7 @@ size_t heads_bwd_workspace_bytes(const peneo_dims& dm, int prec, int batch, int 
 
 int launch_heads_bwd(const peneo_dims& dm, int prec, const void* pack, const void* x, int x_dtype, int64_t x_row_stride,
                      int batch, int n, const float* const dlogits[kNumHeads], const peneo_grads& gr, float* dx,
-                     void* workspace, cudaStream_t st, const DropSpec* drop_in) {
+                     void* workspace, cudaStream_t st, const DropSpec* drop_in, const FusedLossBwd* fused_in) {
   const PackLayout L = pack_layout(dm, prec);
   const DropSpec drop = drop_in ? *drop_in : DropSpec{0u, 1.f, 0u, 0u};
   auto with_drop = [&](Gemm& gm, uint32_t site, uint32_t row0) {  // C2 = Dropout(SiLU(C)) of the forward pass
@@ -668,20 +668,36 @@ int launch_heads_bwd(const peneo_dims& dm, int prec, const void* pack, const voi
         __nv_bfloat16* Gc = reinterpret_cast<__nv_bfloat16*>(ws + pl.off_Gc);
         const __nv_bfloat16* ab16 = reinterpret_cast<const __nv_bfloat16*>(ws + pl.off_ab16);
         // T1: regenerate S and u, store S and G = (dz W_out) SiLU'(u), reduce dW_out += dz^T SiLU(u) into the per-CTA
-        // partial sums (tcgen05, K2's structure)
-        TRY(launch_pair_bwd_prep(pack, L, ab16, n, g0, rows, dlogits, S16, Gc, F(pl.off_dwpart), st,
-                                 drop.thresh ? &drop : nullptr));
+        // partial sums (tcgen05, K2's structure; on CTA pairs unless PENEO_T1_PAIR=0).  With the fused loss, dz is
+        // computed inside T1 from logits + tags and db_out is reduced there as well.
+        static const bool t1_pair = [] { const char* e = getenv("PENEO_T1_PAIR"); return !e || atoi(e) != 0; }();
+        FusedLossBwd fl{};
+        if (fused_in) {
+          fl = *fused_in;
+          for (int h = 0; h < kNumHeads; ++h) fl.dbout[h] = gr.out_b[h];
+        }
+        if (t1_pair || fused_in)
+          TRY(launch_pair_bwd_prep_pair(pack, L, ab16, n, g0, rows, dlogits, fused_in ? &fl : nullptr, S16, Gc,
+                                        F(pl.off_dwpart), st, drop.thresh ? &drop : nullptr));
+        else
+          TRY(launch_pair_bwd_prep(pack, L, ab16, n, g0, rows, dlogits, S16, Gc, F(pl.off_dwpart), st,
+                                   drop.thresh ? &drop : nullptr));
         // dS = G W_mid (all heads in one K = 1920 GEMM) ; dW_mid += G^T S
-        TRY(launch_gemm_ds(Gc, reinterpret_cast<const __nv_bfloat16*>(pk + L.wmid_full_bf16), reinterpret_cast<__nv_bfloat16*>(dS), rows, st));
+        // (CTA-pair kernels by default; PENEO_BWD_PAIR=0 selects the single-CTA ones for A/B studies)
+        static const bool gemm_pair = [] { const char* e = getenv("PENEO_BWD_PAIR"); return !e || atoi(e) != 0; }();
+        TRY((gemm_pair ? launch_gemm_ds_pair : launch_gemm_ds)(Gc, reinterpret_cast<const __nv_bfloat16*>(pk + L.wmid_full_bf16),
+                                                              reinterpret_cast<__nv_bfloat16*>(dS), rows, st));
         float *dwm[kNumHeads], *dbm[kNumHeads];
-        DzPtrs dzp;
+        DzPtrs dzp{};
         for (int h = 0; h < kNumHeads; ++h) {
           dwm[h] = gr.mid_w[h * 8], dbm[h] = gr.mid_b[h * 8];
-          dzp.p[h] = dlogits[h] + g0 * head_classes(h);
+          if (!fused_in) dzp.p[h] = dlogits[h] + g0 * head_classes(h);
         }
-        TRY(launch_gemm_dw(Gc, S16, dwm, dbm, rows, st));  // + db_mid (column sums of G)
-        dbout_kernel<<<dim3(std::min((rows + 1023) / 1024, 296), kNumHeads), 256, 0, st>>>(dzp, rows, d_outb);
-        PENEO_CUDA_TRY(cudaGetLastError());
+        TRY((gemm_pair ? launch_gemm_dw_pair : launch_gemm_dw)(Gc, S16, dwm, dbm, rows, st));  // + db_mid (column sums of G)
+        if (!fused_in) {  // (the fused T1 reduces db_out itself)
+          dbout_kernel<<<dim3(std::min((rows + 1023) / 1024, 296), kNumHeads), 256, 0, st>>>(dzp, rows, d_outb);
+          PENEO_CUDA_TRY(cudaGetLastError());
+        }
       } else {
       for (const Seg& sg : segs) {
         build_s_kernel<<<sg.rows, 128, 0, st>>>(ab, sg.b, n, d, row_start(sg.i0, n), S + sg.off * d);
