@@ -25,6 +25,8 @@ def main():
     ap.add_argument("--precision", default="bf16")
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--hin", type=int, default=768, help="width of the backbone output (960 = LiLT, BASELINE configs[2])")
+    ap.add_argument("--no-fused-loss", action="store_true", help="separate loss kernels + explicit dlogits (A/B)")
     args = ap.parse_args()
 
     class Cfg:
@@ -42,15 +44,16 @@ def main():
     world, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local_rank)
-    dec = PEneoDecoderB200(Cfg, 768)
-    dec.load_state_dict(synth.init_decoder_state(seed=0))
+    dec = PEneoDecoderB200(Cfg, args.hin)
+    dec.load_state_dict(synth.init_decoder_state(hin=args.hin, seed=0))
     dec = dec.cuda().eval()
+    dec.fused_loss = not args.no_fused_loss
     module = dec
     if world > 1:  # what HF Trainer does for the reference: DDP, one process per GPU, gradients averaged over NCCL
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
         dec = torch.nn.parallel.DistributedDataParallel(dec, device_ids=[local_rank])
-    x = synth.hidden_states(args.batch, n, 768, doc_id0=1000 * rank).cuda().requires_grad_(True)
+    x = synth.hidden_states(args.batch, n, args.hin, doc_id0=1000 * rank).cuda().requires_grad_(True)
     docs = [synth.make_document(n, doc_id=1000 * rank + i, style="sibr") for i in range(args.batch)]
     tags = [torch.stack([d.tags()[k] for d in docs]).cuda() for k in range(5)]
 
@@ -76,7 +79,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     p = n * (n + 1) // 2
-    f_heads = 2.0 * n * (768 * 768 + 768 * 384 + 2 * 384 * 384) + 10.0 * p * 384 * 384 + 28.0 * p * 384
+    f_heads = 2.0 * n * (args.hin * 768 + 768 * 384 + 2 * 384 * 384) + 10.0 * p * 384 * 384 + 28.0 * p * 384
     peak = 1427.8
     try:
         peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops_sustained"]
@@ -85,8 +88,8 @@ def main():
     tf = 3.0 * f_heads * args.batch / (ms * 1e-3) / 1e12  # per GPU
     if rank == 0:
         print(json.dumps({"what": "decoder fine-tuning step (fwd + loss + bwd" + (", DDP all-reduce)" if world > 1 else ")"),
-                      "precision": args.precision, "seq_len": args.seq_len, "n_gpus": world,
-                      "batch": args.batch, "ms_per_step": ms, "docs_per_s": world * args.batch / (ms * 1e-3), "loss": float(loss),
+                      "precision": args.precision, "fused_loss": not args.no_fused_loss, "hin": args.hin, "seq_len": args.seq_len, "n_gpus": world,
+                      "batch": args.batch, "ms_per_step": ms, "docs_per_s": world * args.batch / (ms * 1e-3), "loss": float(loss.detach()),
                       "tflops_vs_3F": tf, "frac_of_sustained_bf16_peak": tf / peak,
                       "peak_mem_gb": torch.cuda.max_memory_allocated() / 2**30}))
     if world > 1:

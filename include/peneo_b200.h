@@ -13,6 +13,8 @@
  *                                   (OHEM off) + the ratio-weighted sum     model/peneo_decoder.py:315-336, 375-428; model/custom_loss.py:189-202
  *   peneo_pair_loss_ohem_fwd/bwd .. CrossEntropyLossOHEM with hard-example
  *                                   selection (forward value + d loss/d logits) model/custom_loss.py:204-288
+ *   peneo_pair_heads_loss_fwd ..... the two above fused: heads + loss in one sweep over the pair tiles
+ *   peneo_heads_loss_bwd .......... loss backward + heads backward fused (no d loss / d logits tensor)
  *   peneo_heads_bwd ............... autograd backward of token_proj + pair_heads (implicit in the reference:
  *                                   loss.backward() through model/peneo_decoder.py:349-363)
  *   peneo_scatter_tags ............ HandshakingTaggingScheme.spots2shaking_tag4batch   model/peneo_decoder.py:34-73
@@ -133,6 +135,28 @@ int peneo_pair_loss_bwd(int32_t batch, int32_t n, const float* const logits[PENE
                         const int64_t* const tags[PENEO_NUM_HEADS], const float* class_w_host,
                         const float* ratio_host, const float* grad_out6, const void* workspace,
                         float* const dlogits[PENEO_NUM_HEADS], void* stream);
+
+/* Fused forms for training with the loss inside the pair tiles (PENEO_PREC_BF16, the fused tcgen05 configuration,
+ * OHEM off; peneo_fused_loss_supported() tells).  What model/peneo_decoder.py:355-428 + model/custom_loss.py:189-202 do
+ * in separate passes over [batch, P, C] tensors:
+ *   peneo_pair_heads_loss_fwd = peneo_pair_heads_fwd + peneo_pair_loss_fwd in ONE kernel: the epilogue that writes a
+ *     pair's logits also reduces its w[t] * nll and w[t] (same outputs: logits, out6, loss_workspace);
+ *   peneo_heads_loss_bwd      = peneo_pair_loss_bwd + peneo_heads_bwd without d loss / d logits ever existing in
+ *     memory: the backward tiles compute it in registers from logits + tags + the normalisers in loss_workspace
+ *     (grad_out6 as in peneo_pair_loss_bwd), and reduce db_out on the fly.
+ * loss_workspace: peneo_pair_loss_workspace_bytes(batch, n), written by the forward call, read by the backward call. */
+int peneo_fused_loss_supported(const peneo_dims* dims, int prec);
+int peneo_pair_heads_loss_fwd(const peneo_dims* dims, int prec, const void* pack, const void* ab, int32_t batch, int32_t n,
+                              float* const logits[PENEO_NUM_HEADS], const int64_t* const tags[PENEO_NUM_HEADS],
+                              const float* class_w_host, const float* ratio_host, float* out6, void* loss_workspace,
+                              const peneo_dropout* dropout, void* stream);
+/* (declared here, next to its forward half; the gradient structs are defined below) */
+struct peneo_grads;
+int peneo_heads_loss_bwd(const peneo_dims* dims, int prec, const void* pack, const void* x, int x_dtype,
+                         int64_t x_row_stride, int32_t batch, int32_t n, const float* const logits[PENEO_NUM_HEADS],
+                         const int64_t* const tags[PENEO_NUM_HEADS], const float* class_w_host, const float* ratio_host,
+                         const float* grad_out6, const void* loss_workspace, const struct peneo_grads* grads, float* dx,
+                         void* workspace, const peneo_dropout* dropout, void* stream);
 
 /* Same five sub-losses with online hard-example mining (num_hard_positive / num_hard_negative as in
  * PEneoConfig.peneo_ohem_num_positive / _negative; -1 = keep the whole side).  Reproduces the reference's

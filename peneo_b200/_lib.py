@@ -32,6 +32,9 @@ SYMBOLS = (
     "peneo_pair_loss_workspace_bytes",
     "peneo_pair_loss_fwd",
     "peneo_pair_loss_bwd",
+    "peneo_fused_loss_supported",
+    "peneo_pair_heads_loss_fwd",
+    "peneo_heads_loss_bwd",
     "peneo_pair_loss_ohem_workspace_bytes",
     "peneo_pair_loss_ohem_fwd",
     "peneo_pair_loss_ohem_bwd",
@@ -107,6 +110,12 @@ def load() -> C.CDLL:
                                         vp, vp]
     lib.peneo_pair_loss_bwd.argtypes = [i32, i32, PtrArray5, PtrArray5, C.POINTER(C.c_float), C.POINTER(C.c_float), vp,
                                         vp, PtrArray5, vp]
+    lib.peneo_fused_loss_supported.argtypes = [C.POINTER(Dims), C.c_int]
+    lib.peneo_pair_heads_loss_fwd.argtypes = [C.POINTER(Dims), C.c_int, vp, vp, i32, i32, PtrArray5, PtrArray5,
+                                              C.POINTER(C.c_float), C.POINTER(C.c_float), vp, vp, C.POINTER(Dropout), vp]
+    lib.peneo_heads_loss_bwd.argtypes = [C.POINTER(Dims), C.c_int, vp, vp, C.c_int, i64, i32, i32, PtrArray5, PtrArray5,
+                                         C.POINTER(C.c_float), C.POINTER(C.c_float), vp, vp, C.POINTER(Grads), vp, vp,
+                                         C.POINTER(Dropout), vp]
     lib.peneo_pair_loss_ohem_workspace_bytes.restype = sz
     lib.peneo_pair_loss_ohem_workspace_bytes.argtypes = [i32, i32]
     lib.peneo_pair_loss_ohem_fwd.argtypes = [i32, i32, PtrArray5, PtrArray5, C.POINTER(C.c_float), C.POINTER(C.c_float),

@@ -233,6 +233,65 @@ int peneo_heads_bwd(const peneo_dims* dims, int prec, const void* pack, const vo
 
 size_t peneo_pair_loss_workspace_bytes(int32_t batch, int32_t n) { return pair_loss_workspace_bytes(batch, n); }
 
+int peneo_fused_loss_supported(const peneo_dims* dims, int prec) {
+  return dims && check_dims(dims) == PENEO_OK && prec == PENEO_PREC_BF16 && bf16_supported(*dims) ? 1 : 0;
+}
+
+int peneo_pair_heads_loss_fwd(const peneo_dims* dims, int prec, const void* pack, const void* ab, int32_t batch, int32_t n,
+                              float* const logits[PENEO_NUM_HEADS], const int64_t* const tags[PENEO_NUM_HEADS],
+                              const float* class_w_host, const float* ratio_host, float* out6, void* loss_workspace,
+                              const peneo_dropout* dropout, void* stream) {
+  int rc;
+  if ((rc = check_dims(dims)) != PENEO_OK || (rc = check_prec(dims, prec)) != PENEO_OK) return rc;
+  PENEO_REQUIRE(peneo_fused_loss_supported(dims, prec), "pair_heads_loss_fwd: only the fused tcgen05 configuration "
+                "(PENEO_PREC_BF16, shrink, hid 768, d 384, 2 layers); use pair_heads_fwd + pair_loss_fwd otherwise");
+  PENEO_REQUIRE(pack && ab && logits && tags && class_w_host && out6 && loss_workspace, "pair_heads_loss_fwd: NULL pointer");
+  PENEO_REQUIRE(batch >= 1 && n >= 1 && n <= 46340, "pair_heads_loss_fwd: bad sizes batch=%d n=%d", batch, n);
+  for (int h = 0; h < kNumHeads; ++h) PENEO_REQUIRE(logits[h] && tags[h], "pair_heads_loss_fwd: head %d pointer is NULL", h);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const DropSpec drop = make_drop(dropout);
+  FusedLossFwd fl{};
+  for (int h = 0; h < kNumHeads; ++h) fl.tags[h] = tags[h];
+  for (int c = 0; c < 3; ++c) fl.class_w[c] = class_w_host[c];
+  fl.partial = pair_loss_partial_ptr(loss_workspace);
+  int grid = 0;
+  if ((rc = launch_pair_heads_tc_pair(pack, pack_layout(*dims, prec), static_cast<const __nv_bfloat16*>(ab), batch, n, logits, st,
+                                      drop.thresh ? &drop : nullptr, &fl, &grid)) != PENEO_OK)
+    return rc;
+  return launch_pair_loss_finalize(ratio_host, out6, loss_workspace, grid, st);
+}
+
+int peneo_heads_loss_bwd(const peneo_dims* dims, int prec, const void* pack, const void* x, int x_dtype, int64_t x_row_stride,
+                         int32_t batch, int32_t n, const float* const logits[PENEO_NUM_HEADS],
+                         const int64_t* const tags[PENEO_NUM_HEADS], const float* class_w_host, const float* ratio_host,
+                         const float* grad_out6, const void* loss_workspace, const peneo_grads* grads, float* dx,
+                         void* workspace, const peneo_dropout* dropout, void* stream) {
+  int rc;
+  if ((rc = check_dims(dims)) != PENEO_OK || (rc = check_prec(dims, prec)) != PENEO_OK) return rc;
+  PENEO_REQUIRE(peneo_fused_loss_supported(dims, prec), "heads_loss_bwd: only the fused tcgen05 configuration; use "
+                "pair_loss_bwd + heads_bwd otherwise");
+  PENEO_REQUIRE(pack && x && logits && tags && class_w_host && grad_out6 && loss_workspace && grads && workspace,
+                "heads_loss_bwd: NULL pointer");
+  PENEO_REQUIRE(batch >= 1 && n >= 1 && n <= 46340, "heads_loss_bwd: bad sizes batch=%d n=%d", batch, n);
+  PENEO_REQUIRE((int64_t)batch * n < (1ll << 31), "heads_loss_bwd: too many tokens");
+  PENEO_REQUIRE(x_row_stride >= dims->hin, "heads_loss_bwd: row stride smaller than hin");
+  PENEO_REQUIRE(grads->combine_w && grads->combine_b && grads->shrink_w1 && grads->shrink_b1 && grads->shrink_w2 &&
+                    grads->shrink_b2, "heads_loss_bwd: gradient buffers missing");
+  FusedLossBwd fb{};
+  for (int h = 0; h < kNumHeads; ++h) {
+    PENEO_REQUIRE(logits[h] && tags[h] && grads->out_w[h] && grads->out_b[h] && grads->mid_w[h * 8] && grads->mid_b[h * 8],
+                  "heads_loss_bwd: head %d buffers missing", h);
+    fb.logits[h] = logits[h], fb.tags[h] = tags[h], fb.ratio[h] = ratio_host ? ratio_host[h] : 1.f;
+  }
+  for (int c = 0; c < 3; ++c) fb.class_w[c] = class_w_host[c];
+  fb.grad_out6 = grad_out6;
+  fb.loss_final = pair_loss_final_ptr(loss_workspace);
+  const DropSpec drop = make_drop(dropout);
+  const float* no_dz[kNumHeads] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  return launch_heads_bwd(*dims, prec, pack, x, x_dtype, x_row_stride, batch, n, no_dz, *grads, dx, workspace,
+                          static_cast<cudaStream_t>(stream), drop.thresh ? &drop : nullptr, &fb);
+}
+
 int peneo_pair_loss_fwd(int32_t batch, int32_t n, const float* const logits[PENEO_NUM_HEADS],
                         const int64_t* const tags[PENEO_NUM_HEADS], const float* class_w_host, const float* ratio_host,
                         float* out6, void* workspace, void* stream) {

@@ -31,9 +31,16 @@ int launch_gemm_tc2(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* W,
 int launch_pair_heads_tc(const void* pack, const PackLayout& L, const __nv_bfloat16* ab, int batch, int n,
                          float* const logits[kNumHeads], cudaStream_t st, const DropSpec* drop = nullptr);
 
-// pair_heads_tc2.cu : the same kernel on CTA pairs (cta_group::2, M = 256)
+// pair_heads_tc2.cu : the same kernel on CTA pairs (cta_group::2, M = 256).  With `loss` != NULL the class-weighted cross
+// entropy is reduced inside the tiles (per-CTA fp64 partial sums; *grid_out CTAs wrote them).
+struct FusedLossFwd {
+  const int64_t* tags[kNumHeads];
+  float class_w[3];
+  double* partial;  // [5][grid][2]
+};
 int launch_pair_heads_tc_pair(const void* pack, const PackLayout& L, const __nv_bfloat16* ab, int batch, int n,
-                              float* const logits[kNumHeads], cudaStream_t st, const DropSpec* drop = nullptr);
+                              float* const logits[kNumHeads], cudaStream_t st, const DropSpec* drop = nullptr,
+                              const FusedLossFwd* loss = nullptr, int* grid_out = nullptr);
 
 // pair_heads_generic.cu : unfused tensor-core forward for the configurations K2 does not cover (any d % 64 == 0, any
 // num_layers): S = SiLU(a_i + b_j) per chunk of pairs, one gemm_tc2 per hidden layer and head, output layer as an
@@ -78,6 +85,12 @@ int launch_pair_loss_fwd(int batch, int n, const float* const logits[kNumHeads],
 int launch_pair_loss_bwd(int batch, int n, const float* const logits[kNumHeads], const int64_t* const tags[kNumHeads],
                          const float* class_w, const float* ratio, const float* grad_out, const void* ws,
                          float* const dlogits[kNumHeads], cudaStream_t st);
+// final reduction of per-CTA partial sums written by another kernel (K2 with the fused loss): out6 + the (sum w nll, sum w)
+// pairs the backward pass normalises with
+int launch_pair_loss_finalize(const float* ratio, float* out6, void* ws, int nblocks, cudaStream_t st);
+const double* pair_loss_final_ptr(const void* ws);
+double* pair_loss_partial_ptr(void* ws);
+int pair_loss_max_blocks();
 int launch_scatter_tags(const int32_t* spots, int64_t num_spots, int batch, int n, int64_t* tags, cudaStream_t st);
 
 // ohem.cu

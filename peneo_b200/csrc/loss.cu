@@ -145,6 +145,21 @@ int launch_pair_loss_fwd(int batch, int n, const float* const logits[kNumHeads],
   return PENEO_OK;
 }
 
+int launch_pair_loss_finalize(const float* ratio, float* out6, void* ws, int nblocks, cudaStream_t st) {
+  PENEO_REQUIRE(nblocks >= 1 && nblocks <= kLossBlocks, "pair_loss_finalize: %d partial blocks (max %d)", nblocks, kLossBlocks);
+  LossArgs a{};
+  for (int h = 0; h < kNumHeads; ++h) a.ratio[h] = ratio ? ratio[h] : 1.f;
+  a.partial = static_cast<double*>(ws);
+  a.final_ = a.partial + kNumHeads * kLossBlocks * 2;
+  a.out6 = out6;
+  pair_loss_final_kernel<<<1, 32 * kNumHeads, 0, st>>>(a, nblocks);
+  PENEO_CUDA_TRY(cudaGetLastError());
+  return PENEO_OK;
+}
+const double* pair_loss_final_ptr(const void* ws) { return static_cast<const double*>(ws) + kNumHeads * kLossBlocks * 2; }
+double* pair_loss_partial_ptr(void* ws) { return static_cast<double*>(ws); }
+int pair_loss_max_blocks() { return kLossBlocks; }
+
 int launch_pair_loss_bwd(int batch, int n, const float* const logits[kNumHeads], const int64_t* const tags[kNumHeads],
                          const float* class_w, const float* ratio, const float* grad_out, const void* ws,
                          float* const dlogits[kNumHeads], cudaStream_t st) {

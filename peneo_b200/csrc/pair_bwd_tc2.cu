@@ -252,31 +252,38 @@ __global__ void __launch_bounds__(kThreads, 1) pair_bwd_prep_pair_kernel(const _
       atomicAdd(dst + kLdG, __uint_as_float(d4[1]));
       atomicAdd(dst + 2 * kLdG, __uint_as_float(d4[2]));
     };
-    // dz of (tile, head) for this lane's pair; loaded one chunk ahead of its first use so the latency is hidden
-    auto load_dz = [&](int64_t tile_, int k_, float& z0, float& z1, float& z2) {
-      z0 = z1 = z2 = 0.f;
+    // dz of (tile, head) for this lane's pair.  The global loads are issued one chunk ahead of the first use
+    // (fetch_dz: raw dz, or raw logits + tag in the FUSED form) and turned into dz where they are consumed (make_dz),
+    // so that their latency never sits in the epilogue's dependency chain.
+    auto fetch_dz = [&](int64_t tile_, int k_, float& z0, float& z1, float& z2, int& tg) {
+      z0 = z1 = z2 = 0.f, tg = -1;
       const int64_t lr_ = tile_ * 128 + row;
       if (lr_ < a.rows) {
         const int C = head_classes(k_);
         const int64_t gp_ = a.g0 + lr_;
+        const float* p = (FUSED ? a.logits[k_] : a.dz[k_]) + gp_ * C;
+        z0 = p[0], z1 = p[1];
+        if (C == 3) z2 = p[2];
         if (FUSED) {
-          const float* zp = a.logits[k_] + gp_ * C;
-          const float x0 = zp[0], x1 = zp[1], x2 = C == 3 ? zp[2] : -INFINITY;
-          bool bad;
-          const int t = checked_tag(a.tags[k_][gp_], C, bad);
-          const float mx = fmaxf(fmaxf(x0, x1), x2);
-          const float e0 = expf(x0 - mx), e1 = expf(x1 - mx), e2 = C == 3 ? expf(x2 - mx) : 0.f;
-          const float gsc = bad ? NAN : s_scale[k_] * s_cw[t] / (e0 + e1 + e2);
-          z0 = gsc * e0 - (t == 0 ? s_scale[k_] * s_cw[0] : 0.f);
-          z1 = gsc * e1 - (t == 1 ? s_scale[k_] * s_cw[1] : 0.f);
-          z2 = C == 3 ? gsc * e2 - (t == 2 ? s_scale[k_] * s_cw[2] : 0.f) : 0.f;
-        } else {
-          const float* p = a.dz[k_] + gp_ * C;
-          z0 = p[0], z1 = p[1];
-          if (C == 3) z2 = p[2];
+          const long long t64 = a.tags[k_][gp_];
+          tg = (t64 < 0 || t64 >= C) ? 3 : static_cast<int>(t64);  // 3 = target outside [0, C): poison with NaN
         }
       }
-      if (FUSED && wsel == 0) {  // db_out[k] += sum over pairs of dz (one of the warps that hold this row)
+    };
+    auto make_dz = [&](int k_, float& z0, float& z1, float& z2, int tg) {
+      if (!FUSED) return;
+      if (tg >= 0) {  // dz = scale_k w[t] (softmax(z) - onehot(t))
+        const int C = head_classes(k_);
+        const float x2 = C == 3 ? z2 : -INFINITY;
+        const float mx = fmaxf(fmaxf(z0, z1), x2);
+        const float e0 = __expf(z0 - mx), e1 = __expf(z1 - mx), e2 = C == 3 ? __expf(x2 - mx) : 0.f;
+        const float sw = s_scale[k_] * s_cw[tg == 3 ? 0 : tg];
+        const float gsc = tg == 3 ? NAN : __fdividef(sw, e0 + e1 + e2);
+        z0 = gsc * e0 - (tg == 0 ? sw : 0.f);
+        z1 = gsc * e1 - (tg == 1 ? sw : 0.f);
+        z2 = C == 3 ? gsc * e2 - (tg == 2 ? sw : 0.f) : 0.f;
+      }
+      if (wsel == 0) {  // db_out[k] += sum over pairs of dz (one of the warps that hold this row)
         float r0 = z0, r1 = z1, r2 = z2;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
@@ -288,7 +295,8 @@ __global__ void __launch_bounds__(kThreads, 1) pair_bwd_prep_pair_kernel(const _
     };
     int g = 0;
     float nz0 = 0.f, nz1 = 0.f, nz2 = 0.f;
-    if (my_tiles > 0) load_dz(tile_of(0), 0, nz0, nz1, nz2);
+    int ntg = -1;
+    if (my_tiles > 0) fetch_dz(tile_of(0), 0, nz0, nz1, nz2, ntg);
     for (int it = 0; it < my_tiles; ++it) {
       const int64_t tile = tile_of(it);
       const int64_t lr = tile * 128 + row;          // row inside the chunk
@@ -296,10 +304,14 @@ __global__ void __launch_bounds__(kThreads, 1) pair_bwd_prep_pair_kernel(const _
       float dz0 = 0.f, dz1 = 0.f, dz2 = 0.f;
       for (int c = 0; c < kChunks; ++c, ++g) {
         const int buf = g & 1, k = c / 3;
-        if (c - 3 * k == 0) dz0 = nz0, dz1 = nz1, dz2 = nz2;
+        if (c - 3 * k == 0) {
+          dz0 = nz0, dz1 = nz1, dz2 = nz2;
+          make_dz(k, dz0, dz1, dz2, ntg);
+        }
         if (c - 3 * k == 2) {  // prefetch for the next head (or head 0 of this CTA's next tile)
-          if (k + 1 < kNumHeads) load_dz(tile, k + 1, nz0, nz1, nz2);
-          else if (it + 1 < my_tiles) load_dz(tile_of(it + 1), 0, nz0, nz1, nz2);
+          if (k + 1 < kNumHeads) fetch_dz(tile, k + 1, nz0, nz1, nz2, ntg);
+          else if (it + 1 < my_tiles) fetch_dz(tile_of(it + 1), 0, nz0, nz1, nz2, ntg);
+          else nz0 = nz1 = nz2 = 0.f, ntg = -1;
         }
         if (wsel == kEpiWarps / 4 - 1 && g >= 2) flush_dw(g - 2);
         if (wsel == 0 && c - 3 * k == 0) {
@@ -344,23 +356,26 @@ __global__ void __launch_bounds__(kThreads, 1) pair_bwd_prep_pair_kernel(const _
             uint32_t gq[4], mq[4];
 #pragma unroll
             for (int y = 0; y < 4; ++y) {
-              float mv[2], dv[2];
-#pragma unroll
-              for (int e = 0; e < 2; ++e) {
-                const float h = __uint_as_float(r[8 * v + 2 * y + e]) + hbv[2 * y + e];  // u / 2
-                const float t = ptx::tanh_approx(h);
-                mv[e] = fmaf(h, t, h);                                  // SiLU(u) = u sigmoid(u) = h (1 + tanh h)
-                const float sg = fmaf(0.5f, t, 0.5f), oms = fmaf(-0.5f, t, 0.5f);
-                dv[e] = fmaf(mv[e], oms, sg);                           // SiLU'(u) = sg + m (1 - sg)
-                if (DROP) {  // m_dropped = m * mask / (1 - p) feeds W_out; its gradient carries the same factor
-                  const float ms = drop_keep(a.drop_key[k], a.drop_thresh, static_cast<uint32_t>(gp),
-                                             (c - 3 * k) * 128 + 32 * csel + 8 * v + 2 * y + e) ? a.drop_scale : 0.f;
-                  mv[e] *= ms, dv[e] *= ms;
-                }
+              // tanh in fp32 (one MUFU each), everything after it as packed bf16x2 FMAs: m, SiLU' and g leave as bf16
+              // anyway, and the epilogue is bound by the number of instructions it issues
+              const float h0 = __uint_as_float(r[8 * v + 2 * y]) + hbv[2 * y];          // u / 2
+              const float h1 = __uint_as_float(r[8 * v + 2 * y + 1]) + hbv[2 * y + 1];
+              const uint32_t t2 = ptx::pack_bf16x2(ptx::tanh_approx(h0), ptx::tanh_approx(h1));
+              const uint32_t h2 = ptx::pack_bf16x2(h0, h1);
+              uint32_t m2 = ptx::hfma2_bf16(h2, t2, h2);                     // SiLU(u) = h (1 + tanh h)
+              const uint32_t sg2 = ptx::hfma2_bf16(0x3F003F00u, t2, 0x3F003F00u);  // sigmoid(u) = 0.5 + 0.5 tanh h
+              const uint32_t oms2 = ptx::hfma2_bf16(0xBF00BF00u, t2, 0x3F003F00u); // 1 - sigmoid(u)
+              uint32_t dv2 = ptx::hfma2_bf16(m2, oms2, sg2);                 // SiLU'(u) = sg + m (1 - sg)
+              if (DROP) {  // m_dropped = m * mask / (1 - p) feeds W_out; its gradient carries the same factor
+                const uint32_t col = (c - 3 * k) * 128 + 32 * csel + 8 * v + 2 * y;
+                const float ms0 = drop_keep(a.drop_key[k], a.drop_thresh, static_cast<uint32_t>(gp), col) ? a.drop_scale : 0.f;
+                const float ms1 = drop_keep(a.drop_key[k], a.drop_thresh, static_cast<uint32_t>(gp), col + 1) ? a.drop_scale : 0.f;
+                const uint32_t ms2 = ptx::pack_bf16x2(ms0, ms1);
+                m2 = ptx::hmul2_bf16(m2, ms2), dv2 = ptx::hmul2_bf16(dv2, ms2);
               }
-              mq[y] = ptx::pack_bf16x2(mv[0], mv[1]);
+              mq[y] = m2;
               const uint32_t gm = ptx::hfma2_bf16(dzb2, w2a[y], ptx::hfma2_bf16(dzb1, w1a[y], ptx::hmul2_bf16(dzb0, w0a[y])));
-              gq[y] = ptx::hmul2_bf16(gm, ptx::pack_bf16x2(dv[0], dv[1]));
+              gq[y] = ptx::hmul2_bf16(gm, dv2);
             }
             // G staging tile: row pitch 64 B, 16-byte chunk index XOR ((row >> 1) & 3): conflict-free writes and reads
             *reinterpret_cast<uint4*>(ob + lane * 64 + ((v ^ ((lane >> 1) & 3)) * 16)) = make_uint4(gq[0], gq[1], gq[2], gq[3]);

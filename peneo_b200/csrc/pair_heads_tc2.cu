@@ -42,7 +42,8 @@ struct Smem {
   static constexpr int stage = o + kOStages * kOStageBytes;
   static constexpr int bmid = stage + 128 * kStageRowBytes;  // 1920 floats
   static constexpr int bout = bmid + 5 * D * 4;              // 20 floats
-  static constexpr int bars = bout + 128;
+  static constexpr int loss = bout + 128;                    // 40 doubles (LOSS instantiation)
+  static constexpr int bars = loss + 320;
   static constexpr int total = bars + 512;
 };
 // barrier indices
@@ -63,9 +64,13 @@ struct Args {
   uint32_t drop_thresh;  // training-mode dropout after the hidden SiLU (DROP instantiation only)
   float drop_scale;
   uint32_t drop_key[kNumHeads];
+  // LOSS instantiation: the class-weighted cross entropy of model/custom_loss.py:189-202 is reduced in the tiles
+  const int64_t* tags[kNumHeads];  // int64 [batch*P]
+  float class_w[3];
+  double* loss_partial;            // [5][gridDim.x][2] : per-CTA (sum w nll, sum w), reduced by pair_loss_final_kernel
 };
 
-template <bool DROP>
+template <bool DROP, bool LOSS>
 __global__ void __launch_bounds__(kThreads, 1)
     pair_heads_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmO, const Args a) {
   extern __shared__ unsigned char smem_raw[];
@@ -74,6 +79,7 @@ __global__ void __launch_bounds__(kThreads, 1)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + bCount);
   float* s_bmid = reinterpret_cast<float*>(smem + Smem::bmid);
   float* s_bout = reinterpret_cast<float*>(smem + Smem::bout);
+  double* s_loss = reinterpret_cast<double*>(smem + Smem::loss);  // [4 quadrants][5 heads][2]
 
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
 
@@ -94,6 +100,7 @@ __global__ void __launch_bounds__(kThreads, 1)
   }
   for (int e = threadIdx.x; e < 5 * D; e += kThreads) s_bmid[e] = a.bmid_half[e];
   if (threadIdx.x < 20) s_bout[threadIdx.x] = a.bout[threadIdx.x];
+  if (LOSS && threadIdx.x < 40) s_loss[threadIdx.x] = 0.0;
   ptx::cluster_sync_all();  // both CTAs' barriers exist before anyone (TMA of the peer, remote arrives) touches them
   if (warp == 2) {
     ptx::tmem_alloc_2sm(tmem_slot, 512);
@@ -200,7 +207,18 @@ __global__ void __launch_bounds__(kThreads, 1)
     const uint32_t lane_base = static_cast<uint32_t>(q * 32) << 16;
     const int row = q * 32 + lane;
     // logits of head-global index hg (tile = hg / 5, head = hg % 5)
-    auto emit_z = [&](int hg) {
+    // The logits of head k are emitted by the column group csel == (k & 3): the extra work sits on four different
+    // warps per quadrant instead of always the same one (every chunk waits for its slowest epilogue warp).
+    // LOSS: per-lane fp32 partial sums (slot 0: heads 0-3, slot 1: head 4 — only group 0 owns two heads), reduced once
+    // at the end of the kernel; the pair's tag is fetched when its head starts, three chunks before it is needed.
+    float acc_l[2] = {0.f, 0.f}, acc_w[2] = {0.f, 0.f};
+    long long tag_next = 0;
+    auto fetch_tag = [&](int hg) {
+      const int it = hg / 5, k = hg - it * 5;
+      const int64_t gp = tile_of(it) * 128 + row;
+      tag_next = gp < a.total_pairs ? a.tags[k][gp] : 0;
+    };
+    auto emit_z = [&](int hg, long long tag) {
       ptx::mbar_wait(&bars[bZFull + (hg & 1)], (hg >> 1) & 1);
       ptx::tc_fence_after();
       uint32_t zr[4];
@@ -212,14 +230,29 @@ __global__ void __launch_bounds__(kThreads, 1)
       if (gp < a.total_pairs) {
         const int C = head_classes(k);
         float* dst = a.logits[k] + gp * C;
-        for (int cc = 0; cc < C; ++cc) dst[cc] = __uint_as_float(zr[cc]) + s_bout[k * 4 + cc];
+        const float z0 = __uint_as_float(zr[0]) + s_bout[k * 4], z1 = __uint_as_float(zr[1]) + s_bout[k * 4 + 1];
+        const float z2 = C == 3 ? __uint_as_float(zr[2]) + s_bout[k * 4 + 2] : -INFINITY;
+        dst[0] = z0, dst[1] = z1;
+        if (C == 3) dst[2] = z2;
+        if (LOSS) {  // w[t] (logsumexp(z) - z[t]) and w[t] of this pair
+          const bool bad = tag < 0 || tag >= C;
+          const int t = bad ? 0 : static_cast<int>(tag);
+          const float mx = fmaxf(fmaxf(z0, z1), z2);
+          const float se = __expf(z0 - mx) + __expf(z1 - mx) + (C == 3 ? __expf(z2 - mx) : 0.f);
+          const float zt = t == 0 ? z0 : (t == 1 ? z1 : z2);
+          const float ww = t == 0 ? a.class_w[0] : (t == 1 ? a.class_w[1] : a.class_w[2]);
+          acc_w[k >> 2] += ww;
+          acc_l[k >> 2] += bad ? NAN : ww * (mx + __logf(se) - zt);
+        }
       }
     };
     int g = 0;
+    long long tag_cur = 0;
     for (int it = 0; it < my_tiles; ++it) {
       const int64_t drop_row = tile_of(it) * 128 + row;
       for (int c = 0; c < kChunks; ++c, ++g) {
         const int buf = g & 1;
+        if (LOSS && g % 3 == 0 && csel == ((g / 3) % 5 & 3)) fetch_tag(g / 3);  // consumed by emit_z(g / 3) three chunks on
         ptx::mbar_wait(&bars[bUFull + buf], (g >> 1) & 1);
         ptx::tc_fence_after();
         const uint32_t ut = tmem + lane_base + kColU + 128 * buf + 32 * csel;
@@ -252,10 +285,22 @@ __global__ void __launch_bounds__(kThreads, 1)
         ptx::tc_fence_before();
         __syncwarp();
         if (lane == 0) arrive_leader(&bars[bMReady + buf]);
-        if (csel == 0 && g > 0 && g % 3 == 0) emit_z(g / 3 - 1);
+        if (g > 0 && g % 3 == 0 && csel == ((g / 3 - 1) % 5 & 3)) emit_z(g / 3 - 1, tag_cur);
+        if (LOSS && g % 3 == 0 && csel == ((g / 3) % 5 & 3)) tag_cur = tag_next;  // (after the emit above, which used the old value)
       }
     }
-    if (csel == 0 && g > 0) emit_z(g / 3 - 1);
+    if (g > 0 && csel == ((g / 3 - 1) % 5 & 3)) emit_z(g / 3 - 1, tag_cur);
+    if (LOSS) {  // this warp's partial sums -> (quadrant, head) slots, fixed shuffle tree, fp64 from here on
+#pragma unroll
+      for (int sl = 0; sl < 2; ++sl) {
+        const int k = sl == 0 ? csel : 4;  // group csel owns head csel (slot 0); group 0 also head 4 (slot 1)
+        if (sl == 1 && csel != 0) break;
+        double dl = static_cast<double>(acc_l[sl]), dw = static_cast<double>(acc_w[sl]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) dl += __shfl_xor_sync(0xffffffffu, dl, o), dw += __shfl_xor_sync(0xffffffffu, dw, o);
+        if (lane == 0) s_loss[(q * 5 + k) * 2] = dl, s_loss[(q * 5 + k) * 2 + 1] = dw;
+      }
+    }
   } else if (warp >= kProdWarp0) {
     // ============================== pair producers ==============================
     const int q = warp - kProdWarp0;
@@ -345,13 +390,20 @@ __global__ void __launch_bounds__(kThreads, 1)
 
   ptx::tc_fence_before();
   ptx::cluster_sync_all();  // the peer's tensor-memory reads / remote arrives are finished as well
+  if (LOSS && threadIdx.x < 10) {  // this CTA's partial sums, quadrants added in index order
+    const int k = threadIdx.x >> 1, j = threadIdx.x & 1;
+    double acc = 0.0;
+    for (int qq = 0; qq < 4; ++qq) acc += s_loss[(qq * 5 + k) * 2 + j];
+    a.loss_partial[(static_cast<size_t>(k) * gridDim.x + blockIdx.x) * 2 + j] = acc;
+  }
   if (warp == 2) ptx::tmem_dealloc_2sm(tmem, 512);
 }
 
 }  // namespace k2p
 
 int launch_pair_heads_tc_pair(const void* pack, const PackLayout& L, const __nv_bfloat16* ab, int batch, int n,
-                              float* const logits[kNumHeads], cudaStream_t st, const DropSpec* drop) {
+                              float* const logits[kNumHeads], cudaStream_t st, const DropSpec* drop, const FusedLossFwd* loss,
+                              int* grid_out) {
   using namespace k2p;
   const char* base = static_cast<const char*>(pack);
   Args a{};
@@ -382,15 +434,27 @@ int launch_pair_heads_tc_pair(const void* pack, const PackLayout& L, const __nv_
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr, cfg.numAttrs = 1;
-  if (drop && drop->thresh) {
+  const bool dr = drop && drop->thresh;
+  if (dr) {
     a.drop_thresh = drop->thresh, a.drop_scale = drop->scale;
     for (int h = 0; h < kNumHeads; ++h) a.drop_key[h] = drop_key(*drop, site_head(h, 0));
-    PENEO_CUDA_TRY(cudaFuncSetAttribute(pair_heads_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    PENEO_CUDA_TRY(cudaLaunchKernelEx(&cfg, pair_heads_tc_kernel<true>, tmW, tmO, a));
-  } else {
-    PENEO_CUDA_TRY(cudaFuncSetAttribute(pair_heads_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    PENEO_CUDA_TRY(cudaLaunchKernelEx(&cfg, pair_heads_tc_kernel<false>, tmW, tmO, a));
   }
+  if (loss) {
+    for (int h = 0; h < kNumHeads; ++h) a.tags[h] = loss->tags[h];
+    for (int c = 0; c < 3; ++c) a.class_w[c] = loss->class_w[c];
+    a.loss_partial = loss->partial;
+  }
+  if (grid_out) *grid_out = grid;
+#define GO(DR, LO)                                                                                                 \
+  do {                                                                                                             \
+    PENEO_CUDA_TRY(cudaFuncSetAttribute(pair_heads_tc_kernel<DR, LO>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes)); \
+    PENEO_CUDA_TRY(cudaLaunchKernelEx(&cfg, pair_heads_tc_kernel<DR, LO>, tmW, tmO, a));                           \
+  } while (0)
+  if (dr && loss) GO(true, true);
+  else if (dr) GO(true, false);
+  else if (loss) GO(false, true);
+  else GO(false, false);
+#undef GO
   PENEO_CUDA_TRY(cudaGetLastError());
   return PENEO_OK;
 }

@@ -228,6 +228,10 @@ class PEneoDecoderB200(nn.Module):
         if unfused and ((needs_grad and not self.inference_mode) or drop is not None):
             raise RuntimeError("precision='bf16' is forward-only (no dropout, no backward) for this decoder "
                                "configuration; train it with precision='fp32'")
+        tags = [line_extraction_shaking_tag, ent_linking_head_rel_shaking_tag, ent_linking_tail_rel_shaking_tag,
+                line_grouping_head_rel_shaking_tag, line_grouping_tail_rel_shaking_tag]
+        ohem = (self.link_loss.num_hard_positive, self.link_loss.num_hard_negative)
+        fused_out = None
         if needs_grad and not self.inference_mode:
             if self.precision == "bf16" and not self._explicit_precision and not PEneoDecoderB200._warned_bf16_training:
                 PEneoDecoderB200._warned_bf16_training = True
@@ -238,9 +242,24 @@ class PEneoDecoderB200(nn.Module):
                     "tanh.approx SiLU): parameter gradients agree with the fp32 reference to ~1e-2 relative per tensor, "
                     "like the reference's own --fp16 AMP recipe.  Set config.peneo_b200_precision = 'fp32' for "
                     "fp32-exact (1e-6) training numerics.", stacklevel=2)
-            from .autograd import decoder_forward_with_grad
+            fusable = (self.precision == "bf16" and self.dims.bf16_capable() and ohem == (-1, -1)
+                       and getattr(self, "backward_precision", "bf16") == "bf16" and getattr(self, "fused_loss", True)
+                       and all(torch.is_tensor(t) and t.is_cuda for t in tags))
+            if fusable:
+                # one autograd node for heads + loss: the loss is reduced in K2's epilogue and its backward happens
+                # inside the backward tiles (model/peneo_decoder.py:355-428 as one sweep each way)
+                shape = (sequence_output.shape[0], ops.shaking_len(sequence_output.shape[1]))
+                for tg in tags:
+                    assert tuple(tg.shape) == shape, "invalid input shape"
+                from .train import heads_loss_with_grad
 
-            logits = decoder_forward_with_grad(self, sequence_output, drop)
+                total, subs, logits = heads_loss_with_grad(self, sequence_output, tags, self._class_weights_host(),
+                                                           self.loss_ratio, drop)
+                fused_out = (total, subs)
+            else:
+                from .autograd import decoder_forward_with_grad
+
+                logits = decoder_forward_with_grad(self, sequence_output, drop)
         else:
             pack = self._weight_pack(sequence_output.device)
             logits = ops.heads_forward(pack, sequence_output.detach(), drop)
@@ -248,13 +267,12 @@ class PEneoDecoderB200(nn.Module):
         if self.inference_mode:
             return (le, elh, elt, lgh, lgt, orig_bbox)
 
-        tags = [line_extraction_shaking_tag, ent_linking_head_rel_shaking_tag, ent_linking_tail_rel_shaking_tag,
-                line_grouping_head_rel_shaking_tag, line_grouping_tail_rel_shaking_tag]
         for lg, tg in zip(logits, tags):
             assert len(lg.shape) == len(tg.shape) + 1, "invalid input shape"
             assert lg.shape[:-1] == tg.shape
-        ohem = (self.link_loss.num_hard_positive, self.link_loss.num_hard_negative)
-        if ohem != (-1, -1):
+        if fused_out is not None:
+            total, subs = fused_out
+        elif ohem != (-1, -1):
             from .ohem import ohem_losses
 
             subs = ohem_losses(logits, tags, self.link_loss.weight, ohem)

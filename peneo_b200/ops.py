@@ -161,6 +161,43 @@ def heads_forward(pack: WeightPack, x: torch.Tensor, dropout=None) -> List[torch
     return pair_heads(pack, token_projections(pack, x, dropout), b, n, dropout)
 
 
+def _check_tags(tags: Sequence[torch.Tensor], b: int, p: int) -> List[torch.Tensor]:
+    tg = []
+    for k in range(NUM_HEADS):
+        t = tags[k]
+        _require_cuda(t, "shaking tag")
+        if tuple(t.shape) != (b, p):
+            raise AssertionError("invalid input shape")  # model/peneo_decoder.py:329-331
+        tg.append(t if (t.dtype == torch.int64 and t.is_contiguous()) else t.long().contiguous())
+    return tg
+
+
+def heads_loss_forward(pack: WeightPack, x: torch.Tensor, tags: Sequence[torch.Tensor], class_weights: Sequence[float],
+                       ratios: Optional[Sequence[float]] = None, dropout=None):
+    """Heads + class-weighted CE in one sweep over the pair tiles (``peneo_pair_heads_loss_fwd``): the K2 epilogue that
+    writes a pair's logits also reduces its loss terms.  Returns (logits, out6, ctx); ctx feeds the fused backward."""
+    lib = _lib.load()
+    if x.dim() != 3:
+        raise ValueError("sequence_output must be [batch, seq_len, hidden]")
+    b, n, _ = x.shape
+    p = shaking_len(n)
+    tg = _check_tags(tags, b, p)
+    ab = token_projections(pack, x, dropout)
+    logits = [torch.empty(b, p, c, dtype=torch.float32, device=ab.device) for c in HEAD_CLASSES]
+    out6 = torch.empty(6, dtype=torch.float32, device=ab.device)
+    ws = torch.empty(lib.peneo_pair_loss_workspace_bytes(b, n), dtype=torch.uint8, device=ab.device)
+    w3 = list(class_weights) + [0.0] * (3 - len(class_weights))
+    r5 = [1.0] * 5 if ratios is None else list(ratios)
+    COUNTERS["kernels"] += 2
+    _lib.check(
+        lib.peneo_pair_heads_loss_fwd(pack.dims.c(), pack.prec, pack.buf.data_ptr(), ab.data_ptr(), b, n, _lib.ptrs5(logits),
+                                      _lib.ptrs5(tg), _lib.floats(w3), _lib.floats(r5), out6.data_ptr(), ws.data_ptr(),
+                                      _lib.dropout_arg(dropout), _stream(ab.device)),
+        "peneo_pair_heads_loss_fwd",
+    )
+    return logits, out6, (ws, tg, w3, r5)
+
+
 def pair_loss(logits: Sequence[torch.Tensor], tags: Sequence[torch.Tensor], class_weights: Sequence[float],
               ratios: Optional[Sequence[float]] = None):
     """Weighted-mean CE of the five heads (OHEM off).  Returns (out6, workspace): out6[0:5] are the

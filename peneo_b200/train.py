@@ -39,8 +39,9 @@ def _grad_struct(dims, grads: Dict[str, torch.Tensor]) -> _lib.Grads:
     return g
 
 
-def heads_backward(decoder, x: torch.Tensor, dlogits: List[torch.Tensor], need_dx: bool, dropout=None):
+def heads_backward(decoder, x: torch.Tensor, dlogits: List[torch.Tensor], need_dx: bool, dropout=None, fused=None):
     """x: [B, N, hin] CUDA; dlogits: five fp32 [B, P, C_h]; dropout: the forward pass's (p, seed) or None.
+    ``fused`` = (logits, loss ctx, grad_out6): the loss backward happens inside the pair tiles (``dlogits`` unused).
     Returns ({param_key: grad}, dx | None)."""
     lib = _lib.load()
     dims = decoder.dims
@@ -59,11 +60,23 @@ def heads_backward(decoder, x: torch.Tensor, dlogits: List[torch.Tensor], need_d
     x2 = x2.reshape(b * n, hin)
     if x2.stride(-1) != 1:
         x2 = x2.contiguous()
-    dl = [g if (g.dtype == torch.float32 and g.is_contiguous()) else g.float().contiguous() for g in dlogits]
     dx = torch.empty(b * n, hin, dtype=torch.float32, device=dev) if need_dx else None
     ws = torch.empty(lib.peneo_heads_bwd_workspace_bytes(dims.c(), prec, b, n), dtype=torch.uint8, device=dev)
     gs = _grad_struct(dims, grads)
     ops.COUNTERS["kernels"] += 1
+    if fused is not None:
+        logits, (lws, tg, w3, r5), g6 = fused
+        g6 = g6.detach().to(device=dev, dtype=torch.float32).reshape(6).contiguous()
+        _lib.check(
+            lib.peneo_heads_loss_bwd(dims.c(), prec, pack.buf.data_ptr(), x2.data_ptr(), ops._TORCH_DT[x2.dtype],
+                                     x2.stride(0) if b * n > 1 else hin, b, n, _lib.ptrs5(logits), _lib.ptrs5(tg),
+                                     _lib.floats(w3), _lib.floats(r5), g6.data_ptr(), lws.data_ptr(), gs,
+                                     dx.data_ptr() if dx is not None else None, ws.data_ptr(), _lib.dropout_arg(dropout),
+                                     ops._stream(dev)),
+            "peneo_heads_loss_bwd",
+        )
+        return grads, (dx.view(b, n, hin) if dx is not None else None)
+    dl = [g if (g.dtype == torch.float32 and g.is_contiguous()) else g.float().contiguous() for g in dlogits]
     _lib.check(
         lib.peneo_heads_bwd(dims.c(), prec, pack.buf.data_ptr(), x2.data_ptr(), ops._TORCH_DT[x2.dtype],
                             x2.stride(0) if b * n > 1 else hin, b, n, _lib.ptrs5(dl), gs,
@@ -103,3 +116,49 @@ class _DecoderHeads(torch.autograd.Function):
 def heads_with_grad(decoder, sequence_output: torch.Tensor, dropout=None) -> List[torch.Tensor]:
     params = [p for _, p in _param_items(decoder)]
     return list(_DecoderHeads.apply(decoder, sequence_output, dropout, *params))
+
+
+class _DecoderHeadsLoss(torch.autograd.Function):
+    """Heads + loss as ONE autograd node (fused tcgen05 configuration, OHEM off): forward = K1 + K2 with the loss
+    reduced in K2's epilogue; backward = the backward tiles computing d loss / d logits in registers (no [B, P, C]
+    gradient tensors, no separate loss kernels).  Outputs: out6 (five sub-losses + their ratio-weighted sum) and the
+    five logits tensors.  A gradient arriving on the logits themselves (a caller hanging its own loss on them) takes
+    the unfused route: explicit d loss / d logits + ``peneo_heads_bwd``."""
+
+    @staticmethod
+    def forward(ctx, decoder, x, drop, class_w, ratios, t0, t1, t2, t3, t4, *params):
+        pack = decoder._weight_pack(x.device)
+        logits, out6, lctx = ops.heads_loss_forward(pack, x.detach(), [t0, t1, t2, t3, t4], class_w, ratios, drop)
+        ctx.decoder, ctx.dropout, ctx.lctx, ctx.logits = decoder, drop, lctx, logits
+        ctx.save_for_backward(x)
+        ctx.need_dx = x.requires_grad
+        ctx.set_materialize_grads(False)
+        return (out6, *logits)
+
+    @staticmethod
+    def backward(ctx, g6, *glogits):
+        (x,) = ctx.saved_tensors
+        dec = ctx.decoder
+        if g6 is None:
+            g6 = torch.zeros(6, dtype=torch.float32, device=x.device)
+        if all(g is None for g in glogits):
+            grads, dx = heads_backward(dec, x, None, ctx.need_dx, ctx.dropout, fused=(ctx.logits, ctx.lctx, g6))
+        else:
+            lws, tg, w3, r5 = ctx.lctx
+            b, n = x.shape[0], x.shape[1]
+            dl = ops.pair_loss_backward((lws, ctx.logits, tg, w3, r5, b, n), g6)
+            dl = [d if g is None else d + g.float() for d, g in zip(dl, glogits)]
+            grads, dx = heads_backward(dec, x, dl, ctx.need_dx, ctx.dropout)
+        out = [None, dx.to(x.dtype) if dx is not None else None] + [None] * 8
+        for k, p in _param_items(dec):
+            out.append(grads[k].to(p.dtype) if p.requires_grad else None)
+        return tuple(out)
+
+
+def heads_loss_with_grad(decoder, sequence_output: torch.Tensor, tags, class_w, ratios, dropout=None):
+    """-> (total loss, [five sub-losses], [five logits])"""
+    params = [p for _, p in _param_items(decoder)]
+    out = _DecoderHeadsLoss.apply(decoder, sequence_output, dropout, list(class_w), None if ratios is None else list(ratios),
+                                  *tags, *params)
+    out6, logits = out[0], list(out[1:])
+    return out6[5], [out6[h] for h in range(5)], logits

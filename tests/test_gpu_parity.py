@@ -490,6 +490,56 @@ def test_training_rows_cross_chunk_boundaries(monkeypatch):
         assert rel_err(grads[key], g) <= GRAD_TOL_FP32, key
 
 
+def test_fused_loss_in_the_pair_tiles_equals_the_separate_kernels(monkeypatch):
+    """Training through ONE autograd node (loss reduced in K2's epilogue, d loss / d logits computed in registers
+    inside the backward tiles, no [B, P, C] gradient tensors) against the same decoder with `fused_loss = False`
+    (separate loss forward / backward kernels + explicit dlogits), for non-trivial ratios and an upstream gradient
+    on a sub-loss.  Several backward chunks, rows past the end of the last tile, a phantom second tile of a CTA pair."""
+    monkeypatch.setenv("PENEO_BWD_CHUNK_ROWS", "3000")
+    n, b = 77, 3
+    sd = synth.init_decoder_state(seed=12, trained_like=True)
+    ratios = (1.0, 0.5, 2.0, 1.5, 0.25)
+    x = synth.hidden_states(b, n, 768, doc_id0=40).cuda()
+    docs = [synth.make_document(n, doc_id=900 + i) for i in range(b)]
+    tags = [torch.stack([d.tags()[k] for d in docs]).cuda() for k in range(5)]
+    res = {}
+    for fused in (True, False):
+        dec = PEneoDecoderB200(Cfg(768, inference_mode=False, precision="bf16", ratios=ratios), 768)
+        dec.load_state_dict(sd)
+        dec = dec.cuda().eval()
+        dec.fused_loss = fused
+        xin = x.clone().requires_grad_(True)
+        out = dec(xin, None, *tags)
+        (out.loss + 0.3 * out.ent_linking_t2t_loss).backward()
+        res[fused] = (out, xin.grad.clone(), {k: p.grad.clone() for k, p in dec.named_parameters()})
+    (of, dxf, gf), (ou, dxu, gu) = res[True], res[False]
+    assert abs(of.loss.item() - ou.loss.item()) <= 1e-6 * max(1.0, abs(ou.loss.item()))
+    for name in ("line_extraction_loss", "ent_linking_h2h_loss", "ent_linking_t2t_loss", "line_grouping_h2h_loss",
+                 "line_grouping_t2t_loss"):
+        assert abs(getattr(of, name).item() - getattr(ou, name).item()) <= 1e-6 * max(1.0, abs(getattr(ou, name).item()))
+    for k in ("line_extraction_shaking_outputs", "line_grouping_t2t_shaking_outputs"):
+        assert torch.equal(getattr(of, k), getattr(ou, k))  # the fused epilogue writes the very same logits
+    assert rel_err(dxf, dxu.cpu()) <= 2e-3
+    for key in gu:
+        assert rel_err(gf[key], gu[key].cpu()) <= 2e-3, key
+    # against the fp64 autograd oracle as well (bf16 tolerance)
+    ref_loss, _, ref_grads, _ = orc.loss_and_grads(sd, x.cpu(), [t.cpu() for t in tags], [1.0, 10.0, 10.0], list(ratios))
+    assert abs(of.loss.item() - ref_loss.item()) <= 2e-3 * max(1.0, abs(ref_loss.item()))
+    # a gradient hung on the logits themselves takes the unfused route and must still be right
+    dec = PEneoDecoderB200(Cfg(768, inference_mode=False, precision="bf16", ratios=ratios), 768)
+    dec.load_state_dict(sd)
+    dec = dec.cuda().eval()
+    out = dec(x, None, *tags)
+    (out.loss + out.line_extraction_shaking_outputs.square().mean()).backward()
+    g_extra = {k: p.grad.clone() for k, p in dec.named_parameters()}
+    dec.fused_loss = False
+    dec.zero_grad(set_to_none=True)
+    out = dec(x, None, *tags)
+    (out.loss + out.line_extraction_shaking_outputs.square().mean()).backward()
+    for k, p in dec.named_parameters():
+        assert rel_err(g_extra[k], p.grad.cpu()) <= 2e-3, k
+
+
 # ------------------------------------------------------------------------------------------------
 # OHEM loss (model/custom_loss.py:204-288)
 # ------------------------------------------------------------------------------------------------
