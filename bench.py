@@ -276,7 +276,7 @@ def sweep_leg(dev, rank, world, dist, peaks, clocks, steps=10, warmup=3):
     return out
 
 
-def train_leg(dev, rank, local_rank, world, dist, peaks, steps=10, warmup=3):
+def train_leg(dev, rank, local_rank, world, dist, peaks, steps=15, warmup=6):
     """Fine-tuning step of the decoder: forward + fused loss + backward (+ NCCL gradient all-reduce under torchrun, DDP
     semantics as in the reference's HF Trainer: per-rank batch-global weighted-mean loss, averaged gradients).  Two
     shapes: the headline shape (seq 512, batch 32 per GPU, hidden 768) and BASELINE configs[2] (LiLT: hidden states of

@@ -19,6 +19,7 @@
  *                                   loss.backward() through model/peneo_decoder.py:349-363)
  *   peneo_scatter_tags ............ HandshakingTaggingScheme.spots2shaking_tag4batch   model/peneo_decoder.py:34-73
  *   peneo_decode_spots ............ HandshakingTaggingScheme.get_spots_from_shaking_tag model/peneo_decoder.py:75-115
+ *   peneo_pair_heads_spots_fwd .... pair heads + get_spots_from_shaking_tag fused (no logits in HBM), inference
  *   peneo_decode_resolve .......... parse_matrix_spots + the key/value chain walk of
  *                                   sample_decode_peneo                     pipeline/decode.py:9-69, 169-368
  *
@@ -216,6 +217,16 @@ size_t peneo_decode_spots_workspace_bytes(int32_t batch, int32_t n);
 int peneo_decode_spots(int32_t batch, int32_t n, const void* const in[PENEO_NUM_HEADS], int in_dtype, int32_t cap,
                        int32_t* spot_p, int32_t* spot_tag, float* spot_score, int32_t* counts, void* workspace,
                        void* stream);
+
+/* Heads + spot extraction in one sweep (inference, PENEO_PREC_BF16, the fused tcgen05 configuration): what
+ * peneo_pair_heads_fwd followed by peneo_decode_spots produce — the same compact (p, tag, score) lists and exact
+ * counts, bit-identical scores — without the [batch, P, C] logits ever being written to or read from HBM: the pair
+ * kernel's epilogue classifies every pair (model/peneo_decoder.py:98-114) and keeps only the non-zero predictions,
+ * which a small gather kernel compacts in increasing p.  Feed the result to peneo_decode_resolve. */
+size_t peneo_pair_heads_spots_workspace_bytes(int32_t batch, int32_t n);
+int peneo_pair_heads_spots_fwd(const peneo_dims* dims, int prec, const void* pack, const void* ab, int32_t batch, int32_t n,
+                               int32_t cap, int32_t* spot_p, int32_t* spot_tag, float* spot_score, int32_t* counts,
+                               void* workspace, void* stream);
 
 /* Link resolution for `batch` documents from the compact spots of peneo_decode_spots.
  * Output: one int32 record block per document at out + b * peneo_decode_resolve_doc_ints(n, cap):

@@ -41,6 +41,8 @@ SYMBOLS = (
     "peneo_scatter_tags",
     "peneo_decode_spots_workspace_bytes",
     "peneo_decode_spots",
+    "peneo_pair_heads_spots_workspace_bytes",
+    "peneo_pair_heads_spots_fwd",
     "peneo_decode_resolve_doc_ints",
     "peneo_decode_resolve_workspace_bytes",
     "peneo_decode_resolve",
@@ -126,6 +128,9 @@ def load() -> C.CDLL:
     lib.peneo_decode_spots_workspace_bytes.restype = sz
     lib.peneo_decode_spots_workspace_bytes.argtypes = [i32, i32]
     lib.peneo_decode_spots.argtypes = [i32, i32, PtrArray5, C.c_int, i32, vp, vp, vp, vp, vp, vp]
+    lib.peneo_pair_heads_spots_workspace_bytes.restype = sz
+    lib.peneo_pair_heads_spots_workspace_bytes.argtypes = [i32, i32]
+    lib.peneo_pair_heads_spots_fwd.argtypes = [C.POINTER(Dims), C.c_int, vp, vp, i32, i32, i32, vp, vp, vp, vp, vp, vp]
     lib.peneo_decode_resolve_doc_ints.restype = sz
     lib.peneo_decode_resolve_doc_ints.argtypes = [i32, i32]
     lib.peneo_decode_resolve_workspace_bytes.restype = sz

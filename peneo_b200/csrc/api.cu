@@ -3,6 +3,7 @@
 #include <cstdlib>
 #include <cstring>
 
+#include "classify.cuh"
 #include "common.cuh"
 #include "kernels.h"
 
@@ -198,6 +199,29 @@ int peneo_pair_heads_fwd(const peneo_dims* dims, int prec, const void* pack, con
   if (use_pair)
     return launch_pair_heads_tc_pair(pack, pack_layout(*dims, prec), static_cast<const __nv_bfloat16*>(ab), batch, n, logits, st, dp);
   return launch_pair_heads_tc(pack, pack_layout(*dims, prec), static_cast<const __nv_bfloat16*>(ab), batch, n, logits, st, dp);
+}
+
+size_t peneo_pair_heads_spots_workspace_bytes(int32_t batch, int32_t n) {
+  return batch >= 1 && n >= 1 ? heads_spots_workspace_bytes(batch, n) : 0;
+}
+
+int peneo_pair_heads_spots_fwd(const peneo_dims* dims, int prec, const void* pack, const void* ab, int32_t batch, int32_t n,
+                               int32_t cap, int32_t* spot_p, int32_t* spot_tag, float* spot_score, int32_t* counts,
+                               void* workspace, void* stream) {
+  int rc;
+  if ((rc = check_dims(dims)) != PENEO_OK || (rc = check_prec(dims, prec)) != PENEO_OK) return rc;
+  PENEO_REQUIRE(prec == PENEO_PREC_BF16 && bf16_supported(*dims), "pair_heads_spots_fwd: only the fused tcgen05 configuration "
+                "(PENEO_PREC_BF16, shrink, hid 768, d 384, 2 layers); use pair_heads_fwd + decode_spots otherwise");
+  PENEO_REQUIRE(pack && ab && spot_p && spot_tag && spot_score && counts && workspace, "pair_heads_spots_fwd: NULL pointer");
+  PENEO_REQUIRE(batch >= 1 && batch <= 65535 && n >= 1 && n <= 46340 && cap >= 1, "pair_heads_spots_fwd: bad sizes batch=%d n=%d cap=%d",
+                batch, n, cap);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int64_t tiles = ((int64_t)batch * pair_count(n) + 127) / 128;
+  const TileSpots ts = tile_spots_carve(workspace, tiles + 1);
+  if ((rc = launch_pair_heads_tc_pair(pack, pack_layout(*dims, prec), static_cast<const __nv_bfloat16*>(ab), batch, n, nullptr, st,
+                                      nullptr, nullptr, nullptr, &ts)) != PENEO_OK)
+    return rc;
+  return launch_gather_tile_spots(batch, n, workspace, cap, spot_p, spot_tag, spot_score, counts, st);
 }
 
 size_t peneo_heads_bwd_workspace_bytes(const peneo_dims* dims, int prec, int32_t batch, int32_t n) {

@@ -4,6 +4,7 @@
 //   K4 decode_resolve : 1-1 map resolution (parse_matrix_spots, pipeline/decode.py:9-69) and the
 //                       key/value chain walk of sample_decode_peneo (pipeline/decode.py:216-368)
 // Both are HBM/latency-bound integer work: K3 reads every logit exactly once.
+#include "classify.cuh"
 #include "common.cuh"
 #include "kernels.h"
 
@@ -22,42 +23,12 @@ __device__ __forceinline__ float load_as_float(const void* base, int64_t idx) {
   else if constexpr (DT == PENEO_DT_F16) return __half2float(static_cast<const __half*>(base)[idx]);
   else return 0.f;
 }
-template <int DT>
-__device__ __forceinline__ float round_like(float v) {
-  if constexpr (DT == PENEO_DT_BF16) return __bfloat162float(__float2bfloat16_rn(v));
-  else if constexpr (DT == PENEO_DT_F16) return __half2float(__float2half_rn(v));
-  else return v;
-}
-
-// softmax over C classes the way ATen does it (exp(x - max) / sum in fp32, result rounded to the
-// tensor dtype), then argmax of the *probabilities* (first maximum) and its value.
-template <int DT, int C>
-__device__ __forceinline__ void classify_vals(const float* x, int& pred, float& score);
 template <int DT, int C>
 __device__ __forceinline__ void classify(const void* base, int64_t row, int& pred, float& score) {
   float x[C];
 #pragma unroll
   for (int c = 0; c < C; ++c) x[c] = load_as_float<DT>(base, row * C + c);
   classify_vals<DT, C>(x, pred, score);
-}
-template <int DT, int C>
-__device__ __forceinline__ void classify_vals(const float* x, int& pred, float& score) {
-  float m = x[0];
-#pragma unroll
-  for (int c = 1; c < C; ++c) m = fmaxf(m, x[c]);
-  float e[C], sum = 0.f;
-#pragma unroll
-  for (int c = 0; c < C; ++c) {
-    e[c] = expf(x[c] - m);
-    sum += e[c];
-  }
-  pred = 0;
-  score = round_like<DT>(e[0] / sum);
-#pragma unroll
-  for (int c = 1; c < C; ++c) {
-    const float pc = round_like<DT>(e[c] / sum);
-    if (pc > score) score = pc, pred = c;
-  }
 }
 
 struct SpotArgs {
@@ -251,6 +222,160 @@ int launch_decode_spots(int batch, int n, const void* const in[kNumHeads], int i
     case PENEO_DT_I64: decode_spots_kernel<PENEO_DT_I64><<<grid, 256, 0, st>>>(a); break;
     default: set_error("decode_spots: unsupported dtype %d", in_dtype); return PENEO_E_INVALID;
   }
+  PENEO_CUDA_TRY(cudaGetLastError());
+  return PENEO_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3' : gather of the per-tile spot slots written by K2's spots-only epilogue (pair_heads_tc2.cu, classify.cuh).
+// Same output as decode_spots_kernel — per (document, head) the spots in increasing p — without the logits ever
+// existing in HBM.  One CTA per (chunk of 2048 tiles, head, document); each thread owns 8 consecutive tiles (32
+// slots); CTA-wide exclusive scan of the slot counts, chunks chained by the same decoupled look-back as K3.
+// ------------------------------------------------------------------------------------------------
+constexpr int kGatherTilesPerThread = 8;
+constexpr int kGatherTilesPerCta = 256 * kGatherTilesPerThread;
+
+struct GatherArgs {
+  TileSpots ts;
+  int32_t batch, pairs, cap, chunks;
+  int64_t total_tiles;
+  int32_t* spot_p;
+  int32_t* spot_tag;
+  float* spot_score;
+  int32_t* counts;
+  int32_t* ticket;  // [batch*5]
+  int32_t* status;  // [batch*5*chunks]
+};
+
+__global__ void __launch_bounds__(256) gather_tile_spots_kernel(const GatherArgs a) {
+  __shared__ int32_t wsum[8];
+  __shared__ int32_t s_chunk, s_base;
+  const int h = blockIdx.y, b = blockIdx.z, list = b * kNumHeads + h;
+  const int lane = threadIdx.x % 32, warp = threadIdx.x / 32;
+  if (threadIdx.x == 0) s_chunk = atomicAdd(&a.ticket[list], 1);
+  __syncthreads();
+  const int chunk = s_chunk;
+  const int64_t gp0 = (int64_t)b * a.pairs, gp1 = gp0 + a.pairs;  // this document's range of the batch-flat pair list
+  const int64_t doc_tile0 = gp0 / 128;
+  const int64_t t0 = doc_tile0 + (int64_t)chunk * kGatherTilesPerCta + (int64_t)threadIdx.x * kGatherTilesPerThread;
+  // counts of this thread's 32 slots (only entries that belong to this document)
+  int cnt[kGatherTilesPerThread][4];
+  int mine = 0;
+#pragma unroll
+  for (int t = 0; t < kGatherTilesPerThread; ++t) {
+    const int64_t tile = t0 + t;
+    const bool live = tile < a.total_tiles && tile * 128 < gp1;
+    int4 c4 = make_int4(0, 0, 0, 0);
+    if (live) c4 = *reinterpret_cast<const int4*>(a.ts.cnt + (tile * kNumHeads + h) * 4);
+    int c[4] = {c4.x, c4.y, c4.z, c4.w};
+    if (live && (tile * 128 < gp0 || tile * 128 + 128 > gp1)) {
+      // tile straddles a document boundary: count the entries one by one
+      for (int q = 0; q < 4; ++q) {
+        const int64_t slot = (tile * kNumHeads + h) * 4 + q;
+        int keep = 0;
+        for (int e = 0; e < c[q]; ++e) {
+          const int64_t gp = tile * 128 + (a.ts.meta[slot * 32 + e] & 0xFF);
+          keep += gp >= gp0 && gp < gp1;
+        }
+        c[q] = keep;
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) cnt[t][q] = c[q], mine += c[q];
+  }
+  // CTA-wide exclusive scan of `mine`
+  int incl = mine;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  if (lane == 31) wsum[warp] = incl;
+  __syncthreads();
+  int woff = 0, total = 0;
+  for (int w = 0; w < 8; ++w) {
+    if (w < warp) woff += wsum[w];
+    total += wsum[w];
+  }
+  if (warp == 0) {
+    // decoupled look-back over the preceding chunks of this list (status word: (value << 2) | flag, 1 = own count,
+    // 2 = inclusive prefix) — see decode_spots_kernel
+    int32_t* st = a.status + (int64_t)list * a.chunks;
+    if (lane == 0 && chunk + 1 < a.chunks) {
+      __threadfence();
+      atomicExch(&st[chunk], (total << 2) | 1);
+    }
+    int prefix = 0, look = chunk - 1;
+    while (look >= 0) {
+      const int idx = look - lane;
+      const int v = idx >= 0 ? *reinterpret_cast<volatile int32_t*>(&st[idx]) : 2;
+      const unsigned ready = __ballot_sync(0xffffffffu, v != 0);
+      const unsigned is_p = __ballot_sync(0xffffffffu, (v & 3) == 2);
+      const int first_p = is_p ? __ffs(is_p) - 1 : 32;
+      const unsigned need = first_p >= 31 ? 0xffffffffu : ((1u << (first_p + 1)) - 1u);
+      if ((ready & need) != need) continue;
+      int contrib = lane <= first_p ? (v >> 2) : 0;
+      for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, o);
+      prefix += contrib;
+      if (first_p < 32) break;
+      look -= 32;
+    }
+    if (lane == 0) {
+      __threadfence();
+      atomicExch(&st[chunk], ((prefix + total) << 2) | 2);
+      if (chunk == a.chunks - 1) a.counts[list] = prefix + total;
+      s_base = prefix;
+    }
+  }
+  __syncthreads();
+  int dst = s_base + woff + (incl - mine);
+  const int64_t out0 = (int64_t)list * a.cap;
+#pragma unroll
+  for (int t = 0; t < kGatherTilesPerThread; ++t) {
+    const int64_t tile = t0 + t;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (cnt[t][q] == 0) continue;
+      const int64_t slot = (tile * kNumHeads + h) * 4 + q;
+      const int raw = a.ts.cnt[slot];
+      for (int e = 0; e < raw; ++e) {
+        const int m = a.ts.meta[slot * 32 + e];
+        const int64_t gp = tile * 128 + (m & 0xFF);
+        if (gp < gp0 || gp >= gp1) continue;
+        if (dst < a.cap) {
+          a.spot_p[out0 + dst] = static_cast<int32_t>(gp - gp0);
+          a.spot_tag[out0 + dst] = m >> 8;
+          a.spot_score[out0 + dst] = a.ts.score[slot * 32 + e];
+        }
+        ++dst;
+      }
+    }
+  }
+}
+
+static int64_t heads_spots_tiles(int batch, int n) { return ((int64_t)batch * pair_count(n) + 127) / 128; }
+static int heads_spots_chunks(int n) {  // chunks of kGatherTilesPerCta tiles that can overlap one document
+  return static_cast<int>((pair_count(n) + 127) / 128 / kGatherTilesPerCta + 2);
+}
+size_t heads_spots_workspace_bytes(int batch, int n) {
+  const int64_t tiles = heads_spots_tiles(batch, n) + 1;
+  return align_up(tile_spots_bytes(tiles), 256) + (size_t)batch * kNumHeads * (1 + heads_spots_chunks(n)) * sizeof(int32_t);
+}
+
+int launch_gather_tile_spots(int batch, int n, void* ws, int cap, int32_t* spot_p, int32_t* spot_tag, float* spot_score,
+                             int32_t* counts, cudaStream_t st) {
+  PENEO_REQUIRE(batch >= 1 && batch <= 65535 && n >= 1 && n <= 46340 && cap >= 1, "gather_tile_spots: bad sizes");
+  GatherArgs a{};
+  const int64_t tiles = heads_spots_tiles(batch, n);
+  a.ts = tile_spots_carve(ws, tiles + 1);
+  a.batch = batch, a.pairs = static_cast<int32_t>(pair_count(n)), a.cap = cap, a.chunks = heads_spots_chunks(n);
+  a.total_tiles = tiles;
+  a.spot_p = spot_p, a.spot_tag = spot_tag, a.spot_score = spot_score, a.counts = counts;
+  char* tail = static_cast<char*>(ws) + align_up(tile_spots_bytes(tiles + 1), 256);
+  a.ticket = reinterpret_cast<int32_t*>(tail);
+  a.status = a.ticket + (int64_t)batch * kNumHeads;
+  PENEO_CUDA_TRY(cudaMemsetAsync(tail, 0, (size_t)batch * kNumHeads * (1 + a.chunks) * sizeof(int32_t), st));
+  gather_tile_spots_kernel<<<dim3(a.chunks, kNumHeads, batch), 256, 0, st>>>(a);
   PENEO_CUDA_TRY(cudaGetLastError());
   return PENEO_OK;
 }

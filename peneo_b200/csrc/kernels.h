@@ -38,9 +38,10 @@ struct FusedLossFwd {
   float class_w[3];
   double* partial;  // [5][grid][2]
 };
+struct TileSpots;  // classify.cuh
 int launch_pair_heads_tc_pair(const void* pack, const PackLayout& L, const __nv_bfloat16* ab, int batch, int n,
                               float* const logits[kNumHeads], cudaStream_t st, const DropSpec* drop = nullptr,
-                              const FusedLossFwd* loss = nullptr, int* grid_out = nullptr);
+                              const FusedLossFwd* loss = nullptr, int* grid_out = nullptr, const TileSpots* spots = nullptr);
 
 // pair_heads_generic.cu : unfused tensor-core forward for the configurations K2 does not cover (any d % 64 == 0, any
 // num_layers): S = SiLU(a_i + b_j) per chunk of pairs, one gemm_tc2 per hidden layer and head, output layer as an
@@ -114,6 +115,10 @@ int launch_heads_bwd(const peneo_dims& dm, int prec, const void* pack, const voi
 size_t decode_spots_workspace_bytes(int batch, int n);
 int launch_decode_spots(int batch, int n, const void* const in[kNumHeads], int in_dtype, int cap, int32_t* spot_p,
                         int32_t* spot_tag, float* spot_score, int32_t* counts, void* ws, cudaStream_t st);
+// ordered compaction of the per-tile spot slots K2's spots-only epilogue wrote -> the same compact lists decode_spots gives
+size_t heads_spots_workspace_bytes(int batch, int n);
+int launch_gather_tile_spots(int batch, int n, void* ws, int cap, int32_t* spot_p, int32_t* spot_tag, float* spot_score,
+                             int32_t* counts, cudaStream_t st);
 size_t decode_resolve_doc_ints(int n, int cap);
 size_t decode_resolve_workspace_bytes(int batch, int n);
 int launch_decode_resolve(int batch, int n, int cap, const int32_t* spot_p, const int32_t* spot_tag,

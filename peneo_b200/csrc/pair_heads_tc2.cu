@@ -14,6 +14,7 @@
 
 #include <cstdlib>
 
+#include "classify.cuh"
 #include "common.cuh"
 #include "kernels.h"
 #include "ptx.cuh"
@@ -68,9 +69,12 @@ struct Args {
   const int64_t* tags[kNumHeads];  // int64 [batch*P]
   float class_w[3];
   double* loss_partial;            // [5][gridDim.x][2] : per-CTA (sum w nll, sum w), reduced by pair_loss_final_kernel
+  // SPOTS instantiation: no logits leave the SM; the epilogue classifies each pair (model/peneo_decoder.py:98-114) and
+  // writes the few non-zero predictions into per-tile slots (classify.cuh), gathered in order by decode.cu
+  TileSpots spots;
 };
 
-template <bool DROP, bool LOSS>
+template <bool DROP, bool LOSS, bool SPOTS>
 __global__ void __launch_bounds__(kThreads, 1)
     pair_heads_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmO, const Args a) {
   extern __shared__ unsigned char smem_raw[];
@@ -227,7 +231,28 @@ __global__ void __launch_bounds__(kThreads, 1)
       const int it = hg / 5, k = hg - it * 5;
       const int64_t tile = tile_of(it);
       const int64_t gp = tile * 128 + row;
-      if (gp < a.total_pairs) {
+      if (SPOTS) {
+        // spot extraction fused into the tile: same fast reject and exact softmax as decode_spots_kernel, ordered
+        // compaction of the warp's 32 pairs by ballot; only the spots (a few per thousand pairs) are written
+        const int C = head_classes(k);
+        const float z0 = __uint_as_float(zr[0]) + s_bout[k * 4], z1 = __uint_as_float(zr[1]) + s_bout[k * 4 + 1];
+        const float z2 = C == 3 ? __uint_as_float(zr[2]) + s_bout[k * 4 + 2] : -INFINITY;
+        int pred = 0;
+        float score = 1.f;
+        if (gp < a.total_pairs && !(z0 >= fmaxf(z1, z2))) {
+          const float zz[3] = {z0, z1, z2};
+          if (C == 2) classify_vals<PENEO_DT_F32, 2>(zz, pred, score);
+          else classify_vals<PENEO_DT_F32, 3>(zz, pred, score);
+        }
+        const unsigned mask = __ballot_sync(0xffffffffu, pred != 0);
+        const int64_t slot = (tile * kNumHeads + k) * 4 + q;
+        if (lane == 0) a.spots.cnt[slot] = __popc(mask);
+        if (pred != 0) {
+          const int64_t at = slot * 32 + __popc(mask & ((1u << lane) - 1u));
+          a.spots.meta[at] = row | (pred << 8);
+          a.spots.score[at] = score;
+        }
+      } else if (gp < a.total_pairs) {
         const int C = head_classes(k);
         float* dst = a.logits[k] + gp * C;
         const float z0 = __uint_as_float(zr[0]) + s_bout[k * 4], z1 = __uint_as_float(zr[1]) + s_bout[k * 4 + 1];
@@ -403,14 +428,15 @@ __global__ void __launch_bounds__(kThreads, 1)
 
 int launch_pair_heads_tc_pair(const void* pack, const PackLayout& L, const __nv_bfloat16* ab, int batch, int n,
                               float* const logits[kNumHeads], cudaStream_t st, const DropSpec* drop, const FusedLossFwd* loss,
-                              int* grid_out) {
+                              int* grid_out, const TileSpots* spots) {
   using namespace k2p;
   const char* base = static_cast<const char*>(pack);
   Args a{};
   a.ab = ab;
   a.bmid_half = reinterpret_cast<const float*>(base + L.bmid_half);
   a.bout = reinterpret_cast<const float*>(base + L.bout);
-  for (int h = 0; h < kNumHeads; ++h) a.logits[h] = logits[h];
+  for (int h = 0; h < kNumHeads; ++h) a.logits[h] = logits ? logits[h] : nullptr;
+  if (spots) a.spots = *spots;
   a.n = n;
   a.pairs_per_doc = static_cast<int32_t>(pair_count(n));
   a.total_pairs = (int64_t)batch * a.pairs_per_doc;
@@ -445,15 +471,17 @@ int launch_pair_heads_tc_pair(const void* pack, const PackLayout& L, const __nv_
     a.loss_partial = loss->partial;
   }
   if (grid_out) *grid_out = grid;
-#define GO(DR, LO)                                                                                                 \
+#define GO(DR, LO, SP)                                                                                             \
   do {                                                                                                             \
-    PENEO_CUDA_TRY(cudaFuncSetAttribute(pair_heads_tc_kernel<DR, LO>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes)); \
-    PENEO_CUDA_TRY(cudaLaunchKernelEx(&cfg, pair_heads_tc_kernel<DR, LO>, tmW, tmO, a));                           \
+    PENEO_CUDA_TRY(cudaFuncSetAttribute(pair_heads_tc_kernel<DR, LO, SP>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes)); \
+    PENEO_CUDA_TRY(cudaLaunchKernelEx(&cfg, pair_heads_tc_kernel<DR, LO, SP>, tmW, tmO, a));                       \
   } while (0)
-  if (dr && loss) GO(true, true);
-  else if (dr) GO(true, false);
-  else if (loss) GO(false, true);
-  else GO(false, false);
+  PENEO_REQUIRE(!(spots && (dr || loss)), "pair_heads: the spots-only output is an inference mode (no dropout, no loss)");
+  if (spots) GO(false, false, true);
+  else if (dr && loss) GO(true, true, false);
+  else if (dr) GO(true, false, false);
+  else if (loss) GO(false, true, false);
+  else GO(false, false, false);
 #undef GO
   PENEO_CUDA_TRY(cudaGetLastError());
   return PENEO_OK;

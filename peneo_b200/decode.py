@@ -95,7 +95,10 @@ class PendingDecode:
     ``finish()`` waits for it; documents whose spot lists overflowed the capacity (dense predictions of an
     untrained model) are decoded again, alone, with exactly the capacity their longest list needs."""
 
-    def __init__(self, ins, n, cap, decode_gt, score_thresh, want_spots, d2h_stream=None, k3_events=None):
+    def __init__(self, ins, n, cap, decode_gt, score_thresh, want_spots, d2h_stream=None, k3_events=None, heads=None):
+        # heads = (WeightPack, ab [B * n, 2d]): spot extraction fused into the pair kernel (peneo_pair_heads_spots_fwd):
+        # there are no logits (`ins` is None), the compact spot lists come straight from the heads
+        self.heads = heads
         self.ins, self.n, self.cap = ins, n, cap
         self.decode_gt, self.score_thresh, self.want_spots = decode_gt, score_thresh, want_spots
         self.d2h_stream = d2h_stream  # optional side stream so the record copy does not stall the next batch
@@ -105,22 +108,36 @@ class PendingDecode:
     def _launch(self):
         lib = _lib.load()
         ins, n, cap = self.ins, self.n, self.cap
-        b = ins[0].shape[0]
-        dev = ins[0].device
-        dt = _TORCH_DT[ins[0].dtype]
+        if self.heads is not None:
+            pack, ab = self.heads
+            b, dev = ab.shape[0] // n, ab.device
+        else:
+            b, dev = ins[0].shape[0], ins[0].device
+        self.batch = b
         self.spot_p = torch.empty(b * NUM_HEADS * cap, dtype=torch.int32, device=dev)
         self.spot_tag = torch.empty_like(self.spot_p)
         self.spot_score = torch.empty(b * NUM_HEADS * cap, dtype=torch.float32, device=dev)
         counts = torch.empty(b * NUM_HEADS, dtype=torch.int32, device=dev)
-        ws = torch.empty(max(16, lib.peneo_decode_spots_workspace_bytes(b, n)), dtype=torch.uint8, device=dev)
         if self.k3_events is not None:
             ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
             ev[0].record(torch.cuda.current_stream(dev))
-        _lib.check(
-            lib.peneo_decode_spots(b, n, _lib.ptrs5(ins), dt, cap, self.spot_p.data_ptr(), self.spot_tag.data_ptr(),
-                                   self.spot_score.data_ptr(), counts.data_ptr(), ws.data_ptr(), _stream(dev)),
-            "peneo_decode_spots",
-        )
+        if self.heads is not None:
+            ws = torch.empty(lib.peneo_pair_heads_spots_workspace_bytes(b, n), dtype=torch.uint8, device=dev)
+            _lib.check(
+                lib.peneo_pair_heads_spots_fwd(pack.dims.c(), pack.prec, pack.buf.data_ptr(), ab.data_ptr(), b, n, cap,
+                                               self.spot_p.data_ptr(), self.spot_tag.data_ptr(), self.spot_score.data_ptr(),
+                                               counts.data_ptr(), ws.data_ptr(), _stream(dev)),
+                "peneo_pair_heads_spots_fwd",
+            )
+            COUNTERS["kernels"] += 1  # K2 with the spots-only epilogue + the gather (counted with K4 below as K3)
+        else:
+            ws = torch.empty(max(16, lib.peneo_decode_spots_workspace_bytes(b, n)), dtype=torch.uint8, device=dev)
+            _lib.check(
+                lib.peneo_decode_spots(b, n, _lib.ptrs5(ins), _TORCH_DT[ins[0].dtype], cap, self.spot_p.data_ptr(),
+                                       self.spot_tag.data_ptr(), self.spot_score.data_ptr(), counts.data_ptr(),
+                                       ws.data_ptr(), _stream(dev)),
+                "peneo_decode_spots",
+            )
         if self.k3_events is not None:
             ev[1].record(torch.cuda.current_stream(dev))
             self.k3_events.append(ev)
@@ -158,16 +175,22 @@ class PendingDecode:
 
     def finish(self) -> "DeviceDecode":
         self.event.synchronize()
-        b = self.ins[0].shape[0]
+        b = self.batch
         p = shaking_len(self.n)
         redo, redo_rows = None, {}
         worst = self.counts_h.numpy().reshape(b, NUM_HEADS).max(axis=1)
         if self.cap < p and int(worst.max()) > self.cap:
             # some lists overflowed: decode those documents again (only those) with the capacity they need
             over = np.nonzero(worst > self.cap)[0]
-            idx = torch.as_tensor(over, device=self.ins[0].device)
-            sub = PendingDecode([t.index_select(0, idx) for t in self.ins], self.n, min(p, int(worst.max())),
-                                self.decode_gt, self.score_thresh, self.want_spots, None)
+            idx = torch.as_tensor(over, device=self.spot_p.device)
+            if self.heads is not None:
+                pack, ab = self.heads
+                sub_ab = ab.view(b, self.n, -1).index_select(0, idx).reshape(len(over) * self.n, -1)
+                sub_ins, sub_heads = None, (pack, sub_ab)
+            else:
+                sub_ins, sub_heads = [t.index_select(0, idx) for t in self.ins], None
+            sub = PendingDecode(sub_ins, self.n, min(p, int(worst.max())), self.decode_gt, self.score_thresh,
+                                self.want_spots, None, None, sub_heads)
             self.d2h_bytes += sub.d2h_bytes
             redo, redo_rows = sub.finish(), {int(d): r for r, d in enumerate(over)}
         spots = None
@@ -193,6 +216,19 @@ def device_decode_async(shakings: Sequence[torch.Tensor], n: int, decode_gt: boo
     if cap is None:
         cap = min(p, max(8 * n, 1024))
     return PendingDecode(ins, n, cap, decode_gt, score_thresh, want_spots, d2h_stream, k3_events)
+
+
+def heads_decode_async(pack, ab: torch.Tensor, batch: int, n: int, score_thresh: float = 0, cap: Optional[int] = None,
+                       want_spots: bool = False, d2h_stream=None, k2_events=None) -> PendingDecode:
+    """Pair heads + spot extraction in ONE kernel (no logits in HBM) + link resolution + the D2H copy of the compact
+    records, enqueued on the current stream.  ``ab``: the per-token projections of ``ops.token_projections``.
+    Same results as ``device_decode_async(ops.pair_heads(...))`` — the fused tcgen05 configuration only."""
+    p = shaking_len(n)
+    if ab.shape[0] != batch * n:
+        raise ValueError("ab must hold batch * n token rows")
+    if cap is None:
+        cap = min(p, max(8 * n, 1024))
+    return PendingDecode(None, n, cap, False, score_thresh, want_spots, d2h_stream, k2_events, (pack, ab))
 
 
 def device_decode(shakings: Sequence[torch.Tensor], n: int, decode_gt: bool = False, score_thresh: float = 0,

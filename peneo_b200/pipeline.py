@@ -19,7 +19,7 @@ from . import decode, ops
 
 
 class HeadsDecodePipeline:
-    def __init__(self, decoder, device=None, score_thresh: float = 0.0):
+    def __init__(self, decoder, device=None, score_thresh: float = 0.0, fused_spots: Optional[bool] = None):
         self.decoder = decoder
         self.device = torch.device(device) if device is not None else next(decoder.parameters()).device
         if self.device.type != "cuda":
@@ -28,6 +28,12 @@ class HeadsDecodePipeline:
         self.copy = torch.cuda.Stream(self.device)
         self.d2h = torch.cuda.Stream(self.device)
         self.score_thresh = score_thresh
+        # Spot extraction inside the pair kernel's epilogue (no [B, P, C] logits written or read): the default wherever
+        # the fused tcgen05 kernel runs; `fused_spots=False` keeps the separate K2 -> logits -> K3 route.
+        fusable = decoder.precision == "bf16" and decoder.dims.bf16_capable()
+        if fused_spots and not fusable:
+            raise ValueError("fused_spots needs the fused tcgen05 configuration (precision 'bf16', shrink, 768 -> 384, 2 layers)")
+        self.fused_spots = fusable if fused_spots is None else bool(fused_spots)
         self._queue = deque()
         self.h2d_bytes = 0
         self.wait_s = 0.0      # result(): time blocked on the GPU
@@ -54,16 +60,22 @@ class HeadsDecodePipeline:
                 self.compute.wait_event(ready)
             pack = self.decoder._weight_pack(self.device)
             ab = ops.token_projections(pack, x)
-            if self.k2_events is not None:
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record(self.compute)
-            logits = ops.pair_heads(pack, ab, b, n)
-            if self.k2_events is not None:
-                e1.record(self.compute)
-                self.k2_events.append((e0, e1))
-            self.decoder._pack_read_done(self.device)  # a later re-pack on another stream waits for these kernels
-            pending = decode.device_decode_async(logits, n, score_thresh=self.score_thresh, d2h_stream=self.d2h,
-                                                 k3_events=self.k3_events)
+            if self.fused_spots:
+                # K2 with the spots-only epilogue + gather (timed together as "K2": the gather is ~10 us)
+                pending = decode.heads_decode_async(pack, ab, b, n, score_thresh=self.score_thresh, d2h_stream=self.d2h,
+                                                    k2_events=self.k2_events)
+                self.decoder._pack_read_done(self.device)
+            else:
+                if self.k2_events is not None:
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record(self.compute)
+                logits = ops.pair_heads(pack, ab, b, n)
+                if self.k2_events is not None:
+                    e1.record(self.compute)
+                    self.k2_events.append((e0, e1))
+                self.decoder._pack_read_done(self.device)  # a later re-pack on another stream waits for these kernels
+                pending = decode.device_decode_async(logits, n, score_thresh=self.score_thresh, d2h_stream=self.d2h,
+                                                     k3_events=self.k3_events)
             x.record_stream(self.compute)
         self.d2h_bytes += pending.d2h_bytes
         self._queue.append((pending, list(texts), bboxes))
