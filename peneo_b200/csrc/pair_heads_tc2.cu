@@ -32,7 +32,7 @@ constexpr int kOStageBytes = 2 * 8 * 64 * 2;  // 2 KB: two K-blocks of [8 rows x
 constexpr int kStageRowBytes = D * 2;          // staging: 128 rows x 768 B
 constexpr int kEpiWarps = 16;      // 4 per scheduler: each takes 32 of a chunk's 128 columns
 constexpr int kProdWarp0 = 4 + kEpiWarps;
-constexpr int kProdRows = 2;        // pair rows a producer warp has in flight (register budget: 80 / thread)
+constexpr int kProdRows = 4;        // b_j rows a producer warp has in flight (register budget: 80 / thread)
 constexpr int kThreads = 32 * (kProdWarp0 + 4);
 
 constexpr uint32_t kColS = 0, kColU = 192, kColZ = 448;
@@ -49,7 +49,7 @@ struct Smem {
 };
 // barrier indices
 constexpr int bWFull = 0, bWEmpty = bWFull + kWStages, bOFull = bWEmpty + kWStages, bOEmpty = bOFull + kOStages,
-              bUFull = bOEmpty + kOStages, bMReady = bUFull + 2, bZFull = bMReady + 2, bSFull = bZFull + 2,
+              bUFull = bOEmpty + kOStages, bMReady = bUFull + 2, bZFull = bMReady + 2, bZFree = bZFull + 2, bSFull = bZFree + 2,
               bSFree = bSFull + kKChunks, bCount = bSFree + kKChunks;
 static_assert(bCount * 8 + 16 <= 512, "barrier area too small");
 constexpr int kSmemBytes = Smem::total + 1024;
@@ -98,6 +98,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       ptx::mbar_init(&bars[bUFull + s], 1);
       ptx::mbar_init(&bars[bMReady + s], 2 * kEpiWarps);  // the epilogue warps of both CTAs
       ptx::mbar_init(&bars[bZFull + s], 1);
+      ptx::mbar_init(&bars[bZFree + s], 8);  // the four emitting (producer) warps of each CTA
     }
     for (int s = 0; s < kKChunks; ++s) ptx::mbar_init(&bars[bSFull + s], 8), ptx::mbar_init(&bars[bSFree + s], 1);
     ptx::fence_barrier_init();
@@ -167,6 +168,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       auto mma2 = [&](int gp) {
         const int buf = gp & 1, hg = gp / 3, cpos = gp - hg * 3;
         ptx::mbar_wait(&bars[bMReady + buf], (gp >> 1) & 1);
+        if (cpos == 0 && hg >= 2) ptx::mbar_wait(&bars[bZFree + (hg & 1)], ((hg >> 1) & 1) ^ 1);  // z of head hg - 2 was read
         ptx::mbar_wait(&bars[bOFull + os], oph);
         ptx::tc_fence_after();
         const uint32_t zt = tmem + kColZ + 16 * (hg & 1);
@@ -206,78 +208,17 @@ __global__ void __launch_bounds__(kThreads, 1)
   } else if (warp >= 4 && warp < kProdWarp0) {
     // ============================== epilogue ==============================
     // 16 warps: quadrant q = warp % 4 (TMEM lanes 32 q ..), column slice csel = (warp - 4) / 4 of the chunk's 128 columns.
-    // Four warps per scheduler hide the TMEM-load / MUFU / barrier latencies of one another.
+    // Four warps per scheduler hide the TMEM-load / MUFU / barrier latencies of one another.  Nothing but the hidden
+    // activation happens here: every chunk waits for its slowest epilogue warp, so the logits / loss / spot work of
+    // a finished head is done by the producer warps (below), which are idle two thirds of the time.
     const int q = warp % 4, csel = (warp - 4) / 4;
     const uint32_t lane_base = static_cast<uint32_t>(q * 32) << 16;
     const int row = q * 32 + lane;
-    // logits of head-global index hg (tile = hg / 5, head = hg % 5)
-    // The logits of head k are emitted by the column group csel == (k & 3): the extra work sits on four different
-    // warps per quadrant instead of always the same one (every chunk waits for its slowest epilogue warp).
-    // LOSS: per-lane fp32 partial sums (slot 0: heads 0-3, slot 1: head 4 — only group 0 owns two heads), reduced once
-    // at the end of the kernel; the pair's tag is fetched when its head starts, three chunks before it is needed.
-    float acc_l[2] = {0.f, 0.f}, acc_w[2] = {0.f, 0.f};
-    long long tag_next = 0;
-    auto fetch_tag = [&](int hg) {
-      const int it = hg / 5, k = hg - it * 5;
-      const int64_t gp = tile_of(it) * 128 + row;
-      tag_next = gp < a.total_pairs ? a.tags[k][gp] : 0;
-    };
-    auto emit_z = [&](int hg, long long tag) {
-      ptx::mbar_wait(&bars[bZFull + (hg & 1)], (hg >> 1) & 1);
-      ptx::tc_fence_after();
-      uint32_t zr[4];
-      ptx::tmem_ld_x4(tmem + lane_base + kColZ + 16 * (hg & 1), zr);
-      ptx::tmem_ld_wait();
-      const int it = hg / 5, k = hg - it * 5;
-      const int64_t tile = tile_of(it);
-      const int64_t gp = tile * 128 + row;
-      if (SPOTS) {
-        // spot extraction fused into the tile: same fast reject and exact softmax as decode_spots_kernel, ordered
-        // compaction of the warp's 32 pairs by ballot; only the spots (a few per thousand pairs) are written
-        const int C = head_classes(k);
-        const float z0 = __uint_as_float(zr[0]) + s_bout[k * 4], z1 = __uint_as_float(zr[1]) + s_bout[k * 4 + 1];
-        const float z2 = C == 3 ? __uint_as_float(zr[2]) + s_bout[k * 4 + 2] : -INFINITY;
-        int pred = 0;
-        float score = 1.f;
-        if (gp < a.total_pairs && !(z0 >= fmaxf(z1, z2))) {
-          const float zz[3] = {z0, z1, z2};
-          if (C == 2) classify_vals<PENEO_DT_F32, 2>(zz, pred, score);
-          else classify_vals<PENEO_DT_F32, 3>(zz, pred, score);
-        }
-        const unsigned mask = __ballot_sync(0xffffffffu, pred != 0);
-        const int64_t slot = (tile * kNumHeads + k) * 4 + q;
-        if (lane == 0) a.spots.cnt[slot] = __popc(mask);
-        if (pred != 0) {
-          const int64_t at = slot * 32 + __popc(mask & ((1u << lane) - 1u));
-          a.spots.meta[at] = row | (pred << 8);
-          a.spots.score[at] = score;
-        }
-      } else if (gp < a.total_pairs) {
-        const int C = head_classes(k);
-        float* dst = a.logits[k] + gp * C;
-        const float z0 = __uint_as_float(zr[0]) + s_bout[k * 4], z1 = __uint_as_float(zr[1]) + s_bout[k * 4 + 1];
-        const float z2 = C == 3 ? __uint_as_float(zr[2]) + s_bout[k * 4 + 2] : -INFINITY;
-        dst[0] = z0, dst[1] = z1;
-        if (C == 3) dst[2] = z2;
-        if (LOSS) {  // w[t] (logsumexp(z) - z[t]) and w[t] of this pair
-          const bool bad = tag < 0 || tag >= C;
-          const int t = bad ? 0 : static_cast<int>(tag);
-          const float mx = fmaxf(fmaxf(z0, z1), z2);
-          const float se = __expf(z0 - mx) + __expf(z1 - mx) + (C == 3 ? __expf(z2 - mx) : 0.f);
-          const float zt = t == 0 ? z0 : (t == 1 ? z1 : z2);
-          const float ww = t == 0 ? a.class_w[0] : (t == 1 ? a.class_w[1] : a.class_w[2]);
-          acc_w[k >> 2] += ww;
-          acc_l[k >> 2] += bad ? NAN : ww * (mx + __logf(se) - zt);
-        }
-      }
-    };
     int g = 0;
-    long long tag_cur = 0;
     for (int it = 0; it < my_tiles; ++it) {
       const int64_t drop_row = tile_of(it) * 128 + row;
       for (int c = 0; c < kChunks; ++c, ++g) {
         const int buf = g & 1;
-        if (LOSS && g % 3 == 0 && csel == ((g / 3) % 5 & 3)) fetch_tag(g / 3);  // consumed by emit_z(g / 3) three chunks on
         ptx::mbar_wait(&bars[bUFull + buf], (g >> 1) & 1);
         ptx::tc_fence_after();
         const uint32_t ut = tmem + lane_base + kColU + 128 * buf + 32 * csel;
@@ -310,20 +251,6 @@ __global__ void __launch_bounds__(kThreads, 1)
         ptx::tc_fence_before();
         __syncwarp();
         if (lane == 0) arrive_leader(&bars[bMReady + buf]);
-        if (g > 0 && g % 3 == 0 && csel == ((g / 3 - 1) % 5 & 3)) emit_z(g / 3 - 1, tag_cur);
-        if (LOSS && g % 3 == 0 && csel == ((g / 3) % 5 & 3)) tag_cur = tag_next;  // (after the emit above, which used the old value)
-      }
-    }
-    if (g > 0 && csel == ((g / 3 - 1) % 5 & 3)) emit_z(g / 3 - 1, tag_cur);
-    if (LOSS) {  // this warp's partial sums -> (quadrant, head) slots, fixed shuffle tree, fp64 from here on
-#pragma unroll
-      for (int sl = 0; sl < 2; ++sl) {
-        const int k = sl == 0 ? csel : 4;  // group csel owns head csel (slot 0); group 0 also head 4 (slot 1)
-        if (sl == 1 && csel != 0) break;
-        double dl = static_cast<double>(acc_l[sl]), dw = static_cast<double>(acc_w[sl]);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) dl += __shfl_xor_sync(0xffffffffu, dl, o), dw += __shfl_xor_sync(0xffffffffu, dw, o);
-        if (lane == 0) s_loss[(q * 5 + k) * 2] = dl, s_loss[(q * 5 + k) * 2 + 1] = dw;
       }
     }
   } else if (warp >= kProdWarp0) {
@@ -331,6 +258,79 @@ __global__ void __launch_bounds__(kThreads, 1)
     const int q = warp - kProdWarp0;
     const uint32_t lane_base = static_cast<uint32_t>(q * 32) << 16;
     unsigned char* stg = smem + Smem::stage;
+    const int row = q * 32 + lane;
+    // ---- logits of finished heads (head-global index hg: tile = hg / 5, head = hg % 5).  z sits in one of two TMEM
+    //      accumulators; emit_ready() drains every head whose MMA2 has completed and hands the accumulator back to the
+    //      MMA warp (bZFree).  It is called between the row groups of the s generation and while waiting for s chunks
+    //      to be released, so a head waits a few hundred cycles at most — the accumulator is needed again three chunks
+    //      (~6000 cycles) later.
+    float acc_l[kNumHeads] = {0.f, 0.f, 0.f, 0.f, 0.f}, acc_w[kNumHeads] = {0.f, 0.f, 0.f, 0.f, 0.f};  // LOSS: per-lane sums
+    const int total_heads = my_tiles * kNumHeads;
+    int next_emit = 0;
+    auto emit_z = [&](int hg) {
+      ptx::tc_fence_after();
+      uint32_t zr[4];
+      ptx::tmem_ld_x4(tmem + lane_base + kColZ + 16 * (hg & 1), zr);
+      ptx::tmem_ld_wait();
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) arrive_leader(&bars[bZFree + (hg & 1)]);  // the accumulator may be overwritten (head hg + 2)
+      const int it = hg / 5, k = hg - it * 5;
+      const int64_t tile = tile_of(it);
+      const int64_t gp = tile * 128 + row;
+      const int C = head_classes(k);
+      const float z0 = __uint_as_float(zr[0]) + s_bout[k * 4], z1 = __uint_as_float(zr[1]) + s_bout[k * 4 + 1];
+      const float z2 = C == 3 ? __uint_as_float(zr[2]) + s_bout[k * 4 + 2] : -INFINITY;
+      if (SPOTS) {
+        // spot extraction fused into the tile: same fast reject and exact softmax as decode_spots_kernel, ordered
+        // compaction of the warp's 32 pairs by ballot; only the spots (a few per thousand pairs) are written
+        int pred = 0;
+        float score = 1.f;
+        if (gp < a.total_pairs && !(z0 >= fmaxf(z1, z2))) {
+          const float zz[3] = {z0, z1, z2};
+          if (C == 2) classify_vals<PENEO_DT_F32, 2>(zz, pred, score);
+          else classify_vals<PENEO_DT_F32, 3>(zz, pred, score);
+        }
+        const unsigned mask = __ballot_sync(0xffffffffu, pred != 0);
+        const int64_t slot = (tile * kNumHeads + k) * 4 + q;
+        if (lane == 0) a.spots.cnt[slot] = __popc(mask);
+        if (pred != 0) {
+          const int64_t at = slot * 32 + __popc(mask & ((1u << lane) - 1u));
+          a.spots.meta[at] = row | (pred << 8);
+          a.spots.score[at] = score;
+        }
+      } else if (gp < a.total_pairs) {
+        float* dst = a.logits[k] + gp * C;
+        dst[0] = z0, dst[1] = z1;
+        if (C == 3) dst[2] = z2;
+        if (LOSS) {  // w[t] (logsumexp(z) - z[t]) and w[t] of this pair (model/custom_loss.py:189-202)
+          const long long tag = a.tags[k][gp];
+          const bool bad = tag < 0 || tag >= C;
+          const int t = bad ? 0 : static_cast<int>(tag);
+          const float mx = fmaxf(fmaxf(z0, z1), z2);
+          const float se = __expf(z0 - mx) + __expf(z1 - mx) + (C == 3 ? __expf(z2 - mx) : 0.f);
+          const float zt = t == 0 ? z0 : (t == 1 ? z1 : z2);
+          const float ww = t == 0 ? a.class_w[0] : (t == 1 ? a.class_w[1] : a.class_w[2]);
+#pragma unroll
+          for (int kk = 0; kk < kNumHeads; ++kk)
+            if (kk == k) acc_w[kk] += ww, acc_l[kk] += bad ? NAN : ww * (mx + __logf(se) - zt);
+        }
+      }
+    };
+    // warp-uniform poll: lane 0 tests the barrier, the result is broadcast, then every lane passes the (already
+    // completed) wait itself so that each has observed the phase before touching tensor memory
+    auto poll = [&](uint64_t* bar, uint32_t parity) {
+      int ok = lane == 0 ? static_cast<int>(ptx::mbar_try_wait(bar, parity)) : 0;
+      ok = __shfl_sync(0xffffffffu, ok, 0);
+      if (ok) ptx::mbar_wait(bar, parity);
+      return ok != 0;
+    };
+    auto emit_ready = [&]() {
+      while (next_emit < total_heads && poll(&bars[bZFull + (next_emit & 1)], (next_emit >> 1) & 1)) {
+        emit_z(next_emit);
+        ++next_emit;
+      }
+    };
     for (int it = 0; it < my_tiles; ++it) {
       const int64_t tile = tile_of(it);
       // (row offsets of a_i / b_j for the row this lane will later copy)
@@ -346,40 +346,44 @@ __global__ void __launch_bounds__(kThreads, 1)
           my_b = (b * a.n + j) * (2 * D) + D;
         }
       }
-      // ---- generate s rows [32q, 32q+32) into staging; lane = 4-column group (3 groups per lane)
+      // ---- generate s rows [32q, 32q+32) into staging; lane = 4-column group (3 groups per lane).  Consecutive pairs
+      //      share their row token i (a tile is 128 consecutive pairs of the row-major triangle), so a_i stays in
+      //      registers and is reloaded only where i changes; only the b_j rows are streamed, kProdRows at a time.
+      int64_t cur_a = -2;
+      float af[3][4] = {};
 #pragma unroll 1
       for (int rr = 0; rr < 32; rr += kProdRows) {
-        uint2 av[kProdRows][3], bv[kProdRows][3];
+        if ((rr & 7) == 0) emit_ready();
+        uint2 bv[kProdRows][3];
         int64_t offa[kProdRows];
 #pragma unroll
         for (int u = 0; u < kProdRows; ++u) {
           offa[u] = __shfl_sync(0xffffffffu, my_a, rr + u);
           const int64_t offb = __shfl_sync(0xffffffffu, my_b, rr + u);
 #pragma unroll
-          for (int mth = 0; mth < 3; ++mth) {
-            const int col = 4 * (lane + 32 * mth);
-            if (offa[u] >= 0) {
-              av[u][mth] = __ldg(reinterpret_cast<const uint2*>(a.ab + offa[u] + col));
-              bv[u][mth] = __ldg(reinterpret_cast<const uint2*>(a.ab + offb + col));
-            } else {
-              av[u][mth] = make_uint2(0u, 0u), bv[u][mth] = make_uint2(0u, 0u);
-            }
-          }
+          for (int mth = 0; mth < 3; ++mth)
+            bv[u][mth] = offa[u] >= 0 ? __ldg(reinterpret_cast<const uint2*>(a.ab + offb + 4 * (lane + 32 * mth))) : make_uint2(0u, 0u);
         }
 #pragma unroll
         for (int u = 0; u < kProdRows; ++u) {
           const int r = q * 32 + rr + u;
+          if (offa[u] != cur_a) {  // (warp-uniform) new row token: its projection, bf16 -> fp32 is a 16-bit shift
+            cur_a = offa[u];
+#pragma unroll
+            for (int mth = 0; mth < 3; ++mth) {
+              const uint2 av = cur_a >= 0 ? __ldg(reinterpret_cast<const uint2*>(a.ab + cur_a + 4 * (lane + 32 * mth))) : make_uint2(0u, 0u);
+              af[mth][0] = __uint_as_float(av.x << 16), af[mth][1] = __uint_as_float(av.x & 0xFFFF0000u);
+              af[mth][2] = __uint_as_float(av.y << 16), af[mth][3] = __uint_as_float(av.y & 0xFFFF0000u);
+            }
+          }
 #pragma unroll
           for (int mth = 0; mth < 3; ++mth) {
             const int cg = lane + 32 * mth;  // 4-column group index, 0..95
-            // bf16 -> fp32 is a 16-bit shift
-            const float a0 = __uint_as_float(av[u][mth].x << 16), a1 = __uint_as_float(av[u][mth].x & 0xFFFF0000u);
-            const float a2 = __uint_as_float(av[u][mth].y << 16), a3 = __uint_as_float(av[u][mth].y & 0xFFFF0000u);
             const float b0 = __uint_as_float(bv[u][mth].x << 16), b1 = __uint_as_float(bv[u][mth].x & 0xFFFF0000u);
             const float b2 = __uint_as_float(bv[u][mth].y << 16), b3 = __uint_as_float(bv[u][mth].y & 0xFFFF0000u);
             uint2 o;
-            o.x = ptx::pack_bf16x2(ptx::silu_from_half(a0 + b0), ptx::silu_from_half(a1 + b1));
-            o.y = ptx::pack_bf16x2(ptx::silu_from_half(a2 + b2), ptx::silu_from_half(a3 + b3));
+            o.x = ptx::pack_bf16x2(ptx::silu_from_half(af[mth][0] + b0), ptx::silu_from_half(af[mth][1] + b1));
+            o.y = ptx::pack_bf16x2(ptx::silu_from_half(af[mth][2] + b2), ptx::silu_from_half(af[mth][3] + b3));
             const int chunk16 = (cg >> 1) ^ (r & 7);  // XOR swizzle keeps the row-wise reads below conflict-free
             *reinterpret_cast<uint2*>(stg + r * kStageRowBytes + chunk16 * 16 + (cg & 1) * 8) = o;
           }
@@ -397,7 +401,9 @@ __global__ void __launch_bounds__(kThreads, 1)
           const uint4 t = *reinterpret_cast<const uint4*>(stg + r * kStageRowBytes + chunk16 * 16);
           v[4 * ch] = t.x, v[4 * ch + 1] = t.y, v[4 * ch + 2] = t.z, v[4 * ch + 3] = t.w;
         }
-        if (it > 0) ptx::mbar_wait(&bars[bSFree + kc], (it - 1) & 1);
+        if (it > 0) {
+          while (!poll(&bars[bSFree + kc], (it - 1) & 1)) emit_ready();
+        }
         ptx::tc_fence_after();
         uint32_t lo[16], hi[16];
 #pragma unroll
@@ -410,6 +416,20 @@ __global__ void __launch_bounds__(kThreads, 1)
         if (lane == 0) arrive_leader(&bars[bSFull + kc]);
       }
       __syncwarp();
+    }
+    while (next_emit < total_heads) {  // the heads of the last tile
+      ptx::mbar_wait(&bars[bZFull + (next_emit & 1)], (next_emit >> 1) & 1);
+      emit_z(next_emit);
+      ++next_emit;
+    }
+    if (LOSS) {  // this warp's partial sums -> (quadrant, head) slots: fixed shuffle tree, fp64 from here on
+#pragma unroll
+      for (int k = 0; k < kNumHeads; ++k) {
+        double dl = static_cast<double>(acc_l[k]), dw = static_cast<double>(acc_w[k]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) dl += __shfl_xor_sync(0xffffffffu, dl, o), dw += __shfl_xor_sync(0xffffffffu, dw, o);
+        if (lane == 0) s_loss[(q * 5 + k) * 2] = dl, s_loss[(q * 5 + k) * 2 + 1] = dw;
+      }
     }
   }
 

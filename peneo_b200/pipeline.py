@@ -28,12 +28,20 @@ class HeadsDecodePipeline:
         self.copy = torch.cuda.Stream(self.device)
         self.d2h = torch.cuda.Stream(self.device)
         self.score_thresh = score_thresh
-        # Spot extraction inside the pair kernel's epilogue (no [B, P, C] logits written or read): the default wherever
-        # the fused tcgen05 kernel runs; `fused_spots=False` keeps the separate K2 -> logits -> K3 route.
+        # `fused_spots=True`: spot extraction inside the pair kernel (no [B, P, C] logits written or read, 234 MB per
+        # 32 x seq-512 batch less HBM traffic and memory).  Measured on B200 it is 1.3 % SLOWER end to end than
+        # K2 -> logits -> K3 (6 260 vs 6 340 docs/s in 40-step runs): K2 is paced by its CUDA-core warps, the classify /
+        # ballot work costs them more than the 0.09 ms the stand-alone K3 takes.  So the default is the logits route;
+        # the fused route is for memory-bound deployments (N = 2048: 117 MB of logits per document).
         fusable = decoder.precision == "bf16" and decoder.dims.bf16_capable()
         if fused_spots and not fusable:
             raise ValueError("fused_spots needs the fused tcgen05 configuration (precision 'bf16', shrink, 768 -> 384, 2 layers)")
-        self.fused_spots = fusable if fused_spots is None else bool(fused_spots)
+        if fused_spots is None:  # PENEO_FUSED_SPOTS=0/1 overrides the default (A/B studies)
+            import os
+
+            env = os.environ.get("PENEO_FUSED_SPOTS")
+            fused_spots = False if env is None else (fusable and env != "0")
+        self.fused_spots = bool(fused_spots)
         self._queue = deque()
         self.h2d_bytes = 0
         self.wait_s = 0.0      # result(): time blocked on the GPU

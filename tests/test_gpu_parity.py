@@ -719,9 +719,9 @@ def test_fused_spot_extraction_in_the_pair_kernel_equals_logits_route(n, b, regi
                 print(f"doc {d} head {h}: {len(diff)} pairs classified differently, gaps {gap[diff].tolist()}")
                 assert (gap[diff] <= 2e-7).all(), (d, h, gap[diff])
             assert sum(int((cpu[h].softmax(-1).argmax(-1) != 0).sum()) for h in range(5)) > 0
-    # the serving loop takes the fused route by default for this configuration
-    pipe = HeadsDecodePipeline(dec)
-    assert pipe.fused_spots
+    # the serving loop on the fused route
+    pipe = HeadsDecodePipeline(dec, fused_spots=True)
+    assert pipe.fused_spots and not HeadsDecodePipeline(dec).fused_spots
     pipe.submit(x, texts)
     res = pipe.result()
     for d in range(b):
