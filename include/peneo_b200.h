@@ -49,6 +49,7 @@ extern "C" {
 /* arithmetic modes of the heads */
 #define PENEO_PREC_FP32 0 /* CUDA-core fp32, exact SiLU: meets the 1e-3 logit tolerance */
 #define PENEO_PREC_BF16 1 /* tcgen05 bf16 x bf16 -> fp32: meets the 2e-2 logit tolerance (see peneo_pack_bytes) */
+#define PENEO_PREC_TF32 2 /* peneo_heads_bwd only: PENEO_PREC_FP32 pack and layouts, every GEMM on tcgen05 kind::tf32 */
 
 /* element types of caller tensors */
 #define PENEO_DT_F32 0
@@ -97,9 +98,10 @@ typedef struct peneo_dropout {
 
 /* Bytes of the packed-weight buffer for (dims, prec).  0 if the combination is unsupported.
  * PENEO_PREC_BF16: hin, hid and d in multiples of 64.  shrink = 1, hid = 768 (d = 384), num_layers = 2 runs the fused
- * tcgen05 kernels, forward and backward; every other configuration runs an unfused tensor-core FORWARD
- * (peneo_token_proj_fwd / peneo_pair_heads_fwd without dropout) and has to be trained with PENEO_PREC_FP32:
- * peneo_heads_bwd returns PENEO_E_INVALID for it. */
+ * tcgen05 kernels, forward and backward; every other configuration runs an unfused tensor-core forward
+ * (peneo_token_proj_fwd / peneo_pair_heads_fwd, dropout included) and its backward pass with PENEO_PREC_TF32
+ * (peneo_heads_bwd with a PENEO_PREC_FP32 pack: recompute + gradient GEMMs on tcgen05 kind::tf32) or, exact, with
+ * PENEO_PREC_FP32 on CUDA cores. */
 size_t peneo_pack_bytes(const peneo_dims* dims, int prec);
 /* Convert the fp32 parameters into the kernel layouts (bf16 copies, concatenated and pre-scaled
  * matrices).  Call again whenever a parameter changed. */
@@ -193,7 +195,7 @@ typedef struct peneo_grads {
  * given dlogits[h] = d loss / d logits[h] (fp32 [batch, P, C_h]) computes every parameter gradient
  * and, when dx != NULL, d loss / d x (fp32 [batch*n, hin], contiguous).  The pair activations are
  * recomputed from x chunk by chunk (nothing of size [P, d] is kept from the forward pass).
- * `pack` must be a PENEO_PREC_FP32 pack when prec == PENEO_PREC_FP32. */
+ * `pack` must be a PENEO_PREC_FP32 pack when prec == PENEO_PREC_FP32 or PENEO_PREC_TF32 (any configuration). */
 size_t peneo_heads_bwd_workspace_bytes(const peneo_dims* dims, int prec, int32_t batch, int32_t n);
 int peneo_heads_bwd(const peneo_dims* dims, int prec, const void* pack, const void* x, int x_dtype,
                     int64_t x_row_stride, int32_t batch, int32_t n, const float* const dlogits[PENEO_NUM_HEADS],

@@ -6,9 +6,11 @@ Public surface mirrors the reference (ZeningLin/PEneo):
   decode_peneo / sample_decode_peneo / parse_matrix_spots  <- pipeline/decode.py
   CrossEntropyLossOHEM                <- model/custom_loss.py    CrossEntropyLossOHEM
   evaluation.calculate_*_KVPE_metric  <- pipeline/evaluation.py
+  eval_loop.prediction_loop / StreamingEvaluator  <- pipeline/trainer.py  PEneoTrainer.prediction_loop (per-batch decode)
 """
 from .decode import decode_peneo, parse_matrix_spots, sample_decode_peneo  # noqa: F401
 from .decoder import PEneoDecoderB200, PEneoOutput  # noqa: F401
+from .eval_loop import StreamingEvaluator, prediction_loop  # noqa: F401
 from .loss import CrossEntropyLossOHEM  # noqa: F401
 from .pipeline import HeadsDecodePipeline  # noqa: F401
 from .tagging import HandshakingTaggingScheme  # noqa: F401
@@ -18,6 +20,8 @@ __all__ = [
     "PEneoOutput",
     "HandshakingTaggingScheme",
     "HeadsDecodePipeline",
+    "StreamingEvaluator",
+    "prediction_loop",
     "CrossEntropyLossOHEM",
     "decode_peneo",
     "sample_decode_peneo",

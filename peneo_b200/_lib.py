@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_HERE, "libpeneo_b200.so")
 
 NUM_HEADS = 5
 HEAD_CLASSES = (2, 3, 3, 3, 3)
-PREC_FP32, PREC_BF16 = 0, 1
+PREC_FP32, PREC_BF16, PREC_TF32 = 0, 1, 2
 DT_F32, DT_BF16, DT_F16, DT_I64 = 0, 1, 2, 3
 E_OVERFLOW = -4
 

@@ -33,6 +33,7 @@ static int check_dims(const peneo_dims* dm) {
 }
 
 static int check_prec(const peneo_dims* dm, int prec) {
+  if (prec == PENEO_PREC_TF32) prec = PENEO_PREC_FP32;  // same pack, same layouts: only the backward's GEMM engine differs
   PENEO_REQUIRE(prec == PENEO_PREC_FP32 || prec == PENEO_PREC_BF16, "unknown precision mode %d", prec);
   if (prec == PENEO_PREC_BF16 && !bf16_supported(*dm) && !bf16_generic_supported(*dm)) {
     set_error("PENEO_PREC_BF16 needs hin, hid and d in multiples of 64 (fused path: shrink=1, hid=768, d=384, num_layers=2); "
@@ -189,10 +190,8 @@ int peneo_pair_heads_fwd(const peneo_dims* dims, int prec, const void* pack, con
   const DropSpec* dp = drop.thresh ? &drop : nullptr;
   if (prec == PENEO_PREC_FP32)
     return launch_pair_heads_simt(*dims, pack, static_cast<const float*>(ab), batch, n, logits, st, dp);
-  if (!bf16_supported(*dims)) {  // unfused tensor-core forward (inference: the decoder's dropout is not available here)
-    PENEO_REQUIRE(dp == nullptr, "pair_heads_fwd: training-mode dropout needs PENEO_PREC_FP32 for this configuration");
-    return launch_pair_heads_generic(*dims, pack, pack_layout(*dims, prec), static_cast<const __nv_bfloat16*>(ab), batch, n, logits, st);
-  }
+  if (!bf16_supported(*dims))  // unfused tensor-core forward
+    return launch_pair_heads_generic(*dims, pack, pack_layout(*dims, prec), static_cast<const __nv_bfloat16*>(ab), batch, n, logits, st, dp);
   // Default: the CTA-pair (cta_group::2, M = 256) variant of K2 — same results, half the W_mid traffic per SM,
   // ~3 % faster under the sustained power cap.  PENEO_K2_PAIR=0 selects the single-CTA kernel (A/B studies).
   static const bool use_pair = [] { const char* e = getenv("PENEO_K2_PAIR"); return !e || atoi(e) != 0; }();
@@ -226,7 +225,7 @@ int peneo_pair_heads_spots_fwd(const peneo_dims* dims, int prec, const void* pac
 
 size_t peneo_heads_bwd_workspace_bytes(const peneo_dims* dims, int prec, int32_t batch, int32_t n) {
   if (check_dims(dims) != PENEO_OK || check_prec(dims, prec) != PENEO_OK || batch < 0 || n < 1) return 0;
-  if (prec == PENEO_PREC_BF16 && !bf16_supported(*dims)) return 0;  // forward only: train this configuration in fp32
+  if (prec == PENEO_PREC_BF16 && !bf16_supported(*dims)) return 0;  // this configuration trains with PENEO_PREC_TF32 / FP32
   return heads_bwd_workspace_bytes(*dims, prec, batch, n);
 }
 
@@ -235,8 +234,9 @@ int peneo_heads_bwd(const peneo_dims* dims, int prec, const void* pack, const vo
                     float* dx, void* workspace, const peneo_dropout* dropout, void* stream) {
   int rc;
   if ((rc = check_dims(dims)) != PENEO_OK || (rc = check_prec(dims, prec)) != PENEO_OK) return rc;
-  PENEO_REQUIRE(prec == PENEO_PREC_FP32 || bf16_supported(*dims),
-                "heads_bwd: PENEO_PREC_BF16 is forward-only for this configuration, train it with PENEO_PREC_FP32");
+  PENEO_REQUIRE(prec != PENEO_PREC_BF16 || bf16_supported(*dims),
+                "heads_bwd: PENEO_PREC_BF16 covers the fused configuration only; use PENEO_PREC_TF32 (tensor cores) or "
+                "PENEO_PREC_FP32 with an fp32 pack for this one");
   PENEO_REQUIRE(pack && x && dlogits && grads && workspace, "heads_bwd: NULL pointer");
   PENEO_REQUIRE(batch >= 1 && n >= 1 && n <= 46340, "heads_bwd: bad sizes batch=%d n=%d", batch, n);
   PENEO_REQUIRE((int64_t)batch * n < (1ll << 31), "heads_bwd: too many tokens");

@@ -207,7 +207,7 @@ __global__ void __launch_bounds__(192, 1)
     gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                     const float* __restrict__ bias, void* __restrict__ Cv, int64_t ldc, int64_t M, int N, int K,
                     int kb_per_split, int splits, int n_blocks, int64_t num_items, int act, uint32_t drop_thresh,
-                    float drop_scale, uint32_t drop_key) {
+                    float drop_scale, uint32_t drop_key, uint32_t drop_row0) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);  // by offset: keeps the shared address space
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kG2Stages * kGemmStageBytes);
@@ -338,7 +338,7 @@ __global__ void __launch_bounds__(192, 1)
                   const float h = 0.5f * v[e];
                   v[e] = fmaf(h, ptx::tanh_approx(h), h);
                 }
-                if (ACT == 2) v[e] = drop_keep(drop_key, drop_thresh, static_cast<uint32_t>(m), nb + x + e) ? v[e] * drop_scale : 0.f;
+                if (ACT == 2) v[e] = drop_keep(drop_key, drop_thresh, drop_row0 + static_cast<uint32_t>(m), nb + x + e) ? v[e] * drop_scale : 0.f;
               }
               packed[x / 2] = ptx::pack_bf16x2(v[0], v[1]);
             }
@@ -376,7 +376,7 @@ __global__ void __launch_bounds__(192, 1)
 
 int launch_gemm_tc2(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* W, int64_t ldw, const float* bias, void* C,
                     int64_t ldc, int64_t M, int N, int K, int out_mode, int splits, cudaStream_t st, int act, const DropSpec* drop,
-                    uint32_t site) {
+                    uint32_t site, uint32_t drop_row0) {
   PENEO_REQUIRE(N % 32 == 0 && K >= 1, "gemm_tc2: N %% 32 required (N=%d K=%d)", N, K);
   PENEO_REQUIRE(lda % 8 == 0 && ldw % 8 == 0 && ldc % (out_mode == 0 ? 8 : 4) == 0,
                 "gemm_tc2: leading dimensions not vector aligned (lda=%lld ldw=%lld ldc=%lld)", (long long)lda, (long long)ldw,
@@ -411,7 +411,7 @@ int launch_gemm_tc2(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* W,
       attr_set = true;                                                                                               \
     }                                                                                                                \
     gemm_tc2_kernel<OUT, ACT><<<grid, 192, kG2Smem, st>>>(tmA, tmW, bias, C, ldc, M, N, K, kb_per_split, splits,      \
-                                                          n_blocks, items, act, d_th, d_sc, d_key);                  \
+                                                          n_blocks, items, act, d_th, d_sc, d_key, drop_row0);       \
   }
   PENEO_REQUIRE(out_mode == 0 || !act, "gemm_tc2: the activation is fused for the bf16 output only");
   PENEO_REQUIRE((reinterpret_cast<uintptr_t>(bias) & 15) == 0, "gemm_tc2: bias not 16-byte aligned");

@@ -25,7 +25,7 @@ int launch_gemm_tc(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* W, 
 // C[M, N] (op)= A W^T ; out_mode 0 bf16 store (+bias, SiLU when act), 1 fp32 store, 2 fp32 +=, 3 fp32 atomicAdd with split-K
 int launch_gemm_tc2(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* W, int64_t ldw, const float* bias, void* C,
                     int64_t ldc, int64_t M, int N, int K, int out_mode, int splits, cudaStream_t st, int act = 0,
-                    const DropSpec* drop = nullptr, uint32_t site = 0);
+                    const DropSpec* drop = nullptr, uint32_t site = 0, uint32_t drop_row0 = 0);  // mask row = drop_row0 + m
 
 // pair_heads_tc.cu
 int launch_pair_heads_tc(const void* pack, const PackLayout& L, const __nv_bfloat16* ab, int batch, int n,
@@ -47,7 +47,7 @@ int launch_pair_heads_tc_pair(const void* pack, const PackLayout& L, const __nv_
 // num_layers): S = SiLU(a_i + b_j) per chunk of pairs, one gemm_tc2 per hidden layer and head, output layer as an
 // N = 32 GEMM
 int launch_pair_heads_generic(const peneo_dims& dm, const void* pack, const PackLayout& L, const __nv_bfloat16* ab, int batch,
-                              int n, float* const logits[kNumHeads], cudaStream_t st);
+                              int n, float* const logits[kNumHeads], cudaStream_t st, const DropSpec* drop = nullptr);
 
 // pair_bwd_tc.cu : regenerated S and G = (dz W_out) SiLU'(u) of a chunk of pairs, plus per-CTA partial sums
 // [ctas][3][1920] of dz^T SiLU(u) (bf16 backward)

@@ -1,5 +1,5 @@
 // Unfused tensor-core forward of the pair heads for the configurations the fused K2 does not cover
-// (PENEO_PREC_BF16 with shrink off, d != 384 or num_layers != 2; inference only).  Same math as
+// (PENEO_PREC_BF16 with shrink off, d != 384 or num_layers != 2).  Same math as
 // model/peneo_decoder.py:149-177, 258-269, 355-363, restated per chunk of the batch-flat pair list:
 //
 //   S = SiLU(a_i + b_j)                                    [rows, d] bf16   (build_s_bf16_kernel)
@@ -53,7 +53,7 @@ __global__ void __launch_bounds__(256) extract_logits_kernel(const float* __rest
 }  // namespace
 
 int launch_pair_heads_generic(const peneo_dims& dm, const void* pack, const PackLayout& L, const __nv_bfloat16* ab, int batch,
-                              int n, float* const logits[kNumHeads], cudaStream_t st) {
+                              int n, float* const logits[kNumHeads], cudaStream_t st, const DropSpec* drop) {
   const char* pk = static_cast<const char*>(pack);
   const int d = dm.d, NL = dm.num_layers;
   const int64_t P = pair_count(n), total = (int64_t)batch * P;
@@ -90,8 +90,10 @@ int launch_pair_heads_generic(const peneo_dims& dm, const void* pack, const Pack
       const __nv_bfloat16* in = S;
       for (int l = 0; l + 1 < NL && rc == PENEO_OK; ++l) {
         __nv_bfloat16* out = H[l & 1];
+        // (training mode: the head's nn.Dropout after this SiLU, model/peneo_decoder.py:261, mask row = batch-flat pair)
         rc = launch_gemm_tc2(in, d, reinterpret_cast<const __nv_bfloat16*>(pk + L.g_mid_w[h][l]), d,
-                             reinterpret_cast<const float*>(pk + L.g_mid_b[h][l]), out, d, rows, d, d, 0, 1, st, 1);
+                             reinterpret_cast<const float*>(pk + L.g_mid_b[h][l]), out, d, rows, d, d, 0, 1, st, 1, drop,
+                             site_head(h, l), static_cast<uint32_t>(g0));
         in = out;
       }
       if (rc != PENEO_OK) break;

@@ -481,7 +481,7 @@ struct Plan {
   size_t off_x, off_u1, off_y1, off_u2, off_y, off_ab, off_dab, off_dy, off_dy1;
   size_t off_S, off_dS, off_G, off_U, off_H;
   // bf16 pair part (T1 + MN-major GEMMs): S [rows, 384], G / M [rows, 1920] bf16, bf16 per-token projections
-  size_t off_S16, off_Gc, off_dwpart, off_ab16, off_tokws, tokws_bytes, off_tr;
+  size_t off_S16, off_Gc, off_dwpart, off_ab16, off_tokws, tokws_bytes, off_tr, off_tr2;
   size_t total;
 };
 
@@ -491,13 +491,14 @@ Plan make_plan(const peneo_dims& dm, int prec, int batch, int n) {
   const size_t T = p.tokens, d = dm.d, hid = dm.shrink ? dm.hid : 0, hin = dm.hin;
   p.nU = dm.num_layers - 1;
   p.nH = dm.num_layers >= 3 ? dm.num_layers - 2 : 0;
-  const bool tc = prec == PENEO_PREC_BF16;
-  const int nbuf = tc ? 4 : 3 + p.nU + p.nH;  // fp32: S, dS, G, U.., H.. ; bf16: dS (fp32) + S, G (bf16, 1 + 5 halves)
+  const bool tc = prec == PENEO_PREC_BF16;   // fused tcgen05 pair kernels (T1 + bf16 GEMMs)
+  const bool tf = prec == PENEO_PREC_TF32;   // fp32 buffers, every GEMM on tcgen05 kind::tf32 (needs K-major copies)
+  const int nbuf = tc ? 4 : 3 + p.nU + p.nH + (tf ? 2 : 0);  // fp32: S, dS, G, U.., H.. (+ two transposed operands) ; bf16: dS (fp32) + S, G (bf16, 1 + 5 halves)
   // Pair buffers: up to 262 144 pairs per chunk within ~3 GB (measured: per-chunk launch / wave-quantisation overheads
   // make 64 K-pair chunks 25 % slower end to end), never less than one full pair row (n pairs).  A chunk may span
   // several documents.
   int64_t rows = (int64_t)(3072ull << 20) / ((int64_t)nbuf * d * 4);
-  rows = std::min<int64_t>(rows, 262144);
+  rows = std::min<int64_t>(rows, tf ? 65536 : 262144);
   if (const char* e = getenv("PENEO_BWD_CHUNK_ROWS")) rows = std::max(1, atoi(e));  // test hook: force small chunks
   rows = std::max<int64_t>(n, rows);
   rows = std::min<int64_t>(rows, (int64_t)batch * pair_count(n));
@@ -530,6 +531,13 @@ Plan make_plan(const peneo_dims& dm, int prec, int batch, int n) {
   } else {
     p.off_S = take(cb), p.off_G = take(cb);
     p.off_U = take(cb * p.nU), p.off_H = take(cb * p.nH);
+    if (tf) {
+      // K-major copies for kind::tf32: both [rows, d] operands of dW = G^T Hin (or a [d, d] weight), and the per-token chain's
+      const size_t rp = (rows + 3) / 4 * 4;
+      p.off_tr2 = take(fl(std::max<size_t>(2 * rp * d, d * d)));
+      const size_t wmax = std::max(std::max(hin, hid), 2 * d), tp = (T + 3) / 4 * 4;
+      p.off_tr = take(fl(std::max(2 * tp * wmax, wmax * wmax)));
+    }
   }
   p.total = off + 1024;
   return p;
@@ -544,12 +552,13 @@ size_t heads_bwd_workspace_bytes(const peneo_dims& dm, int prec, int batch, int 
 int launch_heads_bwd(const peneo_dims& dm, int prec, const void* pack, const void* x, int x_dtype, int64_t x_row_stride,
                      int batch, int n, const float* const dlogits[kNumHeads], const peneo_grads& gr, float* dx,
                      void* workspace, cudaStream_t st, const DropSpec* drop_in, const FusedLossBwd* fused_in) {
-  const PackLayout L = pack_layout(dm, prec);
+  const PackLayout L = pack_layout(dm, prec == PENEO_PREC_TF32 ? PENEO_PREC_FP32 : prec);
   const DropSpec drop = drop_in ? *drop_in : DropSpec{0u, 1.f, 0u, 0u};
   auto with_drop = [&](Gemm& gm, uint32_t site, uint32_t row0) {  // C2 = Dropout(SiLU(C)) of the forward pass
     gm.drop_thresh = drop.thresh, gm.drop_scale = drop.scale, gm.drop_key = drop_key(drop, site), gm.row0 = row0;
   };
-  const bool tc = prec == PENEO_PREC_BF16;
+  const bool tc = prec == PENEO_PREC_BF16;    // fused tcgen05 pair kernels
+  const bool tcg = prec != PENEO_PREC_FP32;   // GEMMs on tensor cores (kind::tf32 for everything outside the fused kernels)
   const char* pk = static_cast<const char*>(pack);
   const Plan pl = make_plan(dm, prec, batch, n);
   char* ws = static_cast<char*>(workspace);
@@ -601,19 +610,19 @@ int launch_heads_bwd(const peneo_dims& dm, int prec, const void* pack, const voi
     g = Gemm{}, g.tb = true, g.A = xin, g.lda = ldx, g.B = W(L.f_w1), g.ldb = hin, g.C = F(pl.off_u1), g.ldc = hid;
     g.M = T, g.N = hid, g.K = hin, g.bias = W(L.f_b1), g.C2 = F(pl.off_y1), g.ldc2 = hid;
     with_drop(g, kSiteTok0, 0);
-    TRY(run_gemm(g, st, tc));
+    TRY(run_gemm(g, st, tcg));
     g = Gemm{}, g.tb = true, g.A = F(pl.off_y1), g.lda = hid, g.B = W(L.f_w2), g.ldb = hid, g.C = F(pl.off_u2), g.ldc = d;
     g.M = T, g.N = d, g.K = hid, g.bias = W(L.f_b2), g.C2 = F(pl.off_y), g.ldc2 = d;
     with_drop(g, kSiteTok1, 0);
-    TRY(run_gemm(g, st, tc));
+    TRY(run_gemm(g, st, tcg));
     y = F(pl.off_y), ldy = d;
   }
   float* ab = F(pl.off_ab);
   g = Gemm{}, g.tb = true, g.A = y, g.lda = ldy, g.B = W(L.f_wc), g.ldb = 2 * d, g.C = ab, g.ldc = 2 * d;
   g.M = T, g.N = d, g.K = d;
-  TRY(run_gemm(g, st, tc));
+  TRY(run_gemm(g, st, tcg));
   g.B = W(L.f_wc) + d, g.C = ab + d, g.bias = W(L.f_bc);
-  TRY(run_gemm(g, st, tc));
+  TRY(run_gemm(g, st, tcg));
 
   // ---- pair part, one chunk of whole pair-rows at a time
   float* dab = F(pl.off_dab);
@@ -722,7 +731,7 @@ int launch_heads_bwd(const peneo_dims& dm, int prec, const void* pack, const voi
           g = Gemm{}, g.tb = true, g.A = in, g.lda = d, g.B = W(L.f_mid_w[h][l]), g.ldb = d, g.C = U, g.ldc = d;
           g.M = rows, g.N = d, g.K = d, g.bias = W(L.f_mid_b[h][l]), g.C2 = Hn, g.ldc2 = d;
           with_drop(g, site_head(h, l), row0);
-          TRY(run_gemm(g, st, tc));
+          TRY(run_gemm(g, st, tcg));
           in = Hn;
         }
         {
@@ -743,18 +752,19 @@ int launch_heads_bwd(const peneo_dims& dm, int prec, const void* pack, const voi
         for (int l = NL - 2; l >= 0; --l) {
           const float* Hin = (l == 0) ? S : F(pl.off_H) + (size_t)(l - 1) * cstride;
           // dW_l[out, in] += sum_r G_l[r, out] Hin[r, in]
-          g = Gemm{}, g.ta = true, g.A = Gcur, g.lda = d, g.B = Hin, g.ldb = d, g.C = gr.mid_w[h * 8 + l], g.ldc = d;
+          float* tr2 = prec == PENEO_PREC_TF32 ? F(pl.off_tr2) : nullptr;  // K-major copies for kind::tf32
+          g = Gemm{}, g.scratch = tr2, g.ta = true, g.A = Gcur, g.lda = d, g.B = Hin, g.ldb = d, g.C = gr.mid_w[h * 8 + l], g.ldc = d;
           g.M = d, g.N = d, g.K = rows, g.mode = 2;
-          TRY(run_gemm(g, st, tc));
+          TRY(run_gemm(g, st, tcg));
           // dHin = G_l W_l
-          g = Gemm{}, g.A = Gcur, g.lda = d, g.B = W(L.f_mid_w[h][l]), g.ldb = d, g.M = rows, g.N = d, g.K = d;
+          g = Gemm{}, g.scratch = tr2, g.A = Gcur, g.lda = d, g.B = W(L.f_mid_w[h][l]), g.ldb = d, g.M = rows, g.N = d, g.K = d;
           if (l == 0) {
             g.C = dS, g.ldc = d, g.mode = h > 0 ? 1 : 0;
-            TRY(run_gemm(g, st, tc));
+            TRY(run_gemm(g, st, tcg));
           } else {
             float* Ul = F(pl.off_U) + (size_t)l * cstride;
             g.C = Ul, g.ldc = d, g.mode = 0;
-            TRY(run_gemm(g, st, tc));
+            TRY(run_gemm(g, st, tcg));
             act_bwd_kernel<<<dim3((rows + 31) / 32, (d + 127) / 128), 128, 0, st>>>(
                 Ul, F(pl.off_U) + (size_t)(l - 1) * cstride, rows, d, d, d, gr.mid_b[h * 8 + l - 1], drop.thresh, drop.scale,
                 drop_key(drop, site_head(h, l - 1)), row0);
@@ -784,23 +794,23 @@ int launch_heads_bwd(const peneo_dims& dm, int prec, const void* pack, const voi
 
   // ---- per-token chain backward
   const int tb = (T + 31) / 32;
-  float* tr = tc ? F(pl.off_tr) : nullptr;
+  float* tr = tcg ? F(pl.off_tr) : nullptr;
   // db_c = column sums of dBm
   colsum_kernel<<<dim3(tb, (d + 127) / 128), 128, 0, st>>>(dab + d, T, d, 2 * d, gr.combine_b);
   PENEO_CUDA_TRY(cudaGetLastError());
   // dW_c[:, :d] = dA^T y ; dW_c[:, d:] = dBm^T y
   g = Gemm{}, g.scratch = tr, g.ta = true, g.A = dab, g.lda = 2 * d, g.B = y, g.ldb = ldy, g.C = gr.combine_w, g.ldc = 2 * d;
   g.M = d, g.N = d, g.K = T, g.mode = 2;
-  TRY(run_gemm(g, st, tc));
+  TRY(run_gemm(g, st, tcg));
   g.A = dab + d, g.C = gr.combine_w + d;
-  TRY(run_gemm(g, st, tc));
+  TRY(run_gemm(g, st, tcg));
   // dy = dA W_c[:, :d] + dBm W_c[:, d:]
   float* dy = (dm.shrink || dx == nullptr) ? F(pl.off_dy) : dx;
   const int64_t lddy = (dm.shrink || dx == nullptr) ? d : hin;
   g = Gemm{}, g.scratch = tr, g.A = dab, g.lda = 2 * d, g.B = W(L.f_wc), g.ldb = 2 * d, g.C = dy, g.ldc = lddy, g.M = T, g.N = d, g.K = d;
-  TRY(run_gemm(g, st, tc));
+  TRY(run_gemm(g, st, tcg));
   g.A = dab + d, g.B = W(L.f_wc) + d, g.mode = 1;
-  TRY(run_gemm(g, st, tc));
+  TRY(run_gemm(g, st, tcg));
   if (dm.shrink) {
     // G2 = dy * SiLU'(u2) ; db2 ; dW2 = G2^T y1 ; dy1 = G2 W2
     act_bwd_kernel<<<dim3(tb, (d + 127) / 128), 128, 0, st>>>(dy, F(pl.off_u2), T, d, d, d, gr.shrink_b2, drop.thresh,
@@ -808,20 +818,20 @@ int launch_heads_bwd(const peneo_dims& dm, int prec, const void* pack, const voi
     PENEO_CUDA_TRY(cudaGetLastError());
     g = Gemm{}, g.scratch = tr, g.ta = true, g.A = dy, g.lda = d, g.B = F(pl.off_y1), g.ldb = hid, g.C = gr.shrink_w2, g.ldc = hid;
     g.M = d, g.N = hid, g.K = T, g.mode = 2;
-    TRY(run_gemm(g, st, tc));
+    TRY(run_gemm(g, st, tcg));
     float* dy1 = F(pl.off_dy1);
     g = Gemm{}, g.scratch = tr, g.A = dy, g.lda = d, g.B = W(L.f_w2), g.ldb = hid, g.C = dy1, g.ldc = hid, g.M = T, g.N = hid, g.K = d;
-    TRY(run_gemm(g, st, tc));
+    TRY(run_gemm(g, st, tcg));
     // G1 = dy1 * SiLU'(u1) ; db1 ; dW1 = G1^T x ; dx = G1 W1
     act_bwd_kernel<<<dim3(tb, (hid + 127) / 128), 128, 0, st>>>(dy1, F(pl.off_u1), T, hid, hid, hid, gr.shrink_b1,
                                                                 drop.thresh, drop.scale, drop_key(drop, kSiteTok0), 0u);
     PENEO_CUDA_TRY(cudaGetLastError());
     g = Gemm{}, g.scratch = tr, g.ta = true, g.A = dy1, g.lda = hid, g.B = xin, g.ldb = ldx, g.C = gr.shrink_w1, g.ldc = hin;
     g.M = hid, g.N = hin, g.K = T, g.mode = 2;
-    TRY(run_gemm(g, st, tc));
+    TRY(run_gemm(g, st, tcg));
     if (dx) {
       g = Gemm{}, g.scratch = tr, g.A = dy1, g.lda = hid, g.B = W(L.f_w1), g.ldb = hin, g.C = dx, g.ldc = hin, g.M = T, g.N = hin, g.K = hid;
-      TRY(run_gemm(g, st, tc));
+      TRY(run_gemm(g, st, tcg));
     }
   }
 #undef TRY

@@ -118,9 +118,9 @@ class PEneoDecoderB200(nn.Module):
         self.dims = DecoderDims(input_size, hidden if self.decoder_shrink else 0, d, self.decoder_shrink, self.num_layers)
         prec = _cfg(config, "peneo_b200_precision", None)
         if prec is None:
-            # fused tcgen05 path where it exists; the unfused tensor-core forward only for inference-mode models
-            # (it has no backward: such configurations train on the fp32 path)
-            prec = "bf16" if self.dims.bf16_capable() or (self.inference_mode and self.dims.bf16_forward_capable()) else "fp32"
+            # tensor cores wherever the widths allow it: the fused tcgen05 kernels for the shipped configuration, the
+            # unfused tensor-core forward + kind::tf32 backward for the others
+            prec = "bf16" if self.dims.bf16_forward_capable() else "fp32"
         self.set_precision(prec)
         self._pack: Optional[WeightPack] = None
         self._pack_key = None
@@ -224,10 +224,6 @@ class PEneoDecoderB200(nn.Module):
         if self.training and self.dropout_prob > 0:
             seed = getattr(self, "dropout_seed", None)
             drop = (float(self.dropout_prob), int(torch.randint(0, 2**62, (1,)).item()) if seed is None else int(seed))
-        unfused = self.precision == "bf16" and not self.dims.bf16_capable()
-        if unfused and ((needs_grad and not self.inference_mode) or drop is not None):
-            raise RuntimeError("precision='bf16' is forward-only (no dropout, no backward) for this decoder "
-                               "configuration; train it with precision='fp32'")
         tags = [line_extraction_shaking_tag, ent_linking_head_rel_shaking_tag, ent_linking_tail_rel_shaking_tag,
                 line_grouping_head_rel_shaking_tag, line_grouping_tail_rel_shaking_tag]
         ohem = (self.link_loss.num_hard_positive, self.link_loss.num_hard_negative)

@@ -13,7 +13,7 @@ from typing import Dict, List
 import torch
 
 from . import _lib, ops
-from ._lib import PREC_BF16, PREC_FP32
+from ._lib import PREC_BF16, PREC_FP32, PREC_TF32
 from .ops import HEAD_NAMES, WeightPack
 
 
@@ -49,8 +49,13 @@ def heads_backward(decoder, x: torch.Tensor, dlogits: List[torch.Tensor], need_d
     dev = x.device
     # bf16 mode: the [rows x 384] GEMMs of the pair part run on tcgen05 (bf16 operands, fp32 accumulation);
     # `backward_precision = "fp32"` on the module forces the exact CUDA-core path.
+    # Configurations outside the fused kernels (shrink off, d != 384, num_layers != 2) keep fp32 buffers but run every
+    # recompute / gradient GEMM on tcgen05 kind::tf32 (PREC_TF32, fp32 pack).
     if decoder.precision == "bf16" and getattr(decoder, "backward_precision", "bf16") == "bf16":
-        pack, prec = decoder._weight_pack(dev), PREC_BF16
+        if dims.bf16_capable():
+            pack, prec = decoder._weight_pack(dev), PREC_BF16
+        else:
+            pack, prec = decoder._fp32_pack(dev), PREC_TF32
     else:
         pack, prec = decoder._fp32_pack(dev), PREC_FP32
     grads = {k: torch.empty_like(p, dtype=torch.float32) for k, p in _param_items(decoder)}

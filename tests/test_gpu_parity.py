@@ -728,6 +728,66 @@ def test_fused_spot_extraction_in_the_pair_kernel_equals_logits_route(n, b, regi
         _same_result(res[d], want[d])
 
 
+def test_streaming_prediction_loop_equals_the_accumulate_then_decode_loop():
+    """N3: eval_loop.prediction_loop (decode per batch, nothing retained) against what PEneoTrainer.prediction_loop +
+    compute_metrics do (pipeline/trainer.py:102-183, start/run_rfund.py:243-304): accumulate every sample's logits,
+    decode_peneo over the whole set, calculate_KVPE_metric — same predictions, ground truth, file ids and metrics."""
+    from peneo_b200 import evaluation, prediction_loop
+
+    n, b, nb = 63, 3, 4
+    sd = synth.init_decoder_state(seed=21, trained_like=True)
+    dec = PEneoDecoderB200(Cfg(768, inference_mode=False, precision="fp32"), 768)
+    dec.load_state_dict(sd)
+    dec = dec.cuda().eval()
+
+    class Model(torch.nn.Module):  # stands in for PEneoModel: backbone output comes with the batch
+        def forward(self, hidden, orig_bbox, **kw):
+            return dec(hidden, orig_bbox, kw["line_extraction_shaking_tag"], kw["ent_linking_head_rel_shaking_tag"],
+                       kw["ent_linking_tail_rel_shaking_tag"], kw["line_grouping_head_rel_shaking_tag"],
+                       kw["line_grouping_tail_rel_shaking_tag"], **{k: v for k, v in kw.items() if "shaking_tag" not in k})
+
+    batches = []
+    for s in range(nb):
+        docs = [synth.make_document(n, doc_id=50 + s * b + i) for i in range(b)]
+        # logits that decode to something: planted documents pushed through as "hidden states" would not, so the model
+        # output is replaced below; here: real hidden states, real tags
+        tags = [torch.stack([d.tags()[k] for d in docs]).cuda() for k in range(5)]
+        batches.append({
+            "hidden": synth.hidden_states(b, n, 768, doc_id0=50 + s * b).cuda(),
+            "orig_bbox": torch.tensor([d.bbox for d in docs]).cuda(),
+            "text": [d.text for d in docs], "fname": [f"file{s}_{i}" for i in range(b)], "relations": [None] * b,
+            "line_extraction_shaking_tag": tags[0], "ent_linking_head_rel_shaking_tag": tags[1],
+            "ent_linking_tail_rel_shaking_tag": tags[2], "line_grouping_head_rel_shaking_tag": tags[3],
+            "line_grouping_tail_rel_shaking_tag": tags[4]})
+    model = Model()
+    metrics, detail = prediction_loop(model, batches, return_detail=True)
+    # the reference's way
+    acc = {k: [] for k in range(10)}
+    texts, fnames, bboxes = [], [], []
+    with torch.no_grad():
+        for inp in batches:
+            out = model(**inp)
+            outs = [out.line_extraction_shaking_outputs, out.ent_linking_h2h_shaking_outputs, out.ent_linking_t2t_shaking_outputs,
+                    out.line_grouping_h2h_shaking_outputs, out.line_grouping_t2t_shaking_outputs]
+            tg = [inp["line_extraction_shaking_tag"], inp["ent_linking_head_rel_shaking_tag"], inp["ent_linking_tail_rel_shaking_tag"],
+                  inp["line_grouping_head_rel_shaking_tag"], inp["line_grouping_tail_rel_shaking_tag"]]
+            for k in range(5):
+                acc[k] += list(outs[k])
+                acc[5 + k] += list(tg[k])
+            texts += inp["text"]
+            fnames += inp["fname"]
+            bboxes += out.orig_bbox.tolist()
+    pred, gt, ids = decode_peneo(HandshakingTaggingScheme(), texts, *[acc[k] for k in range(10)], bboxes, fnames)
+    want_metric, want_detail = evaluation.calculate_KVPE_metric(pred, gt, ids)
+    assert ids == [f for inp in batches for f in inp["fname"]]
+    assert detail == want_detail
+    for key, val in want_metric.items():
+        assert metrics[f"eval_{key}"] == val
+    assert metrics["eval_loss"] == out.loss.mean().item() and "eval_line_grouping_h2h_loss" in metrics
+    assert metrics["eval_line_grouping_h2h_loss"] == out.line_grouping_t2t_loss.mean().item()  # the reference's overwrite
+    assert want_detail["num_gt"] > 0  # the ground-truth side decodes to key-value pairs
+
+
 # ------------------------------------------------------------------------------------------------
 # edge cases the callers produce
 # ------------------------------------------------------------------------------------------------
@@ -778,6 +838,8 @@ def test_strided_hidden_states_after_cls_strip():
     (64, 64, True, 3, "fp32", GRAD_TOL_FP32),   # two hidden layers per head: one Dropout after each
     (48, 48, False, 1, "fp32", GRAD_TOL_FP32),  # no shrink, no hidden layer: nothing to drop
     (768, 768, True, 2, "bf16", 3e-2),
+    (128, 128, True, 3, "bf16", 3e-2),   # unfused tensor-core forward (dropout in the GEMM epilogues) + kind::tf32 backward
+    (768, 768, False, 2, "bf16", 3e-2),  # shrink off at the backbone width (D = 768), same route
 ])
 def test_train_mode_dropout_forward_and_backward_match_oracle_with_same_mask(hin, hidden, shrink, L, prec, tol):
     """train() mode: logits, loss and every gradient against the fp64 oracle applying the SAME masks (the oracle
@@ -903,8 +965,8 @@ def test_c_abi_rejects_bad_arguments_with_status_codes():
 ])
 def test_unfused_bf16_forward_matches_oracle(hin, hidden, shrink, L, n, b):
     """Configurations the fused K2 does not cover run PENEO_PREC_BF16 through the unfused tensor-core forward
-    (csrc/pair_heads_generic.cu): logits within the bf16 tolerance of the fp64 oracle, decode identical in shape,
-    and the mode refuses to train."""
+    (csrc/pair_heads_generic.cu): logits within the bf16 tolerance of the fp64 oracle, and train through the
+    kind::tf32 backward (model/peneo_decoder.py:231-292: any num_layers, shrink on or off)."""
     sd = synth.init_decoder_state(hin, hidden, shrink, L, seed=21, trained_like=True)
     x = synth.hidden_states(b, n, hin, doc_id0=5)
     ref = orc.heads_chunked(orc.split_params(sd, torch.float64), x.double())
@@ -917,9 +979,19 @@ def test_unfused_bf16_forward_matches_oracle(hin, hidden, shrink, L, n, b):
         e = rel_err(out[k], ref[k])
         print((hin, hidden, shrink, L), k, f"{e:.3e}")
         assert e <= BF16_TOL, (k, e)
-    # default precision of an inference-mode model with these widths is the tensor-core forward; a trainable one is fp32
+    # tensor cores are the default for these widths, trainable or not
     assert PEneoDecoderB200(Cfg(hidden, shrink, L, inference_mode=True), hin).precision == "bf16"
-    assert PEneoDecoderB200(Cfg(hidden, shrink, L, inference_mode=False), hin).precision == "fp32"
+    assert PEneoDecoderB200(Cfg(hidden, shrink, L, inference_mode=False), hin).precision == "bf16"
+    # ... and they train on tensor cores too: bf16 forward, backward with the recompute and every gradient GEMM on
+    # tcgen05 kind::tf32 (PENEO_PREC_TF32), against the fp64 autograd oracle
     trainable = build(sd, hin, hidden, shrink, L, "bf16", inference_mode=False)
-    with pytest.raises(RuntimeError, match="forward-only"):
-        trainable(x.cuda().requires_grad_(True))
+    docs = [synth.make_document(n, doc_id=640 + i) for i in range(b)]
+    tags = [torch.stack([d.tags()[k] for d in docs]) for k in range(5)]
+    o, dx, grads = _train_step(trainable, x.cuda(), [t.cuda() for t in tags])
+    ref_loss, _s, ref_grads, ref_dx = orc.loss_and_grads(sd, x, tags, [1.0, 10.0, 10.0])
+    assert abs(o.loss.item() - ref_loss.item()) <= 5e-3 * max(1.0, abs(ref_loss.item()))
+    worst = {"dx": rel_err(dx, ref_dx)}
+    for key, g in ref_grads.items():
+        worst[key] = rel_err(grads[key], g)
+    print({k: f"{v:.2e}" for k, v in worst.items() if v > 5e-3})
+    assert max(worst.values()) <= 3e-2, worst
