@@ -27,12 +27,14 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--hin", type=int, default=768, help="width of the backbone output (960 = LiLT, BASELINE configs[2])")
     ap.add_argument("--no-fused-loss", action="store_true", help="separate loss kernels + explicit dlogits (A/B)")
+    ap.add_argument("--no-shrink", action="store_true", help="peneo_decoder_shrink = False (D = hin): unfused tensor-core route")
+    ap.add_argument("--layers", type=int, default=2, help="peneo_classifier_num_layers")
     args = ap.parse_args()
 
     class Cfg:
         backbone_config = {"hidden_size": 768, "hidden_dropout_prob": 0.1}
-        peneo_decoder_shrink = True
-        peneo_classifier_num_layers = 2
+        peneo_decoder_shrink = not args.no_shrink
+        peneo_classifier_num_layers = args.layers
         peneo_loss_ratio = [1.0] * 5
         peneo_category_weights = [1.0, 10.0, 10.0]
         peneo_ohem_num_positive = -1
@@ -45,7 +47,7 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local_rank)
     dec = PEneoDecoderB200(Cfg, args.hin)
-    dec.load_state_dict(synth.init_decoder_state(hin=args.hin, seed=0))
+    dec.load_state_dict(synth.init_decoder_state(args.hin, 768, not args.no_shrink, args.layers, seed=0))
     dec = dec.cuda().eval()
     dec.fused_loss = not args.no_fused_loss
     module = dec
@@ -79,7 +81,9 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     p = n * (n + 1) // 2
-    f_heads = 2.0 * n * (args.hin * 768 + 768 * 384 + 2 * 384 * 384) + 10.0 * p * 384 * 384 + 28.0 * p * 384
+    d = args.hin if args.no_shrink else 384
+    f_tok = 2.0 * n * ((0 if args.no_shrink else args.hin * 768 + 768 * 384) + 2 * d * d)
+    f_heads = f_tok + 10.0 * (args.layers - 1) * p * d * d + 28.0 * p * d
     peak = 1427.8
     try:
         peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops_sustained"]
@@ -88,7 +92,7 @@ def main():
     tf = 3.0 * f_heads * args.batch / (ms * 1e-3) / 1e12  # per GPU
     if rank == 0:
         print(json.dumps({"what": "decoder fine-tuning step (fwd + loss + bwd" + (", DDP all-reduce)" if world > 1 else ")"),
-                      "precision": args.precision, "fused_loss": not args.no_fused_loss, "hin": args.hin, "seq_len": args.seq_len, "n_gpus": world,
+                      "precision": args.precision, "fused_loss": not args.no_fused_loss, "hin": args.hin, "shrink": not args.no_shrink, "layers": args.layers, "seq_len": args.seq_len, "n_gpus": world,
                       "batch": args.batch, "ms_per_step": ms, "docs_per_s": world * args.batch / (ms * 1e-3), "loss": float(loss.detach()),
                       "tflops_vs_3F": tf, "frac_of_sustained_bf16_peak": tf / peak,
                       "peak_mem_gb": torch.cuda.max_memory_allocated() / 2**30}))

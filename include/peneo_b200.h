@@ -7,6 +7,7 @@
  *   peneo_pack_weights ............ parameter reads of PEneoDecoder        model/peneo_decoder.py:204-313
  *   peneo_token_proj_fwd .......... shrink_projection + the per-token half
  *                                   of HandshakingKernel.combine_fc         model/peneo_decoder.py:215-222, 126, 349-350
+ *   peneo_gather_tokens ........... CLS / visual-token strip + dropout + cast before the decoder   model/modeling_peneo.py:134-165
  *   peneo_pair_heads_fwd .......... HandshakingKernel.forward (pair part)
  *                                   + the five classifier heads             model/peneo_decoder.py:149-177, 355-363
  *   peneo_pair_loss_fwd ........... calculate_peneo_loss / CrossEntropyLossOHEM
@@ -118,6 +119,16 @@ size_t peneo_token_proj_workspace_bytes(const peneo_dims* dims, int prec, int64_
 int peneo_token_proj_fwd(const peneo_dims* dims, int prec, const void* pack, const void* x, int x_dtype,
                          int64_t x_row_stride, int64_t tokens, void* ab, void* workspace, const peneo_dropout* dropout,
                          void* stream);
+
+/* Backbone -> decoder seam (model/modeling_peneo.py:134-173): the decoder input is a strided view of the backbone output
+ * (CLS row / visual tokens stripped), passed through nn.Dropout in training, then fed to the first GEMM.  One pass:
+ * token (b, t) is read at x + b * batch_stride + t * row_stride (elements), optionally dropped (in_dropout, NULL = none:
+ * same counter-based mask scheme as peneo_dropout, its own site), cast to out_dtype and written densely as
+ * out[(b * n + t) * hin ..] — the [tokens, hin] matrix peneo_token_proj_fwd / peneo_heads_bwd read in place.
+ * peneo_token_dropout_bwd applies the same mask (and 1 / (1 - p)) to d loss / d x in place. */
+int peneo_gather_tokens(const void* x, int x_dtype, int32_t batch, int32_t n, int32_t hin, int64_t batch_stride,
+                        int64_t row_stride, void* out, int out_dtype, const peneo_dropout* in_dropout, void* stream);
+int peneo_token_dropout_bwd(float* dx, int64_t tokens, int32_t hin, const peneo_dropout* in_dropout, void* stream);
 
 /* Pair scoring + classifier heads for `batch` documents of `n` tokens each.
  * logits[h]: fp32 [batch, n(n+1)/2, C_h], row p(i,j) = i*n - i(i-1)/2 + (j-i). */

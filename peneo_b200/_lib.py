@@ -26,6 +26,8 @@ SYMBOLS = (
     "peneo_pack_weights",
     "peneo_token_proj_workspace_bytes",
     "peneo_token_proj_fwd",
+    "peneo_gather_tokens",
+    "peneo_token_dropout_bwd",
     "peneo_pair_heads_fwd",
     "peneo_heads_bwd_workspace_bytes",
     "peneo_heads_bwd",
@@ -101,6 +103,8 @@ def load() -> C.CDLL:
     lib.peneo_token_proj_workspace_bytes.restype = sz
     lib.peneo_token_proj_workspace_bytes.argtypes = [C.POINTER(Dims), C.c_int, i64]
     lib.peneo_token_proj_fwd.argtypes = [C.POINTER(Dims), C.c_int, vp, vp, C.c_int, i64, i64, vp, vp, C.POINTER(Dropout), vp]
+    lib.peneo_gather_tokens.argtypes = [vp, C.c_int, i32, i32, i32, i64, i64, vp, C.c_int, C.POINTER(Dropout), vp]
+    lib.peneo_token_dropout_bwd.argtypes = [vp, i64, i32, C.POINTER(Dropout), vp]
     lib.peneo_pair_heads_fwd.argtypes = [C.POINTER(Dims), C.c_int, vp, vp, i32, i32, PtrArray5, C.POINTER(Dropout), vp]
     lib.peneo_heads_bwd_workspace_bytes.restype = sz
     lib.peneo_heads_bwd_workspace_bytes.argtypes = [C.POINTER(Dims), C.c_int, i32, i32]

@@ -177,6 +177,22 @@ int peneo_token_proj_fwd(const peneo_dims* dims, int prec, const void* pack, con
   }
 }
 
+int peneo_gather_tokens(const void* x, int x_dtype, int32_t batch, int32_t n, int32_t hin, int64_t batch_stride,
+                        int64_t row_stride, void* out, int out_dtype, const peneo_dropout* in_dropout, void* stream) {
+  PENEO_REQUIRE(x && out && batch >= 0 && n >= 1 && hin >= 4 && hin % 4 == 0, "gather_tokens: bad arguments");
+  PENEO_REQUIRE(row_stride >= hin && batch_stride >= 0, "gather_tokens: bad strides");
+  PENEO_REQUIRE(out_dtype == PENEO_DT_F32 || out_dtype == PENEO_DT_BF16, "gather_tokens: output must be fp32 or bf16");
+  const DropSpec drop = make_drop(in_dropout);
+  return launch_gather_tokens(x, x_dtype, batch_stride, row_stride, batch, n, hin, out, out_dtype, drop.thresh ? &drop : nullptr,
+                              static_cast<cudaStream_t>(stream));
+}
+
+int peneo_token_dropout_bwd(float* dx, int64_t tokens, int32_t hin, const peneo_dropout* in_dropout, void* stream) {
+  PENEO_REQUIRE(dx && tokens >= 0 && hin >= 1, "token_dropout_bwd: bad arguments");
+  const DropSpec drop = make_drop(in_dropout);
+  return launch_token_dropout_bwd(dx, tokens, hin, drop.thresh ? &drop : nullptr, static_cast<cudaStream_t>(stream));
+}
+
 int peneo_pair_heads_fwd(const peneo_dims* dims, int prec, const void* pack, const void* ab, int32_t batch, int32_t n,
                          float* const logits[PENEO_NUM_HEADS], const peneo_dropout* dropout, void* stream) {
   int rc;

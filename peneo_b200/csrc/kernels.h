@@ -10,6 +10,10 @@ int launch_sgemm_nt(const float* A, int64_t lda, const float* W, int64_t ldw, co
                     uint32_t site = 0);
 int launch_cast_rows(const void* src, int src_dtype, int64_t src_stride, void* dst, int dst_dtype, int64_t rows,
                      int cols, cudaStream_t st);
+// backbone -> decoder seam: strip (strided [B, n, cols] view) + optional input dropout + cast, one pass; and the mask on dx
+int launch_gather_tokens(const void* src, int src_dtype, int64_t batch_stride, int64_t row_stride, int batch, int n, int cols,
+                         void* dst, int dst_dtype, const DropSpec* drop, cudaStream_t st);
+int launch_token_dropout_bwd(float* dx, int64_t tokens, int cols, const DropSpec* drop, cudaStream_t st);
 int pack_weights_impl(const peneo_dims& dm, int prec, const peneo_params& P, void* pack, cudaStream_t st);
 int launch_pair_heads_simt(const peneo_dims& dm, const void* pack, const float* ab, int batch, int n,
                            float* const logits[kNumHeads], cudaStream_t st, const DropSpec* drop = nullptr);

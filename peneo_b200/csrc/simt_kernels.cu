@@ -113,6 +113,85 @@ int launch_cast_rows(const void* src, int src_dtype, int64_t src_stride, void* d
 }
 
 // ------------------------------------------------------------------------------------------------
+// Backbone -> decoder seam (model/modeling_peneo.py:134-173): the decoder's input is a strided view of the backbone
+// output ([B, seq + visual tokens, H] minus the CLS row / the visual tokens), then nn.Dropout (training), then the first
+// GEMM.  One pass does the strip, the optional dropout and the cast to the GEMM's operand type, 8 elements per
+// thread: token (b, t) is read at src + b * batch_stride + t * row_stride, written densely at dst[(b * n + t) * cols].
+// ------------------------------------------------------------------------------------------------
+constexpr uint32_t kSiteInput = 2;  // dropout site of modeling_peneo.py:165 (per-token sites 0 and 1 are the shrink MLP's)
+template <typename T>
+__device__ __forceinline__ float to_float(T v) { return static_cast<float>(v); }
+template <typename T>
+__device__ __forceinline__ T from_float(float v) { return static_cast<T>(v); }
+
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(256) gather_tokens_kernel(const TI* __restrict__ src, int64_t batch_stride, int64_t row_stride,
+                                                            int n, TO* __restrict__ dst, int64_t tokens, int cols,
+                                                            uint32_t drop_thresh, float drop_scale, uint32_t drop_key_) {
+  const int groups = cols / 4;
+  const int64_t total = tokens * groups;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t tok = e / groups;
+    const int c = static_cast<int>(e - tok * groups) * 4;
+    const int64_t b = tok / n;
+    const TI* p = src + b * batch_stride + (tok - b * n) * row_stride + c;
+    float v[4] = {to_float(p[0]), to_float(p[1]), to_float(p[2]), to_float(p[3])};
+    if (drop_thresh) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        v[k] = drop_keep(drop_key_, drop_thresh, static_cast<uint32_t>(tok), c + k) ? v[k] * drop_scale : 0.f;
+    }
+    TO* q = dst + tok * cols + c;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) q[k] = from_float<TO>(v[k]);
+  }
+}
+
+int launch_gather_tokens(const void* src, int src_dtype, int64_t batch_stride, int64_t row_stride, int batch, int n, int cols,
+                         void* dst, int dst_dtype, const DropSpec* drop, cudaStream_t st) {
+  const int64_t tokens = (int64_t)batch * n;
+  if (tokens == 0) return PENEO_OK;
+  PENEO_REQUIRE(cols % 4 == 0, "gather_tokens: width must be a multiple of 4");
+  const int blocks = static_cast<int>(std::min<int64_t>((tokens * (cols / 4) + 255) / 256, 148 * 16));
+  const uint32_t th = drop ? drop->thresh : 0u, key = drop ? drop_key(*drop, kSiteInput) : 0u;
+  const float sc = drop ? drop->scale : 1.f;
+#define GATHER_CASE(SD, TI, DD, TO)                                                                                    \
+  if (src_dtype == SD && dst_dtype == DD) {                                                                            \
+    gather_tokens_kernel<TI, TO><<<blocks, 256, 0, st>>>(static_cast<const TI*>(src), batch_stride, row_stride, n,     \
+                                                         static_cast<TO*>(dst), tokens, cols, th, sc, key);           \
+    PENEO_CUDA_TRY(cudaGetLastError());                                                                                \
+    return PENEO_OK;                                                                                                   \
+  }
+  GATHER_CASE(PENEO_DT_F32, float, PENEO_DT_F32, float)
+  GATHER_CASE(PENEO_DT_BF16, __nv_bfloat16, PENEO_DT_F32, float)
+  GATHER_CASE(PENEO_DT_F16, __half, PENEO_DT_F32, float)
+  GATHER_CASE(PENEO_DT_F32, float, PENEO_DT_BF16, __nv_bfloat16)
+  GATHER_CASE(PENEO_DT_BF16, __nv_bfloat16, PENEO_DT_BF16, __nv_bfloat16)
+  GATHER_CASE(PENEO_DT_F16, __half, PENEO_DT_BF16, __nv_bfloat16)
+#undef GATHER_CASE
+  set_error("gather_tokens: unsupported dtype pair %d -> %d", src_dtype, dst_dtype);
+  return PENEO_E_INVALID;
+}
+
+// dx[tok, c] *= mask / (1 - p) of the same input dropout (backward of the seam), in place, fp32
+__global__ void __launch_bounds__(256) token_dropout_bwd_kernel(float* __restrict__ dx, int64_t tokens, int cols,
+                                                                uint32_t drop_thresh, float drop_scale, uint32_t drop_key_) {
+  const int64_t total = tokens * cols;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t tok = e / cols;
+    const int c = static_cast<int>(e - tok * cols);
+    dx[e] = drop_keep(drop_key_, drop_thresh, static_cast<uint32_t>(tok), c) ? dx[e] * drop_scale : 0.f;
+  }
+}
+int launch_token_dropout_bwd(float* dx, int64_t tokens, int cols, const DropSpec* drop, cudaStream_t st) {
+  if (!drop || !drop->thresh || tokens == 0) return PENEO_OK;
+  const int blocks = static_cast<int>(std::min<int64_t>((tokens * cols + 255) / 256, 148 * 16));
+  token_dropout_bwd_kernel<<<blocks, 256, 0, st>>>(dx, tokens, cols, drop->thresh, drop->scale, drop_key(*drop, kSiteInput));
+  PENEO_CUDA_TRY(cudaGetLastError());
+  return PENEO_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // Weight packing
 // ------------------------------------------------------------------------------------------------
 // dst[r, c] = bf16(scale * src[r * ld + col0 + c])

@@ -179,6 +179,11 @@ class PEneoDecoderB200(nn.Module):
             ev.record(cur)
             self._pack_readers[cur.cuda_stream] = ev
 
+    def _input_dropout(self, drop):
+        """(p, seed) of the seam dropout for this step (same seed as the decoder's own dropout, its own mask site)."""
+        p = float(getattr(self, "input_dropout_prob", 0.0))
+        return (p, drop[1]) if (drop is not None and p > 0.0 and self.training) else None
+
     def _class_weights_host(self):
         """The three class weights as Python floats, cached (``.tolist()`` is a device sync)."""
         w = self.link_loss.weight
@@ -220,8 +225,11 @@ class PEneoDecoderB200(nn.Module):
         # The decoder's own nn.Dropout modules (model/peneo_decoder.py:218, 221, 261) are active in train() mode
         # only.  The per-step seed comes from torch's generator, so torch.manual_seed() makes a step reproducible;
         # ``dropout_seed`` (attribute) pins it for tests.
+        # ``input_dropout_prob`` (attribute, default 0): the nn.Dropout PEneoModel applies to the backbone output right
+        # before the decoder (model/modeling_peneo.py:165), fused into the seam's gather pass; to use it replace
+        # ``model.dropout`` by ``nn.Identity()`` and set this attribute to its probability.
         drop = None
-        if self.training and self.dropout_prob > 0:
+        if self.training and (self.dropout_prob > 0 or getattr(self, "input_dropout_prob", 0.0) > 0):
             seed = getattr(self, "dropout_seed", None)
             drop = (float(self.dropout_prob), int(torch.randint(0, 2**62, (1,)).item()) if seed is None else int(seed))
         tags = [line_extraction_shaking_tag, ent_linking_head_rel_shaking_tag, ent_linking_tail_rel_shaking_tag,
@@ -258,7 +266,7 @@ class PEneoDecoderB200(nn.Module):
                 logits = decoder_forward_with_grad(self, sequence_output, drop)
         else:
             pack = self._weight_pack(sequence_output.device)
-            logits = ops.heads_forward(pack, sequence_output.detach(), drop)
+            logits = ops.heads_forward(pack, sequence_output.detach(), drop, self._input_dropout(drop))
         le, elh, elt, lgh, lgt = logits
         if self.inference_mode:
             return (le, elh, elt, lgh, lgt, orig_bbox)

@@ -111,19 +111,52 @@ class WeightPack:
         del keep
 
 
-def token_projections(pack: WeightPack, x: torch.Tensor, dropout=None) -> torch.Tensor:
-    """x: [..., hin] (fp32 / bf16 / fp16, last dim contiguous) -> ab [tokens, 2d]
-    (fp32, or bf16 pre-multiplied by 1/2 in bf16 mode).  ``dropout``: None (eval) or ``(p, seed)``."""
+def seam_tokens(x: torch.Tensor, out_dtype: torch.dtype, in_dropout=None) -> torch.Tensor:
+    """The backbone -> decoder seam (model/modeling_peneo.py:134-165) as at most ONE pass: ``x`` is ``[B, N, hin]``, usually
+    a strided view of the backbone output with the CLS row / visual tokens stripped.  Returns a ``[B * N, hin]`` matrix
+    with a uniform row stride that the kernels read in place: a *view* when ``x`` already is one (B == 1 or a dense batch)
+    in ``out_dtype`` and no input dropout is asked for, otherwise the output of ``peneo_gather_tokens`` (strip + dropout
+    + cast in one kernel — no intermediate ``.contiguous()`` / dropout / cast tensors).  ``in_dropout``: None or (p, seed)."""
+    lib = _lib.load()
+    _require_cuda(x, "sequence_output")
+    if x.dtype not in (torch.float32, torch.bfloat16, torch.float16):
+        x = x.float()
+    if x.dim() == 2:
+        x = x.unsqueeze(0)
+    b, n, hin = x.shape
+    if x.stride(2) != 1:
+        x = x.contiguous()
+    drop_on = in_dropout is not None and in_dropout[0] > 0.0
+    uniform = b == 1 or x.stride(0) == n * x.stride(1)
+    if uniform and not drop_on and x.dtype == out_dtype:
+        return x.as_strided((b * n, hin), (x.stride(1), 1))
+    out = torch.empty(b * n, hin, dtype=out_dtype, device=x.device)
+    COUNTERS["kernels"] += 1
+    _lib.check(
+        lib.peneo_gather_tokens(x.data_ptr(), _TORCH_DT[x.dtype], b, n, hin, x.stride(0), x.stride(1), out.data_ptr(),
+                                _TORCH_DT[out_dtype], _lib.dropout_arg(in_dropout), _stream(x.device)),
+        "peneo_gather_tokens",
+    )
+    return out
+
+
+def token_projections(pack: WeightPack, x: torch.Tensor, dropout=None, in_dropout=None) -> torch.Tensor:
+    """x: [..., hin] (fp32 / bf16 / fp16, last dim contiguous; a strided [B, N, hin] view is consumed in place or through
+    one gather pass, see :func:`seam_tokens`) -> ab [tokens, 2d] (fp32, or bf16 pre-multiplied by 1/2 in bf16 mode).
+    ``dropout``: the decoder's own Dropout modules, None (eval) or ``(p, seed)``; ``in_dropout``: dropout on x itself."""
     lib = _lib.load()
     _require_cuda(x, "sequence_output")
     dm = pack.dims
     if x.shape[-1] != dm.hin:
         raise ValueError(f"last dimension {x.shape[-1]} != input_size {dm.hin}")
-    if x.dtype not in (torch.float32, torch.bfloat16, torch.float16):
-        x = x.float()
-    x2 = x.reshape(-1, dm.hin)
-    if x2.stride(-1) != 1:
-        x2 = x2.contiguous()
+    if x.dim() == 3:
+        x2 = seam_tokens(x, torch.float32 if pack.prec == PREC_FP32 else torch.bfloat16, in_dropout)
+    else:
+        if x.dtype not in (torch.float32, torch.bfloat16, torch.float16):
+            x = x.float()
+        x2 = x.reshape(-1, dm.hin)
+        if x2.stride(-1) != 1:
+            x2 = x2.contiguous()
     tokens = x2.shape[0]
     out_dt = torch.float32 if pack.prec == PREC_FP32 else torch.bfloat16
     ab = torch.empty(tokens, 2 * dm.d, dtype=out_dt, device=x.device)
@@ -153,12 +186,12 @@ def pair_heads(pack: WeightPack, ab: torch.Tensor, batch: int, n: int, dropout=N
     return logits
 
 
-def heads_forward(pack: WeightPack, x: torch.Tensor, dropout=None) -> List[torch.Tensor]:
+def heads_forward(pack: WeightPack, x: torch.Tensor, dropout=None, in_dropout=None) -> List[torch.Tensor]:
     """[B, N, hin] hidden states -> five logits tensors (return order LE, ELh, ELt, LGh, LGt)."""
     if x.dim() != 3:
         raise ValueError("sequence_output must be [batch, seq_len, hidden]")
     b, n, _ = x.shape
-    return pair_heads(pack, token_projections(pack, x, dropout), b, n, dropout)
+    return pair_heads(pack, token_projections(pack, x, dropout, in_dropout), b, n, dropout)
 
 
 def _check_tags(tags: Sequence[torch.Tensor], b: int, p: int) -> List[torch.Tensor]:
@@ -173,7 +206,7 @@ def _check_tags(tags: Sequence[torch.Tensor], b: int, p: int) -> List[torch.Tens
 
 
 def heads_loss_forward(pack: WeightPack, x: torch.Tensor, tags: Sequence[torch.Tensor], class_weights: Sequence[float],
-                       ratios: Optional[Sequence[float]] = None, dropout=None):
+                       ratios: Optional[Sequence[float]] = None, dropout=None, in_dropout=None):
     """Heads + class-weighted CE in one sweep over the pair tiles (``peneo_pair_heads_loss_fwd``): the K2 epilogue that
     writes a pair's logits also reduces its loss terms.  Returns (logits, out6, ctx); ctx feeds the fused backward."""
     lib = _lib.load()
@@ -182,7 +215,7 @@ def heads_loss_forward(pack: WeightPack, x: torch.Tensor, tags: Sequence[torch.T
     b, n, _ = x.shape
     p = shaking_len(n)
     tg = _check_tags(tags, b, p)
-    ab = token_projections(pack, x, dropout)
+    ab = token_projections(pack, x, dropout, in_dropout)
     logits = [torch.empty(b, p, c, dtype=torch.float32, device=ab.device) for c in HEAD_CLASSES]
     out6 = torch.empty(6, dtype=torch.float32, device=ab.device)
     ws = torch.empty(lib.peneo_pair_loss_workspace_bytes(b, n), dtype=torch.uint8, device=ab.device)

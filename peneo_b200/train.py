@@ -39,7 +39,8 @@ def _grad_struct(dims, grads: Dict[str, torch.Tensor]) -> _lib.Grads:
     return g
 
 
-def heads_backward(decoder, x: torch.Tensor, dlogits: List[torch.Tensor], need_dx: bool, dropout=None, fused=None):
+def heads_backward(decoder, x: torch.Tensor, dlogits: List[torch.Tensor], need_dx: bool, dropout=None, fused=None,
+                   in_dropout=None):
     """x: [B, N, hin] CUDA; dlogits: five fp32 [B, P, C_h]; dropout: the forward pass's (p, seed) or None.
     ``fused`` = (logits, loss ctx, grad_out6): the loss backward happens inside the pair tiles (``dlogits`` unused).
     Returns ({param_key: grad}, dx | None)."""
@@ -59,12 +60,9 @@ def heads_backward(decoder, x: torch.Tensor, dlogits: List[torch.Tensor], need_d
     else:
         pack, prec = decoder._fp32_pack(dev), PREC_FP32
     grads = {k: torch.empty_like(p, dtype=torch.float32) for k, p in _param_items(decoder)}
-    x2 = x.detach()
-    if x2.dtype not in (torch.float32, torch.bfloat16, torch.float16):
-        x2 = x2.float()
-    x2 = x2.reshape(b * n, hin)
-    if x2.stride(-1) != 1:
-        x2 = x2.contiguous()
+    # the same seam as the forward pass (strided view in place, or strip + input dropout + cast in one gather pass)
+    xd = x.detach()
+    x2 = ops.seam_tokens(xd, torch.float32 if xd.dtype not in (torch.bfloat16,) else torch.bfloat16, in_dropout)
     dx = torch.empty(b * n, hin, dtype=torch.float32, device=dev) if need_dx else None
     ws = torch.empty(lib.peneo_heads_bwd_workspace_bytes(dims.c(), prec, b, n), dtype=torch.uint8, device=dev)
     gs = _grad_struct(dims, grads)
@@ -80,6 +78,7 @@ def heads_backward(decoder, x: torch.Tensor, dlogits: List[torch.Tensor], need_d
                                      ops._stream(dev)),
             "peneo_heads_loss_bwd",
         )
+        _mask_dx(lib, dx, b * n, hin, in_dropout, dev)
         return grads, (dx.view(b, n, hin) if dx is not None else None)
     dl = [g if (g.dtype == torch.float32 and g.is_contiguous()) else g.float().contiguous() for g in dlogits]
     _lib.check(
@@ -89,7 +88,15 @@ def heads_backward(decoder, x: torch.Tensor, dlogits: List[torch.Tensor], need_d
                             ops._stream(dev)),
         "peneo_heads_bwd",
     )
+    _mask_dx(lib, dx, b * n, hin, in_dropout, dev)
     return grads, (dx.view(b, n, hin) if dx is not None else None)
+
+
+def _mask_dx(lib, dx, tokens, hin, in_dropout, dev):
+    """backward of the input dropout fused into the seam: the regenerated mask on d loss / d sequence_output"""
+    if dx is not None and in_dropout is not None and in_dropout[0] > 0.0:
+        _lib.check(lib.peneo_token_dropout_bwd(dx.data_ptr(), tokens, hin, _lib.dropout_arg(in_dropout), ops._stream(dev)),
+                   "peneo_token_dropout_bwd")
 
 
 class _DecoderHeads(torch.autograd.Function):
@@ -97,7 +104,8 @@ class _DecoderHeads(torch.autograd.Function):
     def forward(ctx, decoder, x, drop, *params):
         pack = decoder._weight_pack(x.device)
         ctx.dropout = drop  # (p, seed) of this step: the backward pass regenerates the same masks
-        logits = ops.heads_forward(pack, x.detach(), drop)
+        ctx.in_dropout = decoder._input_dropout(drop)
+        logits = ops.heads_forward(pack, x.detach(), drop, ctx.in_dropout)
         ctx.decoder = decoder
         ctx.save_for_backward(x)
         ctx.need_dx = x.requires_grad
@@ -111,7 +119,7 @@ class _DecoderHeads(torch.autograd.Function):
         shapes = [(x.shape[0], ops.shaking_len(x.shape[1]), c) for c in ops.HEAD_CLASSES]
         dl = [g if g is not None else torch.zeros(s, dtype=torch.float32, device=x.device)
               for g, s in zip(glogits, shapes)]
-        grads, dx = heads_backward(dec, x, dl, ctx.need_dx, ctx.dropout)
+        grads, dx = heads_backward(dec, x, dl, ctx.need_dx, ctx.dropout, in_dropout=ctx.in_dropout)
         out = [None, dx.to(x.dtype) if dx is not None else None, None]
         for k, p in _param_items(dec):
             out.append(grads[k].to(p.dtype) if p.requires_grad else None)
@@ -133,7 +141,8 @@ class _DecoderHeadsLoss(torch.autograd.Function):
     @staticmethod
     def forward(ctx, decoder, x, drop, class_w, ratios, t0, t1, t2, t3, t4, *params):
         pack = decoder._weight_pack(x.device)
-        logits, out6, lctx = ops.heads_loss_forward(pack, x.detach(), [t0, t1, t2, t3, t4], class_w, ratios, drop)
+        ctx.in_dropout = decoder._input_dropout(drop)
+        logits, out6, lctx = ops.heads_loss_forward(pack, x.detach(), [t0, t1, t2, t3, t4], class_w, ratios, drop, ctx.in_dropout)
         ctx.decoder, ctx.dropout, ctx.lctx, ctx.logits = decoder, drop, lctx, logits
         ctx.save_for_backward(x)
         ctx.need_dx = x.requires_grad
@@ -147,13 +156,14 @@ class _DecoderHeadsLoss(torch.autograd.Function):
         if g6 is None:
             g6 = torch.zeros(6, dtype=torch.float32, device=x.device)
         if all(g is None for g in glogits):
-            grads, dx = heads_backward(dec, x, None, ctx.need_dx, ctx.dropout, fused=(ctx.logits, ctx.lctx, g6))
+            grads, dx = heads_backward(dec, x, None, ctx.need_dx, ctx.dropout, fused=(ctx.logits, ctx.lctx, g6),
+                                       in_dropout=ctx.in_dropout)
         else:
             lws, tg, w3, r5 = ctx.lctx
             b, n = x.shape[0], x.shape[1]
             dl = ops.pair_loss_backward((lws, ctx.logits, tg, w3, r5, b, n), g6)
             dl = [d if g is None else d + g.float() for d, g in zip(dl, glogits)]
-            grads, dx = heads_backward(dec, x, dl, ctx.need_dx, ctx.dropout)
+            grads, dx = heads_backward(dec, x, dl, ctx.need_dx, ctx.dropout, in_dropout=ctx.in_dropout)
         out = [None, dx.to(x.dtype) if dx is not None else None] + [None] * 8
         for k, p in _param_items(dec):
             out.append(grads[k].to(p.dtype) if p.requires_grad else None)

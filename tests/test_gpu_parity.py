@@ -830,6 +830,58 @@ def test_strided_hidden_states_after_cls_strip():
         assert rel_err(h[k], ref[k]) <= 5e-3  # fp16 inputs: input rounding only
 
 
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_backbone_decoder_seam_strip_dropout_cast_in_one_pass(prec):
+    """N4 (model/modeling_peneo.py:134-173): the CLS-stripped view of a [B, S, H] backbone output is consumed without a
+    torch-side copy (one gather kernel: strip + optional input dropout + cast), and the nn.Dropout PEneoModel applies
+    before the decoder (modeling_peneo.py:165) can be folded into that pass: same logits, loss and gradients as applying
+    the very same mask with torch ops in front of an eval-mode decoder."""
+    n, b, p_in, seed = 33, 3, 0.25, 0x5EED5EED
+    tol = GRAD_TOL_FP32 if prec == "fp32" else 3e-2
+    sd = synth.init_decoder_state(seed=19, trained_like=True)
+    full = synth.hidden_states(b, n + 1, 768, doc_id0=9).cuda()
+    docs = [synth.make_document(n, doc_id=860 + i) for i in range(b)]
+    tags = [torch.stack([d.tags()[k] for d in docs]).cuda() for k in range(5)]
+    cfg = Cfg(768, inference_mode=False, precision=prec)
+    cfg.backbone_config["hidden_dropout_prob"] = 0.0  # isolate the seam dropout from the decoder's own Dropout modules
+    dec = PEneoDecoderB200(cfg, 768)
+    dec.load_state_dict(sd)
+    dec = dec.cuda()
+    # (1) strided view, no dropout: one gather launch instead of a torch copy, identical results
+    dec.eval()
+    k0 = ops.COUNTERS["kernels"]
+    view = full[:, 1:]
+    assert not view.is_contiguous()
+    mat = ops.seam_tokens(view, torch.float32)
+    assert ops.COUNTERS["kernels"] == k0 + 1 and torch.equal(mat.view(b, n, 768), view)
+    assert ops.seam_tokens(full[:1, 1:], torch.float32).data_ptr() == full[:1, 1:].data_ptr()  # B == 1: a view, no pass at all
+    with torch.no_grad():
+        a, c = dec(view, None, *tags), dec(view.contiguous(), None, *tags)
+    assert torch.equal(a.line_extraction_shaking_outputs, c.line_extraction_shaking_outputs) and a.loss.item() == c.loss.item()
+    # (2) input dropout fused into the same pass
+    dec.train()
+    dec.input_dropout_prob, dec.dropout_seed = p_in, seed
+    mask = ops.seam_tokens(torch.ones_like(view), torch.float32, (p_in, seed)).view(b, n, 768)
+    kept = (mask != 0).float().mean().item()
+    assert abs(kept - (1 - p_in)) < 0.01 and torch.allclose(mask[mask != 0], torch.tensor(1 / (1 - p_in), device="cuda"))
+    root = full.clone().requires_grad_(True)
+    out = dec(root[:, 1:], None, *tags)
+    out.loss.backward()
+    g_fused = {k: p.grad.clone() for k, p in dec.named_parameters()}
+    dx_fused = root.grad.clone()
+    dec.zero_grad(set_to_none=True)
+    dec.eval()  # reference: the same mask applied with torch ops, decoder without any dropout
+    root2 = full.clone().requires_grad_(True)
+    out2 = dec(root2[:, 1:] * mask, None, *tags)
+    out2.loss.backward()
+    assert abs(out.loss.item() - out2.loss.item()) <= 1e-5 * max(1.0, abs(out2.loss.item()))
+    assert rel_err(out.ent_linking_h2h_shaking_outputs, out2.ent_linking_h2h_shaking_outputs.detach().cpu()) <= 1e-5
+    assert rel_err(dx_fused, root2.grad.cpu()) <= max(tol, 1e-4)
+    assert (dx_fused[:, 0] == 0).all() and (dx_fused[:, 1:][mask == 0] == 0).all()  # CLS row untouched, dropped inputs get no gradient
+    for k, p in dec.named_parameters():
+        assert rel_err(g_fused[k], p.grad.cpu()) <= max(tol, 1e-4), k
+
+
 # ------------------------------------------------------------------------------------------------
 # training-mode dropout (model/peneo_decoder.py:218, 221, 261): regenerable counter-based masks
 # ------------------------------------------------------------------------------------------------
