@@ -53,16 +53,16 @@ def main():
                 while len(pipe):
                     pipe.result(assemble=False)
 
-            run(3)
+            run(10)
             torch.cuda.synchronize()
-            pipe.k2_events = []
+            pipe.k2_events, pipe.kernel_ms = [], {"k2": []}
             t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             t0.record(pipe.compute)
             run(steps)
             t1.record(pipe.compute)
             torch.cuda.synchronize()
             ms = t0.elapsed_time(t1) / steps
-            k2 = sum(a.elapsed_time(c) for a, c in pipe.k2_events) / len(pipe.k2_events)
+            k2 = bench.k2_mean_ms(pipe)
             tf = b * (10.0 * pairs * 384 * 384 + 28.0 * pairs * 384) / (k2 * 1e-3) / 1e12
             print(json.dumps({"seq_len": seq, "pair_dim": n, "batch": b, "steps": steps, "ms_per_step": round(ms, 4),
                               "docs_per_s": round(b / (ms * 1e-3), 1), "k2_ms": round(k2, 4), "k2_tflops": round(tf, 1),

@@ -95,7 +95,11 @@ class PendingDecode:
     ``finish()`` waits for it; documents whose spot lists overflowed the capacity (dense predictions of an
     untrained model) are decoded again, alone, with exactly the capacity their longest list needs."""
 
-    def __init__(self, ins, n, cap, decode_gt, score_thresh, want_spots, d2h_stream=None, k3_events=None, heads=None):
+    def __init__(self, ins, n, cap, decode_gt, score_thresh, want_spots, d2h_stream=None, k3_events=None, heads=None,
+                 host_buffers=None, record_event=True):
+        # host_buffers = (counts_h, rec_h) pinned tensors supplied by the caller and record_event=False: CUDA-graph
+        # capture (no pinned allocation and no event inside the captured region; the caller synchronises the replay)
+        self.host_buffers, self.record_event = host_buffers, record_event
         # heads = (WeightPack, ab [B * n, 2d]): spot extraction fused into the pair kernel (peneo_pair_heads_spots_fwd):
         # there are no logits (`ins` is None), the compact spot lists come straight from the heads
         self.heads = heads
@@ -151,8 +155,11 @@ class PendingDecode:
             "peneo_decode_resolve",
         )
         COUNTERS["kernels"] += 3  # K3 spots, K4a maps, K4b links
-        self.counts_h = torch.empty(counts.shape, dtype=torch.int32, pin_memory=True)
-        self.rec_h = torch.empty(rec.shape, dtype=torch.int32, pin_memory=True)
+        if self.host_buffers is not None:
+            self.counts_h, self.rec_h = self.host_buffers
+        else:
+            self.counts_h = torch.empty(counts.shape, dtype=torch.int32, pin_memory=True)
+            self.rec_h = torch.empty(rec.shape, dtype=torch.int32, pin_memory=True)
         cur = torch.cuda.current_stream(dev)
         if self.d2h_stream is not None and self.d2h_stream != cur:
             ready = torch.cuda.Event()
@@ -168,13 +175,16 @@ class PendingDecode:
         else:
             self.counts_h.copy_(counts, non_blocking=True)
             self.rec_h.copy_(rec, non_blocking=True)
-            self.event = torch.cuda.Event()
-            self.event.record(cur)
+            self.event = None
+            if self.record_event:
+                self.event = torch.cuda.Event()
+                self.event.record(cur)
         self.d2h_bytes = self.counts_h.numel() * 4 + self.rec_h.numel() * 4
         self._keep = (counts, rec, ws, ws2)  # alive until the copies have run
 
     def finish(self) -> "DeviceDecode":
-        self.event.synchronize()
+        if self.event is not None:
+            self.event.synchronize()
         b = self.batch
         p = shaking_len(self.n)
         redo, redo_rows = None, {}
@@ -198,7 +208,8 @@ class PendingDecode:
             cap = self.cap
             spots = (self.spot_p.cpu().numpy().reshape(b, NUM_HEADS, cap), self.spot_tag.cpu().numpy().reshape(b, NUM_HEADS, cap),
                      self.spot_score.cpu().numpy().reshape(b, NUM_HEADS, cap))
-        self._keep = None
+        if self.record_event:
+            self._keep = None
         dd = DeviceDecode(self.n, self.cap, b, self.rec_h.numpy(), self.counts_h.numpy().reshape(b, NUM_HEADS), spots)
         dd.redo, dd.redo_rows = redo, redo_rows
         return dd
