@@ -21,6 +21,8 @@ done > $out/${tag}_train_step.jsonl
 cat $out/${tag}_train_step.jsonl | cut -c1-200
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 800 --csv --log-file $out/${tag}_train_launches.csv \
     python benchmarks/train_step.py --steps 2 --warmup 1 > $out/${tag}_ncu_train.log 2>&1
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 800 --csv --log-file $out/${tag}_train_launches_b32.csv \
+    python benchmarks/train_step.py --seq-len 512 --batch 32 --steps 2 --warmup 1 > $out/${tag}_ncu_train_b32.log 2>&1
 timeout 400 ncu --set full --clock-control none --import-source on -k regex:pair_bwd_prep -s 2 -c 1 -o $out/${tag}_t1 \
     python benchmarks/train_step.py --steps 1 --warmup 0 > $out/${tag}_ncu_t1.log 2>&1
 timeout 400 python benchmarks/decoder_microbench.py > $out/${tag}_decoder_microbench.jsonl 2>/dev/null; tail -3 $out/${tag}_decoder_microbench.jsonl | cut -c1-200

@@ -26,7 +26,7 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC",
     "-Xptxas", "-v",
     "--expt-relaxed-constexpr",
-]
+] + os.environ.get("PENEO_NVCC_EXTRA", "").split()  # A/B experiments: e.g. PENEO_NVCC_EXTRA="-DPENEO_T1_EPI_WARPS=16"
 
 
 def _nvcc() -> str:

@@ -32,12 +32,19 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 static int make_tensor_map_any(void* tmap_out, CUtensorMapDataType dtype, const void* gptr, uint64_t inner, uint64_t outer,
-                               uint64_t row_stride_bytes, uint32_t box_inner, uint32_t box_outer);
+                               uint64_t row_stride_bytes, uint32_t box_inner, uint32_t box_outer,
+                               CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B);
 
 int make_tensor_map_bf16(void* tmap_out, const void* gptr, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes,
                          uint32_t box_inner, uint32_t box_outer) {
   return make_tensor_map_any(tmap_out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, gptr, inner, outer, row_stride_bytes, box_inner,
                              box_outer);
+}
+// 64-byte swizzle (box rows of 32 bf16): the per-warp store tiles of T1
+int make_tensor_map_bf16_sw64(void* tmap_out, const void* gptr, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes,
+                              uint32_t box_inner, uint32_t box_outer) {
+  return make_tensor_map_any(tmap_out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, gptr, inner, outer, row_stride_bytes, box_inner,
+                             box_outer, CU_TENSOR_MAP_SWIZZLE_64B);
 }
 int make_tensor_map_f32(void* tmap_out, const void* gptr, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes,
                         uint32_t box_inner, uint32_t box_outer) {
@@ -46,7 +53,7 @@ int make_tensor_map_f32(void* tmap_out, const void* gptr, uint64_t inner, uint64
 }
 
 static int make_tensor_map_any(void* tmap_out, CUtensorMapDataType dtype, const void* gptr, uint64_t inner, uint64_t outer,
-                               uint64_t row_stride_bytes, uint32_t box_inner, uint32_t box_outer) {
+                               uint64_t row_stride_bytes, uint32_t box_inner, uint32_t box_outer, CUtensorMapSwizzle swizzle) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) {
     set_error("cuTensorMapEncodeTiled entry point unavailable");
@@ -57,7 +64,7 @@ static int make_tensor_map_any(void* tmap_out, CUtensorMapDataType dtype, const 
   cuuint32_t box[2] = {box_inner, box_outer};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(static_cast<CUtensorMap*>(tmap_out), dtype, 2, const_cast<void*>(gptr),
-                  dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed with CUresult %d (inner=%llu outer=%llu stride=%llu box=%ux%u)", (int)r,

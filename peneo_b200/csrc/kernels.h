@@ -137,6 +137,8 @@ int run_probe_rates(double* out, int n_out);
 struct TensorMap2D;
 int make_tensor_map_bf16(void* tmap_out, const void* gptr, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes,
                          uint32_t box_inner, uint32_t box_outer);
+int make_tensor_map_bf16_sw64(void* tmap_out, const void* gptr, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes,
+                              uint32_t box_inner, uint32_t box_outer);
 int make_tensor_map_f32(void* tmap_out, const void* gptr, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes,
                         uint32_t box_inner, uint32_t box_outer);
 

@@ -10,6 +10,11 @@
 //     CTAs) and "m ready" (epilogue warps of both CTAs) — the peer arrives remotely (mapa + mbarrier.arrive);
 //   * everything the MMA releases ("W stage empty", "S chunk free", "u full", "z full", "W_out stage empty") is a
 //     tcgen05.commit multicast to the same barrier in both CTAs.
+//
+// b_mid rides on the tensor cores: the A operand has a constant 25th K step [1, 0, ..., 0] (eight TMEM columns written
+// once) and the B operand of that step is a resident shared-memory tile whose K column 0 holds b_mid / 2 (bf16), so
+// u / 2 + b_mid / 2 arrives complete in the accumulator — one more UMMA per chunk (+4 % tensor work) instead of a
+// broadcast LDS.128 per four elements and an FADD per element in the epilogue warps that pace the kernel.
 #include <cuda.h>
 
 #include <cstdlib>
@@ -35,14 +40,17 @@ constexpr int kProdWarp0 = 4 + kEpiWarps;
 constexpr int kProdRows = 4;        // b_j rows a producer warp has in flight (register budget: 80 / thread)
 constexpr int kThreads = 32 * (kProdWarp0 + 4);
 
-constexpr uint32_t kColS = 0, kColU = 192, kColZ = 448;
+constexpr uint32_t kColS = 0, kColU = 192, kColZ = 448, kColOne = 480;  // [480, 496): the constant "ones" K step of A
+constexpr int kBiasTileBytes = 64 * 128;  // [64 rows (this CTA's half of a chunk's features) x 128 B] SWIZZLE_128B, K-major:
+                                          // the 32-byte K step x of a row belongs to chunk 4 * tile + x (K column 0 = b_mid / 2)
+constexpr int kBiasTiles = 4;             // 15 chunks, four per tile
 
 struct Smem {
   static constexpr int w = 0;
   static constexpr int o = w + kWStages * kWStageBytes;
   static constexpr int stage = o + kOStages * kOStageBytes;
-  static constexpr int bmid = stage + 128 * kStageRowBytes;  // 1920 floats
-  static constexpr int bout = bmid + 5 * D * 4;              // 20 floats
+  static constexpr int bias = stage + 128 * kStageRowBytes;  // bias B-operand tiles (see kBiasTileBytes)
+  static constexpr int bout = bias + kBiasTiles * kBiasTileBytes;  // 20 floats
   static constexpr int loss = bout + 128;                    // 40 doubles (LOSS instantiation)
   static constexpr int bars = loss + 320;
   static constexpr int total = bars + 512;
@@ -52,7 +60,9 @@ constexpr int bWFull = 0, bWEmpty = bWFull + kWStages, bOFull = bWEmpty + kWStag
               bUFull = bOEmpty + kOStages, bMReady = bUFull + 2, bZFull = bMReady + 2, bZFree = bZFull + 2, bSFull = bZFree + 2,
               bSFree = bSFull + kKChunks, bCount = bSFree + kKChunks;
 static_assert(bCount * 8 + 16 <= 512, "barrier area too small");
+static_assert(Smem::stage % 1024 == 0 && Smem::bias % 1024 == 0, "UMMA operand tiles need 1024-byte alignment");
 constexpr int kSmemBytes = Smem::total + 1024;
+static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
 
 struct Args {
   const __nv_bfloat16* ab;  // [batch*n, 768] : 0.5*A | 0.5*Bm
@@ -81,7 +91,6 @@ __global__ void __launch_bounds__(kThreads, 1)
   unsigned char* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);  // by offset: keeps the shared address space
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Smem::bars);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + bCount);
-  float* s_bmid = reinterpret_cast<float*>(smem + Smem::bmid);
   float* s_bout = reinterpret_cast<float*>(smem + Smem::bout);
   double* s_loss = reinterpret_cast<double*>(smem + Smem::loss);  // [4 quadrants][5 heads][2]
 
@@ -103,9 +112,20 @@ __global__ void __launch_bounds__(kThreads, 1)
     for (int s = 0; s < kKChunks; ++s) ptx::mbar_init(&bars[bSFull + s], 8), ptx::mbar_init(&bars[bSFree + s], 1);
     ptx::fence_barrier_init();
   }
-  for (int e = threadIdx.x; e < 5 * D; e += kThreads) s_bmid[e] = a.bmid_half[e];
   if (threadIdx.x < 20) s_bout[threadIdx.x] = a.bout[threadIdx.x];
   if (LOSS && threadIdx.x < 40) s_loss[threadIdx.x] = 0.0;
+  // bias operand tiles: zero, then K column 0 of (chunk c, row r) = b_mid / 2 of feature c * 128 + 64 * rank + r.
+  // Row r of a tile is 128 B, its 16-byte chunk index is XORed with (r & 7) (the SWIZZLE_128B pattern the MMA expects).
+  for (int e = threadIdx.x; e < kBiasTiles * kBiasTileBytes / 16; e += kThreads)
+    reinterpret_cast<uint4*>(smem + Smem::bias)[e] = make_uint4(0u, 0u, 0u, 0u);
+  __syncthreads();
+  for (int e = threadIdx.x; e < kChunks * 64; e += kThreads) {
+    const int c = e >> 6, r = e & 63;
+    const float bh = a.bmid_half[c * 128 + static_cast<int>(rank) * 64 + r];
+    *reinterpret_cast<__nv_bfloat16*>(smem + Smem::bias + (c >> 2) * kBiasTileBytes + r * 128 + (((2 * (c & 3)) ^ (r & 7)) * 16)) =
+        __float2bfloat16_rn(bh);
+  }
+  ptx::fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async proxy
   ptx::cluster_sync_all();  // both CTAs' barriers exist before anyone (TMA of the peer, remote arrives) touches them
   if (warp == 2) {
     ptx::tmem_alloc_2sm(tmem_slot, 512);
@@ -164,6 +184,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       int ws = 0, os = 0;
       uint32_t wph = 0, oph = 0;
       const uint32_t w_base = ptx::smem_u32(smem + Smem::w), o_base = ptx::smem_u32(smem + Smem::o);
+      const uint32_t b_base = ptx::smem_u32(smem + Smem::bias);
       // second GEMM of global chunk gp: z[head] (+)= m(gp) * W_out chunk^T
       auto mma2 = [&](int gp) {
         const int buf = gp & 1, hg = gp / 3, cpos = gp - hg * 3;
@@ -187,6 +208,13 @@ __global__ void __launch_bounds__(kThreads, 1)
       for (int it = 0; it < my_tiles; ++it) {
         for (int c = 0; c < kChunks; ++c, ++g) {
           const uint32_t ut = tmem + kColU + 128 * (g & 1);
+          // u = [1 0 .. 0] x (b_mid / 2 tile): initialises the accumulator (the ones columns were written before the
+          // first "S chunk full" arrival, which the first MMA of the kernel has not passed yet — see the producers)
+          if (g == 0) {
+            ptx::mbar_wait(&bars[bSFull + 0], 0);
+            ptx::tc_fence_after();
+          }
+          ptx::umma_ts_2sm(ut, tmem + kColOne, ptx::umma_desc_sw128(b_base + (c >> 2) * kBiasTileBytes + (c & 3) * 32), idesc1, 0);
           for (int kc = 0; kc < kKChunks; ++kc) {
             if (c == 0) ptx::mbar_wait(&bars[bSFull + kc], it & 1);
             ptx::mbar_wait(&bars[bWFull + ws], wph);
@@ -194,7 +222,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks)
               ptx::umma_ts_2sm(ut, tmem + kColS + 32 * kc + 8 * ks,
-                               ptx::umma_desc_sw128(w_base + ws * kWStageBytes + ks * 32), idesc1, (kc | ks) != 0);
+                               ptx::umma_desc_sw128(w_base + ws * kWStageBytes + ks * 32), idesc1, 1);
             ptx::tc_commit_2sm(&bars[bWEmpty + ws], 3);
             if (c == kChunks - 1) ptx::tc_commit_2sm(&bars[bSFree + kc], 3);
             if (++ws == kWStages) ws = 0, wph ^= 1;
@@ -222,18 +250,15 @@ __global__ void __launch_bounds__(kThreads, 1)
         ptx::mbar_wait(&bars[bUFull + buf], (g >> 1) & 1);
         ptx::tc_fence_after();
         const uint32_t ut = tmem + lane_base + kColU + 128 * buf + 32 * csel;
-        const float* hb = s_bmid + c * 128 + 32 * csel;
         uint32_t r[32];
         ptx::tmem_ld_x32(ut, r);
         ptx::tmem_ld_wait();
         uint32_t packed[16];
 #pragma unroll
         for (int x = 0; x < 32; x += 4) {
-          const float4 b4 = *reinterpret_cast<const float4*>(hb + x);
-          float m0 = __uint_as_float(r[x + 0]) + b4.x, m1 = __uint_as_float(r[x + 1]) + b4.y;
-          float m2 = __uint_as_float(r[x + 2]) + b4.z, m3 = __uint_as_float(r[x + 3]) + b4.w;
-          m0 = ptx::silu_from_half(m0), m1 = ptx::silu_from_half(m1);
-          m2 = ptx::silu_from_half(m2), m3 = ptx::silu_from_half(m3);
+          // the accumulator holds (u + b_mid) / 2 (the bias came through the MMA)
+          float m0 = ptx::silu_from_half(__uint_as_float(r[x + 0])), m1 = ptx::silu_from_half(__uint_as_float(r[x + 1]));
+          float m2 = ptx::silu_from_half(__uint_as_float(r[x + 2])), m3 = ptx::silu_from_half(__uint_as_float(r[x + 3]));
           if (DROP) {  // nn.Dropout after the hidden SiLU (model/peneo_decoder.py:261), regenerable mask
             const uint32_t key = a.drop_key[c / 3], grow = static_cast<uint32_t>(drop_row);
             const uint32_t col = (c % 3) * 128 + 32 * csel + x;
@@ -331,6 +356,14 @@ __global__ void __launch_bounds__(kThreads, 1)
         ++next_emit;
       }
     };
+    {  // the constant K step of the A operand: element 0 = 1.0 (bf16), the other 15 = 0; 16 columns, written once
+      uint32_t one[16];
+#pragma unroll
+      for (int x = 0; x < 16; ++x) one[x] = x == 0 ? 0x00003F80u : 0u;
+      ptx::tmem_st_x16(tmem + lane_base + kColOne, one);
+      ptx::tmem_st_wait();
+      ptx::tc_fence_before();  // ordered before this warp's first "S chunk full" arrival, which the MMA warp waits for
+    }
     for (int it = 0; it < my_tiles; ++it) {
       const int64_t tile = tile_of(it);
       // (row offsets of a_i / b_j for the row this lane will later copy)
