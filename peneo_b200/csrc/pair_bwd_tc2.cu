@@ -10,20 +10,22 @@
 //   * CTA pairs: the two CTAs of a cluster run every UMMA together (M = 256); each owns one 128-pair tile and
 //     supplies half of the W_mid rows of a chunk, so the W stream costs a CTA 384 + 384 wavefronts instead of 768 + 768;
 //   * the W_out rows for dz W_out are read as 16-byte vectors (192 instead of 768 broadcast LDS per chunk);
+//   * b_mid rides on the tensor cores exactly as in K2 (pair_heads_tc2.cu): a constant 25th K step [1, 0, .., 0] of the
+//     A operand times a resident bias tile, so the accumulator already holds (u + b_mid) / 2 — no bias LDS / FADD;
 //   * FUSED: dz_k is computed in registers from the stored logits, the tags and the loss normaliser
 //       dz = (g_total ratio_k + g_k) / Z_k * w[t] * (softmax(z) - onehot(t))      (model/custom_loss.py:189-202)
 //     so d loss / d logits never exists in HBM and db_out = sum dz is reduced here too (no separate loss-backward
 //     and column-sum kernels).
 //
 // dW_out on a CTA pair: the two CTAs hold DIFFERENT pairs (K index), so their products cannot share a B operand.
-// One N = 32 MMA does both: B[k][0:16] = dz^T of CTA 0 (its half of B), B[k][16:32] = dz^T of CTA 1, A rows
-// [0,128) = m^T of CTA 0, [128,256) = m^T of CTA 1; each CTA reads its own product from its own 16 columns of D
-// (the cross terms land in the other 16 columns and are ignored).
+// One N = 16 MMA does both: B[k][0:8] = dz^T of CTA 0 (its half of B: the first 8-row swizzle atom of its dz^T tile),
+// B[k][8:16] = dz^T of CTA 1, A rows [0,128) = m^T of CTA 0, [128,256) = m^T of CTA 1; each CTA reads its own product
+// from its own 8 columns of D (the cross terms land in the other 8 columns and are ignored).
 //
 // Warp roles: warp 0 TMA (W_mid stream), warp 1 MMA issuer (leader CTA only), warp 2 TMEM allocator, warps 4 .. 4 +
 // kEpiWarps epilogue, then four pair-producer warps.  Barriers the MMA waits on live in the LEADER (the peer arrives remotely);
 // everything the MMA releases is a tcgen05.commit multicast to both CTAs.
-// TMEM columns: [0,192) s | [192,320) u buffer 0 | [320,448) u buffer 1 | [448,480) D_w 0 | [480,512) D_w 1
+// TMEM columns: [0,192) s | [192,320) u buffer 0 | [320,448) u buffer 1 | [448,464) D_w 0 | [464,480) D_w 1 | [480,496) ones
 #include <cuda.h>
 
 #include "common.cuh"
@@ -36,7 +38,7 @@ namespace t1p {
 constexpr int D = 384;
 constexpr int kChunks = 15;       // 5 heads x 3 chunks of 128 mid features
 constexpr int kKChunks = 6;       // 384 / 64
-constexpr int kWStages = 6;
+constexpr int kWStages = 4;  // (shared-memory budget; 3 .. 6 stages measure the same: the MMA side is not starved)
 constexpr int kWStageBytes = 64 * 64 * 2;  // 8 KB: this CTA's 64 of the chunk's 128 W_mid rows
 constexpr int kStageRowBytes = D * 2;      // staging: 128 rows x 768 B
 // Epilogue warps: 8 (two per scheduler, two 32-column slices of a chunk each) or 16 (one slice each).  Measured on
@@ -48,7 +50,9 @@ constexpr int kProdRows = kEpiWarps == 8 ? 4 : 2;  // pair rows a producer warp 
 constexpr int kThreads = 32 * (kProdWarp0 + 4);
 constexpr int kLdG = 5 * D;                // row stride of G
 
-constexpr uint32_t kColS = 0, kColU = 192, kColDw = 448;
+constexpr uint32_t kColS = 0, kColU = 192, kColDw = 448, kColOne = 480;
+constexpr int kBiasTileBytes = 64 * 128;  // [64 rows x 128 B] SWIZZLE_128B K-major: the 32-byte K step x of a row belongs to
+constexpr int kBiasTiles = 4;             // chunk 4 * tile + x, its K column 0 = b_mid / 2 of that feature (see K2)
 constexpr int kOutWarpBytes = 32 * 64;  // per epilogue warp: 32 rows x 32 bf16, XOR-swizzled 16-byte chunks
 
 struct Smem {
@@ -56,8 +60,8 @@ struct Smem {
   static constexpr int stage = w + kWStages * kWStageBytes;
   static constexpr int mtile = stage + 128 * kStageRowBytes;  // m chunk, 2 x 2 boxes of [64 pairs x 64 features] bf16
   static constexpr int dzt = mtile + 128 * 128 * 2;           // dz^T, 2 K blocks of [16 x 64 pairs] bf16
-  static constexpr int bmid = dzt + 2 * 16 * 128;             // 1920 floats
-  static constexpr int out = bmid + 5 * D * 4;                // per epilogue warp [32 rows][64 B]
+  static constexpr int bias = dzt + 2 * 16 * 128;             // bias B-operand tiles
+  static constexpr int out = bias + kBiasTiles * kBiasTileBytes;  // per epilogue warp [32 rows][64 B]
   static constexpr int wout = out + kEpiWarps * kOutWarpBytes;        // [3][960] bf16x2: W_out[c] of feature pairs (2f, 2f+1)
   static constexpr int misc = wout + 3 * (5 * D / 2) * 4;     // fused loss: scale[5] | class_w[3] | db_out[5][4]
   static constexpr int bars = misc + 128;
@@ -66,7 +70,8 @@ struct Smem {
 constexpr int bWFull = 0, bWEmpty = bWFull + kWStages, bUFull = bWEmpty + kWStages, bUFree = bUFull + 2,
               bSFull = bUFree + 2, bSFree = bSFull + kKChunks, bMFull = bSFree + kKChunks, bMFree = bMFull + 1,
               bDwFull = bMFree + 1, bDwFree = bDwFull + 2, bCount = bDwFree + 2;
-static_assert(Smem::mtile % 1024 == 0 && Smem::dzt % 1024 == 0 && Smem::stage % 1024 == 0, "UMMA operand tiles need 1024-byte alignment");
+static_assert(Smem::mtile % 1024 == 0 && Smem::dzt % 1024 == 0 && Smem::stage % 1024 == 0 && Smem::bias % 1024 == 0,
+              "UMMA operand tiles need 1024-byte alignment");
 static_assert(Smem::wout % 16 == 0, "W_out rows are read as 16-byte vectors");
 static_assert(Smem::total + 1024 <= 227 * 1024, "shared memory budget");
 static_assert(bCount * 8 + 16 <= 512, "barrier area too small");
@@ -101,7 +106,6 @@ __global__ void __launch_bounds__(kThreads, 1) pair_bwd_prep_pair_kernel(const _
   unsigned char* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Smem::bars);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + bCount);
-  float* s_bmid = reinterpret_cast<float*>(smem + Smem::bmid);
   float* s_scale = reinterpret_cast<float*>(smem + Smem::misc);  // [5]
   float* s_cw = s_scale + 5;                                      // [3]
   float* s_dbout = s_scale + 8;                                   // [5][4]
@@ -119,7 +123,16 @@ __global__ void __launch_bounds__(kThreads, 1) pair_bwd_prep_pair_kernel(const _
     for (int s = 0; s < 2; ++s) ptx::mbar_init(&bars[bDwFull + s], 1), ptx::mbar_init(&bars[bDwFree + s], 8);  // 4 flushing warps per CTA
     ptx::fence_barrier_init();
   }
-  for (int e = threadIdx.x; e < 5 * D; e += kThreads) s_bmid[e] = a.bmid_half[e];
+  // bias operand tiles: zero, then K column 0 of (chunk c, row r) = b_mid / 2 of feature c * 128 + 64 * rank + r
+  for (int e = threadIdx.x; e < kBiasTiles * kBiasTileBytes / 16; e += kThreads)
+    reinterpret_cast<uint4*>(smem + Smem::bias)[e] = make_uint4(0u, 0u, 0u, 0u);
+  __syncthreads();
+  for (int e = threadIdx.x; e < kChunks * 64; e += kThreads) {
+    const int c = e >> 6, r = e & 63;
+    const float bh = a.bmid_half[c * 128 + static_cast<int>(rank) * 64 + r];
+    *reinterpret_cast<__nv_bfloat16*>(smem + Smem::bias + (c >> 2) * kBiasTileBytes + r * 128 + (((2 * (c & 3)) ^ (r & 7)) * 16)) =
+        __float2bfloat16_rn(bh);
+  }
   uint32_t* s_wout = reinterpret_cast<uint32_t*>(smem + Smem::wout);
   for (int e = threadIdx.x; e < 5 * D / 2; e += kThreads) {
     const float4 w0 = a.wout4[2 * e], w1 = a.wout4[2 * e + 1];
@@ -177,12 +190,13 @@ __global__ void __launch_bounds__(kThreads, 1) pair_bwd_prep_pair_kernel(const _
     // ============================== MMA issuer (leader) ==============================
     if (leader && ptx::elect_one()) {
       constexpr uint32_t idesc1 = ptx::umma_idesc_bf16(256, 128);
-      constexpr uint32_t idesc_w = ptx::umma_idesc_bf16_major(256, 32, true, false);
+      constexpr uint32_t idesc_w = ptx::umma_idesc_bf16_major(256, 16, true, false);
       int ws = 0;
       uint32_t wph = 0;
       const uint32_t w_base = ptx::smem_u32(smem + Smem::w);
       const uint32_t m_base = ptx::smem_u32(smem + Smem::mtile), dz_base = ptx::smem_u32(smem + Smem::dzt);
-      // D_w[gw & 1] (32 columns: 16 per CTA) = m(gw)^T-tile x dz^T : 8 K steps of 16 pairs
+      const uint32_t b_base = ptx::smem_u32(smem + Smem::bias);
+      // D_w[gw & 1] (16 columns: 8 per CTA) = m(gw)^T-tile x dz^T : 8 K steps of 16 pairs
       auto issue_dw = [&](int gw) {
         const int wb = gw & 1;
         ptx::mbar_wait(&bars[bMFull], gw & 1);
@@ -190,7 +204,7 @@ __global__ void __launch_bounds__(kThreads, 1) pair_bwd_prep_pair_kernel(const _
         ptx::tc_fence_after();
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks)
-          ptx::umma_ss_2sm(tmem + kColDw + 32 * wb,
+          ptx::umma_ss_2sm(tmem + kColDw + 16 * wb,
                            ptx::umma_desc_mn_sw128(m_base + (ks >> 2) * 16384 + (ks & 3) * 2048, 8192, 1024),
                            ptx::umma_desc_sw128(dz_base + (ks >> 2) * 2048 + (ks & 3) * 32), idesc_w, ks != 0);
         ptx::tc_commit_2sm(&bars[bMFree], 3);
@@ -203,6 +217,13 @@ __global__ void __launch_bounds__(kThreads, 1) pair_bwd_prep_pair_kernel(const _
           ptx::mbar_wait(&bars[bUFree + buf], ((g >> 1) & 1) ^ 1);  // both epilogues drained chunk g - 2
           ptx::tc_fence_after();
           const uint32_t ut = tmem + kColU + 128 * buf;
+          // u = [1 0 .. 0] x (b_mid / 2 tile) initialises the accumulator (the producers wrote the ones columns before
+          // their first "S chunk full" arrival)
+          if (g == 0) {
+            ptx::mbar_wait(&bars[bSFull + 0], 0);
+            ptx::tc_fence_after();
+          }
+          ptx::umma_ts_2sm(ut, tmem + kColOne, ptx::umma_desc_sw128(b_base + (c >> 2) * kBiasTileBytes + (c & 3) * 32), idesc1, 0);
           for (int kc = 0; kc < kKChunks; ++kc) {
             if (c == 0) ptx::mbar_wait(&bars[bSFull + kc], it & 1);
             ptx::mbar_wait(&bars[bWFull + ws], wph);
@@ -210,7 +231,7 @@ __global__ void __launch_bounds__(kThreads, 1) pair_bwd_prep_pair_kernel(const _
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks)
               ptx::umma_ts_2sm(ut, tmem + kColS + 32 * kc + 8 * ks, ptx::umma_desc_sw128(w_base + ws * kWStageBytes + ks * 32),
-                               idesc1, (kc | ks) != 0);
+                               idesc1, 1);
             ptx::tc_commit_2sm(&bars[bWEmpty + ws], 3);
             if (c == kChunks - 1) ptx::tc_commit_2sm(&bars[bSFree + kc], 3);
             if (++ws == kWStages) ws = 0, wph ^= 1;
@@ -242,7 +263,7 @@ __global__ void __launch_bounds__(kThreads, 1) pair_bwd_prep_pair_kernel(const _
       ptx::mbar_wait(&bars[bDwFull + wb], (gw >> 1) & 1);
       ptx::tc_fence_after();
       uint32_t d4[4];
-      ptx::tmem_ld_x4(tmem + lane_base + kColDw + 32 * wb + 16 * rank, d4);
+      ptx::tmem_ld_x4(tmem + lane_base + kColDw + 16 * wb + 8 * rank, d4);
       ptx::tmem_ld_wait();
       ptx::tc_fence_before();
       __syncwarp();
@@ -332,7 +353,6 @@ __global__ void __launch_bounds__(kThreads, 1) pair_bwd_prep_pair_kernel(const _
           const int csel = csel0 + sl;
           const uint32_t ut = tmem + lane_base + kColU + 128 * buf + 32 * csel;
           const int f0 = c * 128 + 32 * csel;  // column in the stacked [0, 1920) feature space
-          const float* hb = s_bmid + f0;
           const uint32_t* wp = s_wout + f0 / 2;  // feature pairs, indexed by the stacked feature index k * 384 + f
           unsigned char* mt = mt0 + (csel >> 1) * 8192;
           uint32_t r[32];
@@ -345,9 +365,7 @@ __global__ void __launch_bounds__(kThreads, 1) pair_bwd_prep_pair_kernel(const _
           }
 #pragma unroll
           for (int v = 0; v < 4; ++v) {
-            // biases and W_out of the 8 features of this group: 16-byte broadcast loads
-            const float4 hq0 = *reinterpret_cast<const float4*>(hb + 8 * v), hq1 = *reinterpret_cast<const float4*>(hb + 8 * v + 4);
-            const float hbv[8] = {hq0.x, hq0.y, hq0.z, hq0.w, hq1.x, hq1.y, hq1.z, hq1.w};
+            // W_out of the 8 features of this group: 16-byte broadcast loads
             const uint4 wq0 = *reinterpret_cast<const uint4*>(wp + 4 * v);
             const uint4 wq1 = *reinterpret_cast<const uint4*>(wp + 5 * D / 2 + 4 * v);
             const uint4 wq2 = *reinterpret_cast<const uint4*>(wp + 5 * D + 4 * v);
@@ -358,8 +376,8 @@ __global__ void __launch_bounds__(kThreads, 1) pair_bwd_prep_pair_kernel(const _
             for (int y = 0; y < 4; ++y) {
               // tanh in fp32 (one MUFU each), everything after it as packed bf16x2 FMAs: m, SiLU' and g leave as bf16
               // anyway, and the epilogue is bound by the number of instructions it issues
-              const float h0 = __uint_as_float(r[8 * v + 2 * y]) + hbv[2 * y];          // u / 2
-              const float h1 = __uint_as_float(r[8 * v + 2 * y + 1]) + hbv[2 * y + 1];
+              const float h0 = __uint_as_float(r[8 * v + 2 * y]);  // (u + b_mid) / 2: the bias came through the MMA
+              const float h1 = __uint_as_float(r[8 * v + 2 * y + 1]);
               const uint32_t t2 = ptx::pack_bf16x2(ptx::tanh_approx(h0), ptx::tanh_approx(h1));
               const uint32_t h2 = ptx::pack_bf16x2(h0, h1);
               uint32_t m2 = ptx::hfma2_bf16(h2, t2, h2);                     // SiLU(u) = h (1 + tanh h)
@@ -419,6 +437,14 @@ __global__ void __launch_bounds__(kThreads, 1) pair_bwd_prep_pair_kernel(const _
     const int q = warp - kProdWarp0;
     const uint32_t lane_base = static_cast<uint32_t>(q * 32) << 16;
     unsigned char* stg = smem + Smem::stage;
+    {  // the constant K step of the A operand: element 0 = 1.0 (bf16), the other 15 = 0; 16 columns, written once
+      uint32_t one[16];
+#pragma unroll
+      for (int x = 0; x < 16; ++x) one[x] = x == 0 ? 0x00003F80u : 0u;
+      ptx::tmem_st_x16(tmem + lane_base + kColOne, one);
+      ptx::tmem_st_wait();
+      ptx::tc_fence_before();  // ordered before this warp's first "S chunk full" arrival, which the MMA warp waits for
+    }
     for (int it = 0; it < my_tiles; ++it) {
       const int64_t tile = tile_of(it);
       int64_t my_a = -1, my_b = -1;
