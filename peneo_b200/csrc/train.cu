@@ -377,50 +377,52 @@ __device__ __forceinline__ float dsilu_tanh(float x) {
   const float sg = fmaf(0.5f, t, 0.5f), oms = fmaf(-0.5f, t, 0.5f);
   return fmaf(x * sg, oms, sg);
 }
-__global__ void __launch_bounds__(128) gv_reduce_tile_kernel(const __nv_bfloat16* __restrict__ dS,
-                                                             const float* __restrict__ ab, int b, int n, int d, int i0,
-                                                             int i1, float* __restrict__ dab) {
-  const int f = 4 * threadIdx.x;  // blockDim.x = d / 4
-  const int it = i0 + blockIdx.y * kGvR, jt = blockIdx.x * kGvC;
-  const int ie = min(it + kGvR, i1), je = min(jt + kGvC, n);
-  if (je <= it) return;  // every pair of the tile has j < i
-  const int64_t ld = 2 * (int64_t)d;
-  const float* abd = ab + (int64_t)b * n * ld + f;
-  float* out = dab + (int64_t)b * n * ld + f;
-  const int p0 = row_start(i0, n);
+// One tile.  INTERIOR (every pair of the tile has i < ie, i <= j < je — all but the diagonal and the last row / column
+// of tiles): no predicates, addresses advance by constants.  Per element: h = a_i / 2 + b_j / 2 (the halves are formed
+// once per row / column), t = tanh(h), SiLU'(2h) = sg (1 + h (1 - t)) with sg = (1 + t) / 2.
+template <bool INTERIOR>
+__device__ __forceinline__ void gv_tile(const __nv_bfloat16* __restrict__ dS, const float* __restrict__ abd,
+                                        float* __restrict__ out, int n, int d, int64_t ld, int p0, int it, int jt, int ie,
+                                        int je) {
   const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
   // the 8 pairs (i, jt .. jt + 7) of row i: 8-byte loads, zero outside the triangle / the document
   auto load_row = [&](int i, uint2 (&v)[kGvC]) {
     // pair (i, j) lives at flat row row_start(i) + (j - i)
-    const __nv_bfloat16* src = dS + ((int64_t)(row_start(i, n) - p0) + (jt - i)) * d + f;
+    const __nv_bfloat16* src = dS + ((int64_t)(row_start(i, n) - p0) + (jt - i)) * d;
 #pragma unroll
     for (int c = 0; c < kGvC; ++c) {
-      const int j = jt + c;
-      v[c] = (i < ie && j >= i && j < je) ? *reinterpret_cast<const uint2*>(src + (int64_t)c * d) : make_uint2(0u, 0u);
+      if (INTERIOR) v[c] = *reinterpret_cast<const uint2*>(src + c * d);
+      else v[c] = (i < ie && jt + c >= i && jt + c < je) ? *reinterpret_cast<const uint2*>(src + (int64_t)c * d) : make_uint2(0u, 0u);
     }
   };
   uint2 v[2][kGvC];
   load_row(it, v[0]);
-  float4 bj[kGvC], cs[kGvC];
+  float4 hb[kGvC], cs[kGvC];
 #pragma unroll
   for (int c = 0; c < kGvC; ++c) {
-    bj[c] = (jt + c < je) ? *reinterpret_cast<const float4*>(abd + (int64_t)(jt + c) * ld + d) : zero4;
+    const float4 b4 = (INTERIOR || jt + c < je) ? *reinterpret_cast<const float4*>(abd + (int64_t)(jt + c) * ld + d) : zero4;
+    hb[c] = make_float4(0.5f * b4.x, 0.5f * b4.y, 0.5f * b4.z, 0.5f * b4.w);
     cs[c] = zero4;
   }
+  auto gvf = [](uint32_t ds_bits, float ha, float hbv) {
+    const float h = ha + hbv;
+    const float t = ptx::tanh_approx(h);
+    const float sg = fmaf(0.5f, t, 0.5f);
+    return __uint_as_float(ds_bits) * sg * fmaf(h, 1.f - t, 1.f);
+  };
 #pragma unroll
   for (int r = 0; r < kGvR; ++r) {
     const int i = it + r;
     if (r + 1 < kGvR) load_row(i + 1, v[(r + 1) & 1]);  // next row in flight while this one is reduced
-    if (i < ie) {
-      const float4 ai = *reinterpret_cast<const float4*>(abd + (int64_t)i * ld);
+    if (INTERIOR || i < ie) {
+      const float4 a4 = *reinterpret_cast<const float4*>(abd + (int64_t)i * ld);
+      const float4 ha = make_float4(0.5f * a4.x, 0.5f * a4.y, 0.5f * a4.z, 0.5f * a4.w);
       float4 rs = zero4;
 #pragma unroll
       for (int c = 0; c < kGvC; ++c) {
         const uint2 w = v[r & 1][c];
-        const float gx = __uint_as_float(w.x << 16) * dsilu_tanh(ai.x + bj[c].x);
-        const float gy = __uint_as_float(w.x & 0xFFFF0000u) * dsilu_tanh(ai.y + bj[c].y);
-        const float gz = __uint_as_float(w.y << 16) * dsilu_tanh(ai.z + bj[c].z);
-        const float gw = __uint_as_float(w.y & 0xFFFF0000u) * dsilu_tanh(ai.w + bj[c].w);
+        const float gx = gvf(w.x << 16, ha.x, hb[c].x), gy = gvf(w.x & 0xFFFF0000u, ha.y, hb[c].y);
+        const float gz = gvf(w.y << 16, ha.z, hb[c].z), gw = gvf(w.y & 0xFFFF0000u, ha.w, hb[c].w);
         rs.x += gx, rs.y += gy, rs.z += gz, rs.w += gw;
         cs[c].x += gx, cs[c].y += gy, cs[c].z += gz, cs[c].w += gw;
       }
@@ -429,7 +431,21 @@ __global__ void __launch_bounds__(128) gv_reduce_tile_kernel(const __nv_bfloat16
   }
 #pragma unroll
   for (int c = 0; c < kGvC; ++c)
-    if (jt + c < je && jt + c >= it) atomicAdd(reinterpret_cast<float4*>(out + (int64_t)(jt + c) * ld + d), cs[c]);
+    if (INTERIOR || (jt + c < je && jt + c >= it)) atomicAdd(reinterpret_cast<float4*>(out + (int64_t)(jt + c) * ld + d), cs[c]);
+}
+__global__ void __launch_bounds__(128, 4) gv_reduce_tile_kernel(const __nv_bfloat16* __restrict__ dS,
+                                                            const float* __restrict__ ab, int b, int n, int d, int i0,
+                                                            int i1, float* __restrict__ dab) {
+  const int f = 4 * threadIdx.x;  // blockDim.x = d / 4
+  const int it = i0 + blockIdx.y * kGvR, jt = blockIdx.x * kGvC;
+  const int ie = min(it + kGvR, i1), je = min(jt + kGvC, n);
+  if (je <= it) return;  // every pair of the tile has j < i
+  const int64_t ld = 2 * (int64_t)d;
+  const float* abd = ab + (int64_t)b * n * ld + f;
+  float* out = dab + (int64_t)b * n * ld + f;
+  const int p0 = row_start(i0, n);
+  if (it + kGvR <= i1 && jt + kGvC <= n && it + kGvR - 1 <= jt) gv_tile<true>(dS + f, abd, out, n, d, ld, p0, it, jt, ie, je);
+  else gv_tile<false>(dS + f, abd, out, n, d, ld, p0, it, jt, ie, je);
 }
 
 constexpr int kD16 = 384;
