@@ -231,18 +231,35 @@ def k2_mean_ms(pipe):
 
 
 def k3_leg(dec, xs_dev, n_eff, dev, iters=12):
-    """The stand-alone spot-extraction kernel K3 (peneo_decode_spots: what decode_peneo / sample_decode_peneo run on
-    logits a caller already holds; the serving pipeline fuses this step into K2's epilogue instead).  Four rotating
-    logits batches of 234 MB each (> the 126 MB L2), CUDA events around the kernel alone."""
-    from peneo_b200 import decode
+    """The stand-alone spot-extraction kernel K3 (peneo_decode_spots: what the pipeline runs after K2 and what
+    decode_peneo / sample_decode_peneo run on logits a caller already holds).  Four rotating logits batches of 234 MB
+    each (> the 126 MB L2); the launches are enqueued back to back through the C ABI (no host synchronisation in
+    between, so the events bracket the workspace memset + kernel and not a launch gap on an idle GPU)."""
+    from peneo_b200 import _lib, decode
+    from peneo_b200.ops import _TORCH_DT, _stream, shaking_len
 
+    lib = _lib.load()
     with torch.no_grad():
         batches = [dec(x)[:5] for x in xs_dev[:4]]
+    ins = [decode._as_batched_inputs(b)[0] for b in batches]
+    b = ins[0][0].shape[0]
+    cap = min(shaking_len(n_eff), max(8 * n_eff, 1024))
+    spot_p = torch.empty(b * 5 * cap, dtype=torch.int32, device=dev)
+    spot_tag, spot_score = torch.empty_like(spot_p), torch.empty(b * 5 * cap, dtype=torch.float32, device=dev)
+    counts = torch.empty(b * 5, dtype=torch.int32, device=dev)
+    ws = torch.empty(max(16, lib.peneo_decode_spots_workspace_bytes(b, n_eff)), dtype=torch.uint8, device=dev)
     ev = []
     for it in range(3 + iters):
         if it == 3:
             ev.clear()
-        decode.device_decode_async(batches[it % len(batches)], n_eff, k3_events=ev).finish()
+        e = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        x = ins[it % len(ins)]
+        e[0].record(torch.cuda.current_stream(dev))
+        _lib.check(lib.peneo_decode_spots(b, n_eff, _lib.ptrs5(x), _TORCH_DT[x[0].dtype], cap, spot_p.data_ptr(),
+                                          spot_tag.data_ptr(), spot_score.data_ptr(), counts.data_ptr(), ws.data_ptr(),
+                                          _stream(dev)), "peneo_decode_spots")
+        e[1].record(torch.cuda.current_stream(dev))
+        ev.append(e)
     torch.cuda.synchronize()
     return sum(a.elapsed_time(b) for a, b in ev) / len(ev)
 

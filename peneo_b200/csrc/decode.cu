@@ -10,8 +10,7 @@
 
 namespace peneo {
 
-constexpr int kSpotChunk = 4096;     // pairs per CTA
-constexpr int kSpotWarpPairs = 512;  // pairs per warp (8 warps)
+constexpr int kSpotWarpPairs = 512;  // pairs per warp chunk (8 warps = 4096 pairs per CTA)
 
 // ------------------------------------------------------------------------------------------------
 // K3
@@ -38,8 +37,7 @@ struct SpotArgs {
   int32_t* spot_tag;
   float* spot_score;
   int32_t* counts;
-  int32_t* ticket;  // [batch*5]
-  int32_t* status;  // [batch*5*chunks] : inclusive prefix + 1, 0 = not ready
+  int32_t* status;  // [batch*5*chunks] : (value << 2) | flag, 0 = not ready
 };
 
 // fp32 logits, 16-byte aligned document: one warp iteration scans 128 pairs, 4 consecutive pairs per lane, read as
@@ -86,25 +84,25 @@ __device__ __forceinline__ int scan_pairs_vec4(const float* __restrict__ doc, in
   return cnt;
 }
 
+// One WARP per 512 consecutive pairs of one (document, head) list; the warps of a CTA are independent (no block-wide
+// barrier): scan -> publish the warp's count -> decoupled look-back over the preceding warp chunks of the list ->
+// write the spots at the exclusive prefix.  Warp chunk w of a list runs in CTA w / 8 (blockIdx.x), i.e. chunks start
+// in index order (CTAs are dispatched in block-index order, the assumption CUB's single-pass scan makes as well), so
+// the look-back never waits for a warp that is not resident yet.
 template <int DT>
 __global__ void __launch_bounds__(256) decode_spots_kernel(const SpotArgs a) {
   __shared__ int32_t buf_p[8][kSpotWarpPairs];
   __shared__ float buf_s[8][kSpotWarpPairs];
   __shared__ uint8_t buf_t[8][kSpotWarpPairs];
-  __shared__ int32_t wcount[8];
-  __shared__ int32_t s_chunk, s_base;
   const int h = blockIdx.y, b = blockIdx.z, list = b * kNumHeads + h;
   const int lane = threadIdx.x % 32, warp = threadIdx.x / 32;
-  // chunks are claimed in start order so the chained prefix below can never wait on a CTA that
-  // has not been scheduled
-  if (threadIdx.x == 0) s_chunk = atomicAdd(&a.ticket[list], 1);
-  __syncthreads();
-  const int chunk = s_chunk;
+  const int chunk = blockIdx.x * 8 + warp;  // warp chunk inside the list
+  if (chunk >= a.chunks) return;
   const int C = head_classes(h);
   const char* base = static_cast<const char*>(a.in[h]);
   const int64_t doc_row0 = (int64_t)b * a.pairs;
   int cnt = 0;
-  const int p0 = chunk * kSpotChunk + warp * kSpotWarpPairs;
+  const int p0 = chunk * kSpotWarpPairs;
   bool scanned = false;
   if constexpr (DT == PENEO_DT_F32) {
     const float* doc = reinterpret_cast<const float*>(base) + doc_row0 * C;
@@ -145,47 +143,34 @@ __global__ void __launch_bounds__(256) decode_spots_kernel(const SpotArgs a) {
     }
     cnt += __popc(mask);
   }
-  if (lane == 0) wcount[warp] = cnt;
-  __syncthreads();
-  if (warp == 0) {
-    // Decoupled look-back (single-pass scan): publish this chunk's own count first, then walk back over the
-    // predecessors 32 at a time, adding their counts until one that already knows its inclusive prefix.
-    // status word: (value << 2) | flag, flag 1 = chunk count, 2 = inclusive prefix, 0 = nothing yet.
-    int total = 0;
-    for (int w = 0; w < 8; ++w) total += wcount[w];
-    int32_t* st = a.status + (int64_t)list * a.chunks;
-    if (lane == 0 && chunk + 1 < a.chunks) {
-      __threadfence();
-      atomicExch(&st[chunk], (total << 2) | 1);
-    }
-    int prefix = 0, look = chunk - 1;
-    while (look >= 0) {
-      const int idx = look - lane;  // lane 0 = nearest predecessor; before the first chunk: prefix 0
-      const int v = idx >= 0 ? *reinterpret_cast<volatile int32_t*>(&st[idx]) : 2;
-      const unsigned ready = __ballot_sync(0xffffffffu, v != 0);
-      const unsigned is_p = __ballot_sync(0xffffffffu, (v & 3) == 2);
-      const int first_p = is_p ? __ffs(is_p) - 1 : 32;
-      const unsigned need = first_p >= 31 ? 0xffffffffu : ((1u << (first_p + 1)) - 1u);
-      if ((ready & need) != need) continue;  // a predecessor inside the window has not published yet
-      int contrib = lane <= first_p ? (v >> 2) : 0;
-      for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, o);
-      prefix += contrib;
-      if (first_p < 32) break;
-      look -= 32;
-    }
-    if (lane == 0) {
-      __threadfence();
-      atomicExch(&st[chunk], ((prefix + total) << 2) | 2);
-      if (chunk == a.chunks - 1) a.counts[list] = prefix + total;
-      s_base = prefix;
-    }
+  // Decoupled look-back (single-pass scan): publish this chunk's own count first, then walk back over the
+  // predecessors 32 at a time, adding their counts until one that already knows its inclusive prefix.
+  // status word: (value << 2) | flag, flag 1 = chunk count, 2 = inclusive prefix, 0 = nothing yet.
+  int32_t* st = a.status + (int64_t)list * a.chunks;
+  if (lane == 0 && chunk + 1 < a.chunks) atomicExch(&st[chunk], (cnt << 2) | (chunk == 0 ? 2 : 1));
+  int prefix = 0, look = chunk - 1;
+  while (look >= 0) {
+    const int idx = look - lane;  // lane 0 = nearest predecessor; before the first chunk: prefix 0
+    const int v = idx >= 0 ? *reinterpret_cast<volatile int32_t*>(&st[idx]) : 2;
+    const unsigned ready = __ballot_sync(0xffffffffu, v != 0);
+    const unsigned is_p = __ballot_sync(0xffffffffu, (v & 3) == 2);
+    const int first_p = is_p ? __ffs(is_p) - 1 : 32;
+    const unsigned need = first_p >= 31 ? 0xffffffffu : ((1u << (first_p + 1)) - 1u);
+    if ((ready & need) != need) continue;  // a predecessor inside the window has not published yet
+    int contrib = lane <= first_p ? (v >> 2) : 0;
+    for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, o);
+    prefix += contrib;
+    if (first_p < 32) break;
+    look -= 32;
   }
-  __syncthreads();
-  int off = s_base;
-  for (int w = 0; w < warp; ++w) off += wcount[w];
+  if (lane == 0) {
+    if (chunk > 0 && chunk + 1 < a.chunks) atomicExch(&st[chunk], ((prefix + cnt) << 2) | 2);
+    if (chunk == a.chunks - 1) a.counts[list] = prefix + cnt;
+  }
+  __syncwarp();  // (the spot buffers of this warp were written by all its lanes)
   const int64_t out0 = (int64_t)list * a.cap;
   for (int r = lane; r < cnt; r += 32) {
-    const int dst = off + r;
+    const int dst = prefix + r;
     if (dst < a.cap) {
       a.spot_p[out0 + dst] = buf_p[warp][r];
       a.spot_tag[out0 + dst] = buf_t[warp][r];
@@ -196,8 +181,8 @@ __global__ void __launch_bounds__(256) decode_spots_kernel(const SpotArgs a) {
 
 size_t decode_spots_workspace_bytes(int batch, int n) {
   const int64_t pairs = pair_count(n);
-  const int64_t chunks = (pairs + kSpotChunk - 1) / kSpotChunk;
-  return static_cast<size_t>((int64_t)batch * kNumHeads * (1 + chunks) * sizeof(int32_t));
+  const int64_t chunks = (pairs + kSpotWarpPairs - 1) / kSpotWarpPairs;
+  return static_cast<size_t>((int64_t)batch * kNumHeads * chunks * sizeof(int32_t));
 }
 
 int launch_decode_spots(int batch, int n, const void* const in[kNumHeads], int in_dtype, int cap, int32_t* spot_p,
@@ -208,13 +193,12 @@ int launch_decode_spots(int batch, int n, const void* const in[kNumHeads], int i
   SpotArgs a{};
   for (int h = 0; h < kNumHeads; ++h) a.in[h] = in[h];
   a.batch = batch, a.n = n, a.pairs = static_cast<int32_t>(pair_count(n)), a.cap = cap;
-  a.chunks = (a.pairs + kSpotChunk - 1) / kSpotChunk;
+  a.chunks = (a.pairs + kSpotWarpPairs - 1) / kSpotWarpPairs;  // warp chunks per list
   a.spot_p = spot_p, a.spot_tag = spot_tag, a.spot_score = spot_score, a.counts = counts;
-  a.ticket = static_cast<int32_t*>(ws);
-  a.status = a.ticket + (int64_t)batch * kNumHeads;
+  a.status = static_cast<int32_t*>(ws);
   PENEO_CUDA_TRY(cudaMemsetAsync(ws, 0, decode_spots_workspace_bytes(batch, n), st));
   PENEO_REQUIRE(batch <= 65535, "decode_spots: batch too large for one launch");
-  dim3 grid(a.chunks, kNumHeads, batch);
+  dim3 grid((a.chunks + 7) / 8, kNumHeads, batch);
   switch (in_dtype) {
     case PENEO_DT_F32: decode_spots_kernel<PENEO_DT_F32><<<grid, 256, 0, st>>>(a); break;
     case PENEO_DT_BF16: decode_spots_kernel<PENEO_DT_BF16><<<grid, 256, 0, st>>>(a); break;
