@@ -16,6 +16,7 @@ outside the timed region, so that about N spots per head survive (SURVEY.md §8d
 from __future__ import annotations
 
 import argparse
+import gc
 import json
 import os
 import subprocess
@@ -317,10 +318,11 @@ def sweep_leg(dev, rank, world, dist, peaks, clocks, steps=10, warmup=3):
     return out
 
 
-def train_leg(dev, rank, local_rank, world, dist, peaks, steps=15, warmup=6):
+def train_leg(dev, rank, local_rank, world, dist, peaks, steps=20, warmup=12):
     """Fine-tuning step of the decoder: forward + fused loss + backward (+ NCCL gradient all-reduce under torchrun, DDP
     semantics as in the reference's HF Trainer: per-rank batch-global weighted-mean loss, averaged gradients).  Two
-    shapes: the headline shape (seq 512, batch 32 per GPU, hidden 768) and BASELINE configs[2] (LiLT: hidden states of
+    shapes (12 warm-up steps: DDP instruments its first 10 iterations with host-GPU synchronisations and logs once after
+    the tenth, a ~40 ms host stall): the headline shape (seq 512, batch 32 per GPU, hidden 768) and BASELINE configs[2] (LiLT: hidden states of
     width 960, seq 1024, batch 4 per GPU, SIBR-shaped documents).  Per GPU, against 3 x F_heads."""
     from peneo_b200 import PEneoDecoderB200, synth
 
@@ -337,7 +339,10 @@ def train_leg(dev, rank, local_rank, world, dist, peaks, steps=15, warmup=6):
         dec = dec.to(dev).eval()  # eval(): the decoder's dropout off, like every parity test of the gradients
         module = dec
         if world > 1:
-            dec = torch.nn.parallel.DistributedDataParallel(dec, device_ids=[local_rank])
+            # broadcast_buffers=False (HF Trainer: ddp_broadcast_buffers=False): the decoder's only buffers are the constant
+            # class weights; with the default the DDP forward synchronises host and GPU every step (measured: the host
+            # sits 27 ms in DDP.forward), so the host cannot run ahead and any host hiccup stalls both GPUs
+            dec = torch.nn.parallel.DistributedDataParallel(dec, device_ids=[local_rank], broadcast_buffers=False)
         x = synth.hidden_states(batch, n, hin, doc_id0=1000 * rank).to(dev).requires_grad_(True)
         docs = [synth.make_document(n, doc_id=1000 * rank + i, style=style) for i in range(batch)]
         tags = [torch.stack([d.tags()[k] for d in docs]).to(dev) for k in range(5)]
@@ -351,16 +356,106 @@ def train_leg(dev, rank, local_rank, world, dist, peaks, steps=15, warmup=6):
 
         for _ in range(warmup):
             step()
+        gc.collect()
+        gc.freeze()  # (as in the serving legs: a full CPython collection takes ~45 ms with torch loaded; one was seen
+        #              inside a 2-GPU step, where it stalled both ranks through the all-reduce)
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        marks = []  # one event per step: the median step is reported next to the mean (a single host stall in a
+        #             short DDP run — the host cannot run far ahead of the GPU there — moves the mean by several ms)
         e0.record()
         for _ in range(steps):
             loss = step()
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            marks.append(ev)
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / steps
+        per_step = sorted(a.elapsed_time(b) for a, b in zip([e0] + marks[:-1], marks))
+        ms_median = per_step[len(per_step) // 2]
+        if os.environ.get("PENEO_BENCH_DEBUG"):
+            sys.stderr.write(f"[train {name[:10]} rank {rank}] per-step device ms (sorted): " + " ".join(f"{v:.2f}" for v in per_step) + "\n")
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        tf = batch * heads_flops_pairs(pairs) / (k2_ms * 1e-3) / 1e12
+        fr = tensor_fracs(tf, peaks, clocks)
+        out.append({"seq_len": seq_len, "pair_dim": n_eff, "batch_per_gpu": batch, "steps": steps,
+                    "docs_per_s": batch * steps * world / (ms * 1e-3), "ms_per_step": ms / steps,
+                    "k2_ms": k2_ms, "k2_tflops": tf, "frac_burst": fr["frac_burst"], "frac_sustained": fr["frac_sustained"],
+                    "fused_spots": pipe.fused_spots,
+                    "spots_per_head_per_doc": float(dd.counts.mean())})
+        del pipe, dec, xs
+        torch.cuda.empty_cache()
+    return out
+
+
+def train_leg(dev, rank, local_rank, world, dist, peaks, steps=20, warmup=12):
+    """Fine-tuning step of the decoder: forward + fused loss + backward (+ NCCL gradient all-reduce under torchrun, DDP
+    semantics as in the reference's HF Trainer: per-rank batch-global weighted-mean loss, averaged gradients).  Two
+    shapes (12 warm-up steps: DDP instruments its first 10 iterations with host-GPU synchronisations and logs once after
+    the tenth, a ~40 ms host stall): the headline shape (seq 512, batch 32 per GPU, hidden 768) and BASELINE configs[2] (LiLT: hidden states of
+    width 960, seq 1024, batch 4 per GPU, SIBR-shaped documents).  Per GPU, against 3 x F_heads."""
+    from peneo_b200 import PEneoDecoderB200, synth
+
+    out = []
+    for name, hin, seq_len, batch, style in (("seq512_b32_h768", 768, 512, 32, "rfund"),
+                                             ("configs[2]: LiLT hin 960, seq 1024, b4", 960, 1024, 4, "sibr")):
+        n = seq_len - 1
+
+        class C(Cfg):
+            inference_mode = False
+
+        dec = PEneoDecoderB200(C, hin)
+        dec.load_state_dict(synth.init_decoder_state(hin=hin, seed=0))
+        dec = dec.to(dev).eval()  # eval(): the decoder's dropout off, like every parity test of the gradients
+        module = dec
+        if world > 1:
+            # broadcast_buffers=False (HF Trainer: ddp_broadcast_buffers=False): the decoder's only buffers are the constant
+            # class weights; with the default the DDP forward synchronises host and GPU every step (measured: the host
+            # sits 27 ms in DDP.forward), so the host cannot run ahead and any host hiccup stalls both GPUs
+            dec = torch.nn.parallel.DistributedDataParallel(dec, device_ids=[local_rank], broadcast_buffers=False)
+        x = synth.hidden_states(batch, n, hin, doc_id0=1000 * rank).to(dev).requires_grad_(True)
+        docs = [synth.make_document(n, doc_id=1000 * rank + i, style=style) for i in range(batch)]
+        tags = [torch.stack([d.tags()[k] for d in docs]).to(dev) for k in range(5)]
+
+        def step():
+            module.zero_grad(set_to_none=True)
+            x.grad = None
+            o = dec(x, None, *tags)
+            o.loss.backward()
+            return o.loss
+
+        for _ in range(warmup):
+            step()
+        gc.collect()
+        gc.freeze()  # (as in the serving legs: a full CPython collection takes ~45 ms with torch loaded; one was seen
+        #              inside a 2-GPU step, where it stalled both ranks through the all-reduce)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        dbg = [] if os.environ.get("PENEO_BENCH_DEBUG") else None  # per-step (host ms, device event) trace to stderr
+        e0.record()
+        for _ in range(steps):
+            th = time.perf_counter()
+            loss = step()
+            if dbg is not None:
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record()
+                dbg.append((time.perf_counter() - th, ev))
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        if dbg:
+            prev = e0
+            for i, (h, ev) in enumerate(dbg):
+                sys.stderr.write(f"[train {name[:10]} rank {rank}] step {i}: device {prev.elapsed_time(ev):7.2f} ms, host {h * 1e3:7.2f} ms\n")
+                prev = ev
         if world > 1:
             t = torch.tensor([ms], device=dev, dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -368,7 +463,8 @@ def train_leg(dev, rank, local_rank, world, dist, peaks, steps=15, warmup=6):
         tf = 3.0 * heads_flops_doc(n, hin) * batch / (ms * 1e-3) / 1e12
         sust = peaks.get("bf16_tflops_sustained", 1427.8)
         out.append({"shape": name, "seq_len": seq_len, "hin": hin, "batch_per_gpu": batch, "steps": steps,
-                    "ms_per_step": ms, "docs_per_s": world * batch / (ms * 1e-3), "loss": float(loss.detach()),
+                    "ms_per_step": ms, "ms_per_step_median": ms_median, "docs_per_s": world * batch / (ms * 1e-3),
+                    "loss": float(loss.detach()),
                     "tflops_vs_3F_per_gpu": tf, "frac_sustained": tf / sust, "frac_burst": tf / peaks.get("bf16_tflops", 1687.9),
                     "collective": f"NCCL all-reduce of {sum(p.numel() for p in module.parameters())} decoder gradients (DDP)"
                                   if world > 1 else "none (1 GPU)",

@@ -24,7 +24,7 @@ def main():
     ap.add_argument("--batch", type=int, default=4)
     ap.add_argument("--precision", default="bf16")
     ap.add_argument("--steps", type=int, default=30)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=12)  # > 10: DDP synchronises host and GPU in its first 10 iterations
     ap.add_argument("--hin", type=int, default=768, help="width of the backbone output (960 = LiLT, BASELINE configs[2])")
     ap.add_argument("--no-fused-loss", action="store_true", help="separate loss kernels + explicit dlogits (A/B)")
     ap.add_argument("--no-shrink", action="store_true", help="peneo_decoder_shrink = False (D = hin): unfused tensor-core route")
@@ -54,7 +54,8 @@ def main():
     if world > 1:  # what HF Trainer does for the reference: DDP, one process per GPU, gradients averaged over NCCL
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-        dec = torch.nn.parallel.DistributedDataParallel(dec, device_ids=[local_rank])
+        # broadcast_buffers=False: only constant buffers (class weights); the default makes DDP.forward a host-GPU sync
+        dec = torch.nn.parallel.DistributedDataParallel(dec, device_ids=[local_rank], broadcast_buffers=False)
     x = synth.hidden_states(args.batch, n, args.hin, doc_id0=1000 * rank).cuda().requires_grad_(True)
     docs = [synth.make_document(n, doc_id=1000 * rank + i, style="sibr") for i in range(args.batch)]
     tags = [torch.stack([d.tags()[k] for d in docs]).cuda() for k in range(5)]
@@ -68,6 +69,10 @@ def main():
 
     for _ in range(args.warmup):
         step()
+    import gc
+
+    gc.collect()
+    gc.freeze()  # a full CPython collection (~45 ms with torch loaded) inside a step stalls every rank of a DDP job
     torch.cuda.synchronize()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
     ev[0].record()
