@@ -470,6 +470,33 @@ def test_training_bf16_tensor_core_backward_at_larger_n(monkeypatch):
     assert not bad, bad
 
 
+def test_training_full_size_chunks_agree_with_small_chunks(monkeypatch):
+    """The default chunking of the bf16 backward at the benchmark size (524 288-pair chunks: 6 x seq-512 documents =
+    784 896 pairs = two chunks, the second one ragged) against 100 000-pair chunks of the same step: the gradients
+    must not depend on where the chunks end (differences: fp32 atomics order only)."""
+    n, b = 511, 6
+    sd = synth.init_decoder_state(seed=3, trained_like=True)
+    x = synth.hidden_states(b, n, 768, doc_id0=21).cuda()
+    docs = [synth.make_document(n, doc_id=900 + i) for i in range(b)]
+    tags = [torch.stack([d.tags()[k] for d in docs]).cuda() for k in range(5)]
+    res = []
+    for rows in (None, "100000"):
+        if rows:
+            monkeypatch.setenv("PENEO_BWD_CHUNK_ROWS", rows)
+        dec = PEneoDecoderB200(Cfg(768, inference_mode=False, precision="bf16"), 768)
+        dec.load_state_dict(sd)
+        dec = dec.cuda().eval()
+        res.append(_train_step(dec, x, tags))
+    (o1, dx1, g1), (o2, dx2, g2) = res
+    assert abs(o1.loss.item() - o2.loss.item()) <= 1e-6 * max(1.0, abs(o2.loss.item()))
+    worst = {"dx": rel_err(dx1, dx2.cpu())}
+    for key in g2:
+        worst[key] = rel_err(g1[key], g2[key].cpu())
+    print({k: f"{v:.2e}" for k, v in worst.items()})
+    bad = {k: v for k, v in worst.items() if v > 1e-3}
+    assert not bad, bad
+
+
 def test_training_rows_cross_chunk_boundaries(monkeypatch):
     """Several pair-row chunks per document in the backward pass (chunk size forced down through the
     PENEO_BWD_CHUNK_ROWS test hook); gradients must not depend on the chunking."""
