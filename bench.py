@@ -231,7 +231,7 @@ def k2_mean_ms(pipe):
     return sum(a.elapsed_time(b) for a, b in pipe.k2_events) / len(pipe.k2_events)
 
 
-def k3_leg(dec, xs_dev, n_eff, dev, iters=12):
+def k3_leg(dec, xs_dev, n_eff, dev, iters=24):
     """The stand-alone spot-extraction kernel K3 (peneo_decode_spots: what the pipeline runs after K2 and what
     decode_peneo / sample_decode_peneo run on logits a caller already holds).  Four rotating logits batches of 234 MB
     each (> the 126 MB L2); the launches are enqueued back to back through the C ABI (no host synchronisation in
@@ -250,6 +250,8 @@ def k3_leg(dec, xs_dev, n_eff, dev, iters=12):
     counts = torch.empty(b * 5, dtype=torch.int32, device=dev)
     ws = torch.empty(max(16, lib.peneo_decode_spots_workspace_bytes(b, n_eff)), dtype=torch.uint8, device=dev)
     ev = []
+    torch.cuda.synchronize()
+    time.sleep(0.25)  # the board comes out of the power-capped K2 loop at ~1.5 GHz; K3 is timed alone, at its own clocks
     for it in range(3 + iters):
         if it == 3:
             ev.clear()
@@ -378,84 +380,6 @@ def train_leg(dev, rank, local_rank, world, dist, peaks, steps=20, warmup=12):
         ms_median = per_step[len(per_step) // 2]
         if os.environ.get("PENEO_BENCH_DEBUG"):
             sys.stderr.write(f"[train {name[:10]} rank {rank}] per-step device ms (sorted): " + " ".join(f"{v:.2f}" for v in per_step) + "\n")
-        if world > 1:
-            t = torch.tensor([ms], device=dev, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        tf = batch * heads_flops_pairs(pairs) / (k2_ms * 1e-3) / 1e12
-        fr = tensor_fracs(tf, peaks, clocks)
-        out.append({"seq_len": seq_len, "pair_dim": n_eff, "batch_per_gpu": batch, "steps": steps,
-                    "docs_per_s": batch * steps * world / (ms * 1e-3), "ms_per_step": ms / steps,
-                    "k2_ms": k2_ms, "k2_tflops": tf, "frac_burst": fr["frac_burst"], "frac_sustained": fr["frac_sustained"],
-                    "fused_spots": pipe.fused_spots,
-                    "spots_per_head_per_doc": float(dd.counts.mean())})
-        del pipe, dec, xs
-        torch.cuda.empty_cache()
-    return out
-
-
-def train_leg(dev, rank, local_rank, world, dist, peaks, steps=20, warmup=12):
-    """Fine-tuning step of the decoder: forward + fused loss + backward (+ NCCL gradient all-reduce under torchrun, DDP
-    semantics as in the reference's HF Trainer: per-rank batch-global weighted-mean loss, averaged gradients).  Two
-    shapes (12 warm-up steps: DDP instruments its first 10 iterations with host-GPU synchronisations and logs once after
-    the tenth, a ~40 ms host stall): the headline shape (seq 512, batch 32 per GPU, hidden 768) and BASELINE configs[2] (LiLT: hidden states of
-    width 960, seq 1024, batch 4 per GPU, SIBR-shaped documents).  Per GPU, against 3 x F_heads."""
-    from peneo_b200 import PEneoDecoderB200, synth
-
-    out = []
-    for name, hin, seq_len, batch, style in (("seq512_b32_h768", 768, 512, 32, "rfund"),
-                                             ("configs[2]: LiLT hin 960, seq 1024, b4", 960, 1024, 4, "sibr")):
-        n = seq_len - 1
-
-        class C(Cfg):
-            inference_mode = False
-
-        dec = PEneoDecoderB200(C, hin)
-        dec.load_state_dict(synth.init_decoder_state(hin=hin, seed=0))
-        dec = dec.to(dev).eval()  # eval(): the decoder's dropout off, like every parity test of the gradients
-        module = dec
-        if world > 1:
-            # broadcast_buffers=False (HF Trainer: ddp_broadcast_buffers=False): the decoder's only buffers are the constant
-            # class weights; with the default the DDP forward synchronises host and GPU every step (measured: the host
-            # sits 27 ms in DDP.forward), so the host cannot run ahead and any host hiccup stalls both GPUs
-            dec = torch.nn.parallel.DistributedDataParallel(dec, device_ids=[local_rank], broadcast_buffers=False)
-        x = synth.hidden_states(batch, n, hin, doc_id0=1000 * rank).to(dev).requires_grad_(True)
-        docs = [synth.make_document(n, doc_id=1000 * rank + i, style=style) for i in range(batch)]
-        tags = [torch.stack([d.tags()[k] for d in docs]).to(dev) for k in range(5)]
-
-        def step():
-            module.zero_grad(set_to_none=True)
-            x.grad = None
-            o = dec(x, None, *tags)
-            o.loss.backward()
-            return o.loss
-
-        for _ in range(warmup):
-            step()
-        gc.collect()
-        gc.freeze()  # (as in the serving legs: a full CPython collection takes ~45 ms with torch loaded; one was seen
-        #              inside a 2-GPU step, where it stalled both ranks through the all-reduce)
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        dbg = [] if os.environ.get("PENEO_BENCH_DEBUG") else None  # per-step (host ms, device event) trace to stderr
-        e0.record()
-        for _ in range(steps):
-            th = time.perf_counter()
-            loss = step()
-            if dbg is not None:
-                ev = torch.cuda.Event(enable_timing=True)
-                ev.record()
-                dbg.append((time.perf_counter() - th, ev))
-        e1.record()
-        torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / steps
-        if dbg:
-            prev = e0
-            for i, (h, ev) in enumerate(dbg):
-                sys.stderr.write(f"[train {name[:10]} rank {rank}] step {i}: device {prev.elapsed_time(ev):7.2f} ms, host {h * 1e3:7.2f} ms\n")
-                prev = ev
         if world > 1:
             t = torch.tensor([ms], device=dev, dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)

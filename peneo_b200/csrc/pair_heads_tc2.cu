@@ -194,8 +194,13 @@ __global__ void __launch_bounds__(kThreads, 1)
         ptx::tc_fence_after();
         const uint32_t zt = tmem + kColZ + 16 * (hg & 1);
         const uint32_t mt = tmem + kColU + 128 * buf;
+#ifdef PENEO_K2_ABLATE_MMA2  // timing experiment only (wrong logits): how much of the tensor pipe the N = 16 GEMM takes
+        constexpr int kSteps2 = 0;
+#else
+        constexpr int kSteps2 = 8;
+#endif
 #pragma unroll
-        for (int ks = 0; ks < 8; ++ks) {
+        for (int ks = 0; ks < kSteps2; ++ks) {
           const uint32_t at = mt + 32 * (ks >> 1) + 8 * (ks & 1);  // m of columns [32 j, 32 j + 32) sits in TMEM columns [32 j, 32 j + 16)
           const uint64_t bd = ptx::umma_desc_sw128(o_base + os * kOStageBytes + (ks / 4) * 1024 + (ks % 4) * 32);
           ptx::umma_ts_2sm(zt, at, bd, idesc2, (cpos | ks) != 0);
