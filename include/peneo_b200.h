@@ -158,19 +158,31 @@ int peneo_pair_loss_bwd(int32_t batch, int32_t n, const float* const logits[PENE
  *   peneo_heads_loss_bwd      = peneo_pair_loss_bwd + peneo_heads_bwd without d loss / d logits ever existing in
  *     memory: the backward tiles compute it in registers from logits + tags + the normalisers in loss_workspace
  *     (grad_out6 as in peneo_pair_loss_bwd), and reduce db_out on the fly.
- * loss_workspace: peneo_pair_loss_workspace_bytes(batch, n), written by the forward call, read by the backward call. */
+ * loss_workspace: peneo_pair_loss_workspace_bytes(batch, n), written by the forward call, read by the backward call.
+ *
+ * `saved` (optional, NULL = recompute): activations the forward call stores as they pass through its registers so that
+ * the backward call needs no recompute GEMM (what autograd keeps for model/peneo_decoder.py:256-271, in bf16):
+ *   h  bf16 [batch * P, 5 * d]  pre-activations (W_mid s + b_mid) / 2 of the five hidden layers; the backward call
+ *                               OVERWRITES it with the gradient G, so one forward's buffers serve one backward;
+ *   s  bf16 [batch * P, d]      pair representations SiLU(a_i + b_j).
+ * 4.5 KB per pair (18.8 GB for 32 seq-512 documents): pass NULL when that does not fit — the backward then regenerates
+ * both on the tensor cores chunk by chunk (~3 GB of scratch). */
+typedef struct peneo_saved_act {
+  void* h;
+  void* s;
+} peneo_saved_act;
 int peneo_fused_loss_supported(const peneo_dims* dims, int prec);
 int peneo_pair_heads_loss_fwd(const peneo_dims* dims, int prec, const void* pack, const void* ab, int32_t batch, int32_t n,
                               float* const logits[PENEO_NUM_HEADS], const int64_t* const tags[PENEO_NUM_HEADS],
                               const float* class_w_host, const float* ratio_host, float* out6, void* loss_workspace,
-                              const peneo_dropout* dropout, void* stream);
+                              const peneo_dropout* dropout, void* stream, const peneo_saved_act* saved);
 /* (declared here, next to its forward half; the gradient structs are defined below) */
 struct peneo_grads;
 int peneo_heads_loss_bwd(const peneo_dims* dims, int prec, const void* pack, const void* x, int x_dtype,
                          int64_t x_row_stride, int32_t batch, int32_t n, const float* const logits[PENEO_NUM_HEADS],
                          const int64_t* const tags[PENEO_NUM_HEADS], const float* class_w_host, const float* ratio_host,
                          const float* grad_out6, const void* loss_workspace, const struct peneo_grads* grads, float* dx,
-                         void* workspace, const peneo_dropout* dropout, void* stream);
+                         void* workspace, const peneo_dropout* dropout, void* stream, const peneo_saved_act* saved);
 
 /* Same five sub-losses with online hard-example mining (num_hard_positive / num_hard_negative as in
  * PEneoConfig.peneo_ohem_num_positive / _negative; -1 = keep the whole side).  Reproduces the reference's

@@ -73,6 +73,12 @@ class Dropout(C.Structure):
     _fields_ = [("p", C.c_float), ("seed", C.c_uint64)]
 
 
+class SavedAct(C.Structure):
+    """peneo_saved_act: activations the fused forward stores for a backward pass without recompute (both or NULL)."""
+
+    _fields_ = [("h", C.c_void_p), ("s", C.c_void_p)]
+
+
 class Grads(C.Structure):
     _fields_ = Params._fields_
 
@@ -118,10 +124,11 @@ def load() -> C.CDLL:
                                         vp, PtrArray5, vp]
     lib.peneo_fused_loss_supported.argtypes = [C.POINTER(Dims), C.c_int]
     lib.peneo_pair_heads_loss_fwd.argtypes = [C.POINTER(Dims), C.c_int, vp, vp, i32, i32, PtrArray5, PtrArray5,
-                                              C.POINTER(C.c_float), C.POINTER(C.c_float), vp, vp, C.POINTER(Dropout), vp]
+                                              C.POINTER(C.c_float), C.POINTER(C.c_float), vp, vp, C.POINTER(Dropout), vp,
+                                              C.POINTER(SavedAct)]
     lib.peneo_heads_loss_bwd.argtypes = [C.POINTER(Dims), C.c_int, vp, vp, C.c_int, i64, i32, i32, PtrArray5, PtrArray5,
                                          C.POINTER(C.c_float), C.POINTER(C.c_float), vp, vp, C.POINTER(Grads), vp, vp,
-                                         C.POINTER(Dropout), vp]
+                                         C.POINTER(Dropout), vp, C.POINTER(SavedAct)]
     lib.peneo_pair_loss_ohem_workspace_bytes.restype = sz
     lib.peneo_pair_loss_ohem_workspace_bytes.argtypes = [i32, i32]
     lib.peneo_pair_loss_ohem_fwd.argtypes = [i32, i32, PtrArray5, PtrArray5, C.POINTER(C.c_float), C.POINTER(C.c_float),

@@ -280,7 +280,7 @@ int peneo_fused_loss_supported(const peneo_dims* dims, int prec) {
 int peneo_pair_heads_loss_fwd(const peneo_dims* dims, int prec, const void* pack, const void* ab, int32_t batch, int32_t n,
                               float* const logits[PENEO_NUM_HEADS], const int64_t* const tags[PENEO_NUM_HEADS],
                               const float* class_w_host, const float* ratio_host, float* out6, void* loss_workspace,
-                              const peneo_dropout* dropout, void* stream) {
+                              const peneo_dropout* dropout, void* stream, const peneo_saved_act* saved) {
   int rc;
   if ((rc = check_dims(dims)) != PENEO_OK || (rc = check_prec(dims, prec)) != PENEO_OK) return rc;
   PENEO_REQUIRE(peneo_fused_loss_supported(dims, prec), "pair_heads_loss_fwd: only the fused tcgen05 configuration "
@@ -294,6 +294,10 @@ int peneo_pair_heads_loss_fwd(const peneo_dims* dims, int prec, const void* pack
   for (int h = 0; h < kNumHeads; ++h) fl.tags[h] = tags[h];
   for (int c = 0; c < 3; ++c) fl.class_w[c] = class_w_host[c];
   fl.partial = pair_loss_partial_ptr(loss_workspace);
+  if (saved) {
+    PENEO_REQUIRE(saved->h && saved->s, "pair_heads_loss_fwd: saved->h and saved->s must both be given");
+    fl.save_h = static_cast<__nv_bfloat16*>(saved->h), fl.save_s = static_cast<__nv_bfloat16*>(saved->s);
+  }
   int grid = 0;
   if ((rc = launch_pair_heads_tc_pair(pack, pack_layout(*dims, prec), static_cast<const __nv_bfloat16*>(ab), batch, n, logits, st,
                                       drop.thresh ? &drop : nullptr, &fl, &grid)) != PENEO_OK)
@@ -305,7 +309,7 @@ int peneo_heads_loss_bwd(const peneo_dims* dims, int prec, const void* pack, con
                          int32_t batch, int32_t n, const float* const logits[PENEO_NUM_HEADS],
                          const int64_t* const tags[PENEO_NUM_HEADS], const float* class_w_host, const float* ratio_host,
                          const float* grad_out6, const void* loss_workspace, const peneo_grads* grads, float* dx,
-                         void* workspace, const peneo_dropout* dropout, void* stream) {
+                         void* workspace, const peneo_dropout* dropout, void* stream, const peneo_saved_act* saved) {
   int rc;
   if ((rc = check_dims(dims)) != PENEO_OK || (rc = check_prec(dims, prec)) != PENEO_OK) return rc;
   PENEO_REQUIRE(peneo_fused_loss_supported(dims, prec), "heads_loss_bwd: only the fused tcgen05 configuration; use "
@@ -326,6 +330,10 @@ int peneo_heads_loss_bwd(const peneo_dims* dims, int prec, const void* pack, con
   for (int c = 0; c < 3; ++c) fb.class_w[c] = class_w_host[c];
   fb.grad_out6 = grad_out6;
   fb.loss_final = pair_loss_final_ptr(loss_workspace);
+  if (saved) {
+    PENEO_REQUIRE(saved->h && saved->s, "heads_loss_bwd: saved->h and saved->s must both be given");
+    fb.save_h = static_cast<__nv_bfloat16*>(saved->h), fb.save_s = static_cast<__nv_bfloat16*>(saved->s);
+  }
   const DropSpec drop = make_drop(dropout);
   const float* no_dz[kNumHeads] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   return launch_heads_bwd(*dims, prec, pack, x, x_dtype, x_row_stride, batch, n, no_dz, *grads, dx, workspace,

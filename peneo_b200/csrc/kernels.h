@@ -41,6 +41,10 @@ struct FusedLossFwd {
   const int64_t* tags[kNumHeads];
   float class_w[3];
   double* partial;  // [5][grid][2]
+  // optional (both or none): the pre-activations (u + b_mid) / 2, bf16 [batch * P, 1920], and s, bf16 [batch * P, 384],
+  // saved for a backward pass without recompute (pair_bwd_elem.cu)
+  __nv_bfloat16* save_h = nullptr;
+  __nv_bfloat16* save_s = nullptr;
 };
 struct TileSpots;  // classify.cuh
 int launch_pair_heads_tc_pair(const void* pack, const PackLayout& L, const __nv_bfloat16* ab, int batch, int n,
@@ -68,7 +72,15 @@ struct FusedLossBwd {
   const double* loss_final;         // device: [5][2] = (sum w nll, sum w) of the forward loss (workspace of pair_loss_fwd)
   float ratio[kNumHeads], class_w[3];
   float* dbout[kNumHeads];          // db_out gradient buffers (accumulated into)
+  // optional (both or none): what the forward pass saved (FusedLossFwd::save_h / save_s); the backward then runs
+  // pair_bwd_elem.cu instead of T1 and turns save_h into G in place
+  __nv_bfloat16* save_h = nullptr;
+  __nv_bfloat16* save_s = nullptr;
 };
+// pair_bwd_elem.cu : T1e, the hidden-activation backward from saved pre-activations (in place: h -> G)
+int pair_bwd_elem_max_ctas();
+int launch_pair_bwd_elem(const void* pack, const PackLayout& L, int64_t g0, int rows, const FusedLossBwd& fused,
+                         __nv_bfloat16* hg, float* dwout_part, int* ctas_out, cudaStream_t st, const DropSpec* drop = nullptr);
 int launch_pair_bwd_prep_pair(const void* pack, const PackLayout& L, const __nv_bfloat16* ab, int n, int64_t g0, int rows,
                               const float* const dz[kNumHeads], const FusedLossBwd* fused, __nv_bfloat16* S,
                               __nv_bfloat16* G, float* dwout_part, cudaStream_t st, const DropSpec* drop = nullptr);

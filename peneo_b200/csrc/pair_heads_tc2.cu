@@ -30,7 +30,7 @@ namespace k2p {
 constexpr int D = 384;
 constexpr int kChunks = 15;       // 5 heads x 3 chunks of 128 mid features
 constexpr int kKChunks = 6;       // 384 / 64
-constexpr int kWStages = 8;
+constexpr int kWStages = 6;  // (8 before the h store tiles needed the room; 3 .. 8 stages measure the same)
 constexpr int kWStageBytes = 64 * 64 * 2;  // 8 KB: this CTA's 64 of the chunk's 128 rows
 constexpr int kOStages = 3;
 constexpr int kOStageBytes = 2 * 8 * 64 * 2;  // 2 KB: two K-blocks of [8 rows x 64] (this CTA's half of 16)
@@ -50,7 +50,8 @@ struct Smem {
   static constexpr int o = w + kWStages * kWStageBytes;
   static constexpr int stage = o + kOStages * kOStageBytes;
   static constexpr int bias = stage + 128 * kStageRowBytes;  // bias B-operand tiles (see kBiasTileBytes)
-  static constexpr int bout = bias + kBiasTiles * kBiasTileBytes;  // 20 floats
+  static constexpr int hstage = bias + kBiasTiles * kBiasTileBytes;  // SAVE: per epilogue warp one [32 rows x 64 B] TMA store tile (SWIZZLE_64B)
+  static constexpr int bout = hstage + kEpiWarps * 2048;  // 20 floats
   static constexpr int loss = bout + 128;                    // 40 doubles (LOSS instantiation)
   static constexpr int bars = loss + 320;
   static constexpr int total = bars + 512;
@@ -60,7 +61,8 @@ constexpr int bWFull = 0, bWEmpty = bWFull + kWStages, bOFull = bWEmpty + kWStag
               bUFull = bOEmpty + kOStages, bMReady = bUFull + 2, bZFull = bMReady + 2, bZFree = bZFull + 2, bSFull = bZFree + 2,
               bSFree = bSFull + kKChunks, bCount = bSFree + kKChunks;
 static_assert(bCount * 8 + 16 <= 512, "barrier area too small");
-static_assert(Smem::stage % 1024 == 0 && Smem::bias % 1024 == 0, "UMMA operand tiles need 1024-byte alignment");
+static_assert(Smem::stage % 1024 == 0 && Smem::bias % 1024 == 0 && Smem::hstage % 1024 == 0,
+              "UMMA operand / TMA store tiles need 1024-byte alignment");
 constexpr int kSmemBytes = Smem::total + 1024;
 static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
 
@@ -79,14 +81,20 @@ struct Args {
   const int64_t* tags[kNumHeads];  // int64 [batch*P]
   float class_w[3];
   double* loss_partial;            // [5][gridDim.x][2] : per-CTA (sum w nll, sum w), reduced by pair_loss_final_kernel
+  // SAVE instantiation (training, with LOSS): the pre-activations (u + b_mid) / 2 (bf16 [pairs, 1920]) and s (bf16
+  // [pairs, 384]) are stored as they pass through the registers of the epilogue / producer warps, so that the backward
+  // pass needs no recompute GEMM (pair_bwd_elem.cu)
+  __nv_bfloat16* save_h;
+  __nv_bfloat16* save_s;
   // SPOTS instantiation: no logits leave the SM; the epilogue classifies each pair (model/peneo_decoder.py:98-114) and
   // writes the few non-zero predictions into per-tile slots (classify.cuh), gathered in order by decode.cu
   TileSpots spots;
 };
 
-template <bool DROP, bool LOSS, bool SPOTS>
+template <bool DROP, bool LOSS, bool SPOTS, bool SAVE>
 __global__ void __launch_bounds__(kThreads, 1)
-    pair_heads_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmO, const Args a) {
+    pair_heads_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmO,
+                         const __grid_constant__ CUtensorMap tmH, const Args a) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);  // by offset: keeps the shared address space
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Smem::bars);
@@ -101,6 +109,7 @@ __global__ void __launch_bounds__(kThreads, 1)
   if (threadIdx.x == 0) {
     ptx::prefetch_tmap(&tmW);
     ptx::prefetch_tmap(&tmO);
+    if (SAVE) ptx::prefetch_tmap(&tmH);
     for (int s = 0; s < kWStages; ++s) ptx::mbar_init(&bars[bWFull + s], 2), ptx::mbar_init(&bars[bWEmpty + s], 1);
     for (int s = 0; s < kOStages; ++s) ptx::mbar_init(&bars[bOFull + s], 2), ptx::mbar_init(&bars[bOEmpty + s], 1);
     for (int s = 0; s < 2; ++s) {
@@ -259,8 +268,13 @@ __global__ void __launch_bounds__(kThreads, 1)
         ptx::tmem_ld_x32(ut, r);
         ptx::tmem_ld_wait();
         uint32_t packed[16];
+        uint32_t hsave[SAVE ? 16 : 1];
 #pragma unroll
         for (int x = 0; x < 32; x += 4) {
+          if (SAVE) {
+            hsave[x / 2] = ptx::pack_bf16x2(__uint_as_float(r[x + 0]), __uint_as_float(r[x + 1]));
+            hsave[x / 2 + 1] = ptx::pack_bf16x2(__uint_as_float(r[x + 2]), __uint_as_float(r[x + 3]));
+          }
           // the accumulator holds (u + b_mid) / 2 (the bias came through the MMA)
           float m0 = ptx::silu_from_half(__uint_as_float(r[x + 0])), m1 = ptx::silu_from_half(__uint_as_float(r[x + 1]));
           float m2 = ptx::silu_from_half(__uint_as_float(r[x + 2])), m3 = ptx::silu_from_half(__uint_as_float(r[x + 3]));
@@ -281,8 +295,32 @@ __global__ void __launch_bounds__(kThreads, 1)
         ptx::tc_fence_before();
         __syncwarp();
         if (lane == 0) arrive_leader(&bars[bMReady + buf]);
+#ifndef PENEO_K2_ABLATE_SAVE_H  // (timing experiment only)
+        if (SAVE) {
+#else
+        if (false) {
+#endif
+          // this warp's [32 pairs x 32 features] of pre-activations leave as ONE TMA store from a swizzled tile (a
+          // direct STG.128 per lane touches 32 lines per instruction: measured 2.2 x slower for the whole kernel)
+          unsigned char* hst = smem + Smem::hstage + (warp - 4) * 2048;
+          if (lane == 0) ptx::bulk_wait_group_read<0>();  // the previous chunk's store has read the tile
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            *reinterpret_cast<uint4*>(hst + lane * 64 + ((j ^ ((lane >> 1) & 3)) * 16)) =
+                make_uint4(hsave[4 * j], hsave[4 * j + 1], hsave[4 * j + 2], hsave[4 * j + 3]);
+          ptx::fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {  // rows past the end of the pair list are clipped by the tensor map
+            // (evict-first: 15.7 GB of write-once data per 32 x seq-512 batch must not push W_mid / ab out of the L2;
+            //  measured 6.30 -> 6.01 ms for the launch)
+            ptx::tma_store_2d_hint(&tmH, hst, c * 128 + 32 * csel, static_cast<int32_t>(drop_row - lane), ptx::l2_policy_evict_first());
+            ptx::bulk_commit_group();
+          }
+        }
       }
     }
+    if (SAVE && lane == 0) ptx::bulk_wait_group<0>();
   } else if (warp >= kProdWarp0) {
     // ============================== pair producers ==============================
     const int q = warp - kProdWarp0;
@@ -424,6 +462,12 @@ __global__ void __launch_bounds__(kThreads, 1)
             o.y = ptx::pack_bf16x2(ptx::silu_from_half(af[mth][2] + b2), ptx::silu_from_half(af[mth][3] + b3));
             const int chunk16 = (cg >> 1) ^ (r & 7);  // XOR swizzle keeps the row-wise reads below conflict-free
             *reinterpret_cast<uint2*>(stg + r * kStageRowBytes + chunk16 * 16 + (cg & 1) * 8) = o;
+#ifndef PENEO_K2_ABLATE_SAVE_S  // (timing experiment only)
+            if (SAVE && offa[u] >= 0)  // (the warp's 32 lanes cover 256 contiguous bytes of the pair's s row)
+#else
+            if (false)
+#endif
+              __stcs(reinterpret_cast<uint2*>(a.save_s + (tile * 128 + r) * D + 4 * cg), o);  // write-once stream: evict first
           }
         }
       }
@@ -502,7 +546,7 @@ int launch_pair_heads_tc_pair(const void* pack, const PackLayout& L, const __nv_
   PENEO_REQUIRE(tiles < (1ll << 31), "pair_heads: too many pairs for one launch");
   a.num_tiles = static_cast<int32_t>(tiles);
   if (tiles == 0) return PENEO_OK;
-  alignas(64) CUtensorMap tmW, tmO;
+  alignas(64) CUtensorMap tmW, tmO, tmH;
   int rc;
   // boxes are the per-CTA halves: 64 of a chunk's 128 W_mid rows, 8 of its 16 (padded) W_out rows
   if ((rc = make_tensor_map_bf16(&tmW, base + L.wmid_bf16, D, 5 * D, D * 2, 64, 64)) != PENEO_OK) return rc;
@@ -527,19 +571,30 @@ int launch_pair_heads_tc_pair(const void* pack, const PackLayout& L, const __nv_
     for (int h = 0; h < kNumHeads; ++h) a.tags[h] = loss->tags[h];
     for (int c = 0; c < 3; ++c) a.class_w[c] = loss->class_w[c];
     a.loss_partial = loss->partial;
+    a.save_h = loss->save_h, a.save_s = loss->save_s;
+    PENEO_REQUIRE((a.save_h == nullptr) == (a.save_s == nullptr), "pair_heads: save_h and save_s go together");
+  }
+  const bool save = loss && a.save_h;
+  if (save) {
+    PENEO_REQUIRE(a.total_pairs < (1ll << 31), "pair_heads: too many pairs for the saved activations");
+    if ((rc = make_tensor_map_bf16_sw64(&tmH, a.save_h, 5 * D, a.total_pairs, 5 * D * 2, 32, 32)) != PENEO_OK) return rc;
+  } else {
+    tmH = tmW;  // (unused)
   }
   if (grid_out) *grid_out = grid;
-#define GO(DR, LO, SP)                                                                                             \
+#define GO(DR, LO, SP, SV)                                                                                         \
   do {                                                                                                             \
-    PENEO_CUDA_TRY(cudaFuncSetAttribute(pair_heads_tc_kernel<DR, LO, SP>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes)); \
-    PENEO_CUDA_TRY(cudaLaunchKernelEx(&cfg, pair_heads_tc_kernel<DR, LO, SP>, tmW, tmO, a));                       \
+    PENEO_CUDA_TRY(cudaFuncSetAttribute(pair_heads_tc_kernel<DR, LO, SP, SV>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes)); \
+    PENEO_CUDA_TRY(cudaLaunchKernelEx(&cfg, pair_heads_tc_kernel<DR, LO, SP, SV>, tmW, tmO, tmH, a));              \
   } while (0)
   PENEO_REQUIRE(!(spots && (dr || loss)), "pair_heads: the spots-only output is an inference mode (no dropout, no loss)");
-  if (spots) GO(false, false, true);
-  else if (dr && loss) GO(true, true, false);
-  else if (dr) GO(true, false, false);
-  else if (loss) GO(false, true, false);
-  else GO(false, false, false);
+  if (spots) GO(false, false, true, false);
+  else if (dr && save) GO(true, true, false, true);
+  else if (save) GO(false, true, false, true);
+  else if (dr && loss) GO(true, true, false, false);
+  else if (dr) GO(true, false, false, false);
+  else if (loss) GO(false, true, false, false);
+  else GO(false, false, false, false);
 #undef GO
   PENEO_CUDA_TRY(cudaGetLastError());
   return PENEO_OK;

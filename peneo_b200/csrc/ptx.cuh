@@ -49,9 +49,27 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// Blocking wait.  PENEO_MBAR_SUSPEND_NS > 0 passes a suspend-time hint: the warp may sleep in hardware until the phase
+// completes (or the hint elapses) instead of re-issuing the test every few dozen cycles.
+#ifndef PENEO_MBAR_SUSPEND_NS
+#define PENEO_MBAR_SUSPEND_NS 0
+#endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+#if PENEO_MBAR_SUSPEND_NS > 0
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred P;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\t"
+        "selp.b32 %0, 1, 0, P;\n\t}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(PENEO_MBAR_SUSPEND_NS)
+        : "memory");
+  } while (!ok);
+#else
   while (!mbar_try_wait(bar, parity)) {
   }
+#endif
 }
 
 // ---------------------------------------------------------------- TMA
@@ -72,6 +90,18 @@ __device__ __forceinline__ void tma_store_2d(const void* tmap, const void* smem_
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
                    reinterpret_cast<uint64_t>(tmap)),
                "r"(smem_u32(smem_src)), "r"(x), "r"(y)
+               : "memory");
+}
+// the same with an L2 eviction policy for the written lines (createpolicy: evict_first for write-once streams)
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ void tma_store_2d_hint(const void* tmap, const void* smem_src, int32_t x, int32_t y, uint64_t policy) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3}], [%1], %4;" ::"l"(
+                   reinterpret_cast<uint64_t>(tmap)),
+               "r"(smem_u32(smem_src)), "r"(x), "r"(y), "l"(policy)
                : "memory");
 }
 __device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }

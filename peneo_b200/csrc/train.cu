@@ -459,7 +459,7 @@ struct DzPtrs {
 struct HeadPtrs {  // per-head gradient destinations, passed by value (no device-side pointer table, no sync)
   float* p[kNumHeads];
 };
-constexpr int kDwPartCtas = 256;  // upper bound of T1's grid (one CTA per SM)
+constexpr int kDwPartCtas = 320;  // upper bound of T1's grid (one CTA per SM) and of T1e's (two per SM)
 __global__ void __launch_bounds__(128) dwout_finish_kernel(const float* __restrict__ part, int ctas,
                                                            HeadPtrs dWout) {
   const int fs = blockIdx.x * 128 + threadIdx.x;  // stacked feature index in [0, 1920)
@@ -649,6 +649,7 @@ int launch_heads_bwd(const peneo_dims& dm, int prec, const void* pack, const voi
     int dev = 0;
     PENEO_CUDA_TRY(cudaGetDevice(&dev));
     PENEO_CUDA_TRY(cudaDeviceGetAttribute(&dw_ctas, cudaDevAttrMultiProcessorCount, dev));  // T1's grid never exceeds it
+    if (fused_in && fused_in->save_h) dw_ctas = std::min(2 * dw_ctas, pair_bwd_elem_max_ctas());  // T1e: two CTAs per SM
     PENEO_REQUIRE(dw_ctas <= kDwPartCtas, "device has %d SMs, dW_out partial buffer holds %d", dw_ctas, kDwPartCtas);
     TRY(zero(F(pl.off_dwpart), (size_t)dw_ctas * 3 * 5 * d));
     // bf16 per-token projections (0.5-scaled A | Bm) for T1, exactly what the forward pass used (same dropout)
@@ -691,6 +692,11 @@ int launch_heads_bwd(const peneo_dims& dm, int prec, const void* pack, const voi
       if (tc) {
         __nv_bfloat16* S16 = reinterpret_cast<__nv_bfloat16*>(ws + pl.off_S16);
         __nv_bfloat16* Gc = reinterpret_cast<__nv_bfloat16*>(ws + pl.off_Gc);
+        const bool saved = fused_in && fused_in->save_h;
+        if (saved) {  // the forward pass stored h and s for every pair: G is formed in place, no scratch copies
+          S16 = fused_in->save_s + g0 * d;
+          Gc = fused_in->save_h + g0 * (5 * d);
+        }
         const __nv_bfloat16* ab16 = reinterpret_cast<const __nv_bfloat16*>(ws + pl.off_ab16);
         // T1: regenerate S and u, store S and G = (dz W_out) SiLU'(u), reduce dW_out += dz^T SiLU(u) into the per-CTA
         // partial sums (tcgen05, K2's structure; on CTA pairs unless PENEO_T1_PAIR=0).  With the fused loss, dz is
@@ -701,7 +707,9 @@ int launch_heads_bwd(const peneo_dims& dm, int prec, const void* pack, const voi
           fl = *fused_in;
           for (int h = 0; h < kNumHeads; ++h) fl.dbout[h] = gr.out_b[h];
         }
-        if (t1_pair || fused_in)
+        if (saved)
+          TRY(launch_pair_bwd_elem(pack, L, g0, rows, fl, Gc, F(pl.off_dwpart), nullptr, st, drop.thresh ? &drop : nullptr));
+        else if (t1_pair || fused_in)
           TRY(launch_pair_bwd_prep_pair(pack, L, ab16, n, g0, rows, dlogits, fused_in ? &fl : nullptr, S16, Gc,
                                         F(pl.off_dwpart), st, drop.thresh ? &drop : nullptr));
         else

@@ -205,10 +205,20 @@ def _check_tags(tags: Sequence[torch.Tensor], b: int, p: int) -> List[torch.Tens
     return tg
 
 
+def saved_activation_budget_bytes() -> int:
+    """How much the training forward may keep for the backward (h + s, 4.5 KB per pair).  ``PENEO_SAVE_ACT_GB`` (0 =
+    never save: the backward regenerates the activations on the tensor cores); default 24 GB."""
+    import os
+
+    return int(float(os.environ.get("PENEO_SAVE_ACT_GB", "24")) * 2**30)
+
+
 def heads_loss_forward(pack: WeightPack, x: torch.Tensor, tags: Sequence[torch.Tensor], class_weights: Sequence[float],
-                       ratios: Optional[Sequence[float]] = None, dropout=None, in_dropout=None):
+                       ratios: Optional[Sequence[float]] = None, dropout=None, in_dropout=None, save: bool = False):
     """Heads + class-weighted CE in one sweep over the pair tiles (``peneo_pair_heads_loss_fwd``): the K2 epilogue that
-    writes a pair's logits also reduces its loss terms.  Returns (logits, out6, ctx); ctx feeds the fused backward."""
+    writes a pair's logits also reduces its loss terms.  Returns (logits, out6, ctx); ctx feeds the fused backward.
+    ``save``: also keep the hidden pre-activations and the pair representations (bf16, 4.5 KB per pair) when they fit
+    the budget, so that the backward pass needs no recompute GEMM."""
     lib = _lib.load()
     if x.dim() != 3:
         raise ValueError("sequence_output must be [batch, seq_len, hidden]")
@@ -222,13 +232,19 @@ def heads_loss_forward(pack: WeightPack, x: torch.Tensor, tags: Sequence[torch.T
     w3 = list(class_weights) + [0.0] * (3 - len(class_weights))
     r5 = [1.0] * 5 if ratios is None else list(ratios)
     COUNTERS["kernels"] += 2
+    saved = None
+    d = pack.dims.d
+    if save and b * p * 6 * d * 2 <= saved_activation_budget_bytes():
+        saved = (torch.empty(b * p, 5 * d, dtype=torch.bfloat16, device=ab.device),
+                 torch.empty(b * p, d, dtype=torch.bfloat16, device=ab.device))
+    sa = _lib.SavedAct(saved[0].data_ptr(), saved[1].data_ptr()) if saved is not None else None
     _lib.check(
         lib.peneo_pair_heads_loss_fwd(pack.dims.c(), pack.prec, pack.buf.data_ptr(), ab.data_ptr(), b, n, _lib.ptrs5(logits),
                                       _lib.ptrs5(tg), _lib.floats(w3), _lib.floats(r5), out6.data_ptr(), ws.data_ptr(),
-                                      _lib.dropout_arg(dropout), _stream(ab.device)),
+                                      _lib.dropout_arg(dropout), _stream(ab.device), sa),
         "peneo_pair_heads_loss_fwd",
     )
-    return logits, out6, (ws, tg, w3, r5)
+    return logits, out6, (ws, tg, w3, r5, saved)
 
 
 def pair_loss(logits: Sequence[torch.Tensor], tags: Sequence[torch.Tensor], class_weights: Sequence[float],

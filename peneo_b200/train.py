@@ -68,14 +68,17 @@ def heads_backward(decoder, x: torch.Tensor, dlogits: List[torch.Tensor], need_d
     gs = _grad_struct(dims, grads)
     ops.COUNTERS["kernels"] += 1
     if fused is not None:
-        logits, (lws, tg, w3, r5), g6 = fused
+        logits, (lws, tg, w3, r5, saved), g6 = fused
         g6 = g6.detach().to(device=dev, dtype=torch.float32).reshape(6).contiguous()
+        # saved = (h, s) of the forward pass, consumed here (h becomes G in place): a second backward through the same
+        # graph finds them gone and regenerates the activations instead
+        sa = _lib.SavedAct(saved[0].data_ptr(), saved[1].data_ptr()) if saved is not None else None
         _lib.check(
             lib.peneo_heads_loss_bwd(dims.c(), prec, pack.buf.data_ptr(), x2.data_ptr(), ops._TORCH_DT[x2.dtype],
                                      x2.stride(0) if b * n > 1 else hin, b, n, _lib.ptrs5(logits), _lib.ptrs5(tg),
                                      _lib.floats(w3), _lib.floats(r5), g6.data_ptr(), lws.data_ptr(), gs,
                                      dx.data_ptr() if dx is not None else None, ws.data_ptr(), _lib.dropout_arg(dropout),
-                                     ops._stream(dev)),
+                                     ops._stream(dev), sa),
             "peneo_heads_loss_bwd",
         )
         _mask_dx(lib, dx, b * n, hin, in_dropout, dev)
@@ -142,7 +145,8 @@ class _DecoderHeadsLoss(torch.autograd.Function):
     def forward(ctx, decoder, x, drop, class_w, ratios, t0, t1, t2, t3, t4, *params):
         pack = decoder._weight_pack(x.device)
         ctx.in_dropout = decoder._input_dropout(drop)
-        logits, out6, lctx = ops.heads_loss_forward(pack, x.detach(), [t0, t1, t2, t3, t4], class_w, ratios, drop, ctx.in_dropout)
+        logits, out6, lctx = ops.heads_loss_forward(pack, x.detach(), [t0, t1, t2, t3, t4], class_w, ratios, drop, ctx.in_dropout,
+                                                    save=True)
         ctx.decoder, ctx.dropout, ctx.lctx, ctx.logits = decoder, drop, lctx, logits
         ctx.save_for_backward(x)
         ctx.need_dx = x.requires_grad
@@ -158,8 +162,9 @@ class _DecoderHeadsLoss(torch.autograd.Function):
         if all(g is None for g in glogits):
             grads, dx = heads_backward(dec, x, None, ctx.need_dx, ctx.dropout, fused=(ctx.logits, ctx.lctx, g6),
                                        in_dropout=ctx.in_dropout)
+            ctx.lctx = ctx.lctx[:4] + (None,)  # the saved activations were consumed (h now holds G)
         else:
-            lws, tg, w3, r5 = ctx.lctx
+            lws, tg, w3, r5, _ = ctx.lctx
             b, n = x.shape[0], x.shape[1]
             dl = ops.pair_loss_backward((lws, ctx.logits, tg, w3, r5, b, n), g6)
             dl = [d if g is None else d + g.float() for d, g in zip(dl, glogits)]
