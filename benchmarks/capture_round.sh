@@ -14,15 +14,20 @@ timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --c
 # one full capture of the dominant kernel (K2 on CTA pairs)
 timeout 400 ncu --set full --clock-control none --import-source on -k regex:pair_heads_tc -s 3 -c 1 -o $out/${tag}_k2 \
     python bench.py --steps 2 --warmup 3 > $out/${tag}_ncu_k2.log 2>&1
-# training step: three shapes + launch list
+# training step: three shapes (activations saved by the forward pass; the last line again with PENEO_SAVE_ACT_GB=0 = recompute route)
 for args in "--seq-len 1024 --batch 4" "--seq-len 512 --batch 4" "--seq-len 512 --batch 32"; do
   timeout 200 python benchmarks/train_step.py $args 2>/dev/null | tail -1
 done > $out/${tag}_train_step.jsonl
+PENEO_SAVE_ACT_GB=0 timeout 200 python benchmarks/train_step.py --seq-len 512 --batch 32 2>/dev/null | tail -1 >> $out/${tag}_train_step.jsonl
 cat $out/${tag}_train_step.jsonl | cut -c1-200
-timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 800 --csv --log-file $out/${tag}_train_launches.csv \
-    python benchmarks/train_step.py --steps 2 --warmup 1 > $out/${tag}_ncu_train.log 2>&1
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 800 --csv --log-file $out/${tag}_train_launches_b32.csv \
     python benchmarks/train_step.py --seq-len 512 --batch 32 --steps 2 --warmup 1 > $out/${tag}_ncu_train_b32.log 2>&1
-timeout 400 ncu --set full --clock-control none --import-source on -k regex:pair_bwd_prep -s 2 -c 1 -o $out/${tag}_t1 \
-    python benchmarks/train_step.py --steps 1 --warmup 0 > $out/${tag}_ncu_t1.log 2>&1
+PENEO_SAVE_ACT_GB=0 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 800 --csv --log-file $out/${tag}_train_launches_b32_recompute.csv \
+    python benchmarks/train_step.py --seq-len 512 --batch 32 --steps 2 --warmup 1 > /dev/null 2>&1
+timeout 400 ncu --set full --clock-control none --import-source on -k regex:pair_bwd_elem -s 2 -c 1 -o $out/${tag}_t1e \
+    python benchmarks/train_step.py --seq-len 512 --batch 32 --steps 1 --warmup 0 > $out/${tag}_ncu_t1.log 2>&1
+PENEO_SAVE_ACT_GB=0 timeout 400 ncu --set full --clock-control none --import-source on -k regex:pair_bwd_prep -s 2 -c 1 -o $out/${tag}_t1 \
+    python benchmarks/train_step.py --seq-len 512 --batch 32 --steps 1 --warmup 0 >> $out/${tag}_ncu_t1.log 2>&1
+timeout 400 ncu --set full --clock-control none --import-source on -k regex:pair_heads_tc -s 1 -c 1 -o $out/${tag}_k2save \
+    python benchmarks/train_step.py --seq-len 512 --batch 32 --steps 1 --warmup 1 >> $out/${tag}_ncu_t1.log 2>&1
 timeout 400 python benchmarks/decoder_microbench.py > $out/${tag}_decoder_microbench.jsonl 2>/dev/null; tail -3 $out/${tag}_decoder_microbench.jsonl | cut -c1-200

@@ -652,9 +652,11 @@ int launch_heads_bwd(const peneo_dims& dm, int prec, const void* pack, const voi
     if (fused_in && fused_in->save_h) dw_ctas = std::min(2 * dw_ctas, pair_bwd_elem_max_ctas());  // T1e: two CTAs per SM
     PENEO_REQUIRE(dw_ctas <= kDwPartCtas, "device has %d SMs, dW_out partial buffer holds %d", dw_ctas, kDwPartCtas);
     TRY(zero(F(pl.off_dwpart), (size_t)dw_ctas * 3 * 5 * d));
-    // bf16 per-token projections (0.5-scaled A | Bm) for T1, exactly what the forward pass used (same dropout)
-    TRY(token_proj_fwd_bf16(dm, L, pk, x, x_dtype, x_row_stride, T, ws + pl.off_ab16, ws + pl.off_tokws, st,
-                            drop.thresh ? &drop : nullptr));
+    // bf16 per-token projections (0.5-scaled A | Bm) for T1, exactly what the forward pass used (same dropout);
+    // not needed when the forward pass saved s and the pre-activations (T1e reads neither a_i nor b_j)
+    if (!(fused_in && fused_in->save_h))
+      TRY(token_proj_fwd_bf16(dm, L, pk, x, x_dtype, x_row_stride, T, ws + pl.off_ab16, ws + pl.off_tokws, st,
+                              drop.thresh ? &drop : nullptr));
     for (int h = 0; h < kNumHeads; ++h) d_outw.p[h] = gr.out_w[h], d_outb.p[h] = gr.out_b[h];
   }
   float *S = F(pl.off_S), *dS = F(pl.off_dS), *G = F(pl.off_G);
