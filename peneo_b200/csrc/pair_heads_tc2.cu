@@ -28,22 +28,39 @@ namespace peneo {
 namespace k2p {
 
 constexpr int D = 384;
-constexpr int kChunks = 15;       // 5 heads x 3 chunks of 128 mid features
+// Width of a chunk of hidden features = N of the first GEMM's UMMAs.  128 (default): two accumulator buffers, the MMA
+// warp needs m(g - 1) before it may issue u(g + 1).  64: FOUR buffers, the second GEMM lags three chunks behind, so the
+// hand-off latencies between tensor pipe and epilogue are hidden — measured on B200: 5.73 ms against 4.44 ms per
+// launch, i.e. the TS-form UMMA (A operand read from TMEM: 4 KB per instruction whatever N is) does not run N = 64 at
+// full rate, which costs more than the deeper pipeline gains.  Kept as a build option for the record.
+#ifndef PENEO_K2_CHUNK_COLS
+#define PENEO_K2_CHUNK_COLS 128
+#endif
+constexpr int kChunkCols = PENEO_K2_CHUNK_COLS;
+static_assert(kChunkCols == 128 || kChunkCols == 64, "chunk width");
+constexpr int kHeadChunks = D / kChunkCols;        // chunks per head: 3 / 6
+constexpr int kChunks = kNumHeads * kHeadChunks;   // 15 / 30
+constexpr int kUBufs = 256 / kChunkCols;           // accumulator buffers in the 256 TMEM columns [192, 448): 2 / 4
+constexpr int kLag = kUBufs - 1;                   // the second GEMM of chunk g - kLag is issued after the first GEMM of chunk g
 constexpr int kKChunks = 6;       // 384 / 64
-constexpr int kWStages = 6;  // (8 before the h store tiles needed the room; 3 .. 8 stages measure the same)
-constexpr int kWStageBytes = 64 * 64 * 2;  // 8 KB: this CTA's 64 of the chunk's 128 rows
-constexpr int kOStages = 3;
-constexpr int kOStageBytes = 2 * 8 * 64 * 2;  // 2 KB: two K-blocks of [8 rows x 64] (this CTA's half of 16)
+constexpr int kWStageBytes = (kChunkCols / 2) * 64 * 2;  // 8 / 4 KB: this CTA's half of the chunk's W_mid rows x 64 K columns
+constexpr int kWStages = 48 * 1024 / kWStageBytes;       // 48 KB ring: 6 / 12 stages
+constexpr int kOStages = 2 * kUBufs;  // (a W_out stage is released kLag chunks after it was filled: the ring must be deeper than the lag)
+constexpr int kOKBlocks = kChunkCols / 64;               // 64-wide K blocks of the second GEMM per chunk
+constexpr int kOStageBytes = kOKBlocks * 8 * 64 * 2;     // 2 / 1 KB: K blocks of [8 rows x 64] (this CTA's half of 16)
 constexpr int kStageRowBytes = D * 2;          // staging: 128 rows x 768 B
-constexpr int kEpiWarps = 16;      // 4 per scheduler: each takes 32 of a chunk's 128 columns
+constexpr int kEpiWarps = 16;      // 4 per scheduler: each takes 32 columns of a chunk (64-column chunks: of every other chunk)
+constexpr int kColGroups = kChunkCols / 32;           // 32-column slices per chunk: 4 / 2
+constexpr int kEpiSets = kEpiWarps / (4 * kColGroups);  // sets of warps taking chunks in turn: 1 / 2
 constexpr int kProdWarp0 = 4 + kEpiWarps;
 constexpr int kProdRows = 4;        // b_j rows a producer warp has in flight (register budget: 80 / thread)
 constexpr int kThreads = 32 * (kProdWarp0 + 4);
 
 constexpr uint32_t kColS = 0, kColU = 192, kColZ = 448, kColOne = 480;  // [480, 496): the constant "ones" K step of A
-constexpr int kBiasTileBytes = 64 * 128;  // [64 rows (this CTA's half of a chunk's features) x 128 B] SWIZZLE_128B, K-major:
-                                          // the 32-byte K step x of a row belongs to chunk 4 * tile + x (K column 0 = b_mid / 2)
-constexpr int kBiasTiles = 4;             // 15 chunks, four per tile
+constexpr int kBiasRows = kChunkCols / 2;      // this CTA's half of a chunk's features
+constexpr int kBiasTileBytes = kBiasRows * 128;  // [rows x 128 B] SWIZZLE_128B, K-major: the 32-byte K step x of a row belongs
+                                                 // to chunk 4 * tile + x (K column 0 = b_mid / 2)
+constexpr int kBiasTiles = (kChunks + 3) / 4;    // four chunks per tile
 
 struct Smem {
   static constexpr int w = 0;
@@ -54,13 +71,13 @@ struct Smem {
   static constexpr int bout = hstage + kEpiWarps * 2048;  // 20 floats
   static constexpr int loss = bout + 128;                    // 40 doubles (LOSS instantiation)
   static constexpr int bars = loss + 320;
-  static constexpr int total = bars + 512;
+  static constexpr int total = bars + 1024;
 };
 // barrier indices
 constexpr int bWFull = 0, bWEmpty = bWFull + kWStages, bOFull = bWEmpty + kWStages, bOEmpty = bOFull + kOStages,
-              bUFull = bOEmpty + kOStages, bMReady = bUFull + 2, bZFull = bMReady + 2, bZFree = bZFull + 2, bSFull = bZFree + 2,
+              bUFull = bOEmpty + kOStages, bMReady = bUFull + kUBufs, bZFull = bMReady + kUBufs, bZFree = bZFull + 2, bSFull = bZFree + 2,
               bSFree = bSFull + kKChunks, bCount = bSFree + kKChunks;
-static_assert(bCount * 8 + 16 <= 512, "barrier area too small");
+static_assert(bCount * 8 + 16 <= 1024, "barrier area too small");
 static_assert(Smem::stage % 1024 == 0 && Smem::bias % 1024 == 0 && Smem::hstage % 1024 == 0,
               "UMMA operand / TMA store tiles need 1024-byte alignment");
 constexpr int kSmemBytes = Smem::total + 1024;
@@ -112,9 +129,11 @@ __global__ void __launch_bounds__(kThreads, 1)
     if (SAVE) ptx::prefetch_tmap(&tmH);
     for (int s = 0; s < kWStages; ++s) ptx::mbar_init(&bars[bWFull + s], 2), ptx::mbar_init(&bars[bWEmpty + s], 1);
     for (int s = 0; s < kOStages; ++s) ptx::mbar_init(&bars[bOFull + s], 2), ptx::mbar_init(&bars[bOEmpty + s], 1);
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < kUBufs; ++s) {
       ptx::mbar_init(&bars[bUFull + s], 1);
-      ptx::mbar_init(&bars[bMReady + s], 2 * kEpiWarps);  // the epilogue warps of both CTAs
+      ptx::mbar_init(&bars[bMReady + s], 2 * kEpiWarps / kEpiSets);  // the epilogue warps (of this chunk's set) of both CTAs
+    }
+    for (int s = 0; s < 2; ++s) {
       ptx::mbar_init(&bars[bZFull + s], 1);
       ptx::mbar_init(&bars[bZFree + s], 8);  // the four emitting (producer) warps of each CTA
     }
@@ -128,9 +147,9 @@ __global__ void __launch_bounds__(kThreads, 1)
   for (int e = threadIdx.x; e < kBiasTiles * kBiasTileBytes / 16; e += kThreads)
     reinterpret_cast<uint4*>(smem + Smem::bias)[e] = make_uint4(0u, 0u, 0u, 0u);
   __syncthreads();
-  for (int e = threadIdx.x; e < kChunks * 64; e += kThreads) {
-    const int c = e >> 6, r = e & 63;
-    const float bh = a.bmid_half[c * 128 + static_cast<int>(rank) * 64 + r];
+  for (int e = threadIdx.x; e < kChunks * kBiasRows; e += kThreads) {
+    const int c = e / kBiasRows, r = e % kBiasRows;
+    const float bh = a.bmid_half[c * kChunkCols + static_cast<int>(rank) * kBiasRows + r];
     *reinterpret_cast<__nv_bfloat16*>(smem + Smem::bias + (c >> 2) * kBiasTileBytes + r * 128 + (((2 * (c & 3)) ^ (r & 7)) * 16)) =
         __float2bfloat16_rn(bh);
   }
@@ -166,17 +185,22 @@ __global__ void __launch_bounds__(kThreads, 1)
         for (int c = 0; c < kChunks; ++c) {
           for (int kc = 0; kc < kKChunks; ++kc) {
             ptx::mbar_wait(&bars[bWEmpty + ws], wph ^ 1);
-            // this CTA's 64 rows of the chunk; both halves complete on the leader's barrier
+            // this CTA's half of the chunk's rows; both halves complete on the leader's barrier
             ptx::tma_load_2d_2sm(smem + Smem::w + ws * kWStageBytes, &tmW, &bars[bWFull + ws], kc * 64,
-                                 c * 128 + static_cast<int>(rank) * 64);
+                                 c * kChunkCols + static_cast<int>(rank) * (kChunkCols / 2));
             if (leader) ptx::mbar_arrive_expect_tx(&bars[bWFull + ws], 2 * kWStageBytes);
             else ptx::mbar_arrive_remote(&bars[bWFull + ws], 0);
             if (++ws == kWStages) ws = 0, wph ^= 1;
           }
           ptx::mbar_wait(&bars[bOEmpty + os], oph ^ 1);
           unsigned char* od = smem + Smem::o + os * kOStageBytes;
-          ptx::tma_load_2d_2sm(od, &tmO, &bars[bOFull + os], 0, c * 16 + static_cast<int>(rank) * 8);
-          ptx::tma_load_2d_2sm(od + 1024, &tmO, &bars[bOFull + os], 64, c * 16 + static_cast<int>(rank) * 8);
+          // W_out is packed [15 x 16 rows, 128 features]: row block = 128-feature chunk, this CTA's 8 of its 16 rows
+          if (kChunkCols == 128) {
+            ptx::tma_load_2d_2sm(od, &tmO, &bars[bOFull + os], 0, c * 16 + static_cast<int>(rank) * 8);
+            ptx::tma_load_2d_2sm(od + 1024, &tmO, &bars[bOFull + os], 64, c * 16 + static_cast<int>(rank) * 8);
+          } else {
+            ptx::tma_load_2d_2sm(od, &tmO, &bars[bOFull + os], (c & 1) * 64, (c >> 1) * 16 + static_cast<int>(rank) * 8);
+          }
           if (leader) ptx::mbar_arrive_expect_tx(&bars[bOFull + os], 2 * kOStageBytes);
           else ptx::mbar_arrive_remote(&bars[bOFull + os], 0);
           if (++os == kOStages) os = 0, oph ^= 1;
@@ -188,7 +212,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     // (elect_one, not lane == 0: ptxas then treats the region as uniform and keeps descriptors in
     //  uniform registers instead of emitting a per-instruction R2UR waterfall loop)
     if (leader && ptx::elect_one()) {
-      constexpr uint32_t idesc1 = ptx::umma_idesc_bf16(256, 128);  // M = 256 across the CTA pair
+      constexpr uint32_t idesc1 = ptx::umma_idesc_bf16(256, kChunkCols);  // M = 256 across the CTA pair
       constexpr uint32_t idesc2 = ptx::umma_idesc_bf16(256, 16);
       int ws = 0, os = 0;
       uint32_t wph = 0, oph = 0;
@@ -196,17 +220,17 @@ __global__ void __launch_bounds__(kThreads, 1)
       const uint32_t b_base = ptx::smem_u32(smem + Smem::bias);
       // second GEMM of global chunk gp: z[head] (+)= m(gp) * W_out chunk^T
       auto mma2 = [&](int gp) {
-        const int buf = gp & 1, hg = gp / 3, cpos = gp - hg * 3;
-        ptx::mbar_wait(&bars[bMReady + buf], (gp >> 1) & 1);
+        const int buf = gp % kUBufs, hg = gp / kHeadChunks, cpos = gp - hg * kHeadChunks;
+        ptx::mbar_wait(&bars[bMReady + buf], (gp / kUBufs) & 1);
         if (cpos == 0 && hg >= 2) ptx::mbar_wait(&bars[bZFree + (hg & 1)], ((hg >> 1) & 1) ^ 1);  // z of head hg - 2 was read
         ptx::mbar_wait(&bars[bOFull + os], oph);
         ptx::tc_fence_after();
         const uint32_t zt = tmem + kColZ + 16 * (hg & 1);
-        const uint32_t mt = tmem + kColU + 128 * buf;
+        const uint32_t mt = tmem + kColU + kChunkCols * buf;
 #ifdef PENEO_K2_ABLATE_MMA2  // timing experiment only (wrong logits): how much of the tensor pipe the N = 16 GEMM takes
         constexpr int kSteps2 = 0;
 #else
-        constexpr int kSteps2 = 8;
+        constexpr int kSteps2 = kChunkCols / 16;
 #endif
 #pragma unroll
         for (int ks = 0; ks < kSteps2; ++ks) {
@@ -215,13 +239,13 @@ __global__ void __launch_bounds__(kThreads, 1)
           ptx::umma_ts_2sm(zt, at, bd, idesc2, (cpos | ks) != 0);
         }
         ptx::tc_commit_2sm(&bars[bOEmpty + os], 3);
-        if (cpos == 2) ptx::tc_commit_2sm(&bars[bZFull + (hg & 1)], 3);
+        if (cpos == kHeadChunks - 1) ptx::tc_commit_2sm(&bars[bZFull + (hg & 1)], 3);
         if (++os == kOStages) os = 0, oph ^= 1;
       };
       int g = 0;
       for (int it = 0; it < my_tiles; ++it) {
         for (int c = 0; c < kChunks; ++c, ++g) {
-          const uint32_t ut = tmem + kColU + 128 * (g & 1);
+          const uint32_t ut = tmem + kColU + kChunkCols * (g % kUBufs);
           // u = [1 0 .. 0] x (b_mid / 2 tile): initialises the accumulator (the ones columns were written before the
           // first "S chunk full" arrival, which the first MMA of the kernel has not passed yet — see the producers)
           if (g == 0) {
@@ -241,11 +265,11 @@ __global__ void __launch_bounds__(kThreads, 1)
             if (c == kChunks - 1) ptx::tc_commit_2sm(&bars[bSFree + kc], 3);
             if (++ws == kWStages) ws = 0, wph ^= 1;
           }
-          ptx::tc_commit_2sm(&bars[bUFull + (g & 1)], 3);
-          if (g > 0) mma2(g - 1);
+          ptx::tc_commit_2sm(&bars[bUFull + (g % kUBufs)], 3);
+          if (g >= kLag) mma2(g - kLag);  // (u(g + 1) overwrites the buffer of chunk g + 1 - kUBufs = g - kLag)
         }
       }
-      if (g > 0) mma2(g - 1);
+      for (int gp = g > kLag ? g - kLag : 0; gp < g; ++gp) mma2(gp);
     }
   } else if (warp >= 4 && warp < kProdWarp0) {
     // ============================== epilogue ==============================
@@ -253,17 +277,20 @@ __global__ void __launch_bounds__(kThreads, 1)
     // Four warps per scheduler hide the TMEM-load / MUFU / barrier latencies of one another.  Nothing but the hidden
     // activation happens here: every chunk waits for its slowest epilogue warp, so the logits / loss / spot work of
     // a finished head is done by the producer warps (below), which are idle two thirds of the time.
-    const int q = warp % 4, csel = (warp - 4) / 4;
+    // (64-column chunks: two sets of eight warps take the chunks in turn — kChunks is even, so a warp's chunks have the
+    //  parity of its set in every tile)
+    const int q = warp % 4, csel = ((warp - 4) / 4) % kColGroups, eset = (warp - 4) / (4 * kColGroups);
     const uint32_t lane_base = static_cast<uint32_t>(q * 32) << 16;
     const int row = q * 32 + lane;
-    int g = 0;
+    static_assert(kChunks % kEpiSets == 0, "chunk interleave");
     for (int it = 0; it < my_tiles; ++it) {
       const int64_t drop_row = tile_of(it) * 128 + row;
-      for (int c = 0; c < kChunks; ++c, ++g) {
-        const int buf = g & 1;
-        ptx::mbar_wait(&bars[bUFull + buf], (g >> 1) & 1);
+      for (int c = eset; c < kChunks; c += kEpiSets) {
+        const int g = it * kChunks + c;
+        const int buf = g % kUBufs;
+        ptx::mbar_wait(&bars[bUFull + buf], (g / kUBufs) & 1);
         ptx::tc_fence_after();
-        const uint32_t ut = tmem + lane_base + kColU + 128 * buf + 32 * csel;
+        const uint32_t ut = tmem + lane_base + kColU + kChunkCols * buf + 32 * csel;
         uint32_t r[32];
         ptx::tmem_ld_x32(ut, r);
         ptx::tmem_ld_wait();
@@ -279,8 +306,8 @@ __global__ void __launch_bounds__(kThreads, 1)
           float m0 = ptx::silu_from_half(__uint_as_float(r[x + 0])), m1 = ptx::silu_from_half(__uint_as_float(r[x + 1]));
           float m2 = ptx::silu_from_half(__uint_as_float(r[x + 2])), m3 = ptx::silu_from_half(__uint_as_float(r[x + 3]));
           if (DROP) {  // nn.Dropout after the hidden SiLU (model/peneo_decoder.py:261), regenerable mask
-            const uint32_t key = a.drop_key[c / 3], grow = static_cast<uint32_t>(drop_row);
-            const uint32_t col = (c % 3) * 128 + 32 * csel + x;
+            const uint32_t key = a.drop_key[c / kHeadChunks], grow = static_cast<uint32_t>(drop_row);
+            const uint32_t col = (c % kHeadChunks) * kChunkCols + 32 * csel + x;
             m0 = drop_keep(key, a.drop_thresh, grow, col) ? m0 * a.drop_scale : 0.f;
             m1 = drop_keep(key, a.drop_thresh, grow, col + 1) ? m1 * a.drop_scale : 0.f;
             m2 = drop_keep(key, a.drop_thresh, grow, col + 2) ? m2 * a.drop_scale : 0.f;
@@ -314,7 +341,7 @@ __global__ void __launch_bounds__(kThreads, 1)
           if (lane == 0) {  // rows past the end of the pair list are clipped by the tensor map
             // (evict-first: 15.7 GB of write-once data per 32 x seq-512 batch must not push W_mid / ab out of the L2;
             //  measured 6.30 -> 6.01 ms for the launch)
-            ptx::tma_store_2d_hint(&tmH, hst, c * 128 + 32 * csel, static_cast<int32_t>(drop_row - lane), ptx::l2_policy_evict_first());
+            ptx::tma_store_2d_hint(&tmH, hst, c * kChunkCols + 32 * csel, static_cast<int32_t>(drop_row - lane), ptx::l2_policy_evict_first());
             ptx::bulk_commit_group();
           }
         }
@@ -549,7 +576,7 @@ int launch_pair_heads_tc_pair(const void* pack, const PackLayout& L, const __nv_
   alignas(64) CUtensorMap tmW, tmO, tmH;
   int rc;
   // boxes are the per-CTA halves: 64 of a chunk's 128 W_mid rows, 8 of its 16 (padded) W_out rows
-  if ((rc = make_tensor_map_bf16(&tmW, base + L.wmid_bf16, D, 5 * D, D * 2, 64, 64)) != PENEO_OK) return rc;
+  if ((rc = make_tensor_map_bf16(&tmW, base + L.wmid_bf16, D, 5 * D, D * 2, 64, kChunkCols / 2)) != PENEO_OK) return rc;
   if ((rc = make_tensor_map_bf16(&tmO, base + L.wout_bf16, 128, 15 * 16, 128 * 2, 64, 8)) != PENEO_OK) return rc;
   int dev = 0, sms = 148;
   PENEO_CUDA_TRY(cudaGetDevice(&dev));
