@@ -235,8 +235,11 @@ def heads_loss_forward(pack: WeightPack, x: torch.Tensor, tags: Sequence[torch.T
     saved = None
     d = pack.dims.d
     if save and b * p * 6 * d * 2 <= saved_activation_budget_bytes():
-        saved = (torch.empty(b * p, 5 * d, dtype=torch.bfloat16, device=ab.device),
-                 torch.empty(b * p, d, dtype=torch.bfloat16, device=ab.device))
+        try:
+            saved = (torch.empty(b * p, 5 * d, dtype=torch.bfloat16, device=ab.device),
+                     torch.empty(b * p, d, dtype=torch.bfloat16, device=ab.device))
+        except torch.cuda.OutOfMemoryError:  # no room next to the backbone's activations: regenerate in the backward pass
+            saved = None
     sa = _lib.SavedAct(saved[0].data_ptr(), saved[1].data_ptr()) if saved is not None else None
     _lib.check(
         lib.peneo_pair_heads_loss_fwd(pack.dims.c(), pack.prec, pack.buf.data_ptr(), ab.data_ptr(), b, n, _lib.ptrs5(logits),
