@@ -96,10 +96,12 @@ class PendingDecode:
     untrained model) are decoded again, alone, with exactly the capacity their longest list needs."""
 
     def __init__(self, ins, n, cap, decode_gt, score_thresh, want_spots, d2h_stream=None, k3_events=None, heads=None,
-                 host_buffers=None, record_event=True):
+                 host_buffers=None, record_event=True, defer_d2h=False):
         # host_buffers = (counts_h, rec_h) pinned tensors supplied by the caller and record_event=False: CUDA-graph
-        # capture (no pinned allocation and no event inside the captured region; the caller synchronises the replay)
-        self.host_buffers, self.record_event = host_buffers, record_event
+        # capture (no pinned allocation and no event inside the captured region; the caller synchronises the replay).
+        # defer_d2h: the copies of the records are not enqueued here either — the caller issues them (d2h_copy) on its
+        # own stream after every replay, so that they overlap the next batch instead of sitting in the compute stream
+        self.host_buffers, self.record_event, self.defer_d2h = host_buffers, record_event, defer_d2h
         # heads = (WeightPack, ab [B * n, 2d]): spot extraction fused into the pair kernel (peneo_pair_heads_spots_fwd):
         # there are no logits (`ins` is None), the compact spot lists come straight from the heads
         self.heads = heads
@@ -161,7 +163,10 @@ class PendingDecode:
             self.counts_h = torch.empty(counts.shape, dtype=torch.int32, pin_memory=True)
             self.rec_h = torch.empty(rec.shape, dtype=torch.int32, pin_memory=True)
         cur = torch.cuda.current_stream(dev)
-        if self.d2h_stream is not None and self.d2h_stream != cur:
+        self._dev_out = (counts, rec)
+        if self.defer_d2h:
+            self.event = None
+        elif self.d2h_stream is not None and self.d2h_stream != cur:
             ready = torch.cuda.Event()
             ready.record(cur)
             with torch.cuda.stream(self.d2h_stream):
@@ -181,6 +186,12 @@ class PendingDecode:
                 self.event.record(cur)
         self.d2h_bytes = self.counts_h.numel() * 4 + self.rec_h.numel() * 4
         self._keep = (counts, rec, ws, ws2)  # alive until the copies have run
+
+    def d2h_copy(self):
+        """Enqueue the two record copies on the current stream (graph mode: called after every replay)."""
+        counts, rec = self._dev_out
+        self.counts_h.copy_(counts, non_blocking=True)
+        self.rec_h.copy_(rec, non_blocking=True)
 
     def finish(self) -> "DeviceDecode":
         if self.event is not None:

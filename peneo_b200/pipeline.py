@@ -37,6 +37,7 @@ class _GraphSlot:
         ext = lambda: torch.cuda.Event(enable_timing=True, external=True)  # noqa: E731  (timed inside the graph)
         self.k2_ev = (ext(), ext())
         self.done = torch.cuda.Event()
+        self.kernels_done = torch.cuda.Event()
         self.graph = torch.cuda.CUDAGraph()
         k0 = ops.COUNTERS["kernels"]
         with torch.cuda.stream(pipe.compute), torch.no_grad():
@@ -53,7 +54,8 @@ class _GraphSlot:
         if pipe.fused_spots:
             if ev:
                 ev[0][0].record(pipe.compute)
-            pending = decode.PendingDecode(None, n, cap, False, pipe.score_thresh, False, None, None, (pack, ab), host, False)
+            pending = decode.PendingDecode(None, n, cap, False, pipe.score_thresh, False, None, None, (pack, ab), host, False,
+                                           defer_d2h=True)
             if ev:
                 ev[0][1].record(pipe.compute)
             return pending
@@ -63,7 +65,8 @@ class _GraphSlot:
         if ev:
             ev[0][1].record(pipe.compute)
         ins, _ = decode._as_batched_inputs(logits)
-        pending = decode.PendingDecode(ins, n, cap, False, pipe.score_thresh, False, None, None, None, host, False)
+        pending = decode.PendingDecode(ins, n, cap, False, pipe.score_thresh, False, None, None, None, host, False,
+                                       defer_d2h=True)
         return pending
 
 
@@ -172,8 +175,14 @@ class HeadsDecodePipeline:
         with torch.cuda.stream(self.compute), torch.no_grad():
             self.decoder._weight_pack(self.device)  # re-packs (eagerly, same buffer) if a parameter changed
             slot.graph.replay()
-            slot.done.record(self.compute)
+            slot.kernels_done.record(self.compute)
             self.decoder._pack_read_done(self.device)  # a later re-pack on another stream waits for this replay
+        # the record blocks go home on the D2H stream (4.6 MB per 32 x seq-512 batch: ~0.1 ms of PCIe time that would
+        # otherwise sit between this batch's kernels and the next batch's in the compute stream)
+        with torch.cuda.stream(self.d2h):
+            self.d2h.wait_event(slot.kernels_done)
+            slot.pending.d2h_copy()
+            slot.done.record(self.d2h)
         ops.COUNTERS["kernels"] += slot.kernels
         slot.pending.d2h_bytes = slot.d2h_bytes
         self.d2h_bytes += slot.d2h_bytes
