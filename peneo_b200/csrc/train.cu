@@ -371,12 +371,6 @@ __global__ void __launch_bounds__(128) gv_reduce_kernel(const float* __restrict_
 // every pair is one contiguous 4 d-byte read, 8 of them in flight per thread).  b_j and the 8 column sums stay in
 // registers; 8 + 8 vector REDs per 64 pairs.  Tiles below the diagonal exit.
 constexpr int kGvR = 8, kGvC = 8;
-// SiLU'(x) with one MUFU (tanh.approx), the same approximation the bf16 forward pass uses for SiLU itself
-__device__ __forceinline__ float dsilu_tanh(float x) {
-  const float t = ptx::tanh_approx(0.5f * x);
-  const float sg = fmaf(0.5f, t, 0.5f), oms = fmaf(-0.5f, t, 0.5f);
-  return fmaf(x * sg, oms, sg);
-}
 // One tile.  INTERIOR (every pair of the tile has i < ie, i <= j < je — all but the diagonal and the last row / column
 // of tiles): no predicates, addresses advance by constants.  Per element: h = a_i / 2 + b_j / 2 (the halves are formed
 // once per row / column), t = tanh(h), SiLU'(2h) = sg (1 + h (1 - t)) with sg = (1 + t) / 2.
