@@ -427,7 +427,10 @@ __device__ __forceinline__ void gv_tile(const __nv_bfloat16* __restrict__ dS, co
   for (int c = 0; c < kGvC; ++c)
     if (INTERIOR || (jt + c < je && jt + c >= it)) atomicAdd(reinterpret_cast<float4*>(out + (int64_t)(jt + c) * ld + d), cs[c]);
 }
-__global__ void __launch_bounds__(128, 4) gv_reduce_tile_kernel(const __nv_bfloat16* __restrict__ dS,
+#ifndef PENEO_GV_MINBLOCKS
+#define PENEO_GV_MINBLOCKS 4
+#endif
+__global__ void __launch_bounds__(128, PENEO_GV_MINBLOCKS) gv_reduce_tile_kernel(const __nv_bfloat16* __restrict__ dS,
                                                             const float* __restrict__ ab, int b, int n, int d, int i0,
                                                             int i1, float* __restrict__ dab) {
   const int f = 4 * threadIdx.x;  // blockDim.x = d / 4
@@ -663,6 +666,15 @@ int launch_heads_bwd(const peneo_dims& dm, int prec, const void* pack, const voi
     int64_t off;  // first row of the segment inside the chunk
   };
   std::vector<Seg> segs;
+  if (tc && fused_in && fused_in->save_h) {
+    // activations saved by the forward pass: h -> G in place for the WHOLE batch in one launch (T1e needs no per-chunk
+    // scratch); the chunk loop below only runs the two GEMMs and the dA / dBm reduction on views of it
+    PENEO_REQUIRE((int64_t)batch * P < (1ll << 31), "heads_bwd: too many pairs for one launch of the saved-activation backward");
+    FusedLossBwd fl = *fused_in;
+    for (int h = 0; h < kNumHeads; ++h) fl.dbout[h] = gr.out_b[h];
+    TRY(launch_pair_bwd_elem(pack, L, 0, static_cast<int>((int64_t)batch * P), fl, fused_in->save_h, F(pl.off_dwpart), nullptr, st,
+                             drop.thresh ? &drop : nullptr));
+  }
   int cb = 0, ci0 = 0;  // next (document, pair-row) not yet assigned to a chunk
   while (cb < batch) {
     segs.clear();
@@ -703,9 +715,9 @@ int launch_heads_bwd(const peneo_dims& dm, int prec, const void* pack, const voi
           fl = *fused_in;
           for (int h = 0; h < kNumHeads; ++h) fl.dbout[h] = gr.out_b[h];
         }
-        if (saved)
-          TRY(launch_pair_bwd_elem(pack, L, g0, rows, fl, Gc, F(pl.off_dwpart), nullptr, st, drop.thresh ? &drop : nullptr));
-        else if (t1_pair || fused_in)
+        if (saved) {
+          // (G of this chunk already stands in save_h: see above)
+        } else if (t1_pair || fused_in)
           TRY(launch_pair_bwd_prep_pair(pack, L, ab16, n, g0, rows, dlogits, fused_in ? &fl : nullptr, S16, Gc,
                                         F(pl.off_dwpart), st, drop.thresh ? &drop : nullptr));
         else
