@@ -44,7 +44,10 @@ constexpr int kUBufs = 256 / kChunkCols;           // accumulator buffers in the
 constexpr int kLag = kUBufs - 1;                   // the second GEMM of chunk g - kLag is issued after the first GEMM of chunk g
 constexpr int kKChunks = 6;       // 384 / 64
 constexpr int kWStageBytes = (kChunkCols / 2) * 64 * 2;  // 8 / 4 KB: this CTA's half of the chunk's W_mid rows x 64 K columns
-constexpr int kWStages = 48 * 1024 / kWStageBytes;       // 48 KB ring: 6 / 12 stages
+#ifndef PENEO_K2_WRING_KB
+#define PENEO_K2_WRING_KB 48
+#endif
+constexpr int kWStages = PENEO_K2_WRING_KB * 1024 / kWStageBytes;  // 48 KB ring: 6 / 12 stages
 constexpr int kOStages = 2 * kUBufs;  // (a W_out stage is released kLag chunks after it was filled: the ring must be deeper than the lag)
 constexpr int kOKBlocks = kChunkCols / 64;               // 64-wide K blocks of the second GEMM per chunk
 constexpr int kOStageBytes = kOKBlocks * 8 * 64 * 2;     // 2 / 1 KB: K blocks of [8 rows x 64] (this CTA's half of 16)
@@ -62,13 +65,32 @@ constexpr int kBiasTileBytes = kBiasRows * 128;  // [rows x 128 B] SWIZZLE_128B,
                                                  // to chunk 4 * tile + x (K column 0 = b_mid / 2)
 constexpr int kBiasTiles = (kChunks + 3) / 4;    // four chunks per tile
 
+#ifdef PENEO_K2_PROFILE
+// Diagnostic build (-DPENEO_K2_PROFILE): cycles the MMA-issuing thread spends waiting on each kind of barrier, summed
+// over the leader CTAs: [0] S chunk full, [1] W stage full, [2] m ready, [3] z free, [4] W_out stage full, [5] total
+// cycles of the issuing loop, [6] leader CTAs.  Read with peneo_debug_k2_profile().
+__device__ unsigned long long g_k2_prof[8];
+#define K2_WAIT(slot, call)                       \
+  do {                                            \
+    const long long t0_ = clock64();              \
+    call;                                         \
+    prof[slot] += clock64() - t0_;                \
+  } while (0)
+#else
+#define K2_WAIT(slot, call) call
+#endif
+
 struct Smem {
   static constexpr int w = 0;
   static constexpr int o = w + kWStages * kWStageBytes;
   static constexpr int stage = o + kOStages * kOStageBytes;
   static constexpr int bias = stage + 128 * kStageRowBytes;  // bias B-operand tiles (see kBiasTileBytes)
   static constexpr int hstage = bias + kBiasTiles * kBiasTileBytes;  // SAVE: per epilogue warp one [32 rows x 64 B] TMA store tile (SWIZZLE_64B)
+#ifdef PENEO_K2_NO_HSTAGE  // (timing experiment for the inference instantiations only: SAVE would overrun)
+  static constexpr int bout = hstage;
+#else
   static constexpr int bout = hstage + kEpiWarps * 2048;  // 20 floats
+#endif
   static constexpr int loss = bout + 128;                    // 40 doubles (LOSS instantiation)
   static constexpr int bars = loss + 320;
   static constexpr int total = bars + 1024;
@@ -218,12 +240,16 @@ __global__ void __launch_bounds__(kThreads, 1)
       uint32_t wph = 0, oph = 0;
       const uint32_t w_base = ptx::smem_u32(smem + Smem::w), o_base = ptx::smem_u32(smem + Smem::o);
       const uint32_t b_base = ptx::smem_u32(smem + Smem::bias);
+#ifdef PENEO_K2_PROFILE
+      long long prof[6] = {0, 0, 0, 0, 0, 0};
+      const long long prof_t0 = clock64();
+#endif
       // second GEMM of global chunk gp: z[head] (+)= m(gp) * W_out chunk^T
       auto mma2 = [&](int gp) {
         const int buf = gp % kUBufs, hg = gp / kHeadChunks, cpos = gp - hg * kHeadChunks;
-        ptx::mbar_wait(&bars[bMReady + buf], (gp / kUBufs) & 1);
-        if (cpos == 0 && hg >= 2) ptx::mbar_wait(&bars[bZFree + (hg & 1)], ((hg >> 1) & 1) ^ 1);  // z of head hg - 2 was read
-        ptx::mbar_wait(&bars[bOFull + os], oph);
+        K2_WAIT(2, ptx::mbar_wait(&bars[bMReady + buf], (gp / kUBufs) & 1));
+        if (cpos == 0 && hg >= 2) K2_WAIT(3, ptx::mbar_wait(&bars[bZFree + (hg & 1)], ((hg >> 1) & 1) ^ 1));  // z of head hg - 2 was read
+        K2_WAIT(4, ptx::mbar_wait(&bars[bOFull + os], oph));
         ptx::tc_fence_after();
         const uint32_t zt = tmem + kColZ + 16 * (hg & 1);
         const uint32_t mt = tmem + kColU + kChunkCols * buf;
@@ -254,8 +280,8 @@ __global__ void __launch_bounds__(kThreads, 1)
           }
           ptx::umma_ts_2sm(ut, tmem + kColOne, ptx::umma_desc_sw128(b_base + (c >> 2) * kBiasTileBytes + (c & 3) * 32), idesc1, 0);
           for (int kc = 0; kc < kKChunks; ++kc) {
-            if (c == 0) ptx::mbar_wait(&bars[bSFull + kc], it & 1);
-            ptx::mbar_wait(&bars[bWFull + ws], wph);
+            if (c == 0) K2_WAIT(0, ptx::mbar_wait(&bars[bSFull + kc], it & 1));
+            K2_WAIT(1, ptx::mbar_wait(&bars[bWFull + ws], wph));
             ptx::tc_fence_after();
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks)
@@ -270,6 +296,11 @@ __global__ void __launch_bounds__(kThreads, 1)
         }
       }
       for (int gp = g > kLag ? g - kLag : 0; gp < g; ++gp) mma2(gp);
+#ifdef PENEO_K2_PROFILE
+      prof[5] = clock64() - prof_t0;
+      for (int i = 0; i < 6; ++i) atomicAdd(&g_k2_prof[i], static_cast<unsigned long long>(prof[i]));
+      atomicAdd(&g_k2_prof[6], 1ull);
+#endif
     }
   } else if (warp >= 4 && warp < kProdWarp0) {
     // ============================== epilogue ==============================
@@ -554,6 +585,17 @@ __global__ void __launch_bounds__(kThreads, 1)
 }
 
 }  // namespace k2p
+
+#ifdef PENEO_K2_PROFILE
+extern "C" int peneo_debug_k2_profile(unsigned long long* out_host, int reset) {
+  if (cudaMemcpyFromSymbol(out_host, k2p::g_k2_prof, 8 * sizeof(unsigned long long)) != cudaSuccess) return -1;
+  if (reset) {
+    const unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (cudaMemcpyToSymbol(k2p::g_k2_prof, z, sizeof(z)) != cudaSuccess) return -1;
+  }
+  return 0;
+}
+#endif
 
 int launch_pair_heads_tc_pair(const void* pack, const PackLayout& L, const __nv_bfloat16* ab, int batch, int n,
                               float* const logits[kNumHeads], cudaStream_t st, const DropSpec* drop, const FusedLossFwd* loss,
