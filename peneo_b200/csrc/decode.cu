@@ -17,6 +17,7 @@ namespace peneo {
 #define PENEO_K3_UNROLL 2
 #endif
 constexpr int kK3Unroll = PENEO_K3_UNROLL;
+constexpr int kSpotWarps = 4096 / PENEO_K3_WARP_PAIRS;  // warps per CTA: 4096 pairs (36 KB of spot buffers) per CTA
 #ifndef PENEO_K3_LOOK_WINDOWS
 #define PENEO_K3_LOOK_WINDOWS 1  // measured on B200: 1 window 70 us, 4 windows 76 us, 8 windows 85 us (polling traffic on the status lines costs more than the extra rounds)
 #endif
@@ -101,13 +102,13 @@ __device__ __forceinline__ int scan_pairs_vec4(const float* __restrict__ doc, in
 // in index order (CTAs are dispatched in block-index order, the assumption CUB's single-pass scan makes as well), so
 // the look-back never waits for a warp that is not resident yet.
 template <int DT>
-__global__ void __launch_bounds__(256) decode_spots_kernel(const SpotArgs a) {
-  __shared__ int32_t buf_p[8][kSpotWarpPairs];
-  __shared__ float buf_s[8][kSpotWarpPairs];
-  __shared__ uint8_t buf_t[8][kSpotWarpPairs];
+__global__ void __launch_bounds__(32 * kSpotWarps) decode_spots_kernel(const SpotArgs a) {
+  __shared__ int32_t buf_p[kSpotWarps][kSpotWarpPairs];
+  __shared__ float buf_s[kSpotWarps][kSpotWarpPairs];
+  __shared__ uint8_t buf_t[kSpotWarps][kSpotWarpPairs];
   const int h = blockIdx.y, b = blockIdx.z, list = b * kNumHeads + h;
   const int lane = threadIdx.x % 32, warp = threadIdx.x / 32;
-  const int chunk = blockIdx.x * 8 + warp;  // warp chunk inside the list
+  const int chunk = blockIdx.x * kSpotWarps + warp;  // warp chunk inside the list
   if (chunk >= a.chunks) return;
   const int C = head_classes(h);
   const char* base = static_cast<const char*>(a.in[h]);
@@ -226,12 +227,12 @@ int launch_decode_spots(int batch, int n, const void* const in[kNumHeads], int i
   a.status = static_cast<int32_t*>(ws);
   PENEO_CUDA_TRY(cudaMemsetAsync(ws, 0, decode_spots_workspace_bytes(batch, n), st));
   PENEO_REQUIRE(batch <= 65535, "decode_spots: batch too large for one launch");
-  dim3 grid((a.chunks + 7) / 8, kNumHeads, batch);
+  dim3 grid((a.chunks + kSpotWarps - 1) / kSpotWarps, kNumHeads, batch);
   switch (in_dtype) {
-    case PENEO_DT_F32: decode_spots_kernel<PENEO_DT_F32><<<grid, 256, 0, st>>>(a); break;
-    case PENEO_DT_BF16: decode_spots_kernel<PENEO_DT_BF16><<<grid, 256, 0, st>>>(a); break;
-    case PENEO_DT_F16: decode_spots_kernel<PENEO_DT_F16><<<grid, 256, 0, st>>>(a); break;
-    case PENEO_DT_I64: decode_spots_kernel<PENEO_DT_I64><<<grid, 256, 0, st>>>(a); break;
+    case PENEO_DT_F32: decode_spots_kernel<PENEO_DT_F32><<<grid, 32 * kSpotWarps, 0, st>>>(a); break;
+    case PENEO_DT_BF16: decode_spots_kernel<PENEO_DT_BF16><<<grid, 32 * kSpotWarps, 0, st>>>(a); break;
+    case PENEO_DT_F16: decode_spots_kernel<PENEO_DT_F16><<<grid, 32 * kSpotWarps, 0, st>>>(a); break;
+    case PENEO_DT_I64: decode_spots_kernel<PENEO_DT_I64><<<grid, 32 * kSpotWarps, 0, st>>>(a); break;
     default: set_error("decode_spots: unsupported dtype %d", in_dtype); return PENEO_E_INVALID;
   }
   PENEO_CUDA_TRY(cudaGetLastError());
