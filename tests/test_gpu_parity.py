@@ -916,6 +916,30 @@ def test_tiny_documents_heads_and_decode(n):
         _same_result(got, want)
 
 
+@pytest.mark.parametrize("n,b", [(1, 1), (2, 1), (5, 3), (16, 1)])
+def test_tiny_documents_training_both_backward_routes(monkeypatch, n, b):
+    """Training at sizes below one 128-pair tile (1 ... 136 pairs in the batch: a single partial tile, the phantom second
+    tile of the CTA pair, 32-row tiles of the saved-activation backward mostly empty): loss and gradients against the
+    fp64 autograd oracle on both routes of the bf16 mode."""
+    sd = synth.init_decoder_state(seed=31, trained_like=True)
+    x = synth.hidden_states(b, n, 768, doc_id0=3)
+    docs = [synth.make_document(n, doc_id=40 + i) for i in range(b)]
+    tags = [torch.stack([d.tags()[k] for d in docs]) for k in range(5)]
+    ref_loss, _, ref_grads, ref_dx = orc.loss_and_grads(sd, x, tags, [1.0, 10.0, 10.0])
+    for save_gb in ("24", "0"):
+        monkeypatch.setenv("PENEO_SAVE_ACT_GB", save_gb)
+        dec = PEneoDecoderB200(Cfg(768, inference_mode=False, precision="bf16"), 768)
+        dec.load_state_dict(sd)
+        dec = dec.cuda().eval()
+        out, dx, grads = _train_step(dec, x.cuda(), [t.cuda() for t in tags])
+        assert abs(out.loss.item() - ref_loss.item()) <= 2e-3 * max(1.0, abs(ref_loss.item())), (n, b, save_gb)
+        worst = {"dx": rel_err(dx, ref_dx)}
+        for key, g in ref_grads.items():
+            worst[key] = rel_err(grads[key], g)
+        bad = {k: v for k, v in worst.items() if v > 3e-2}
+        assert not bad, (n, b, save_gb, bad)
+
+
 def test_strided_hidden_states_after_cls_strip():
     """PEneoModel.forward hands the decoder `sequence_output[:, 1:]` (model/modeling_peneo.py:142, 158): a
     view whose batch stride is (N + 1) * H.  Also bf16 / fp16 inputs under autocast."""
