@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define PENEO_ABI_VERSION 3
+#define PENEO_ABI_VERSION 4
 
 #define PENEO_OK 0
 #define PENEO_E_INVALID -1     /* bad argument / unsupported configuration */

@@ -149,7 +149,7 @@ def load() -> C.CDLL:
     lib.peneo_decode_resolve.argtypes = [i32, i32, i32, vp, vp, vp, vp, C.c_int, C.c_float, vp, vp, vp]
     lib.peneo_selftest.argtypes = [C.POINTER(C.c_uint32), C.c_char_p, sz]
     lib.peneo_probe_rates.argtypes = [C.POINTER(C.c_double), C.c_int]
-    if lib.peneo_abi_version() != 3:
+    if lib.peneo_abi_version() != 4:
         raise RuntimeError("libpeneo_b200.so ABI version mismatch; rebuild with `python -m peneo_b200.build --force`")
     _lib = lib
     return lib

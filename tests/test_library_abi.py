@@ -30,7 +30,7 @@ def test_every_declared_symbol_is_exported(lib):
 def test_abi_version_and_sizes(lib):
     from peneo_b200 import _lib
 
-    assert lib.peneo_abi_version() == 3
+    assert lib.peneo_abi_version() == 4
     dims = _lib.Dims(768, 768, 384, 1, 2)
     assert lib.peneo_pack_bytes(dims, _lib.PREC_BF16) > 5 * 384 * 384 * 2
     assert lib.peneo_pack_bytes(dims, _lib.PREC_FP32) > 1_900_000 * 4
