@@ -93,15 +93,22 @@ def allreduce_gradients(params: Iterable[torch.nn.Parameter], group=None, averag
     if not grads or not (dist.is_available() and dist.is_initialized()):
         return 0
     world = dist.get_world_size(group)
+    # one flat fp32 bucket: a single cat, ONE collective (NCCL averages inside the all-reduce), one fused copy back
     flat = torch.cat([g.reshape(-1).float() for g in grads])
-    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
-    if average:
+    nccl = dist.get_backend(group) == "nccl"
+    dist.all_reduce(flat, op=dist.ReduceOp.AVG if (average and nccl) else dist.ReduceOp.SUM, group=group)
+    if average and not nccl:
         flat /= world
-    off = 0
+    views, off = [], 0
     for g in grads:
         k = g.numel()
-        g.copy_(flat[off : off + k].view_as(g).to(g.dtype))
+        views.append(flat[off : off + k].view_as(g))
         off += k
+    if all(g.dtype == torch.float32 for g in grads):
+        torch._foreach_copy_(grads, views)
+    else:
+        for g, v in zip(grads, views):
+            g.copy_(v)
     return flat.numel() * 4
 
 
