@@ -51,7 +51,8 @@ constexpr int kWStages = PENEO_K2_WRING_KB * 1024 / kWStageBytes;  // 48 KB ring
 constexpr int kOStages = 2 * kUBufs;  // (a W_out stage is released kLag chunks after it was filled: the ring must be deeper than the lag)
 constexpr int kOKBlocks = kChunkCols / 64;               // 64-wide K blocks of the second GEMM per chunk
 constexpr int kOStageBytes = kOKBlocks * 8 * 64 * 2;     // 2 / 1 KB: K blocks of [8 rows x 64] (this CTA's half of 16)
-constexpr int kStageRowBytes = D * 2;          // staging: 128 rows x 768 B
+constexpr int kStageRowBytes = D * 2;          // staging: 128 rows x 768 B ...
+constexpr int kStageBoxBytes = 128 * 128;      // ... as six [128 rows x 64 features] boxes in the TMA SWIZZLE_128B layout
 constexpr int kEpiWarps = 16;      // 4 per scheduler: each takes 32 columns of a chunk (64-column chunks: of every other chunk)
 constexpr int kColGroups = kChunkCols / 32;           // 32-column slices per chunk: 4 / 2
 constexpr int kEpiSets = kEpiWarps / (4 * kColGroups);  // sets of warps taking chunks in turn: 1 / 2
@@ -133,7 +134,7 @@ struct Args {
 template <bool DROP, bool LOSS, bool SPOTS, bool SAVE>
 __global__ void __launch_bounds__(kThreads, 1)
     pair_heads_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmO,
-                         const __grid_constant__ CUtensorMap tmH, const Args a) {
+                         const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUtensorMap tmS, const Args a) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);  // by offset: keeps the shared address space
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Smem::bars);
@@ -148,7 +149,7 @@ __global__ void __launch_bounds__(kThreads, 1)
   if (threadIdx.x == 0) {
     ptx::prefetch_tmap(&tmW);
     ptx::prefetch_tmap(&tmO);
-    if (SAVE) ptx::prefetch_tmap(&tmH);
+    if (SAVE) ptx::prefetch_tmap(&tmH), ptx::prefetch_tmap(&tmS);
     for (int s = 0; s < kWStages; ++s) ptx::mbar_init(&bars[bWFull + s], 2), ptx::mbar_init(&bars[bWEmpty + s], 1);
     for (int s = 0; s < kOStages; ++s) ptx::mbar_init(&bars[bOFull + s], 2), ptx::mbar_init(&bars[bOEmpty + s], 1);
     for (int s = 0; s < kUBufs; ++s) {
@@ -483,6 +484,10 @@ __global__ void __launch_bounds__(kThreads, 1)
       // ---- generate s rows [32q, 32q+32) into staging; lane = 4-column group (3 groups per lane).  Consecutive pairs
       //      share their row token i (a tile is 128 consecutive pairs of the row-major triangle), so a_i stays in
       //      registers and is reloaded only where i changes; only the b_j rows are streamed, kProdRows at a time.
+      if (SAVE) {  // the TMA stores of the previous tile's s have read this warp's rows of the staging boxes
+        if (lane == 0) ptx::bulk_wait_group_read<0>();
+        __syncwarp();
+      }
       int64_t cur_a = -2;
       float af[3][4] = {};
 #pragma unroll 1
@@ -518,15 +523,29 @@ __global__ void __launch_bounds__(kThreads, 1)
             uint2 o;
             o.x = ptx::pack_bf16x2(ptx::silu_from_half(af[mth][0] + b0), ptx::silu_from_half(af[mth][1] + b1));
             o.y = ptx::pack_bf16x2(ptx::silu_from_half(af[mth][2] + b2), ptx::silu_from_half(af[mth][3] + b3));
-            const int chunk16 = (cg >> 1) ^ (r & 7);  // XOR swizzle keeps the row-wise reads below conflict-free
-            *reinterpret_cast<uint2*>(stg + r * kStageRowBytes + chunk16 * 16 + (cg & 1) * 8) = o;
-#ifndef PENEO_K2_ABLATE_SAVE_S  // (timing experiment only)
-            if (SAVE && offa[u] >= 0)  // (the warp's 32 lanes cover 256 contiguous bytes of the pair's s row)
-#else
-            if (false)
-#endif
-              __stcs(reinterpret_cast<uint2*>(a.save_s + (tile * 128 + r) * D + 4 * cg), o);  // write-once stream: evict first
+            // box = 64-feature K chunk, 128 B per row inside it, 16-byte chunk index XOR (row & 7): the layout a TMA store
+            // with SWIZZLE_128B expects, conflict-free for these writes and for the row-wise reads below
+            const int chunk16 = ((cg >> 1) & 7) ^ (r & 7);
+            *reinterpret_cast<uint2*>(stg + (cg >> 4) * kStageBoxBytes + r * 128 + chunk16 * 16 + (cg & 1) * 8) = o;
           }
+        }
+      }
+#ifndef PENEO_K2_ABLATE_SAVE_S  // (timing experiment only)
+      if (SAVE) {
+#else
+      if (false) {
+#endif
+        // s of this warp's 32 pairs leaves as six TMA stores straight from the staging boxes (rows past the end of the
+        // pair list are clipped); the boxes are rewritten only after wait_group.read at the top of the next tile
+        ptx::fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          const uint64_t pol = ptx::l2_policy_evict_first();
+          const int32_t row0 = static_cast<int32_t>(tile * 128 + q * 32);
+#pragma unroll
+          for (int kc = 0; kc < kKChunks; ++kc)
+            ptx::tma_store_2d_hint(&tmS, stg + kc * kStageBoxBytes + q * 32 * 128, kc * 64, row0, pol);
+          ptx::bulk_commit_group();
         }
       }
       __syncwarp();
@@ -537,8 +556,7 @@ __global__ void __launch_bounds__(kThreads, 1)
         uint32_t v[32];
 #pragma unroll
         for (int ch = 0; ch < 8; ++ch) {
-          const int chunk16 = (kc * 8 + ch) ^ (r & 7);
-          const uint4 t = *reinterpret_cast<const uint4*>(stg + r * kStageRowBytes + chunk16 * 16);
+          const uint4 t = *reinterpret_cast<const uint4*>(stg + kc * kStageBoxBytes + r * 128 + ((ch ^ (r & 7)) * 16));
           v[4 * ch] = t.x, v[4 * ch + 1] = t.y, v[4 * ch + 2] = t.z, v[4 * ch + 3] = t.w;
         }
         if (it > 0) {
@@ -557,6 +575,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       }
       __syncwarp();
     }
+    if (SAVE && lane == 0) ptx::bulk_wait_group<0>();  // every s store of this warp has been written
     while (next_emit < total_heads) {  // the heads of the last tile
       ptx::mbar_wait(&bars[bZFull + (next_emit & 1)], (next_emit >> 1) & 1);
       emit_z(next_emit);
@@ -615,7 +634,7 @@ int launch_pair_heads_tc_pair(const void* pack, const PackLayout& L, const __nv_
   PENEO_REQUIRE(tiles < (1ll << 31), "pair_heads: too many pairs for one launch");
   a.num_tiles = static_cast<int32_t>(tiles);
   if (tiles == 0) return PENEO_OK;
-  alignas(64) CUtensorMap tmW, tmO, tmH;
+  alignas(64) CUtensorMap tmW, tmO, tmH, tmS;
   int rc;
   // boxes are the per-CTA halves: 64 of a chunk's 128 W_mid rows, 8 of its 16 (padded) W_out rows
   if ((rc = make_tensor_map_bf16(&tmW, base + L.wmid_bf16, D, 5 * D, D * 2, 64, kChunkCols / 2)) != PENEO_OK) return rc;
@@ -647,14 +666,15 @@ int launch_pair_heads_tc_pair(const void* pack, const PackLayout& L, const __nv_
   if (save) {
     PENEO_REQUIRE(a.total_pairs < (1ll << 31), "pair_heads: too many pairs for the saved activations");
     if ((rc = make_tensor_map_bf16_sw64(&tmH, a.save_h, 5 * D, a.total_pairs, 5 * D * 2, 32, 32)) != PENEO_OK) return rc;
+    if ((rc = make_tensor_map_bf16(&tmS, a.save_s, D, a.total_pairs, D * 2, 64, 32)) != PENEO_OK) return rc;
   } else {
-    tmH = tmW;  // (unused)
+    tmH = tmW, tmS = tmW;  // (unused)
   }
   if (grid_out) *grid_out = grid;
 #define GO(DR, LO, SP, SV)                                                                                         \
   do {                                                                                                             \
     PENEO_CUDA_TRY(cudaFuncSetAttribute(pair_heads_tc_kernel<DR, LO, SP, SV>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes)); \
-    PENEO_CUDA_TRY(cudaLaunchKernelEx(&cfg, pair_heads_tc_kernel<DR, LO, SP, SV>, tmW, tmO, tmH, a));              \
+    PENEO_CUDA_TRY(cudaLaunchKernelEx(&cfg, pair_heads_tc_kernel<DR, LO, SP, SV>, tmW, tmO, tmH, tmS, a));         \
   } while (0)
   PENEO_REQUIRE(!(spots && (dr || loss)), "pair_heads: the spots-only output is an inference mode (no dropout, no loss)");
   if (spots) GO(false, false, true, false);
