@@ -19,7 +19,7 @@ LIB = os.path.join(HERE, "libpeneo_b200.so")
 GLUE = os.path.join(HERE, "_hostglue" + (sysconfig.get_config_var("EXT_SUFFIX") or ".so"))
 STAMP = os.path.join(HERE, "csrc", ".build_stamp")
 
-SOURCES = ["api.cu", "simt_kernels.cu", "gemm_tc.cu", "pair_heads_tc.cu", "pair_heads_tc2.cu", "pair_heads_generic.cu", "pair_bwd_tc.cu", "pair_bwd_tc2.cu", "pair_bwd_elem.cu", "gemm_bwd_tc.cu", "gemm_bwd_tc2.cu", "gemm_tf32.cu", "loss.cu", "ohem.cu", "train.cu", "decode.cu", "selftest.cu"]
+SOURCES = ["api.cu", "simt_kernels.cu", "gemm_tc.cu", "pair_heads_tc.cu", "pair_heads_tc2.cu", "pair_heads_generic.cu", "pair_bwd_tc.cu", "pair_bwd_tc2.cu", "pair_bwd_elem.cu", "gemm_ds_fused.cu", "gemm_bwd_tc.cu", "gemm_bwd_tc2.cu", "gemm_tf32.cu", "loss.cu", "ohem.cu", "train.cu", "decode.cu", "selftest.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",

@@ -81,6 +81,11 @@ struct FusedLossBwd {
 int pair_bwd_elem_max_ctas();
 int launch_pair_bwd_elem(const void* pack, const PackLayout& L, int64_t g0, int rows, const FusedLossBwd& fused,
                          __nv_bfloat16* hg, float* dwout_part, int* ctas_out, cudaStream_t st, const DropSpec* drop = nullptr);
+// gemm_ds_fused.cu : T1f, the same transform inside the operand stage of the dS GEMM (h -> G in shared memory, dS = G W_mid
+// on CTA pairs, G written back over h for the dW_mid GEMM)
+int launch_gemm_ds_fused(const void* pack, const PackLayout& L, __nv_bfloat16* hg, const __nv_bfloat16* wmid_full,
+                         __nv_bfloat16* dS, int64_t g0, int rows, const FusedLossBwd& fused, float* dwout_part,
+                         cudaStream_t st, const DropSpec* drop = nullptr);
 int launch_pair_bwd_prep_pair(const void* pack, const PackLayout& L, const __nv_bfloat16* ab, int n, int64_t g0, int rows,
                               const float* const dz[kNumHeads], const FusedLossBwd* fused, __nv_bfloat16* S,
                               __nv_bfloat16* G, float* dwout_part, cudaStream_t st, const DropSpec* drop = nullptr);

@@ -666,7 +666,11 @@ int launch_heads_bwd(const peneo_dims& dm, int prec, const void* pack, const voi
     int64_t off;  // first row of the segment inside the chunk
   };
   std::vector<Seg> segs;
-  if (tc && fused_in && fused_in->save_h) {
+  // saved activations: T1e once over the whole batch followed by the plain dS GEMM per chunk (default), or — PENEO_T1F=1,
+  // experimental — T1f, the same transform inside the dS GEMM's operand stage (gemm_ds_fused.cu: parity-green, but
+  // measured 1.46 ms per 524 288-pair chunk against 0.71 + 0.58 ms for T1e + the plain GEMM)
+  const bool t1f = [] { const char* e = getenv("PENEO_T1F"); return e && atoi(e) != 0; }();
+  if (tc && fused_in && fused_in->save_h && !t1f) {
     // activations saved by the forward pass: h -> G in place for the WHOLE batch in one launch (T1e needs no per-chunk
     // scratch); the chunk loop below only runs the two GEMMs and the dA / dBm reduction on views of it
     PENEO_REQUIRE((int64_t)batch * P < (1ll << 31), "heads_bwd: too many pairs for one launch of the saved-activation backward");
@@ -726,8 +730,13 @@ int launch_heads_bwd(const peneo_dims& dm, int prec, const void* pack, const voi
         // dS = G W_mid (all heads in one K = 1920 GEMM) ; dW_mid += G^T S
         // (CTA-pair kernels by default; PENEO_BWD_PAIR=0 selects the single-CTA ones for A/B studies)
         static const bool gemm_pair = [] { const char* e = getenv("PENEO_BWD_PAIR"); return !e || atoi(e) != 0; }();
-        TRY((gemm_pair ? launch_gemm_ds_pair : launch_gemm_ds)(Gc, reinterpret_cast<const __nv_bfloat16*>(pk + L.wmid_full_bf16),
-                                                              reinterpret_cast<__nv_bfloat16*>(dS), rows, st));
+        if (saved && t1f)
+          TRY(launch_gemm_ds_fused(pack, L, Gc, reinterpret_cast<const __nv_bfloat16*>(pk + L.wmid_full_bf16),
+                                   reinterpret_cast<__nv_bfloat16*>(dS), g0, rows, fl, F(pl.off_dwpart), st,
+                                   drop.thresh ? &drop : nullptr));
+        else
+          TRY((gemm_pair ? launch_gemm_ds_pair : launch_gemm_ds)(Gc, reinterpret_cast<const __nv_bfloat16*>(pk + L.wmid_full_bf16),
+                                                                reinterpret_cast<__nv_bfloat16*>(dS), rows, st));
         float *dwm[kNumHeads], *dbm[kNumHeads];
         DzPtrs dzp{};
         for (int h = 0; h < kNumHeads; ++h) {

@@ -574,12 +574,14 @@ def test_fused_loss_in_the_pair_tiles_equals_the_separate_kernels(monkeypatch, s
         assert rel_err(g_extra[k], p.grad.cpu()) <= 2e-3, k
 
 
+@pytest.mark.parametrize("t1f", ["0", "1"])
 @pytest.mark.parametrize("drop", [False, True])
-def test_saved_activation_backward_vs_fp64_oracle_and_recompute(monkeypatch, drop):
+def test_saved_activation_backward_vs_fp64_oracle_and_recompute(monkeypatch, drop, t1f):
     """The backward from saved activations (pair_bwd_elem.cu) at N = 120 with several chunks and a ragged last tile:
     gradients against the fp64 autograd oracle (bf16 tolerance; with the decoder's dropout active the oracle applies the
     same regenerated masks) and against the recompute route of the same step."""
     monkeypatch.setenv("PENEO_BWD_CHUNK_ROWS", "2500")
+    monkeypatch.setenv("PENEO_T1F", t1f)  # "1": the experimental route with the transform inside the dS GEMM (gemm_ds_fused.cu)
     n, b = 120, 2
     sd = synth.init_decoder_state(seed=21, trained_like=True)
     x = synth.hidden_states(b, n, 768, doc_id0=33).cuda()
